@@ -1,0 +1,117 @@
+"""Generate tests/golden/*.npz by EXECUTING THE UNMODIFIED REFERENCE (build container only).
+
+    python oracle/make_golden.py            # writes tests/golden/{c1_b32,tiny_B,tiny_B_mask,tiny_B_cap}.npz
+
+For each case: seeded state_dict (tvts_b200.synthetic.make_state_dict) is loaded strict=True into the
+reference modules, the reference forward + the trainer's loss lines (v2/trainer/trainer.py:479-496)
+run on a seeded batch, and outputs + per-parameter gradient fingerprints are stored.  The fixtures
+are small (no weights: they are regenerated from the seed on the GPU box).
+"""
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+warnings.filterwarnings("ignore")
+
+import ref_shims  # noqa: E402
+from tvts_b200 import config as C  # noqa: E402
+from tvts_b200.synthetic import make_batch, make_state_dict  # noqa: E402
+
+
+def build_reference_model(cfg):
+    """A reference TVTSv2_B_* instance with cfg's dims (the class hard-codes B/16|B/32 dims in __init__,
+    so for tiny dims the submodules are built with the reference constructors and attached to an
+    un-initialised instance; forward()/compute_text()/compute_video() are the reference's own)."""
+    from torch import nn
+    import model.model_dist_TVTSv2_ViT_B_32 as ref_model
+    from model.video_encoder_ViT_B_32 import VisionTransformer
+    from model.sort_transformer import SortTransformer
+    from CLIP.clip.model import CLIP
+
+    m = ref_model.TVTSv2_B_32.__new__(ref_model.TVTSv2_B_32)
+    nn.Module.__init__(m)
+    clip_model = CLIP(cfg.embed_dim, cfg.resolution, 1, 64, cfg.patch, cfg.context, cfg.vocab,
+                      cfg.text_width, cfg.text_heads, cfg.text_layers)
+    m.text_model = clip_model.transformer
+    m.text_token_embedding = clip_model.token_embedding
+    m.text_positional_embedding = clip_model.positional_embedding
+    m.text_ln_final = clip_model.ln_final
+    m.text_projection = clip_model.text_projection
+    m.video_model = VisionTransformer(input_resolution=cfg.resolution, patch_size=cfg.patch, width=cfg.width,
+                                      layers=cfg.layers, heads=cfg.heads, output_dim=cfg.embed_dim,
+                                      num_frames=cfg.num_frames, mask_ratio=cfg.mask_ratio)
+    m.n_trans = cfg.n_trans
+    m.pred_model = SortTransformer(num_classes=cfg.n_trans, embed_dim=cfg.embed_dim, num_heads=cfg.sort_heads)
+    return m, ref_model.sim_matrix
+
+
+def run_case(name, cfg, batch, frames, n_trans, seed):
+    from model.loss import NormSoftmaxLoss
+    m, sim_matrix = build_reference_model(cfg)
+    sd = make_state_dict(cfg, seed=1234)
+    m.load_state_dict(sd, strict=True)
+    m.train()
+    data = make_batch(cfg, batch, frames, n_trans=n_trans, seed=seed)
+    text_e, video_e, pred = m(data)
+    # trainer lines 481-494 at world_size 1 (all_gather of one rank is the identity)
+    loss1 = NormSoftmaxLoss(cfg.temperature)(sim_matrix(video_e, text_e))
+    if pred is not None:
+        loss2 = torch.nn.CrossEntropyLoss()(pred.reshape(-1, pred.shape[-1]), data["label"].reshape(-1)) * 2
+    else:
+        loss2 = torch.zeros(())
+    (loss1 + loss2).backward()
+    out = {
+        "text_emb": text_e.detach().numpy(), "video_emb": video_e.detach().numpy(),
+        "loss1": np.float64(loss1.item()), "loss2": np.float64(loss2.item()),
+        "batch": batch, "frames": frames, "n_trans": n_trans, "seed": seed,
+    }
+    if pred is not None:
+        out["pred_order"] = pred.detach().numpy()
+    names, norms, heads = [], [], []
+    for k, p in m.named_parameters():
+        if p.grad is None:
+            continue
+        names.append(k)
+        norms.append(p.grad.double().norm().item())
+        heads.append(p.grad.reshape(-1)[:8].double().numpy().copy() if p.numel() >= 8
+                     else np.pad(p.grad.reshape(-1).double().numpy(), (0, 8 - p.numel())))
+    out["grad_names"] = np.array(names)
+    out["grad_norms"] = np.array(norms)
+    out["grad_heads"] = np.stack(heads)
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, **out)
+
+    # immediately pin the restatement
+    import tvts_oracle as O
+    l1, l2, (te, ve, pr), grads = O.step_with_grads(sd, data["text"], data["video"], data["keep_ind"], data["label"], cfg)
+    err = lambda a, b: float((a - b).abs().max())
+    print(f"[{name}] loss1 ref {loss1.item():.7f} oracle {l1.item():.7f} | loss2 ref {loss2.item():.7f} oracle {l2.item():.7f}")
+    print(f"   max|d text_emb| {err(te, text_e.detach()):.2e}  max|d video_emb| {err(ve, video_e.detach()):.2e}"
+          + (f"  max|d pred| {err(pr, pred.detach()):.2e}" if pred is not None else ""))
+    worst = 0.0
+    for k, nrm in zip(names, norms):
+        gn = grads[k].double().norm().item() if k in grads else 0.0
+        worst = max(worst, abs(gn - nrm) / (nrm + 1e-12))
+    print(f"   worst relative grad-norm deviation over {len(names)} params: {worst:.2e}   -> {path} ({os.path.getsize(path)} B)")
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    ref_shims.install("v2")
+    run_case("tiny_B", C.TINY_B, batch=3, frames=2, n_trans=4, seed=11)
+    run_case("tiny_B_mask", C.TINY_B_MASK, batch=2, frames=3, n_trans=4, seed=12)
+    run_case("tiny_B_cap", C.TINY_B, batch=4, frames=2, n_trans=1, seed=13)       # caption mode: pred_order None
+    run_case("c1_b32", C.TVTSV2_B_32, batch=4, frames=2, n_trans=4, seed=0)       # BASELINE.json configs[0]
+
+
+if __name__ == "__main__":
+    main()
