@@ -1,0 +1,398 @@
+// tcgen05 GEMM for the TVTS hot path: every nn.Linear / projection of the video tower, text tower and
+// sort head, in forward, dgrad and wgrad form (reference call sites
+// v2/model/video_encoder_ViT_B_16.py:41,74,105-109,233).
+//
+//   C[M,N] = epilogue( sum_k A[m,k] * B[n,k] )       bf16 operands, fp32 accumulation in TMEM
+//
+// Operand layouts (either operand independently):
+//   K-major : X[rows, K] row-major (the contraction index is contiguous)    -> forward / dgrad
+//   MN-major: X[K, rows] row-major (the row index is contiguous)            -> wgrad straight from
+//             the [tokens, features] activations with tokens as the contraction, no transposes
+//
+// Structure: persistent CTAs (one per SM), warp-specialised:
+//   warp 0  TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1  MMA issuer    (one thread, tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16 per instruction)
+//   warp 2  TMEM allocator (2 x BN fp32 columns: double-buffered accumulator so the epilogue of tile i
+//           overlaps the MMAs of tile i+1)
+//   warps 4-7 epilogue    (tcgen05.ld 32x32b -> per-warp smem transpose -> coalesced 128-bit global I/O
+//           with fused bias / QuickGELU|GELU / residual add / activation-derivative / split-K reduction)
+#include <cuda.h>
+#include "common.cuh"
+#include "../../include/tvts_b200.h"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kStages = 4;
+constexpr int kThreads = 256;
+constexpr int kEpiWarps = 4;
+constexpr int kStagePitch = 36;  // floats per staging row (32 + 4 pad: conflict-free v4 writes and reads)
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_BYTES = kEpiWarps * 32 * kStagePitch * 4;
+  static constexpr int BAR_OFFSET = kStages * STAGE_BYTES + EPI_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + tmem ptr + alignment slack
+};
+
+struct EpiParams {
+  void* out;
+  void* out_pre;
+  const float* bias;
+  const float* residual;
+  const bf16* aux;
+  long long ldo, ldr, ldaux;
+  int out_dtype;   // 0 fp32, 1 bf16
+  int act;         // applied to acc + bias
+  int dact;        // multiply by act'(aux) (dgrad through an activation)
+  int accumulate;  // 0 store, 1 red.add into fp32 out (split-K / grad accumulation)
+  float alpha;
+};
+
+struct GemmShape {
+  int M, N, K;
+  int m_tiles, n_tiles, k_blocks, splits, kb_per_split;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            GemmShape s, EpiParams ep, int dbg_lbo, int dbg_sbo, int dbg_kadv) {
+  using L = SmemLayout<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const uint32_t bar_base = smem_base + L::BAR_OFFSET;
+  auto full_bar = [&](int i) { return bar_base + 8u * i; };
+  auto empty_bar = [&](int i) { return bar_base + 8u * (kStages + i); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * kStages + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * kStages + 2 + i); };
+  const uint32_t tmem_holder = bar_base + 8u * (2 * kStages + 4);
+  volatile uint32_t* tmem_holder_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFFSET + 8 * (2 * kStages + 4));
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(full_bar(i), 1);
+      mbar_init(empty_bar(i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar(i), 1);
+      mbar_init(tempty_bar(i), kEpiWarps * 32);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_holder, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder_gen;
+
+  const int total_units = s.m_tiles * s.n_tiles * s.splits;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      const int split = unit % s.splits;
+      const int tile = unit / s.splits;
+      const int n_blk = tile % s.n_tiles;
+      const int m_blk = tile / s.n_tiles;
+      const int kb0 = split * s.kb_per_split;
+      const int kb1 = min(kb0 + s.kb_per_split, s.k_blocks);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_arrive_expect_tx(full_bar(stage), L::STAGE_BYTES);
+        const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
+        const uint32_t sb = sa + L::A_BYTES;
+        if (!A_MN) {
+          tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BLOCK_M / 64; ++j)
+            tma_load_2d(sa + j * (64 * BLOCK_K * 2), &tmap_a, full_bar(stage), m_blk * BLOCK_M + j * 64, kb * BLOCK_K);
+        }
+        if (!B_MN) {
+          tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BLOCK_K, n_blk * BN);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_2d(sb + j * (64 * BLOCK_K * 2), &tmap_b, full_bar(stage), n_blk * BN + j * 64, kb * BLOCK_K);
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer (single thread) =====================
+    // instruction descriptor: D=f32 (bit4), A=B=bf16 (bits 7,10), major bits 15/16, N>>3 at 17, M>>4 at 24
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+    // K-major SW128: 8-row groups are 1024 B apart (SBO); LBO unused.  Advance 32 B per UMMA_K inside the row.
+    // MN-major SW128: 64-element MN groups are one TMA box (8192 B) apart (LBO); 8-k-row groups 1024 B apart (SBO);
+    //                 UMMA_K = 16 k-rows = 2 groups -> advance 2048 B.
+    const uint32_t a_lbo = A_MN ? (dbg_lbo ? dbg_lbo : 64 * BLOCK_K * 2) : 16;
+    const uint32_t a_sbo = A_MN ? (dbg_sbo ? dbg_sbo : 1024) : 1024;
+    const uint32_t a_adv = A_MN ? (dbg_kadv ? dbg_kadv : 2048) : UMMA_K * 2;
+    const uint32_t b_lbo = B_MN ? (dbg_lbo ? dbg_lbo : 64 * BLOCK_K * 2) : 16;
+    const uint32_t b_sbo = B_MN ? (dbg_sbo ? dbg_sbo : 1024) : 1024;
+    const uint32_t b_adv = B_MN ? (dbg_kadv ? dbg_kadv : 2048) : UMMA_K * 2;
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
+      const int split = unit % s.splits;
+      const int kb0 = split * s.kb_per_split;
+      const int kb1 = min(kb0 + s.kb_per_split, s.k_blocks);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
+        const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          const uint64_t da = umma_smem_desc(sa + k * a_adv, a_lbo, a_sbo);
+          const uint64_t db = umma_smem_desc(sb + k * b_adv, b_lbo, b_sbo);
+          umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tfull_bar(acc));
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    float* stg = reinterpret_cast<float*>(smem_gen + kStages * L::STAGE_BYTES) + q * 32 * kStagePitch;
+    int it = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
+      const int tile = unit / s.splits;
+      const bool first_split = (unit % s.splits) == 0;  // bias / residual are added by one split only
+      const int n_blk = tile % s.n_tiles;
+      const int m_blk = tile / s.n_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row_base = m_blk * BLOCK_M + q * 32;
+      const int col_base = n_blk * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = col_base + c * 32;
+        if (col0 >= s.N) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, v);
+        tmem_ld_wait();
+        if (row_base < s.M) {
+          // row-per-thread -> smem
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 f = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                   __uint_as_float(v[4 * j + 3]));
+            *reinterpret_cast<float4*>(stg + lane * kStagePitch + 4 * j) = f;
+          }
+          __syncwarp();
+          // coalesced phase: 8 lanes cover 32 columns of one row; 4 rows per instruction
+          const int cq = (lane & 7) * 4;
+          const int gcol = col0 + cq;
+          const bool col_ok = gcol < s.N;
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ep.bias != nullptr && col_ok && first_split) bias4 = *reinterpret_cast<const float4*>(ep.bias + gcol);
+#pragma unroll
+          for (int r4 = 0; r4 < 8; ++r4) {
+            const int rl = r4 * 4 + (lane >> 3);
+            const long long grow = row_base + rl;
+            if (grow < s.M && col_ok) {
+              float4 a = *reinterpret_cast<const float4*>(stg + rl * kStagePitch + cq);
+              a.x = a.x * ep.alpha + bias4.x; a.y = a.y * ep.alpha + bias4.y;
+              a.z = a.z * ep.alpha + bias4.z; a.w = a.w * ep.alpha + bias4.w;
+              if (ep.out_pre != nullptr) {
+                uint2 p = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+                *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out_pre) + grow * ep.ldo + gcol) = p;
+              }
+              if (ep.act != TVTS_ACT_NONE) {
+                a.x = act_fwd(a.x, ep.act); a.y = act_fwd(a.y, ep.act);
+                a.z = act_fwd(a.z, ep.act); a.w = act_fwd(a.w, ep.act);
+              }
+              if (ep.dact != TVTS_ACT_NONE) {
+                uint2 p = *reinterpret_cast<const uint2*>(ep.aux + grow * ep.ldaux + gcol);
+                float2 p0 = unpack_bf16x2(p.x), p1 = unpack_bf16x2(p.y);
+                a.x *= act_bwd(p0.x, ep.dact); a.y *= act_bwd(p0.y, ep.dact);
+                a.z *= act_bwd(p1.x, ep.dact); a.w *= act_bwd(p1.y, ep.dact);
+              }
+              if (ep.residual != nullptr && first_split) {
+                float4 r = *reinterpret_cast<const float4*>(ep.residual + grow * ep.ldr + gcol);
+                a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+              }
+              if (ep.out_dtype == 1) {
+                uint2 p = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+                *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + grow * ep.ldo + gcol) = p;
+              } else {
+                float* o = reinterpret_cast<float*>(ep.out) + grow * ep.ldo + gcol;
+                if (ep.accumulate) {
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+                } else {
+                  *reinterpret_cast<float4*>(o) = a;
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 2-D bf16 tensor map: inner (contiguous) extent d0, outer extent d1, outer stride ld elements.
+int make_tmap(CUtensorMap* m, const void* ptr, long long d0, long long d1, long long ld, int box0, int box1) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return tvts_set_error(TVTS_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  cuuint64_t dims[2] = {(cuuint64_t)d0, (cuuint64_t)d1};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return tvts_set_error(TVTS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): ptr=%p dims=%lld,%lld ld=%lld box=%d,%d", (int)r, ptr,
+                          d0, d1, ld, box0, box1);
+  return TVTS_OK;
+}
+
+int g_dbg_lbo = 0, g_dbg_sbo = 0, g_dbg_kadv = 0;
+
+template <int BN, bool A_MN, bool B_MN>
+int launch(const tvts_gemm_args* g, const GemmShape& s, const EpiParams& ep, cudaStream_t stream) {
+  CUtensorMap ta, tb;
+  int rc;
+  if (!A_MN) rc = make_tmap(&ta, g->a, g->K, g->M, g->lda, BLOCK_K, BLOCK_M);
+  else rc = make_tmap(&ta, g->a, g->M, g->K, g->lda, 64, BLOCK_K);
+  if (rc) return rc;
+  if (!B_MN) rc = make_tmap(&tb, g->b, g->K, g->N, g->ldb, BLOCK_K, BN);
+  else rc = make_tmap(&tb, g->b, g->N, g->K, g->ldb, 64, BLOCK_K);
+  if (rc) return rc;
+  auto kern = gemm_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TVTS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BN>::TOTAL));
+    attr_set = true;
+  }
+  const int units = s.m_tiles * s.n_tiles * s.splits;
+  const int grid = units < tvts_num_sms() ? units : tvts_num_sms();
+  kern<<<grid, kThreads, SmemLayout<BN>::TOTAL, stream>>>(ta, tb, s, ep, g_dbg_lbo, g_dbg_sbo, g_dbg_kadv);
+  TVTS_LAUNCH_CHECK();
+  return TVTS_OK;
+}
+
+}  // namespace
+
+extern "C" int tvts_gemm_debug_set(int lbo, int sbo, int kadv) {
+  g_dbg_lbo = lbo; g_dbg_sbo = sbo; g_dbg_kadv = kadv;
+  return TVTS_OK;
+}
+
+extern "C" int tvts_gemm(const tvts_gemm_args* g, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  TVTS_REQUIRE(g != nullptr, "tvts_gemm: null args");
+  TVTS_REQUIRE(g->M > 0 && g->N > 0 && g->K > 0, "tvts_gemm: empty problem M=%lld N=%lld K=%lld", g->M, g->N, g->K);
+  TVTS_REQUIRE(g->M < (1ll << 31) && g->N < (1ll << 31) && g->K < (1ll << 31), "tvts_gemm: dims exceed int32");
+  TVTS_REQUIRE(g->a && g->b && g->out, "tvts_gemm: null operand pointer");
+  TVTS_REQUIRE(g->N % 4 == 0, "tvts_gemm: N=%lld must be a multiple of 4", g->N);
+  TVTS_REQUIRE(g->lda % 8 == 0 && g->ldb % 8 == 0, "tvts_gemm: operand leading dims must be multiples of 8 elements (lda=%lld ldb=%lld)",
+               g->lda, g->ldb);
+  TVTS_REQUIRE(((uintptr_t)g->a % 16 == 0) && ((uintptr_t)g->b % 16 == 0) && ((uintptr_t)g->out % 16 == 0),
+               "tvts_gemm: pointers must be 16-byte aligned");
+  TVTS_REQUIRE(g->ldo % 4 == 0, "tvts_gemm: ldo=%lld must be a multiple of 4", g->ldo);
+  TVTS_REQUIRE(!(g->accumulate && g->out_dtype != 0), "tvts_gemm: accumulate requires fp32 output");
+  TVTS_REQUIRE(!(g->splits > 1 && !g->accumulate), "tvts_gemm: split-K requires accumulate=1 into a pre-initialised fp32 output");
+  TVTS_REQUIRE(!(g->dact && !g->aux), "tvts_gemm: dact needs aux");
+  TVTS_REQUIRE(!(g->splits > 1 && (g->act || g->dact || g->out_pre)), "tvts_gemm: split-K cannot be combined with act/dact/out_pre");
+  if (g->residual) TVTS_REQUIRE(g->ldr % 4 == 0 && (uintptr_t)g->residual % 16 == 0, "tvts_gemm: residual alignment");
+  if (g->bias) TVTS_REQUIRE((uintptr_t)g->bias % 16 == 0, "tvts_gemm: bias alignment");
+  if (g->aux) TVTS_REQUIRE(g->ldaux % 4 == 0 && (uintptr_t)g->aux % 8 == 0, "tvts_gemm: aux alignment");
+
+  EpiParams ep;
+  ep.out = g->out; ep.out_pre = g->out_pre; ep.bias = g->bias; ep.residual = g->residual;
+  ep.aux = reinterpret_cast<const bf16*>(g->aux);
+  ep.ldo = g->ldo; ep.ldr = g->ldr; ep.ldaux = g->ldaux;
+  ep.out_dtype = g->out_dtype; ep.act = g->act; ep.dact = g->dact; ep.accumulate = g->accumulate;
+  ep.alpha = g->alpha == 0.0f ? 1.0f : g->alpha;
+
+  const bool small_n = g->N <= 128;
+  const int BN = small_n ? 128 : 256;
+  GemmShape s;
+  s.M = (int)g->M; s.N = (int)g->N; s.K = (int)g->K;
+  s.m_tiles = (s.M + BLOCK_M - 1) / BLOCK_M;
+  s.n_tiles = (s.N + BN - 1) / BN;
+  s.k_blocks = (s.K + BLOCK_K - 1) / BLOCK_K;
+  int splits = g->splits;
+  if (splits <= 0) {  // auto: fill the machine when the output grid alone cannot (wgrad: small output, very deep K)
+    splits = 1;
+    if (g->accumulate) {
+      const int tiles = s.m_tiles * s.n_tiles;
+      const int sms = tvts_num_sms();
+      if (tiles < sms) splits = (2 * sms + tiles - 1) / tiles;
+      const int max_splits = (s.k_blocks + 3) / 4;  // keep >= 4 k-blocks per unit
+      if (splits > max_splits) splits = max_splits;
+      if (splits < 1) splits = 1;
+    }
+  }
+  if (splits > s.k_blocks) splits = s.k_blocks;
+  s.kb_per_split = (s.k_blocks + splits - 1) / splits;
+  s.splits = (s.k_blocks + s.kb_per_split - 1) / s.kb_per_split;
+
+#define TVTS_DISPATCH(BN_)                                                          \
+  if (!g->a_mn && !g->b_mn) return launch<BN_, false, false>(g, s, ep, stream);     \
+  if (g->a_mn && g->b_mn) return launch<BN_, true, true>(g, s, ep, stream);         \
+  if (!g->a_mn && g->b_mn) return launch<BN_, false, true>(g, s, ep, stream);       \
+  return launch<BN_, true, false>(g, s, ep, stream);
+  if (small_n) { TVTS_DISPATCH(128) } else { TVTS_DISPATCH(256) }
+#undef TVTS_DISPATCH
+}
