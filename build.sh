@@ -4,7 +4,7 @@ set -e
 cd "$(dirname "$0")"
 mkdir -p tvts_b200/lib build
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --use_fast_math"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --use_fast_math"
 objs=""
 pids=""
 for f in tvts_b200/csrc/*.cu; do

@@ -18,6 +18,8 @@ def run_case(spec):
     dev = "cuda"
     M, N, K = spec["M"], spec["N"], spec["K"]
     a_mn, b_mn = spec.get("a_mn", 0), spec.get("b_mn", 0)
+    if spec.get("epi"):
+        L.lib().tvts_gemm_debug_epi(spec["epi"])
     if spec.get("dbg"):
         L.lib().tvts_gemm_debug_set(*spec["dbg"])
     A = torch.randn(M, K, device=dev) * 0.5
@@ -109,6 +111,13 @@ CASES = [
     dict(name="mn_ab_alt_swapped", M=256, N=512, K=256, a_mn=1, b_mn=1, dbg=(1024, 8192, 2048)),
     dict(name="mn_ab_alt_adv", M=256, N=512, K=256, a_mn=1, b_mn=1, dbg=(8192, 1024, 32)),
 ]
+EPI = [
+    dict(name="epi0_qkv", M=25152, N=2304, K=768, bf16_out=True, perf=True),
+    dict(name="epi1_qkv_nostore", M=25152, N=2304, K=768, bf16_out=True, perf=True, epi=1),
+    dict(name="epi2_qkv_direct", M=25152, N=2304, K=768, bf16_out=True, perf=True, epi=2),
+    dict(name="epi3_qkv_skip", M=25152, N=2304, K=768, bf16_out=True, perf=True, epi=3),
+    dict(name="epi3_8192_skip", M=8192, N=8192, K=8192, bf16_out=True, perf=True, epi=3),
+]
 PERF = [
     dict(name="perf_qkv", M=25152, N=2304, K=768, bf16_out=True, perf=True),
     dict(name="perf_proj_res", M=25152, N=768, K=768, mode="bias_act_res", perf=True),
@@ -127,6 +136,13 @@ def main():
     cases = list(CASES)
     if "--perf" in sys.argv:
         cases += PERF
+    if "--epi" in sys.argv:
+        cases = list(EPI)
+    if "--one" in sys.argv:
+        name = sys.argv[sys.argv.index("--one") + 1]
+        spec = [c for c in CASES + PERF + EPI if c["name"] == name][0]
+        print(run_case(spec))
+        return
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     log = open(os.path.join(ROOT, "gpurun_out", "gemm_bringup.log"), "w")
     for spec in cases:
@@ -134,7 +150,7 @@ def main():
             p = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", json.dumps(spec)],
                                capture_output=True, text=True, timeout=120)
             out = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
-            msg = out[-1][7:] if out else ("FAIL rc=%d %s" % (p.returncode, (p.stderr or "")[-400:].replace("\n", " | ")))
+            msg = out[-1][7:] if out else ("FAIL rc=%d %s" % (p.returncode, (p.stderr or "")[-300:].replace("\n", " | ")))
         except subprocess.TimeoutExpired:
             msg = "TIMEOUT"
         line = f"{spec['name']:24s} {msg}"

@@ -62,7 +62,7 @@ struct GemmShape {
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-            GemmShape s, EpiParams ep, int dbg_lbo, int dbg_sbo, int dbg_kadv) {
+            GemmShape s, EpiParams ep, int dbg_lbo, int dbg_sbo, int dbg_kadv, int dbg_epi) {
   using L = SmemLayout<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -197,9 +197,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       for (int c = 0; c < BN / 32; ++c) {
         const int col0 = col_base + c * 32;
         if (col0 >= s.N) break;  // warp-uniform
+        if (dbg_epi == 3) break;
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, v);
         tmem_ld_wait();
+        if (dbg_epi == 2) {
+          const long long grow = row_base + lane;
+          if (grow < s.M) {
+            bf16* o = reinterpret_cast<bf16*>(ep.out) + grow * ep.ldo + col0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 pk = make_uint4(pack_bf16x2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+                                    pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                                    pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                                    pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+              *reinterpret_cast<uint4*>(o + 8 * j) = pk;
+            }
+          }
+          continue;
+        }
         if (row_base < s.M) {
           // row-per-thread -> smem
 #pragma unroll
@@ -241,6 +257,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 float4 r = *reinterpret_cast<const float4*>(ep.residual + grow * ep.ldr + gcol);
                 a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
               }
+              if (dbg_epi == 1) continue;
               if (ep.out_dtype == 1) {
                 uint2 p = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
                 *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + grow * ep.ldo + gcol) = p;
@@ -306,7 +323,7 @@ int make_tmap(CUtensorMap* m, const void* ptr, long long d0, long long d1, long 
   return TVTS_OK;
 }
 
-int g_dbg_lbo = 0, g_dbg_sbo = 0, g_dbg_kadv = 0;
+int g_dbg_lbo = 0, g_dbg_sbo = 0, g_dbg_kadv = 0, g_dbg_epi = 0;
 
 template <int BN, bool A_MN, bool B_MN>
 int launch(const tvts_gemm_args* g, const GemmShape& s, const EpiParams& ep, cudaStream_t stream) {
@@ -326,13 +343,17 @@ int launch(const tvts_gemm_args* g, const GemmShape& s, const EpiParams& ep, cud
   }
   const int units = s.m_tiles * s.n_tiles * s.splits;
   const int grid = units < tvts_num_sms() ? units : tvts_num_sms();
-  kern<<<grid, kThreads, SmemLayout<BN>::TOTAL, stream>>>(ta, tb, s, ep, g_dbg_lbo, g_dbg_sbo, g_dbg_kadv);
+  kern<<<grid, kThreads, SmemLayout<BN>::TOTAL, stream>>>(ta, tb, s, ep, g_dbg_lbo, g_dbg_sbo, g_dbg_kadv, g_dbg_epi);
   TVTS_LAUNCH_CHECK();
   return TVTS_OK;
 }
 
 }  // namespace
 
+extern "C" int tvts_gemm_debug_epi(int mode) {
+  g_dbg_epi = mode;
+  return TVTS_OK;
+}
 extern "C" int tvts_gemm_debug_set(int lbo, int sbo, int kadv) {
   g_dbg_lbo = lbo; g_dbg_sbo = sbo; g_dbg_kadv = kadv;
   return TVTS_OK;
