@@ -1,0 +1,317 @@
+"""TEST INFRASTRUCTURE ONLY -- a torch (CPU or GPU) restatement of every C-ABI op of libtvts_b200.so.
+
+Two uses, both inside tests/:
+  * `-m "not gpu"`: `install()` monkeypatches tvts_b200._lib.call / .gemm so the host-side orchestration
+    (tvts_b200/engine.py, the model mirror, the trainer) can be checked against the oracle without a GPU;
+  * `-m gpu`: the per-kernel parity tests run the real kernel and this restatement on the same inputs.
+The product never imports this module (tvts_b200/_lib.py raises if the native library is missing).
+"""
+import math
+
+import torch
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _act(x, a):
+    if a in (1, "quick_gelu"):
+        return x * torch.sigmoid(1.702 * x)
+    if a in (2, "gelu"):
+        return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
+    return x
+
+
+def _dact(x, a):
+    if a in (1, "quick_gelu"):
+        s = torch.sigmoid(1.702 * x)
+        return s * (1.0 + 1.702 * x * (1.0 - s))
+    if a in (2, "gelu"):
+        return 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0))) + x * torch.exp(-0.5 * x * x) / math.sqrt(2.0 * math.pi)
+    return torch.ones_like(x)
+
+
+def gemm(a, b, out, *, M, N, K, lda, ldb, ldo=None, a_mn=False, b_mn=False, bias=None, residual=None, ldr=None,
+         aux=None, ldaux=None, out_pre=None, act=None, dact=None, accumulate=False, splits=0, alpha=1.0):
+    A = a.reshape(-1)[: (K if a_mn else M) * lda].view(-1, lda)
+    A = A[:K, :M].t() if a_mn else A[:M, :K]
+    Bm = b.reshape(-1)[: (K if b_mn else N) * ldb].view(-1, ldb)
+    Bm = Bm[:K, :N].t() if b_mn else Bm[:N, :K]
+    v = alpha * (A.float() @ Bm.float().t())
+    if bias is not None:
+        v = v + bias.float()
+    o = out.view(M, -1)[:, :N]
+    if out_pre is not None:
+        out_pre.view(M, -1)[:, :N].copy_(v.to(BF16))
+    v = _act(v, act)
+    if dact:
+        v = v * _dact(aux.view(M, -1)[:, :N].float(), dact)
+    if residual is not None:
+        v = v + residual.view(M, -1)[:, :N]
+    if accumulate:
+        o.add_(v.to(o.dtype))
+    else:
+        o.copy_(v.to(o.dtype))
+    return out
+
+
+def _sets(mode, N, T, n):
+    """list of (stationary tokens, streamed tokens) index lists"""
+    if mode == 0:
+        return [(list(range(N)), list(range(N)))]
+    groups = []
+    if mode == 1:
+        for f in range(T):
+            g = [1 + f * n + i for i in range(n)]
+            groups.append((g, [0] + g))
+    else:
+        for i in range(n):
+            g = [1 + f * n + i for f in range(T)]
+            groups.append((g, [0] + g))
+    groups.append(([0], list(range(N))))
+    return groups
+
+
+def _attn_mask(N, mode, T, n, causal, device):
+    m = torch.zeros(N, N, dtype=torch.bool, device=device)
+    for q, k in _sets(mode, N, T, n):
+        qi = torch.tensor(q, device=device)
+        ki = torch.tensor(k, device=device)
+        m[qi[:, None], ki[None, :]] = True
+    if causal:
+        m &= torch.ones(N, N, dtype=torch.bool, device=device).tril()
+    return m
+
+
+def _attn_probs(qkv, B, N, H, d, mode, T, n, causal, scale):
+    x = qkv.view(B, N, 3, H, d).float()
+    q, k, v = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)  # [B,H,N,d]
+    s = (q @ k.transpose(-1, -2)) * scale
+    mask = _attn_mask(N, mode, T, n, causal, qkv.device)
+    s = s.masked_fill(~mask, float("-inf"))
+    return q, k, v, s
+
+
+def attn_fwd(qkv, out, lse, B, N, H, d, mode, T, n, causal, scale):
+    q, k, v, s = _attn_probs(qkv, B, N, H, d, mode, T, n, causal, scale)
+    l = torch.logsumexp(s, -1)
+    p = torch.exp(s - l[..., None])
+    o = (p @ v).transpose(1, 2).reshape(B * N, H * d)
+    out.view(B * N, H * d).copy_(o.to(BF16))
+    lse.view(B, H, N).copy_(l)
+
+
+def attn_bwd(qkv, out, dout, lse, delta, dqkv, B, N, H, d, mode, T, n, causal, scale):
+    q, k, v, s = _attn_probs(qkv, B, N, H, d, mode, T, n, causal, scale)
+    p = torch.exp(s - lse.view(B, H, N)[..., None])
+    do = dout.view(B, N, H, d).float().transpose(1, 2)
+    o = out.view(B, N, H, d).float().transpose(1, 2)
+    dl = (do * o).sum(-1)
+    delta.view(B, H, N).copy_(dl)
+    dp = do @ v.transpose(-1, -2)
+    ds = p * (dp - dl[..., None])
+    dq = (ds @ k) * scale
+    dk = (ds.transpose(-1, -2) @ q) * scale
+    dv = p.transpose(-1, -2) @ do
+    r = torch.stack([dq, dk, dv], 0).permute(1, 3, 0, 2, 4)  # [B,N,3,H,d]
+    dqkv.view(B, N, 3, H, d).copy_(r.to(BF16))
+
+
+def layernorm_fwd(x, g, b, y, y_bf16, mean, rstd, M, D, eps):
+    x = x.view(M, D)
+    mu = x.mean(-1, keepdim=True)
+    xc = x - mu
+    rs = torch.rsqrt((xc * xc).mean(-1, keepdim=True) + eps)
+    y.view(M, D).copy_((xc * rs * g + b).to(y.dtype))
+    if mean is not None:
+        mean.copy_(mu.view(-1))
+    if rstd is not None:
+        rstd.copy_(rs.view(-1))
+
+
+def layernorm_bwd(dy, dy_bf16, x, mean, rstd, g, res1, res2, dx, dxb, dg, db, M, D):
+    d = dy.view(M, D).float()
+    xh = (x.view(M, D) - mean[:, None]) * rstd[:, None]
+    gy = d * g
+    s1 = gy.mean(-1, keepdim=True)
+    s2 = (gy * xh).mean(-1, keepdim=True)
+    o = rstd[:, None] * (gy - s1 - xh * s2)
+    if res1 is not None:
+        o = o + res1.view(M, D)
+    if res2 is not None:
+        o = o + res2.view(M, D)
+    if dx is not None:
+        dx.view(M, D).copy_(o)
+    if dxb is not None:
+        dxb.view(M, D).copy_(o.to(BF16))
+    if dg is not None:
+        dg.add_((d * xh).sum(0))
+        db.add_(d.sum(0))
+
+
+def cast_bf16(src, dst, n):
+    dst.view(-1).copy_(src.reshape(-1).to(BF16))
+
+
+def colsum_bf16(x, out, M, N, ld):
+    out.add_(x.view(M, ld)[:, :N].float().sum(0))
+
+
+def patch_gather(video, keep, cols, B, T, R, p, n):
+    g = R // p
+    v = video.view(B, T, 3, g, p, g, p).permute(0, 1, 3, 5, 2, 4, 6).reshape(B, T, g * g, 3 * p * p)
+    idx = keep.view(B, 1, n, 1).expand(B, T, n, 3 * p * p)
+    cols.view(B, T, n, -1).copy_(torch.gather(v, 2, idx).to(BF16))
+
+
+def video_assemble(tok, cls, pos, tem, keep, x0, B, T, n, D):
+    t = tok.view(B, T, n, D) + pos[1:][keep.view(B, n)][:, None] + tem[:T][None, :, None, :]
+    x = x0.view(B, 1 + T * n, D)
+    x[:, 0] = cls + pos[0]
+    x[:, 1:] = t.reshape(B, T * n, D)
+
+
+def video_assemble_bwd(dx0, keep, dcls, dpos, dtem, dtok, B, T, n, D):
+    d = dx0.view(B, 1 + T * n, D)
+    dcls.add_(d[:, 0].sum(0))
+    dpos[0].add_(d[:, 0].sum(0))
+    dt = d[:, 1:].reshape(B, T, n, D)
+    dtem[:T].add_(dt.sum((0, 2)))
+    dpos.index_add_(0, (1 + keep.view(B, n)).reshape(-1), dt.sum(1).reshape(B * n, D))
+    dtok.view(B, T, n, D).copy_(dt.to(BF16))
+
+
+def text_embed(tok, is64, table, pos, x, rows, L, W):
+    x.view(rows, L, W).copy_(table[tok.view(rows, L).long()] + pos)
+
+
+def text_embed_bwd(dx, tok, is64, dtable, dpos, rows, L, W):
+    d = dx.view(rows, L, W)
+    if dpos is not None:
+        dpos.add_(d.sum(0))
+    if dtable is not None:
+        dtable.index_add_(0, tok.view(-1).long(), d.reshape(rows * L, W))
+
+
+def argmax_rows(tok, is64, flat_idx, rows, L):
+    flat_idx.copy_(torch.arange(rows, device=tok.device) * L + tok.view(rows, L).long().argmax(-1))
+
+
+def gather_rows(src, idx, dst, rows, D):
+    dst.view(rows, D).copy_(src.view(-1, D)[idx])
+
+
+def scatter_rows(src, idx, dst, rows, D, accumulate):
+    if accumulate:
+        dst.view(-1, D).index_add_(0, idx, src.view(rows, D))
+    else:
+        dst.view(-1, D)[idx] = src.view(rows, D)
+
+
+def group_mean(t, out, nt, B, E):
+    out.view(B, E).copy_(t.view(nt, B, E).mean(0))
+
+
+def group_mean_bwd(dout, dt, dt_bf16, nt, B, E):
+    v = (dout.view(1, B, E) / nt).expand(nt, B, E)
+    if dt is not None:
+        dt.view(nt, B, E).copy_(v)
+    if dt_bf16 is not None:
+        dt_bf16.view(nt, B, E).copy_(v.to(BF16))
+
+
+def sort_concat(vtok, t, te, z, B, N, nt, E):
+    zz = z.view(B, N + nt, E)
+    te = te.view(2, E)
+    zz[:, :N] = vtok.view(B, N, E) + te[0]
+    zz[:, N:] = t.view(nt, B, E).permute(1, 0, 2) + te[1]
+
+
+def sort_concat_bwd(dz, dvtok, dte, B, N, nt, E):
+    d = dz.view(B, N + nt, E)
+    dvtok.view(B, N, E).copy_(d[:, :N])
+    dte.view(2, E)[0].add_(d[:, :N].sum((0, 1)))
+    dte.view(2, E)[1].add_(d[:, N:].sum((0, 1)))
+
+
+def add_rows(src, dst, rows, D, lds, ldd):
+    dst.view(-1)[: rows * ldd].view(rows, ldd)[:, :D].add_(src.view(-1)[: rows * lds].view(rows, lds)[:, :D])
+
+
+def small_linear_fwd(x, w, bias, y, R, K, O):
+    y.view(R, O).copy_(x.view(R, K) @ w.view(O, K).t() + (bias if bias is not None else 0))
+
+
+def small_linear_bwd(dy, x, w, dx, dw, db, R, K, O):
+    dy = dy.view(R, O)
+    dx.view(R, K).copy_(dy @ w.view(O, K))
+    dw.view(O, K).add_(dy.t() @ x.view(R, K))
+    if db is not None:
+        db.add_(dy.sum(0))
+
+
+def normalize_rows(x, xn, norm, rows, E, eps):
+    nr = x.view(rows, E).norm(dim=1)
+    norm.copy_(nr)
+    xn.view(rows, E).copy_(x.view(rows, E) / nr.clamp_min(eps)[:, None])
+
+
+def sim_matrix(an, bn, S, Ra, Rb, E, scale):
+    S.view(Ra, Rb).copy_(scale * an.view(Ra, E) @ bn.view(Rb, E).t())
+
+
+def sim_matrix_bwd(G, self_n, other_n, self_norm, dself, R_self, R_other, E, row0, nrows, transposed, scale, eps):
+    Gm = G.view(R_other, R_self).t() if transposed else G.view(R_self, R_other)
+    dn = scale * Gm[row0:row0 + nrows] @ other_n.view(R_other, E)
+    sn = self_n.view(R_self, E)[row0:row0 + nrows]
+    nr = self_norm[row0:row0 + nrows]
+    proj = (dn - sn * (sn * dn).sum(-1, keepdim=True)) / nr.clamp_min(eps)[:, None]
+    clamped = (nr <= eps)[:, None]
+    dself.view(nrows, E).copy_(torch.where(clamped, dn / eps, proj))
+
+
+def nsl_fwd(S, lse_r, lse_c, loss, Bg, temperature):
+    x = S.view(Bg, Bg) / temperature
+    lr, lc = torch.logsumexp(x, 1), torch.logsumexp(x, 0)
+    lse_r.copy_(lr)
+    lse_c.copy_(lc)
+    d = torch.diagonal(x)
+    loss.copy_(-(d - lr).mean() - (d - lc).mean())
+
+
+def nsl_bwd(S, lse_r, lse_c, gout, G, Bg, temperature):
+    x = S.view(Bg, Bg) / temperature
+    g = (gout if gout is not None else 1.0) / temperature / Bg
+    G.view(Bg, Bg).copy_((torch.exp(x - lse_r[:, None]) + torch.exp(x - lse_c[None, :]) - 2 * torch.eye(Bg, device=S.device)) * g)
+
+
+def sort_ce(logits, labels, gout, loss, dlogits, R, C, weight):
+    x = logits.view(R, C)
+    l = torch.logsumexp(x, 1)
+    if loss is not None:
+        loss.copy_(weight * (l - x[torch.arange(R, device=x.device), labels]).mean())
+    if dlogits is not None:
+        g = (gout if gout is not None else 1.0) * weight / R
+        oh = torch.zeros_like(x)
+        oh[torch.arange(R, device=x.device), labels] = 1.0
+        dlogits.view(R, C).copy_((torch.exp(x - l[:, None]) - oh) * g)
+
+
+OPS = {k: v for k, v in list(globals().items()) if callable(v) and not k.startswith("_") and k not in ("install", "uninstall", "gemm")}
+
+_saved = {}
+
+
+def install():
+    """Route tvts_b200._lib.call / gemm to the restatement above (CPU tests of the host logic)."""
+    from tvts_b200 import _lib as L
+    if _saved:
+        return
+    _saved["call"], _saved["gemm"] = L.call, L.gemm
+    L.call = lambda name, *args: OPS[name](*args)
+    L.gemm = gemm
+
+
+def uninstall():
+    from tvts_b200 import _lib as L
+    if _saved:
+        L.call, L.gemm = _saved.pop("call"), _saved.pop("gemm")

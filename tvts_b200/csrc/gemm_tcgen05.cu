@@ -14,8 +14,10 @@
 //   warp 1  MMA issuer    (one thread, tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16 per instruction)
 //   warp 2  TMEM allocator (2 x BN fp32 columns: double-buffered accumulator so the epilogue of tile i
 //           overlaps the MMAs of tile i+1)
-//   warps 4-7 epilogue    (tcgen05.ld 32x32b -> per-warp smem transpose -> coalesced 128-bit global I/O
-//           with fused bias / QuickGELU|GELU / residual add / activation-derivative / split-K reduction)
+//   warps 4-11 epilogue   (tcgen05.ld 32x32b: one accumulator row per thread -> 128-bit global I/O with fused
+//           bias / QuickGELU|GELU / residual add / activation-derivative / split-K reduction.  A shared-memory
+//           transpose for fully coalesced stores was measured 2x slower on B200 (bank conflicts + smem port
+//           contention with the UMMA operand reads, profiles/r1_gemm_epilogue.md), so rows are stored directly.)
 #include <cuda.h>
 #include "common.cuh"
 #include "../../include/tvts_b200.h"
@@ -26,17 +28,15 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kStages = 4;
-constexpr int kThreads = 256;
-constexpr int kEpiWarps = 4;
-constexpr int kStagePitch = 36;  // floats per staging row (32 + 4 pad: conflict-free v4 writes and reads)
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 128 + kEpiWarps * 32;
 
 template <int BN>
 struct SmemLayout {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_BYTES = kEpiWarps * 32 * kStagePitch * 4;
-  static constexpr int BAR_OFFSET = kStages * STAGE_BYTES + EPI_BYTES;
+  static constexpr int BAR_OFFSET = kStages * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + tmem ptr + alignment slack
 };
 
@@ -178,9 +178,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       umma_commit(tfull_bar(acc));
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int q = warp & 3;  // TMEM lane quadrant this warp may read
-    float* stg = reinterpret_cast<float*>(smem_gen + kStages * L::STAGE_BYTES) + q * 32 * kStagePitch;
+    // ===================== epilogue: 8 warps, row-per-thread, direct 128-bit global I/O =====================
+    // TMEM lane quadrant q = warp % 4 (hardware restriction); the two warps of a quadrant split the tile's columns.
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    constexpr int COLS_PER_WARP = BN / 2;
     int it = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
       const int tile = unit / s.splits;
@@ -191,87 +193,97 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row_base = m_blk * BLOCK_M + q * 32;
-      const int col_base = n_blk * BN;
+      const long long grow = (long long)m_blk * BLOCK_M + q * 32 + lane;
+      const bool row_ok = grow < s.M;
+      const int col_base = n_blk * BN + half * COLS_PER_WARP;
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * COLS_PER_WARP;
+      const bool use_res = ep.residual != nullptr && first_split;
+      const bool use_bias = ep.bias != nullptr && first_split;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
         const int col0 = col_base + c * 32;
-        if (col0 >= s.N) break;  // warp-uniform
-        if (dbg_epi == 3) break;
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, v);
-        tmem_ld_wait();
-        if (dbg_epi == 2) {
-          const long long grow = row_base + lane;
-          if (grow < s.M) {
-            bf16* o = reinterpret_cast<bf16*>(ep.out) + grow * ep.ldo + col0;
+        if (col0 >= s.N || dbg_epi == 3) break;  // warp-uniform
+        // issue the independent global loads first so their latency overlaps the TMEM load
+        float4 r4[8];
+        uint4 x4[4];
+        if (use_res && row_ok) {
+          const float* rp = ep.residual + grow * ep.ldr + col0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 pk = make_uint4(pack_bf16x2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
-                                    pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
-                                    pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
-                                    pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
-              *reinterpret_cast<uint4*>(o + 8 * j) = pk;
-            }
-          }
-          continue;
+          for (int j = 0; j < 8; ++j)
+            r4[j] = (col0 + 4 * j < s.N) ? *reinterpret_cast<const float4*>(rp + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (row_base < s.M) {
-          // row-per-thread -> smem
+        if (ep.dact != TVTS_ACT_NONE && row_ok) {
+          const bf16* ap = ep.aux + grow * ep.ldaux + col0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            x4[j] = (col0 + 8 * j < s.N) ? *reinterpret_cast<const uint4*>(ap + 8 * j) : make_uint4(0, 0, 0, 0);
+        }
+        uint32_t v[32];
+        tmem_ld_32x32(t_base + c * 32, v);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * ep.alpha;
+        if (use_bias) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float4 f = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                                   __uint_as_float(v[4 * j + 3]));
-            *reinterpret_cast<float4*>(stg + lane * kStagePitch + 4 * j) = f;
-          }
-          __syncwarp();
-          // coalesced phase: 8 lanes cover 32 columns of one row; 4 rows per instruction
-          const int cq = (lane & 7) * 4;
-          const int gcol = col0 + cq;
-          const bool col_ok = gcol < s.N;
-          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ep.bias != nullptr && col_ok && first_split) bias4 = *reinterpret_cast<const float4*>(ep.bias + gcol);
-#pragma unroll
-          for (int r4 = 0; r4 < 8; ++r4) {
-            const int rl = r4 * 4 + (lane >> 3);
-            const long long grow = row_base + rl;
-            if (grow < s.M && col_ok) {
-              float4 a = *reinterpret_cast<const float4*>(stg + rl * kStagePitch + cq);
-              a.x = a.x * ep.alpha + bias4.x; a.y = a.y * ep.alpha + bias4.y;
-              a.z = a.z * ep.alpha + bias4.z; a.w = a.w * ep.alpha + bias4.w;
-              if (ep.out_pre != nullptr) {
-                uint2 p = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
-                *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out_pre) + grow * ep.ldo + gcol) = p;
-              }
-              if (ep.act != TVTS_ACT_NONE) {
-                a.x = act_fwd(a.x, ep.act); a.y = act_fwd(a.y, ep.act);
-                a.z = act_fwd(a.z, ep.act); a.w = act_fwd(a.w, ep.act);
-              }
-              if (ep.dact != TVTS_ACT_NONE) {
-                uint2 p = *reinterpret_cast<const uint2*>(ep.aux + grow * ep.ldaux + gcol);
-                float2 p0 = unpack_bf16x2(p.x), p1 = unpack_bf16x2(p.y);
-                a.x *= act_bwd(p0.x, ep.dact); a.y *= act_bwd(p0.y, ep.dact);
-                a.z *= act_bwd(p1.x, ep.dact); a.w *= act_bwd(p1.y, ep.dact);
-              }
-              if (ep.residual != nullptr && first_split) {
-                float4 r = *reinterpret_cast<const float4*>(ep.residual + grow * ep.ldr + gcol);
-                a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
-              }
-              if (dbg_epi == 1) continue;
-              if (ep.out_dtype == 1) {
-                uint2 p = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
-                *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + grow * ep.ldo + gcol) = p;
-              } else {
-                float* o = reinterpret_cast<float*>(ep.out) + grow * ep.ldo + gcol;
-                if (ep.accumulate) {
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
-                } else {
-                  *reinterpret_cast<float4*>(o) = a;
-                }
-              }
+            if (col0 + 4 * j < s.N) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + j);
+              f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
             }
           }
-          __syncwarp();
+        }
+        if (ep.out_pre != nullptr) {
+          bf16* o = reinterpret_cast<bf16*>(ep.out_pre) + grow * ep.ldo + col0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (col0 + 8 * j < s.N)
+              *reinterpret_cast<uint4*>(o + 8 * j) =
+                  make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                             pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+        }
+        if (ep.act != TVTS_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], ep.act);
+        }
+        if (ep.dact != TVTS_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 p0 = unpack_bf16x2(x4[j].x), p1 = unpack_bf16x2(x4[j].y), p2 = unpack_bf16x2(x4[j].z), p3 = unpack_bf16x2(x4[j].w);
+            f[8 * j] *= act_bwd(p0.x, ep.dact); f[8 * j + 1] *= act_bwd(p0.y, ep.dact);
+            f[8 * j + 2] *= act_bwd(p1.x, ep.dact); f[8 * j + 3] *= act_bwd(p1.y, ep.dact);
+            f[8 * j + 4] *= act_bwd(p2.x, ep.dact); f[8 * j + 5] *= act_bwd(p2.y, ep.dact);
+            f[8 * j + 6] *= act_bwd(p3.x, ep.dact); f[8 * j + 7] *= act_bwd(p3.y, ep.dact);
+          }
+        }
+        if (use_res) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { f[4 * j] += r4[j].x; f[4 * j + 1] += r4[j].y; f[4 * j + 2] += r4[j].z; f[4 * j + 3] += r4[j].w; }
+        }
+        if (dbg_epi == 1) continue;
+        if (ep.out_dtype == 1) {
+          bf16* o = reinterpret_cast<bf16*>(ep.out) + grow * ep.ldo + col0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (col0 + 8 * j < s.N)
+              *reinterpret_cast<uint4*>(o + 8 * j) =
+                  make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                             pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+        } else {
+          float* o = reinterpret_cast<float*>(ep.out) + grow * ep.ldo + col0;
+          if (ep.accumulate) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (col0 + 4 * j < s.N)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * j), "f"(f[4 * j]), "f"(f[4 * j + 1]),
+                             "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
+                             : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (col0 + 4 * j < s.N) *reinterpret_cast<float4*>(o + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          }
         }
       }
       tc_fence_before();
@@ -371,13 +383,16 @@ extern "C" int tvts_gemm(const tvts_gemm_args* g, void* stream_) {
   TVTS_REQUIRE(((uintptr_t)g->a % 16 == 0) && ((uintptr_t)g->b % 16 == 0) && ((uintptr_t)g->out % 16 == 0),
                "tvts_gemm: pointers must be 16-byte aligned");
   TVTS_REQUIRE(g->ldo % 4 == 0, "tvts_gemm: ldo=%lld must be a multiple of 4", g->ldo);
+  if (g->out_dtype == 1 || g->out_pre || g->aux)
+    TVTS_REQUIRE(g->N % 8 == 0 && g->ldo % 8 == 0 && g->ldaux % 8 == 0, "tvts_gemm: bf16 outputs/aux need N, ldo, ldaux multiples of 8");
   TVTS_REQUIRE(!(g->accumulate && g->out_dtype != 0), "tvts_gemm: accumulate requires fp32 output");
   TVTS_REQUIRE(!(g->splits > 1 && !g->accumulate), "tvts_gemm: split-K requires accumulate=1 into a pre-initialised fp32 output");
   TVTS_REQUIRE(!(g->dact && !g->aux), "tvts_gemm: dact needs aux");
   TVTS_REQUIRE(!(g->splits > 1 && (g->act || g->dact || g->out_pre)), "tvts_gemm: split-K cannot be combined with act/dact/out_pre");
   if (g->residual) TVTS_REQUIRE(g->ldr % 4 == 0 && (uintptr_t)g->residual % 16 == 0, "tvts_gemm: residual alignment");
   if (g->bias) TVTS_REQUIRE((uintptr_t)g->bias % 16 == 0, "tvts_gemm: bias alignment");
-  if (g->aux) TVTS_REQUIRE(g->ldaux % 4 == 0 && (uintptr_t)g->aux % 8 == 0, "tvts_gemm: aux alignment");
+  if (g->aux) TVTS_REQUIRE((uintptr_t)g->aux % 16 == 0, "tvts_gemm: aux alignment");
+  if (g->out_pre) TVTS_REQUIRE((uintptr_t)g->out_pre % 16 == 0, "tvts_gemm: out_pre alignment");
 
   EpiParams ep;
   ep.out = g->out; ep.out_pre = g->out_pre; ep.bias = g->bias; ep.residual = g->residual;
