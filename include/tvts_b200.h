@@ -63,6 +63,104 @@ int tvts_gemm_debug_set(int lbo_bytes, int sbo_bytes, int k_advance_bytes);
 /* debug knob: 0 normal epilogue, 1 no global stores, 2 direct row-per-thread bf16 stores, 3 skip epilogue (timing experiments) */
 int tvts_gemm_debug_epi(int mode);
 
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm (fp32 statistics, one warp per row).  Replaces LayerNorm.forward of
+ * v2/model/video_encoder_ViT_B_16.py:79-85, v2/CLIP/clip/model.py:157-163, nn.LayerNorm(eps=1e-6) of
+ * v2/model/sort_transformer.py:73,76,100 and their backward.  D must be a multiple of 128 (<= 1280).
+ *   fwd: y = (x-mean)*rstd*gamma+beta as bf16 (GEMM operand) or f32; mean/rstd [M] saved for backward
+ *   bwd: dx = LN'(dy) + res1 + res2 (both optional) as f32 and/or bf16; dgamma/dbeta [D] are ACCUMULATED (atomicAdd)
+ */
+int tvts_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int64_t y_is_bf16, float* mean, float* rstd,
+                       int64_t M, int64_t D, float eps, void* stream);
+int tvts_layernorm_bwd(const void* dy, int64_t dy_is_bf16, const float* x, const float* mean, const float* rstd, const float* gamma,
+                       const float* res1, const float* res2, float* dx, void* dx_bf16, float* dgamma, float* dbeta, int64_t M,
+                       int64_t D, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Grouped multi-head attention, head dim 64, on the packed qkv buffer [B, N, 3, H, 64] (bf16) written by the qkv GEMM.
+ *   mode 0 FULL  (+causal): v2/CLIP/clip/model.py:185-188 (nn.MultiheadAttention + mask :330-336),
+ *                           v2/model/sort_transformer.py:9-13,43-57
+ *   mode 1 SPACE / mode 2 TIME: VarAttention, v2/model/video_encoder_ViT_B_16.py:38-76 (N = 1 + T*n, token 0 = CLS)
+ * out [B, N, H, 64] bf16; lse [B, H, N] f32 (saved for backward); scale multiplies q.k (reference: q * d^-0.5, :45).
+ * bwd writes every element of dqkv (same layout as qkv); delta_ws is a [B, H, N] f32 workspace.
+ */
+int tvts_attn_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n,
+                  int64_t causal, float scale, void* stream);
+int tvts_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv, int64_t B, int64_t N,
+                  int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Video token front end (v2/model/video_encoder_ViT_B_16.py:176-216).
+ *   patch_gather: video [B,T,3,R,R] f32 + keep_ind [B,n] int64 -> im2col rows of the KEPT patches only,
+ *                 cols [(b*T+t)*n+j, c*p*p+u*p+v] bf16 (Conv2d k=s=p is a per-patch linear map, so the tube mask
+ *                 :200-216 is applied before the patch-embed GEMM)
+ *   video_assemble: x0[b,0] = cls + pos[0]; x0[b,1+t*n+j] = tok[(b*T+t)*n+j] + pos[1+keep[b,j]] + tem[t]
+ *   video_assemble_bwd: dcls/dpos/dtem ACCUMULATED (atomicAdd), dtok written as bf16 (operand of the conv1 wgrad GEMM)
+ */
+int tvts_patch_gather(const float* video, const int64_t* keep_ind, void* cols, int64_t B, int64_t T, int64_t R, int64_t p, int64_t n,
+                      void* stream);
+int tvts_video_assemble(const float* tok, const float* cls, const float* pos, const float* tem, const int64_t* keep_ind, float* x0,
+                        int64_t B, int64_t T, int64_t n, int64_t D, void* stream);
+int tvts_video_assemble_bwd(const float* dx0, const int64_t* keep_ind, float* dcls, float* dpos, float* dtem, void* dtok_bf16, int64_t B,
+                            int64_t T, int64_t n, int64_t D, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Text front end / pooling (v2/model/model_dist_TVTSv2_ViT_B_16.py:97-111).  tokens int32 or int64 [rows, L].
+ *   text_embed: x[r,l] = table[tok[r,l]] + pos[l];  bwd: dtable scatter-add, dpos column sums (both ACCUMULATED, optional)
+ *   argmax_rows: flat_idx[r] = r*L + argmax_l tok[r,l] (first maximum = EOT position, exact)
+ *   gather_rows / scatter_rows: f32 rows by int64 row index (EOT pooling, sort-head transcript rows)
+ *   group_mean: t [nt*B, E] clip-major -> mean over the nt transcripts (:74-76) and its backward
+ */
+int tvts_text_embed(const void* tokens, int64_t tok_is_i64, const float* table, const float* pos, float* x, int64_t rows, int64_t L,
+                    int64_t W, void* stream);
+int tvts_text_embed_bwd(const float* dx, const void* tokens, int64_t tok_is_i64, float* dtable, float* dpos, int64_t rows, int64_t L,
+                        int64_t W, void* stream);
+int tvts_argmax_rows(const void* tokens, int64_t tok_is_i64, int64_t* flat_idx, int64_t rows, int64_t L, void* stream);
+int tvts_gather_rows(const float* src, const int64_t* idx, float* dst, int64_t rows, int64_t D, void* stream);
+int tvts_scatter_rows(const float* src, const int64_t* idx, float* dst, int64_t rows, int64_t D, int64_t accumulate, void* stream);
+int tvts_group_mean(const float* t, float* out, int64_t nt, int64_t B, int64_t E, void* stream);
+int tvts_group_mean_bwd(const float* dout, float* dt, void* dt_bf16, int64_t nt, int64_t B, int64_t E, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sort head glue (v2/model/sort_transformer.py:124-142).
+ *   sort_concat: z[b,i<N] = vtok[b,i] + type_embed[0]; z[b,N+tr] = t[tr*B+b] + type_embed[1]
+ *   sort_concat_bwd: dvtok written, dtype_embed ACCUMULATED
+ *   small_linear: the E -> n_trans classifier head in fp32 (fwd; bwd: dx written, dw/db ACCUMULATED)
+ */
+int tvts_sort_concat(const float* vtok, const float* t, const float* type_embed, float* z, int64_t B, int64_t N, int64_t nt, int64_t E,
+                     void* stream);
+int tvts_sort_concat_bwd(const float* dz, float* dvtok, float* dtype_embed, int64_t B, int64_t N, int64_t nt, int64_t E, void* stream);
+int tvts_small_linear_fwd(const float* x, const float* w, const float* bias, float* y, int64_t R, int64_t K, int64_t O, void* stream);
+int tvts_small_linear_bwd(const float* dy, const float* x, const float* w, float* dx, float* dw, float* db, int64_t R, int64_t K,
+                          int64_t O, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Elementwise helpers around the GEMMs: fp32->bf16 operand cast, bias gradient (column sums, ACCUMULATED),
+ * strided row add.
+ */
+int tvts_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
+int tvts_colsum_bf16(const void* x, float* out, int64_t M, int64_t N, int64_t ld, void* stream);
+int tvts_add_rows(const float* src, float* dst, int64_t rows, int64_t D, int64_t ld_src, int64_t ld_dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Losses (fp32).  sim_matrix = v2/model/model_dist_TVTSv2_ViT_B_16.py:119-127; NormSoftmaxLoss = v2/model/loss.py:13-25;
+ * sort CE = v2/trainer/trainer.py:487-492 (weight 2, int64 labels).  gout (device scalar, optional) = upstream gradient.
+ *   normalize_rows: xn = x / max(||x||, eps), norm saved
+ *   sim_matrix: S[Ra,Rb] = scale * an . bn^T;  sim_matrix_bwd: gradient w.r.t. rows [row0,row0+nrows) of one side
+ *               (transposed=0: the `a` side with coefficients G[row,:]; 1: the `b` side with G[:,row])
+ *   nsl_fwd: loss = -mean diag log_softmax(S/T, rows) - mean diag log_softmax(S/T, cols); nsl_bwd: G = dloss/dS
+ *   sort_ce: loss (optional) and dlogits (optional)
+ */
+int tvts_normalize_rows(const float* x, float* xn, float* norm, int64_t rows, int64_t E, float eps, void* stream);
+int tvts_sim_matrix(const float* an, const float* bn, float* S, int64_t Ra, int64_t Rb, int64_t E, float scale, void* stream);
+int tvts_sim_matrix_bwd(const float* G, const float* self_n, const float* other_n, const float* self_norm, float* dself, int64_t R_self,
+                        int64_t R_other, int64_t E, int64_t row0, int64_t nrows, int64_t transposed, float scale, float eps, void* stream);
+int tvts_nsl_fwd(const float* S, float* lse_r, float* lse_c, float* loss, int64_t Bg, float temperature, void* stream);
+int tvts_nsl_bwd(const float* S, const float* lse_r, const float* lse_c, const float* gout, float* G, int64_t Bg, float temperature,
+                 void* stream);
+int tvts_sort_ce(const float* logits, const int64_t* labels, const float* gout, float* loss, float* dlogits, int64_t R, int64_t C,
+                 float weight, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
