@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Benchmark of the TVTSv2 pre-training hot path (BASELINE.json metric: video-text pairs/s, ViT-B/16, 8x224^2 frames, fwd+bwd).
+
+  python bench.py [--gpus N --steps K --warmup W]              this repo's CUDA path (one process per GPU; torchrun for N>1)
+  python bench.py --impl reference [--steps K --warmup W]      the reference algorithm on the host cores (CPU oracle port)
+
+A step = one pass of the trainer step (v2/trainer/trainer.py:463-499) over one synthetic batch: text tower + video tower +
+sort head forward, embedding all-gather, InfoNCE + 2*sort-CE, full backward, gradient all-reduce (N>1) and the AdamW update.
+Weak scaling: every rank processes `batch` pairs (c3: 32/GPU -> global 256 at 8 GPUs = BASELINE.json configs[2]).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "video-text pairs/sec (ViT-B/16, 8x224^2 frames) fwd+bwd"
+UNIT = "pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", help="c3 = ViT-B/16 T=8 batch 32/GPU (headline); c2 = ViT-B/32 T=8 batch 64")
+    ap.add_argument("--batch", type=int, default=0, help="override per-GPU batch")
+    ap.add_argument("--n-trans", type=int, default=4, help="transcripts per clip (4 = both losses, 1 = InfoNCE only)")
+    ap.add_argument("--no-optimizer", action="store_true", help="leave the AdamW update out of the step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-batch", type=int, default=2)
+    return ap.parse_args()
+
+
+def peaks():
+    """Roofline denominators: MEASURED_PEAKS.json if the driver left it here, else the copy of those measurements recorded
+    in BASELINE.md / SURVEY.md section 8d, else the profiling guide's fallback."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            d = json.load(open(p))
+            return {"bf16_sustained": float(d.get("bf16_tflops_sustained", d.get("bf16_tflops"))), "bf16_burst": float(d["bf16_tflops"]),
+                    "hbm": float(d["hbm_gbs"]), "source": "MEASURED_PEAKS.json"}
+        except Exception:
+            pass
+    return {"bf16_sustained": 1410.1, "bf16_burst": 1675.6, "hbm": 6457.0,
+            "source": "MEASURED_PEAKS.json values as recorded in BASELINE.md (file not present at run time)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------- workload
+def workload(args):
+    from tvts_b200 import config as C
+    wl = C.WORKLOADS[args.workload]
+    batch = args.batch or wl.batch
+    return wl.arch, batch, wl.frames, args.n_trans
+
+
+def algorithmic_flops_per_pair(cfg, T, n_trans):
+    """2*MAC FLOPs of fwd+bwd for one video-text pair (bwd = 2x fwd for trainable parts, 1x for the
+    frozen text layers; here every layer is trained, matching what the timed step computes)."""
+    p, D, L, E = cfg.patch, cfg.width, cfg.layers, cfg.embed_dim
+    n = cfg.kept_per_frame
+    N = 1 + T * n
+    f_video = 2 * T * n * (3 * p * p) * D + L * (32 * N * D * D + 4 * n * T * (T + 1) * D + 4 * T * n * (n + 1) * D + 8 * N * D) + 2 * N * D * E
+    W = cfg.text_width
+    f_text = cfg.text_layers * (24 * 77 * W * W + 4 * 77 * 77 * W) + 2 * W * E
+    S = N + n_trans
+    f_sort = cfg.sort_depth * (24 * S * E * E + 4 * S * S * E) if n_trans > 1 else 0
+    return 3.0 * (f_video + n_trans * f_text + f_sort)
+
+
+# ---------------------------------------------------------------------------------------------------------------- CPU legs
+def cpu_oracle_steps(cfg, batch, frames, n_trans, steps, warmup, max_seconds=1e9):
+    """fwd+bwd of the oracle (torch CPU fp32, all host threads) on a `batch`-pair sample of the workload."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import tvts_oracle as O
+    from tvts_b200.synthetic import make_batch, make_state_dict
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = make_state_dict(cfg, seed=1234)
+    data = make_batch(cfg, batch, frames, n_trans=n_trans, seed=0)
+    times = []
+    t_begin = time.perf_counter()
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.step_with_grads(sd, data["text"], data["video"], data["keep_ind"], data["label"], cfg)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        if times and time.perf_counter() - t_begin > max_seconds:
+            break
+    return times, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg, batch, frames, n_trans = workload(args)
+    sample = args.cpu_sample_batch
+    times, cores = cpu_oracle_steps(cfg, sample, frames, n_trans, args.steps, min(args.warmup, 1), max_seconds=240)
+    ms = 1e3 * sum(times) / len(times)
+    val = sample / (ms / 1e3)
+    sample_desc = f"{sample} pairs of the {args.workload} shape ({cfg.name}, T={frames}, n_trans={n_trans}) per step, oracle fwd+bwd fp32, {len(times)} timed steps"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+            "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {cfg.name} T={frames} n_trans={n_trans}, CPU sample batch {sample}"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_desc},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import types
+
+    import torch
+    import torch.distributed as dist
+
+    from tvts_b200 import _lib
+    from tvts_b200 import modules as M
+    from tvts_b200 import optim
+    from tvts_b200.synthetic import make_batch, make_state_dict
+    from tvts_b200.trainer import TrainStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print(f"bench.py: WORLD_SIZE={world} but --gpus {args.gpus}; using {world}", file=sys.stderr)
+    _lib.lib()   # fail loudly if the CUDA library is missing
+
+    cfg, batch, frames, n_trans = workload(args)
+    model = M.TVTSv2Base(types.SimpleNamespace(local_rank=local_rank), arch=cfg)
+    model.load_state_dict(make_state_dict(cfg, seed=1234), strict=True)
+    model = model.to(dev)
+    opt = None if args.no_optimizer else optim.build_reference_optimizer(model)
+    step = TrainStep(model, opt, cfg.temperature, dev)
+
+    host = make_batch(cfg, batch, frames, n_trans=n_trans, seed=0, rank=rank)
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(data, steps, fetch_loss, prof):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _lib.launch_count()
+        if prof:
+            _lib.lib().tvts_prof_enable(1)
+        e0.record()
+        last = None
+        for _ in range(steps):
+            l1, l2 = step(data)
+            if fetch_loss:
+                last = (l1 + l2).item()          # device->host read of the step result, every step
+        e1.record()
+        barrier()
+        if prof:
+            _lib.lib().tvts_prof_enable(0)
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if last is None:
+            last = (l1 + l2).item()
+        return t.item(), _lib.launch_count() - n0, last
+
+    # warm-up (also builds the bf16 weight cache, optimizer state and allocator pools)
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total, launches, loss = timed(resident, args.steps, False, True)
+    clocks = sampler.stop() if rank == 0 else None
+
+    import ctypes
+    t_ms, t_fl, t_by = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+    _lib.lib().tvts_prof_collect.restype = ctypes.c_longlong
+    n_gemm = _lib.lib().tvts_prof_collect(ctypes.byref(t_ms), ctypes.byref(t_fl), ctypes.byref(t_by))
+
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            step(pinned)
+        ms_e2e, _, _ = timed(pinned, args.steps, True, False)
+        e2e = {"value": world * batch * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+               "ms_per_step": ms_e2e / args.steps}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        sample = args.cpu_sample_batch
+        times, cores = cpu_oracle_steps(cfg, sample, frames, n_trans, 2, 1, max_seconds=40)
+        cms = sum(times) / len(times)
+        cpu = {"value": sample / cms, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{sample} pairs of the {args.workload} shape per step, oracle fwd+bwd fp32 (no optimizer), {len(times)} timed steps after 1 warm-up"}
+
+    if rank == 0:
+        pk = peaks()
+        ms_step = ms_total / args.steps
+        value = world * batch * args.steps / (ms_total / 1e3)
+        achieved = (t_fl.value / 1e12) / (t_ms.value / 1e3) if t_ms.value > 0 else None
+        flops_pair = algorithmic_flops_per_pair(cfg, frames, n_trans)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {cfg.name} T={frames} batch {batch}/GPU n_trans={n_trans} (global batch {world * batch})",
+                       "step": "fwd+bwd" + ("+grad_allreduce" if world > 1 else "") + ("" if args.no_optimizer else "+adamw"),
+                       "parallelism": f"dp{world}", "l2": "per-step inputs (154 MB video) and activations (>10 GB) exceed the 126 MB L2",
+                       "numerics": "bf16 GEMM operands, fp32 accumulate/residual/LN/softmax/loss, fp32 master weights"},
+            "clocks": clocks, "gpu_launches": launches, "loss": loss,
+            "step_model_tflops": flops_pair * batch / (ms_step / 1e3) / 1e12,
+            "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05)", "achieved": achieved, "peak": pk["bf16_sustained"],
+                         "unit": "TFLOP/s", "frac": (achieved / pk["bf16_sustained"]) if achieved else None, "traffic": None,
+                         "launches": int(n_gemm), "gemm_ms_per_step": t_ms.value / args.steps,
+                         "gemm_share_of_step": (t_ms.value / args.steps) / ms_step, "peak_source": pk["source"] + " (sustained figure: kernel timed inside a long step)"},
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

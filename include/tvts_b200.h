@@ -27,6 +27,12 @@ const char* tvts_last_error(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches claim) */
 long long tvts_launch_count(void);
 
+/* live timing of the GEMM launches (bench.py roofline): enable(1) resets and starts recording one CUDA-event pair per
+ * tvts_gemm launch on its stream; after synchronising, collect() returns the number of launches recorded and their summed
+ * device time (ms), algorithmic FLOPs (2*M*N*K) and bytes. */
+int tvts_prof_enable(int on);
+long long tvts_prof_collect(double* total_ms, double* total_flops, double* total_bytes);
+
 /* ------------------------------------------------------------------------------------------------
  * GEMM:  out[M,N] = epilogue(alpha * sum_k A[m,k]*B[n,k])      (tcgen05 + TMA, bf16 in / fp32 accumulate)
  * replaces every nn.Linear / `x @ proj` on the path:
@@ -160,6 +166,15 @@ int tvts_nsl_bwd(const float* S, const float* lse_r, const float* lse_c, const f
                  void* stream);
 int tvts_sort_ce(const float* logits, const int64_t* labels, const float* gout, float* loss, float* dlogits, int64_t R, int64_t C,
                  float weight, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer: transformers==4.10.2 AdamW (v2/train_dist_TVTSv2_ViT_B_16.py:119-125) over one flat arena, single launch.
+ * p/g/m/v are fp32 arenas with identical layout (tensors padded to whole chunks of chunk_elems); p_bf16 (optional) receives
+ * the bf16 copy of the updated weights; chunk_tensor[c] = tensor index of chunk c; table[t] = {lr*sqrt(1-b2^t)/(1-b1^t),
+ * lr*weight_decay, active (0 = skip: no gradient this step), 0}.  g is multiplied by grad_scale first.
+ */
+int tvts_adamw_flat(float* p, const float* g, float* m, float* v, void* p_bf16, const int32_t* chunk_tensor, const float* table,
+                    int64_t n_chunks, int64_t chunk_elems, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

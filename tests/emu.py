@@ -296,6 +296,21 @@ def sort_ce(logits, labels, gout, loss, dlogits, R, C, weight):
         dlogits.view(R, C).copy_((torch.exp(x - l[:, None]) - oh) * g)
 
 
+def adamw_flat(p, g, m, v, pb, chunk_tensor, table, n_chunks, chunk, b1, b2, eps, gscale):
+    t = table[chunk_tensor.long()]                                   # [n_chunks, 4]
+    step = t[:, 0:1]; lrwd = t[:, 1:2]; act = t[:, 2:3] != 0
+    P, G, Mm, V = (x.view(n_chunks, chunk) for x in (p, g, m, v))
+    gg = G * gscale
+    m2 = Mm * b1 + (1.0 - b1) * gg
+    v2 = V * b2 + (1.0 - b2) * gg * gg
+    x = P - step * (m2 / (v2.sqrt() + eps))
+    x = torch.where(lrwd > 0, x - lrwd * x, x)
+    Mm.copy_(torch.where(act, m2, Mm)); V.copy_(torch.where(act, v2, V)); P.copy_(torch.where(act, x, P))
+    if pb is not None:
+        PB = pb.view(n_chunks, chunk)
+        PB.copy_(torch.where(act, P.to(torch.bfloat16), PB))
+
+
 OPS = {k: v for k, v in list(globals().items()) if callable(v) and not k.startswith("_") and k not in ("install", "uninstall", "gemm")}
 
 _saved = {}

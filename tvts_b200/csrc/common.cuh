@@ -40,6 +40,8 @@ void tvts_count_launch(int n);
   } while (0)
 
 int tvts_num_sms();  // cached SM count of the current device
+bool tvts_prof_begin(cudaStream_t stream, double flops, double bytes, int* slot);  // live launch timing (api.cu)
+void tvts_prof_end(cudaStream_t stream, int slot);
 
 typedef __nv_bfloat16 bf16;
 

@@ -355,7 +355,10 @@ int launch(const tvts_gemm_args* g, const GemmShape& s, const EpiParams& ep, cud
   }
   const int units = s.m_tiles * s.n_tiles * s.splits;
   const int grid = units < tvts_num_sms() ? units : tvts_num_sms();
+  int prof_slot;
+  tvts_prof_begin(stream, 2.0 * (double)s.M * (double)s.N * (double)s.K, 0.0, &prof_slot);
   kern<<<grid, kThreads, SmemLayout<BN>::TOTAL, stream>>>(ta, tb, s, ep, g_dbg_lbo, g_dbg_sbo, g_dbg_kadv, g_dbg_epi);
+  tvts_prof_end(stream, prof_slot);
   TVTS_LAUNCH_CHECK();
   return TVTS_OK;
 }

@@ -32,6 +32,9 @@ class _WeightCache:
         self._c = {}
 
     def get(self, p):
+        fs = _flat()
+        if fs is not None and fs.has(p):
+            return fs.bf16_view(p)          # arena copy, kept current by the fused optimizer kernel
         key = id(p)
         ent = self._c.get(key)
         ver = p._version
@@ -51,6 +54,11 @@ class _WeightCache:
 
 
 WEIGHTS = _WeightCache()
+
+
+def _flat():
+    from . import optim
+    return optim.current()
 
 
 # --------------------------------------------------------------------------------------------------
@@ -173,6 +181,7 @@ class ParamView:
         self.t = dict(zip(names, tensors))
         self.needs = dict(zip(names, needs))
         self.grads = {}
+        self.direct = set()
 
     def __getitem__(self, k):
         return self.t[k]
@@ -187,12 +196,30 @@ class ParamView:
         """fp32 zero-initialised gradient accumulator for parameter k (created on first use)."""
         g = self.grads.get(k)
         if g is None:
-            g = torch.zeros_like(self.t[k], dtype=F32, memory_format=torch.contiguous_format)
+            fs = _flat()
+            if fs is not None and fs.has(self.t[k]):
+                g = fs.grad_view(self.t[k])     # zeroed by FlatState.zero_grad() at the start of the step
+                self.direct.add(k)
+            else:
+                g = torch.zeros_like(self.t[k], dtype=F32, memory_format=torch.contiguous_format)
             self.grads[k] = g
         return g
 
     def grad_tuple(self):
-        return tuple(self.grads.get(k) if self.needs.get(k, False) else None for k in self.names)
+        """Gradients in parameter order for autograd; arena-backed ones are attached to .grad directly (no copy through
+        AccumulateGrad) and reported as None."""
+        out = []
+        for k in self.names:
+            g = self.grads.get(k) if self.needs.get(k, False) else None
+            if g is not None and k in self.direct:
+                p = self.t[k]
+                if p.grad is None:
+                    p.grad = g
+                elif p.grad.data_ptr() != g.data_ptr():
+                    p.grad.add_(g)
+                g = None
+            out.append(g)
+        return tuple(out)
 
 
 def _linear_bwd(P, wname, bname, dy_bf, x_bf):

@@ -1,0 +1,227 @@
+"""Parameter-group policy and optimizer of the reference entry script, on a flat arena with one fused CUDA kernel.
+
+Mirrors (paths relative to /root/reference):
+  param groups / freezing    v2/train_dist_TVTSv2_ViT_B_16.py:66-124   (4 groups: new/CLIP x decay/no-decay; text layers 0-8 frozen)
+  transformers.AdamW         v2/train_dist_TVTSv2_ViT_B_16.py:125      (transformers==4.10.2, un-vendored: betas (0.9,0.999),
+                             eps 1e-6, correct_bias=True, decoupled weight decay applied after the update; parameters whose
+                             grad is None are skipped and their step counter does not advance)
+  per-epoch decay            v2/trainer/trainer.py:402-411             (param_group['lr'] *= 0.1: just mutate .param_groups)
+
+FlatState owns ONE fp32 arena each for master weights, gradients and the two moments (same offsets, each tensor padded to
+a whole chunk) plus a bf16 arena with the GEMM-operand copy of the weights.  The nn.Parameters are re-pointed at views of
+the master arena, the engine writes gradients straight into the gradient arena (engine.ParamView.gbuf), the gradient
+all-reduce is one NCCL call over the arena, and `AdamW.step()` is one kernel launch (tvts_adamw_flat) that also refreshes
+the bf16 copy.
+"""
+import math
+
+import torch
+
+from . import _lib as L
+
+CHUNK = 4096
+
+_CURRENT = None
+
+
+def current():
+    return _CURRENT
+
+
+class FlatState:
+    def __init__(self, params, chunk=CHUNK):
+        """params: list of trainable nn.Parameters (all on one CUDA/CPU device, fp32)."""
+        global _CURRENT
+        self.params = list(params)
+        assert self.params, "FlatState needs at least one parameter"
+        dev = self.params[0].device
+        self.device = dev
+        self.chunk = chunk
+        self.offsets, self.index = [], {}
+        off = 0
+        chunk_tensor = []
+        for i, p in enumerate(self.params):
+            assert p.dtype == torch.float32 and p.device == dev
+            self.offsets.append(off)
+            self.index[id(p)] = i
+            nch = (p.numel() + chunk - 1) // chunk
+            chunk_tensor += [i] * nch
+            off += nch * chunk
+        self.total = off
+        self.n_chunks = len(chunk_tensor)
+        self.p = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.g = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.bf = torch.zeros(off, dtype=torch.bfloat16, device=dev)
+        self.chunk_tensor = torch.tensor(chunk_tensor, dtype=torch.int32, device=dev)
+        self.synced = [-1] * len(self.params)       # parameter ._version for which self.bf holds the bf16 copy
+        self.touched = set()
+        with torch.no_grad():
+            for i, p in enumerate(self.params):
+                view = self.p[self.offsets[i]: self.offsets[i] + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                if p.grad is not None:
+                    p.grad = None
+        _CURRENT = self
+
+    def release(self):
+        global _CURRENT
+        if _CURRENT is self:
+            _CURRENT = None
+
+    # ---- views -------------------------------------------------------------------------------------------------
+    def has(self, p):
+        i = self.index.get(id(p))
+        return i is not None and self.params[i] is p
+
+    def _view(self, arena, p):
+        i = self.index[id(p)]
+        return arena[self.offsets[i]: self.offsets[i] + p.numel()].view(p.shape)
+
+    def grad_view(self, p):
+        self.touched.add(self.index[id(p)])
+        return self._view(self.g, p)
+
+    def bf16_view(self, p):
+        """bf16 operand copy of p, re-cast only if p changed outside the fused optimizer."""
+        i = self.index[id(p)]
+        view = self._view(self.bf, p)
+        if self.synced[i] != p._version:
+            L.call("cast_bf16", p.detach(), view, p.numel())
+            self.synced[i] = p._version
+        return view
+
+    # ---- step bookkeeping ----------------------------------------------------------------------------------------
+    def zero_grad(self):
+        """One memset over the gradient arena; every parameter's .grad becomes None (torch 2.x zero_grad semantics)."""
+        self.g.zero_()
+        for i in self.touched:
+            self.params[i].grad = None
+        self.touched.clear()
+
+    def publish_grads(self, params=None):
+        """Attach arena views as .grad of every parameter the backward wrote (what autograd's AccumulateGrad would do)."""
+        for i in self.touched:
+            p = self.params[i]
+            if p.grad is None:
+                p.grad = self._view(self.g, p)
+
+
+def reference_param_groups(named_parameters, text_layers=12, tune_from=9):
+    """The 4 optimizer groups of the reference entry script; freezes (requires_grad=False) the un-tuned text layers."""
+    no_decay_names = ["bias", "LayerNorm", "ln_", "norm"]
+    text_tune_layers = ["resblocks.%d." % i for i in range(tune_from, text_layers)]
+    decay_clip, no_decay_clip, decay_new, no_decay_new = [], [], [], []
+    for name, param in named_parameters:
+        nd = any(s in name for s in no_decay_names)
+        if "video_model" in name:
+            if "timeattn" in name or "ln_3" in name:
+                (no_decay_new if nd else decay_new).append(param)
+            else:
+                (no_decay_clip if nd else decay_clip).append(param)
+        elif "text" in name:
+            if "resblocks" in name:
+                if any(tl in name for tl in text_tune_layers):
+                    (no_decay_clip if nd else decay_clip).append(param)
+                else:
+                    param.requires_grad = False
+            else:
+                (no_decay_clip if nd else decay_clip).append(param)
+        else:
+            (no_decay_new if nd else decay_new).append(param)
+    return [
+        {"params": decay_new, "weight_decay": 0.05, "lr": 1e-4},
+        {"params": no_decay_new, "weight_decay": 0.0, "lr": 1e-4},
+        {"params": decay_clip, "weight_decay": 0.05, "lr": 1e-7},
+        {"params": no_decay_clip, "weight_decay": 0.0, "lr": 1e-7},
+    ]
+
+
+class AdamW:
+    """transformers.AdamW semantics (see module docstring) over a FlatState; `param_groups` is mutable like torch's."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, correct_bias=True):
+        groups = list(params)
+        if groups and not isinstance(groups[0], dict):
+            groups = [{"params": groups}]
+        self.param_groups = []
+        for g in groups:
+            d = {"lr": lr, "betas": betas, "eps": eps, "weight_decay": weight_decay, "correct_bias": correct_bias}
+            d.update(g)
+            d["params"] = [p for p in d["params"] if p.requires_grad]
+            self.param_groups.append(d)
+        flat = [p for g in self.param_groups for p in g["params"]]
+        self.flat = FlatState(flat)
+        self.steps = [0] * len(flat)
+        self.group_of = [gi for gi, g in enumerate(self.param_groups) for _ in g["params"]]
+        b, e = self.param_groups[0]["betas"], self.param_groups[0]["eps"]
+        assert all(g["betas"] == b and g["eps"] == e for g in self.param_groups), "per-group betas/eps are not supported"
+        self._ring = [torch.zeros(len(flat), 4, dtype=torch.float32).pin_memory() if self.flat.device.type == "cuda"
+                      else torch.zeros(len(flat), 4, dtype=torch.float32) for _ in range(4)]
+        self._ring_ev = [None] * 4
+        self._slot = 0
+        self.table = torch.zeros(len(flat), 4, dtype=torch.float32, device=self.flat.device)
+
+    def zero_grad(self, set_to_none=True):
+        self.flat.zero_grad()
+
+    def step(self, grad_scale=1.0):
+        fs = self.flat
+        slot = self._slot
+        self._slot = (slot + 1) % len(self._ring)
+        if self._ring_ev[slot] is not None:
+            self._ring_ev[slot].synchronize()
+        host = self._ring[slot]
+        rows = host.numpy()
+        for i, p in enumerate(fs.params):
+            if p.grad is None:
+                rows[i, 2] = 0.0
+                continue
+            g = self.param_groups[self.group_of[i]]
+            self.steps[i] += 1
+            t = self.steps[i]
+            b1, b2 = g["betas"]
+            step_size = g["lr"]
+            if g["correct_bias"]:
+                step_size = step_size * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
+            rows[i, 0] = step_size
+            rows[i, 1] = g["lr"] * g["weight_decay"] if g["weight_decay"] > 0.0 else 0.0
+            rows[i, 2] = 1.0
+        self.table.copy_(host, non_blocking=True)
+        if fs.device.type == "cuda":
+            ev = torch.cuda.Event()
+            ev.record()
+            self._ring_ev[slot] = ev
+        b1, b2 = self.param_groups[0]["betas"]
+        L.call("adamw_flat", fs.p, fs.g, fs.m, fs.v, fs.bf, self.chunk_tensor_arg(), self.table, fs.n_chunks, fs.chunk, float(b1), float(b2),
+               float(self.param_groups[0]["eps"]), float(grad_scale))
+        for i, p in enumerate(fs.params):
+            if p.grad is not None:
+                fs.synced[i] = p._version      # the kernel refreshed the bf16 copy of every active tensor
+
+    def chunk_tensor_arg(self):
+        return self.flat.chunk_tensor
+
+    def state_dict(self):
+        fs = self.flat
+        return {"steps": list(self.steps), "exp_avg": fs.m.clone(), "exp_avg_sq": fs.v.clone(),
+                "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
+
+    def load_state_dict(self, sd):
+        self.steps = list(sd["steps"])
+        self.flat.m.copy_(sd["exp_avg"])
+        self.flat.v.copy_(sd["exp_avg_sq"])
+        for g, s in zip(self.param_groups, sd["param_groups"]):
+            g.update(s)
+
+
+def build_reference_optimizer(model, text_layers=None, tune_from=None):
+    """What v2/train_dist_TVTSv2_ViT_B_16.py:66-125 builds for `model` (H/14: layers 0-17 frozen, :71 of the H_14 script)."""
+    if text_layers is None:
+        text_layers = model.arch.text_layers
+    if tune_from is None:
+        tune_from = (text_layers * 3) // 4
+    groups = reference_param_groups(list(model.named_parameters()), text_layers, tune_from)
+    return AdamW(groups)

@@ -1,0 +1,147 @@
+"""The training step of the reference trainer on the B200 kernels (data-parallel, one process per GPU).
+
+Mirrors (paths relative to /root/reference):
+  AllGather_multi                      v2/trainer/trainer.py:41-57    all_gather forward, LOCAL-SLICE backward (no reduce)
+  Trainer_TVTSv2_*._train_epoch body   v2/trainer/trainer.py:463-499  tokens/video -> model -> gathers -> sim_matrix ->
+                                       NormSoftmaxLoss + 2*CE(sort) -> backward -> optimizer.step
+  DDP gradient averaging               v2/base/base_trainer.py:23-25  (find_unused_parameters=True semantics: parameters that
+                                       received no gradient on ANY rank keep grad=None and are skipped by the optimizer)
+
+The two embedding gathers of the reference are fused into ONE NCCL all-gather of the concatenated [B_local, 2E] buffer;
+the gradient all-reduce runs over a flat fp32 arena (one NCCL call per arena chunk), averaged by 1/W like DDP.
+"""
+import torch
+import torch.distributed as dist
+
+from . import engine as E
+from . import modules as M
+
+
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def _rank():
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+class AllGather_multi(torch.autograd.Function):
+    """apply(tensor, n_gpu, args) -> rank-ordered concatenation; backward = this rank's slice of grad_output.
+    (`args.rank` is the GLOBAL rank, v2/trainer/trainer.py:53-57.)"""
+
+    @staticmethod
+    def forward(ctx, tensor, n_gpu, args):
+        W = _world()
+        tensor = tensor.contiguous()
+        ctx.rank = getattr(args, "rank", _rank()) if args is not None else _rank()
+        ctx.batch_size = tensor.shape[0]
+        if W == 1:
+            return tensor.clone()
+        out = torch.empty((W * tensor.shape[0],) + tuple(tensor.shape[1:]), dtype=tensor.dtype, device=tensor.device)
+        dist.all_gather_into_tensor(out, tensor)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return grad_output[ctx.batch_size * ctx.rank: ctx.batch_size * (ctx.rank + 1)], None, None
+
+
+class _GatherPair(torch.autograd.Function):
+    """Both embedding gathers of trainer.py:481-482 as ONE collective: [B_local, E] x2 -> [Bg, E] x2."""
+
+    @staticmethod
+    def forward(ctx, video, text):
+        W, r = _world(), _rank()
+        B, Edim = video.shape
+        ctx.B, ctx.r = B, r
+        if W == 1:
+            return video.clone(), text.clone()
+        local = torch.cat([video, text], 1).contiguous()
+        out = torch.empty((W * B, 2 * Edim), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local)
+        return out[:, :Edim].contiguous(), out[:, Edim:].contiguous()
+
+    @staticmethod
+    def backward(ctx, gv, gt):
+        s = slice(ctx.B * ctx.r, ctx.B * (ctx.r + 1))
+        return gv[s], gt[s]
+
+
+def gather_embeddings(video_embeds, text_embeds):
+    return _GatherPair.apply(video_embeds, text_embeds)
+
+
+def average_flat(fs):
+    """Gradient averaging over the flat arena: one NCCL all-reduce (AVG), no flatten / unflatten copies."""
+    if _world() == 1:
+        return 0
+    dist.all_reduce(fs.g, op=dist.ReduceOp.AVG)
+    return fs.g.numel() * 4
+
+
+def average_gradients(params):
+    """DDP semantics on explicit buffers: all-reduce(sum)/W of every parameter that has a gradient on this rank.
+    All ranks run the same graph on the hot path (same n_trans per step), so the set of parameters with gradients is
+    identical across ranks; parameters without one stay grad=None (find_unused_parameters behaviour under torch 2.x)."""
+    W = _world()
+    if W == 1:
+        return 0
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return 0
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.mul_(1.0 / W)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+    return flat.numel() * 4
+
+
+class TrainStep:
+    """One optimizer step of Trainer_TVTSv2_*._train_epoch for a tokenised batch.
+
+    data: {'video' [B,T,3,R,R] f32, 'text' [n_trans*B, ctx] int (clip-major), 'keep_ind' [B,n] int64, 'label' [B,n_trans] int64}
+    (host or device tensors; host tensors are copied like trainer.py:474-475,489).
+    Returns (loss1, loss2) as 0-d device tensors (no host sync here; the caller decides when to .item())."""
+
+    def __init__(self, model, optimizer=None, temperature=0.05, device=None):
+        self.model = model
+        self.optimizer = optimizer
+        self.loss = M.NormSoftmaxLoss(temperature)
+        self.device = device if device is not None else next(model.parameters()).device
+        self.params = [p for p in model.parameters() if p.requires_grad]   # after the optimizer applied the freeze policy
+
+    def to_device(self, data):
+        out = {}
+        for k, v in data.items():
+            out[k] = v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v
+        return out
+
+    def __call__(self, data):
+        data = self.to_device(data)
+        flat = getattr(self.optimizer, "flat", None)
+        if flat is not None:
+            self.optimizer.zero_grad()              # one memset over the gradient arena
+        else:
+            for p in self.params:                   # optimizer.zero_grad() (torch 2.x: set_to_none)
+                p.grad = None
+        text_embeds, video_embeds, pred_order = self.model(data)
+        video_all, text_all = gather_embeddings(video_embeds, text_embeds)
+        output = M.sim_matrix(video_all, text_all)                      # rows videos, cols texts (trainer.py:484)
+        loss1 = self.loss(output)
+        if pred_order is not None:
+            loss2 = E.sort_ce(pred_order, data["label"], 2.0)           # trainer.py:487-492
+            (loss1 + loss2).backward()
+        else:
+            loss2 = torch.zeros((), device=loss1.device)
+            loss1.backward()
+        if flat is not None:
+            average_flat(flat)
+        else:
+            average_gradients(self.params)
+        if self.optimizer is not None:
+            self.optimizer.step()
+        return loss1.detach(), loss2.detach()
