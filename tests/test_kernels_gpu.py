@@ -115,6 +115,14 @@ ATTN_CASES = [
     (2, 2, 2, 2, 49, 99, False),    # time
     (1, 2, 1, 3, 98, 295, False),   # space, B/16 masked (2 stationary chunks, 2 streamed tiles)
     (1, 2, 2, 8, 5, 41, False),     # time, T=8
+    (2, 3, 2, 12, 7, 85, False),    # time, T=12 (the shipped 3x4-frame configs)
+    (1, 2, 2, 16, 6, 97, False),    # time, T=16: 17 keys -> third key tile / second key m-tile
+    (1, 2, 2, 20, 3, 61, False),    # time, T>16: streamed fallback with strided groups
+    (1, 2, 1, 2, 196, 393, False),  # space, unmasked B/16 frame: 4 stationary chunks, 4 streamed tiles
+    (2, 2, 1, 8, 98, 785, False),   # space, c3 shape
+    (2, 2, 2, 8, 98, 785, False),   # time, c3 shape
+    (1, 2, 0, 0, 0, 789, False),    # sort head at c3: 13 chunks x 13 tiles
+    (3, 2, 0, 0, 0, 130, True),     # causal across several tiles (dK/dV start tile > 0)
 ]
 
 

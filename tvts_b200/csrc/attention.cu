@@ -4,26 +4,32 @@
 //   mode SPACE : divided space attention of VarAttention (v2/model/video_encoder_ViT_B_16.py:38-76, '(b f) n d'):
 //                a patch token attends to [CLS ; the n kept tokens of its own frame]; CLS attends to all N tokens
 //   mode TIME  : divided time attention ('(b n) f d'): a patch token attends to [CLS ; the T tokens of its slot]
-// The reference materialises q_/k_/v_/cls_k/cls_v copies with rearrange/repeat/cat; here the grouping is pure index
-// arithmetic on the packed qkv buffer [B, N, 3, H, 64] written by the qkv GEMM, so nothing is copied.
+// The reference materialises q_/k_/v_/cls_k/cls_v copies with rearrange/repeat/cat and an eager softmax; here the grouping
+// is pure index arithmetic on the packed qkv buffer [B, N, 3, H, 64] written by the qkv GEMM, so nothing is copied and the
+// score matrix never leaves registers.
 //
-// One kernel shape serves forward, dQ and dK/dV ("vector-stationary"): a CTA owns up to 32/64 STATIONARY tokens of one
-// (batch, head, group) and streams the group's other side through shared memory in tiles of 64 rows:
-//   forward / dQ : stationary = queries, streamed = keys (+values)
-//   dK,dV        : stationary = keys,    streamed = queries (+dO)       (same index sets: the relation is symmetric)
-// dots are computed lane-per-streamed-row (conflict-free padded smem rows), accumulations lane-per-2-dims.
-// fp32 math, bf16 I/O, exact softmax (online max/sum in forward; saved log-sum-exp in backward).
+// These kernels are HBM-bound (attention is < 4 % of the path's FLOPs): sequences are 9 .. 789 tokens of head dim 64, so
+// the math runs on warp-level tensor-core MMAs (mma.sync m16n8k16 bf16, fp32 accumulate) fed by ldmatrix from XOR-swizzled
+// shared-memory tiles that are filled with 16-byte cp.async copies (fully coalesced 128-byte rows).
+//   * "streamed" kernels (FULL, SPACE, and the CLS row/column of SPACE/TIME): a CTA owns 64 STATIONARY tokens (16 per warp) of
+//     one (batch, head, group) and streams the group's other side through double-buffered 64-row tiles, flash-attention style:
+//         forward / dQ : stationary = queries, streamed = keys (+values)
+//         dK,dV        : stationary = keys,    streamed = queries (+dO)     (same index sets: the relation is symmetric)
+//   * "time" kernels: one WARP per (batch, head, slot): T <= 16 queries x (T+1) keys fit one MMA tile; forward and the whole
+//     backward (dq, dk, dv of the slot) each run in a single pass.
+// fp32 softmax statistics (online max/sum in forward; saved log-sum-exp in backward), bf16 I/O.
 #include "common.cuh"
 #include "../../include/tvts_b200.h"
 
 namespace {
 
-constexpr int HD = 64;        // head dim
-constexpr int KT = 64;        // streamed rows per smem tile
-constexpr int PITCH = 33;     // u32 per smem row (32 + 1 pad)
+constexpr int HD = 64;          // head dim
+constexpr int BM = 64;          // stationary rows per CTA (streamed kernels): 4 warps x 16
+constexpr int BN = 64;          // streamed rows per tile
 constexpr int kWarps = 4;
-constexpr int SC_FWD = 64;    // stationary rows per CTA (forward)
-constexpr int SC_BWD = 32;    // stationary rows per CTA (backward)
+constexpr int kThreads = kWarps * 32;
+constexpr int TILE_BYTES = 64 * 128;   // 64 rows x 64 bf16
+constexpr float LOG2E = 1.4426950408889634f;
 
 struct AttnShape {
   int B, N, H;
@@ -31,6 +37,7 @@ struct AttnShape {
   int T, n;    // frames, kept tokens per frame (modes 1, 2)
   int causal;  // mode 0 only
   float scale;
+  int cls_only;  // modes 1/2: launch covers only the CLS group (used next to the time kernels)
 };
 
 struct Sets {
@@ -38,37 +45,38 @@ struct Sets {
   int sm_has0, sm_base, sm_stride, sm_count;
 };
 
-__host__ __device__ inline int chunks_per_group(const AttnShape& a, int sc) {
-  if (a.mode == 0) return (a.N + sc - 1) / sc;
+__host__ __device__ inline int chunks_per_group(const AttnShape& a) {
+  if (a.mode == 0) return (a.N + BM - 1) / BM;
   const int len = a.mode == 1 ? a.n : a.T;
-  return (len + sc - 1) / sc;
+  return (len + BM - 1) / BM;
 }
-__host__ __device__ inline int num_blocks_x(const AttnShape& a, int sc) {
-  if (a.mode == 0) return chunks_per_group(a, sc);
+__host__ __device__ inline int num_blocks_x(const AttnShape& a) {
+  if (a.mode == 0) return chunks_per_group(a);
+  if (a.cls_only) return 1;
   const int groups = a.mode == 1 ? a.T : a.n;
-  return groups * chunks_per_group(a, sc) + 1;  // + the CLS group
+  return groups * chunks_per_group(a) + 1;  // + the CLS group
 }
 
-__device__ inline Sets decode_sets(const AttnShape& a, int bx, int sc) {
+__device__ inline Sets decode_sets(const AttnShape& a, int bx) {
   Sets s;
   if (a.mode == 0) {
-    s.st_base = bx * sc; s.st_stride = 1; s.st_count = min(sc, a.N - s.st_base);
+    s.st_base = bx * BM; s.st_stride = 1; s.st_count = min(BM, a.N - s.st_base);
     s.sm_has0 = 0; s.sm_base = 0; s.sm_stride = 1; s.sm_count = a.N;
     return s;
   }
-  const int cpg = chunks_per_group(a, sc);
+  const int cpg = chunks_per_group(a);
   const int groups = a.mode == 1 ? a.T : a.n;
-  const int g = bx / cpg, c = bx - g * cpg;
+  const int g = a.cls_only ? groups : bx / cpg, c = a.cls_only ? 0 : bx - g * cpg;
   if (g >= groups) {  // CLS token <-> all tokens
     s.st_base = 0; s.st_stride = 1; s.st_count = 1;
     s.sm_has0 = 0; s.sm_base = 0; s.sm_stride = 1; s.sm_count = a.N;
     return s;
   }
   if (a.mode == 1) {
-    s.st_base = 1 + g * a.n + c * sc; s.st_stride = 1; s.st_count = min(sc, a.n - c * sc);
+    s.st_base = 1 + g * a.n + c * BM; s.st_stride = 1; s.st_count = min(BM, a.n - c * BM);
     s.sm_has0 = 1; s.sm_base = 1 + g * a.n; s.sm_stride = 1; s.sm_count = a.n;
   } else {
-    s.st_base = 1 + g + c * sc * a.n; s.st_stride = a.n; s.st_count = min(sc, a.T - c * sc);
+    s.st_base = 1 + g + c * BM * a.n; s.st_stride = a.n; s.st_count = min(BM, a.T - c * BM);
     s.sm_has0 = 1; s.sm_base = 1 + g; s.sm_stride = a.n; s.sm_count = a.T;
   }
   return s;
@@ -78,122 +86,199 @@ __device__ __forceinline__ int streamed_token(const Sets& s, int k) {
   return (s.sm_has0 && k == 0) ? 0 : s.sm_base + (k - s.sm_has0) * s.sm_stride;
 }
 
-// load 64 bf16 (one head row, 128 B) as 64 floats into registers; all lanes read the same address (broadcast)
-__device__ __forceinline__ void load_row_f32(const bf16* p, float* r, float mul) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    uint4 u = reinterpret_cast<const uint4*>(p)[i];
-    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-    r[8 * i + 0] = a.x * mul; r[8 * i + 1] = a.y * mul; r[8 * i + 2] = b.x * mul; r[8 * i + 3] = b.y * mul;
-    r[8 * i + 4] = c.x * mul; r[8 * i + 5] = c.y * mul; r[8 * i + 6] = d.x * mul; r[8 * i + 7] = d.y * mul;
-  }
+// ------------------------------------------------------------------------------------------------ primitives
+// byte offset of 16-byte chunk `c` (0..7) of row `r` inside a [rows][128 B] tile; the XOR keeps ldmatrix conflict-free
+__device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + (((c ^ r) & 7) << 4)); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+// D(16x8, fp32) += A(16x16 bf16, row) * B(16x8 bf16, col)
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// cooperative tile load: rows [k0, k0+cnt) of the streamed list, 64 bf16 each, into padded smem (u32 pairs)
-__device__ __forceinline__ void load_tile(uint32_t* dst, const bf16* base, long long row_stride, const Sets& s, int k0, int cnt) {
-  for (int i = threadIdx.x; i < cnt * 8; i += kWarps * 32) {
+// A fragments (16 rows starting at row0, all 64 dims = 4 k-steps) of a swizzled tile
+__device__ __forceinline__ void load_a_frags(uint32_t tile, int row0, int lane, uint32_t a[4][4]) {
+  const int r = row0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) ldsm_x4(tile + swz(r, 2 * kk + (lane >> 4)), a[kk][0], a[kk][1], a[kk][2], a[kk][3]);
+}
+// B fragments with the tile's ROWS as the n index (S = A . tile^T): n-tiles j, j+1 (rows 8j..8j+15), k-step kk (dims 16kk..)
+__device__ __forceinline__ void load_b_rows(uint32_t tile, int j, int kk, int lane, uint32_t& b0, uint32_t& b1, uint32_t& c0, uint32_t& c1) {
+  const int r = 8 * j + (lane & 7) + ((lane >> 4) & 1) * 8;
+  ldsm_x4(tile + swz(r, 2 * kk + ((lane >> 3) & 1)), b0, b1, c0, c1);
+}
+// B fragments with the tile's ROWS as the k index (O = P . tile): k-step kk (rows 16kk..16kk+15), n-tiles jd, jd+1 (dims 8jd..)
+__device__ __forceinline__ void load_b_cols(uint32_t tile, int kk, int jd, int lane, uint32_t& b0, uint32_t& b1, uint32_t& c0, uint32_t& c1) {
+  const int r = 16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8;
+  ldsm_x4_t(tile + swz(r, jd + (lane >> 4)), b0, b1, c0, c1);
+}
+
+// cooperative 64-row tile load (rows >= cnt are zero-filled); token(r) gives the token index of tile row r
+template <typename TokFn>
+__device__ __forceinline__ void load_tile(uint32_t tile, const bf16* base, long long row_stride, int cnt, TokFn token) {
+  for (int i = threadIdx.x; i < 64 * 8; i += kThreads) {
     const int r = i >> 3, c = i & 7;
-    const int tok = streamed_token(s, k0 + r);
-    uint4 u = reinterpret_cast<const uint4*>(base + (long long)tok * row_stride)[c];
-    uint32_t* d = dst + r * PITCH + c * 4;
-    d[0] = u.x; d[1] = u.y; d[2] = u.z; d[3] = u.w;
+    const bool ok = r < cnt;
+    const long long tok = ok ? token(r) : 0;
+    cp_async16(tile + swz(r, c), base + tok * row_stride + c * 8, ok);
   }
 }
 
-__device__ __forceinline__ float dot_row(const float* a, const uint32_t* row) {
-  float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-  for (int w = 0; w < 32; ++w) {
-    float2 k = unpack_bf16x2(row[w]);
-    s0 = fmaf(a[2 * w], k.x, s0);
-    s1 = fmaf(a[2 * w + 1], k.y, s1);
-  }
-  return s0 + s1;
-}
-
-// ------------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(kWarps * 32) attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
-                                                               float* __restrict__ lse, AttnShape a) {
-  __shared__ uint32_t Ks[KT * PITCH];
-  __shared__ uint32_t Vs[KT * PITCH];
-  __shared__ float st_acc[SC_FWD][HD];
-  __shared__ float st_m[SC_FWD], st_l[SC_FWD];
+// ================================================================================================ streamed forward
+__global__ void __launch_bounds__(kThreads) attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse,
+                                                            AttnShape a) {
+  __shared__ __align__(128) uint8_t smem[5 * TILE_BYTES];   // Q | K0 | V0 | K1 | V1
+  const uint32_t sQ = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
   const int h = blockIdx.y, b = blockIdx.z;
-  const Sets s = decode_sets(a, blockIdx.x, SC_FWD);
+  const Sets s = decode_sets(a, blockIdx.x);
   const long long rs = 3LL * a.H * HD;
   const bf16* qb = qkv + (long long)b * a.N * rs + (long long)h * HD;
   const bf16* kb = qb + (long long)a.H * HD;
   const bf16* vb = kb + (long long)a.H * HD;
   const int total = s.sm_has0 + s.sm_count;
-  int t_end = (total + KT - 1) / KT;
-  if (a.causal) {
-    const int last = s.st_base + (s.st_count - 1) * s.st_stride;  // largest query index of the chunk
-    t_end = min(t_end, last / KT + 1);
-  }
+  int t_end = (total + BN - 1) / BN;
+  if (a.causal) t_end = min(t_end, (s.st_base + (s.st_count - 1) * s.st_stride) / BN + 1);
+
+  load_tile(sQ, qb, rs, s.st_count, [&](int r) { return s.st_base + r * s.st_stride; });
+  auto issue = [&](int t) {
+    const uint32_t sK = sQ + (1 + 2 * (t & 1)) * TILE_BYTES, sV = sK + TILE_BYTES;
+    const int k0 = t * BN, cnt = min(BN, total - k0);
+    load_tile(sK, kb, rs, cnt, [&](int r) { return streamed_token(s, k0 + r); });
+    load_tile(sV, vb, rs, cnt, [&](int r) { return streamed_token(s, k0 + r); });
+  };
+  issue(0);
+  cp_async_commit();
+
+  const bool warp_active = warp * 16 < s.st_count;   // warp-uniform
+  uint32_t qa[4][4];
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const float sl2 = a.scale * LOG2E;
+  const int row0 = warp * 16 + g, row1 = row0 + 8;
+  const int qtok0 = s.st_base + row0 * s.st_stride, qtok1 = s.st_base + row1 * s.st_stride;
+
   for (int t = 0; t < t_end; ++t) {
-    const int k0 = t * KT;
-    const int cnt = min(KT, total - k0);
+    if (t + 1 < t_end) issue(t + 1);
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
-    load_tile(Ks, kb, rs, s, k0, cnt);
-    load_tile(Vs, vb, rs, s, k0, cnt);
-    __syncthreads();
-    for (int r = warp; r < s.st_count; r += kWarps) {
-      const int qi = s.st_base + r * s.st_stride;
-      float q[HD];
-      load_row_f32(qb + (long long)qi * rs, q, a.scale);
-      float m_old = -INFINITY, l = 0.f, acc0 = 0.f, acc1 = 0.f;
-      if (t > 0) { m_old = st_m[r]; l = st_l[r]; acc0 = st_acc[r][2 * lane]; acc1 = st_acc[r][2 * lane + 1]; }
-      float sc[KT / 32];
-      float mt = -INFINITY;
+    if (t == 0) load_a_frags(sQ, warp * 16, lane, qa);
+    if (warp_active) {
+      const uint32_t sK = sQ + (1 + 2 * (t & 1)) * TILE_BYTES, sV = sK + TILE_BYTES;
+      const int k0 = t * BN, cnt = min(BN, total - k0);
+      float sc[8][4];
 #pragma unroll
-      for (int kk = 0; kk < KT / 32; ++kk) {
-        const int key = kk * 32 + lane;
-        float v = -INFINITY;
-        if (key < cnt) {
-          const int tok = streamed_token(s, k0 + key);
-          if (!a.causal || tok <= qi) v = dot_row(q, Ks + key * PITCH);
-        }
-        sc[kk] = v;
-        mt = fmaxf(mt, v);
-      }
-      mt = warp_max(mt);
-      const float m_new = fmaxf(m_old, mt);
-      float corr = 0.f, psum = 0.f;
-      if (m_new != -INFINITY) {
-        corr = __expf(m_old - m_new);
+      for (int j = 0; j < 8; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
 #pragma unroll
-        for (int kk = 0; kk < KT / 32; ++kk) {
-          sc[kk] = __expf(sc[kk] - m_new);
-          psum += sc[kk];
-        }
-      } else {
+      for (int j = 0; j < 8; j += 2) {
 #pragma unroll
-        for (int kk = 0; kk < KT / 32; ++kk) sc[kk] = 0.f;
-      }
-      psum = warp_sum(psum);
-      l = l * corr + psum;
-      acc0 *= corr; acc1 *= corr;
-#pragma unroll
-      for (int kk = 0; kk < KT / 32; ++kk) {
-        const int lim = min(32, cnt - kk * 32);
-        for (int j = 0; j < lim; ++j) {
-          const float p = __shfl_sync(0xffffffffu, sc[kk], j);
-          const float2 v = unpack_bf16x2(Vs[(kk * 32 + j) * PITCH + lane]);
-          acc0 = fmaf(p, v.x, acc0);
-          acc1 = fmaf(p, v.y, acc1);
+        for (int kk = 0; kk < 4; ++kk) {
+          uint32_t b0, b1, c0, c1;
+          load_b_rows(sK, j, kk, lane, b0, b1, c0, c1);
+          mma16816(sc[j], qa[kk], b0, b1);
+          mma16816(sc[j + 1], qa[kk], c0, c1);
         }
       }
-      if (t + 1 < t_end) {
-        st_acc[r][2 * lane] = acc0; st_acc[r][2 * lane + 1] = acc1;
-        if (lane == 0) { st_m[r] = m_new; st_l[r] = l; }
-      } else {
-        const float inv = 1.0f / l;
-        reinterpret_cast<uint32_t*>(out + ((long long)b * a.N + qi) * a.H * HD + (long long)h * HD)[lane] =
-            pack_bf16x2(acc0 * inv, acc1 * inv);
-        if (lane == 0) lse[((long long)b * a.H + h) * a.N + qi] = m_new + __logf(l);
+      // mask + row max
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int key = 8 * j + 2 * t4 + e;
+          bool ok = key < cnt;
+          bool ok0 = ok, ok1 = ok;
+          if (a.causal && ok) {
+            const int tok = streamed_token(s, k0 + key);
+            ok0 = tok <= qtok0; ok1 = tok <= qtok1;
+          }
+          if (!ok0) sc[j][e] = -INFINITY;
+          if (!ok1) sc[j][2 + e] = -INFINITY;
+          mx0 = fmaxf(mx0, sc[j][e]);
+          mx1 = fmaxf(mx1, sc[j][2 + e]);
+        }
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+      const float mu0 = mn0 == -INFINITY ? 0.f : mn0, mu1 = mn1 == -INFINITY ? 0.f : mn1;
+      const float corr0 = exp2f((m0 - mu0) * sl2), corr1 = exp2f((m1 - mu1) * sl2);   // m = -inf -> 0
+      m0 = mn0; m1 = mn1;
+      float ps0 = 0.f, ps1 = 0.f;
+      uint32_t pa[4][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float p00 = exp2f((sc[j][0] - mu0) * sl2), p01 = exp2f((sc[j][1] - mu0) * sl2);
+        const float p10 = exp2f((sc[j][2] - mu1) * sl2), p11 = exp2f((sc[j][3] - mu1) * sl2);
+        ps0 += p00 + p01; ps1 += p10 + p11;
+        pa[j >> 1][(j & 1) * 2] = pack_bf16x2(p00, p01);
+        pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p10, p11);
+      }
+      l0 = l0 * corr0 + ps0; l1 = l1 * corr1 + ps1;   // per-thread partial sums; reduced across the quad at the end
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { o[j][0] *= corr0; o[j][1] *= corr0; o[j][2] *= corr1; o[j][3] *= corr1; }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int jd = 0; jd < 8; jd += 2) {
+          uint32_t b0, b1, c0, c1;
+          load_b_cols(sV, kk, jd, lane, b0, b1, c0, c1);
+          mma16816(o[jd], pa[kk], b0, b1);
+          mma16816(o[jd + 1], pa[kk], c0, c1);
+        }
       }
     }
+    __syncthreads();   // everyone done with this stage's K/V before it is refilled
+  }
+  cp_async_wait<0>();
+  if (!warp_active) return;
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+  // stage the warp's 16 output rows in its slice of the Q tile (its fragments are in registers), then 16-byte row stores
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t w0 = pack_bf16x2(o[j][0] * inv0, o[j][1] * inv0), w1 = pack_bf16x2(o[j][2] * inv1, o[j][3] * inv1);
+    *reinterpret_cast<uint32_t*>(smem + swz(row0, j) + 4 * t4) = w0;
+    *reinterpret_cast<uint32_t*>(smem + swz(row1, j) + 4 * t4) = w1;
+  }
+  __syncwarp();
+  const long long ro = (long long)a.H * HD;
+  bf16* ob = out + (long long)b * a.N * ro + (long long)h * HD;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = warp * 16 + i * 4 + (lane >> 3), c = lane & 7;
+    if (r < s.st_count) {
+      const uint4 v = *reinterpret_cast<const uint4*>(smem + swz(r, c));
+      *reinterpret_cast<uint4*>(ob + (long long)(s.st_base + r * s.st_stride) * ro + c * 8) = v;
+    }
+  }
+  if (t4 == 0) {
+    float* lb = lse + ((long long)b * a.H + h) * a.N;
+    if (row0 < s.st_count) lb[qtok0] = m0 * a.scale + __logf(l0);
+    if (row1 < s.st_count) lb[qtok1] = m1 * a.scale + __logf(l1);
   }
 }
 
@@ -213,24 +298,26 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __re
   if (lane == 0) delta[((long long)b * H + h) * N + i] = s;
 }
 
-// ------------------------------------------------------------------------------------------------ backward
-// ROLE 0: stationary = query i  (a = q_i, b = dO_i), streamed rows X = K_j, Y = V_j      -> dq_i = scale * sum_j ds_ij K_j
-// ROLE 1: stationary = key j    (a = k_j, b = v_j),  streamed rows X = Q_i, Y = dO_i     -> dk_j = scale * sum_i ds_ij Q_i
-//                                                                                            dv_j = sum_i p_ij dO_i
-// with p_ij = exp(scale q_i.k_j - lse_i), ds_ij = p_ij (dO_i.v_j - delta_i).
+// ================================================================================================ streamed backward
+// ROLE 0: stationary = query i (tiles Q, dO), streamed X = K, Y = V        -> dq_i = scale * sum_j ds_ij k_j
+// ROLE 1: stationary = key j   (tiles K, V),  streamed X = Q, Y = dO       -> dk_j = scale * sum_i ds_ij q_i ; dv_j = sum_i p_ij do_i
+// with p_ij = exp(scale q_i.k_j - lse_i), ds_ij = p_ij (do_i.v_j - delta_i).  In ROLE 1 the register tiles hold the TRANSPOSED
+// score matrix (rows = keys), so P^T / dS^T are directly the A operands of the dV / dK products.
 template <int ROLE>
-__global__ void __launch_bounds__(kWarps * 32) attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
-                                                               const float* __restrict__ lse, const float* __restrict__ delta,
-                                                               bf16* __restrict__ dqkv, AttnShape a) {
-  __shared__ uint32_t Xs[KT * PITCH];
-  __shared__ uint32_t Ys[KT * PITCH];
-  __shared__ float Ls[KT], Ds[KT];
-  __shared__ float st_acc[SC_BWD][ROLE == 1 ? 2 * HD : HD];
+__global__ void __launch_bounds__(kThreads) attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+                                                            const float* __restrict__ lse, const float* __restrict__ delta,
+                                                            bf16* __restrict__ dqkv, AttnShape a) {
+  __shared__ __align__(128) uint8_t smem[4 * TILE_BYTES + 2 * 2 * BN * 4];   // A-side(2 tiles; reused as stages) | X0 Y0 | ... see below
+  // layout: [0] stationary tile 0 (Q or K) -> after fragment load reused as X stage 1
+  //         [1] stationary tile 1 (dO or V) -> reused as Y stage 1
+  //         [2] X stage 0, [3] Y stage 0 ; then lse/delta of the streamed rows (ROLE 1) for 2 stages
+  const uint32_t s0 = smem_u32(smem);
+  float* LsDs = reinterpret_cast<float*>(smem + 4 * TILE_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
   const int h = blockIdx.y, b = blockIdx.z;
-  const Sets s = decode_sets(a, blockIdx.x, SC_BWD);
-  const long long rs = 3LL * a.H * HD;   // qkv token stride
-  const long long ro = (long long)a.H * HD;  // out/dout token stride
+  const Sets s = decode_sets(a, blockIdx.x);
+  const long long rs = 3LL * a.H * HD, ro = (long long)a.H * HD;
   const bf16* qb = qkv + (long long)b * a.N * rs + (long long)h * HD;
   const bf16* kb = qb + ro;
   const bf16* vb = kb + ro;
@@ -242,89 +329,463 @@ __global__ void __launch_bounds__(kWarps * 32) attn_bwd_kernel(const bf16* __res
   const bf16* xs_base = ROLE == 0 ? kb : qb;
   const bf16* ys_base = ROLE == 0 ? vb : dob;
   const long long ys_stride = ROLE == 0 ? rs : ro;
-
   const int total = s.sm_has0 + s.sm_count;
-  int t_begin = 0, t_end = (total + KT - 1) / KT;
+  int t_begin = 0, t_end = (total + BN - 1) / BN;
   if (a.causal) {
-    if (ROLE == 0) t_end = min(t_end, (s.st_base + (s.st_count - 1) * s.st_stride) / KT + 1);
-    else t_begin = s.st_base / KT;  // queries before the first key of the chunk never see it
+    if (ROLE == 0) t_end = min(t_end, (s.st_base + (s.st_count - 1) * s.st_stride) / BN + 1);
+    else t_begin = s.st_base / BN;  // queries before the first key of the chunk never see it
   }
-  for (int t = t_begin; t < t_end; ++t) {
-    const int k0 = t * KT;
-    const int cnt = min(KT, total - k0);
-    __syncthreads();
-    load_tile(Xs, xs_base, rs, s, k0, cnt);
-    load_tile(Ys, ys_base, ys_stride, s, k0, cnt);
+  auto st_tok = [&](int r) { return s.st_base + r * s.st_stride; };
+  // stage buffers: stage 0 -> tiles 2,3 ; stage 1 -> tiles 0,1 (free once the stationary fragments are in registers)
+  auto issue = [&](int t, int stage) {
+    const uint32_t sX = s0 + (stage == 0 ? 2 : 0) * TILE_BYTES, sY = sX + TILE_BYTES;
+    const int k0 = t * BN, cnt = min(BN, total - k0);
+    load_tile(sX, xs_base, rs, cnt, [&](int r) { return streamed_token(s, k0 + r); });
+    load_tile(sY, ys_base, ys_stride, cnt, [&](int r) { return streamed_token(s, k0 + r); });
     if (ROLE == 1) {
-      for (int i = threadIdx.x; i < cnt; i += kWarps * 32) {
-        const int tok = streamed_token(s, k0 + i);
-        Ls[i] = lse_b[tok];
-        Ds[i] = delta_b[tok];
+      for (int i = threadIdx.x; i < BN; i += kThreads) {
+        float l_ = 0.f, d_ = 0.f;
+        if (i < cnt) { const int tok = streamed_token(s, k0 + i); l_ = lse_b[tok]; d_ = delta_b[tok]; }
+        LsDs[stage * 2 * BN + i] = l_ * LOG2E;
+        LsDs[stage * 2 * BN + BN + i] = d_;
+      }
+    }
+  };
+  // stationary tiles
+  if (ROLE == 0) {
+    load_tile(s0, qb, rs, s.st_count, st_tok);
+    load_tile(s0 + TILE_BYTES, dob, ro, s.st_count, st_tok);
+  } else {
+    load_tile(s0, kb, rs, s.st_count, st_tok);
+    load_tile(s0 + TILE_BYTES, vb, rs, s.st_count, st_tok);
+  }
+  issue(t_begin, 0);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  uint32_t fa[4][4], fb[4][4];   // ROLE 0: Q, dO ; ROLE 1: K, V   (A operands, 16 rows of this warp)
+  load_a_frags(s0, warp * 16, lane, fa);
+  load_a_frags(s0 + TILE_BYTES, warp * 16, lane, fb);
+  __syncthreads();               // tiles 0,1 may now be overwritten (stage 1)
+
+  const bool warp_active = warp * 16 < s.st_count;
+  const int row0 = warp * 16 + g, row1 = row0 + 8;
+  const int stok0 = st_tok(row0), stok1 = st_tok(row1);
+  float lse0 = 0.f, lse1 = 0.f, dl0 = 0.f, dl1 = 0.f;
+  if (ROLE == 0) {
+    if (row0 < s.st_count) { lse0 = lse_b[stok0] * LOG2E; dl0 = delta_b[stok0]; }
+    if (row1 < s.st_count) { lse1 = lse_b[stok1] * LOG2E; dl1 = delta_b[stok1]; }
+  }
+  const float sl2 = a.scale * LOG2E;
+  float acc0[8][4], acc1[8][4];   // ROLE 0: acc0 = dQ ; ROLE 1: acc0 = dK, acc1 = dV
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    acc0[j][0] = acc0[j][1] = acc0[j][2] = acc0[j][3] = 0.f;
+    if (ROLE == 1) acc1[j][0] = acc1[j][1] = acc1[j][2] = acc1[j][3] = 0.f;
+  }
+
+  for (int t = t_begin; t < t_end; ++t) {
+    const int stage = (t - t_begin) & 1;
+    if (t + 1 < t_end) issue(t + 1, stage ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    if (warp_active) {
+      const uint32_t sX = s0 + (stage == 0 ? 2 : 0) * TILE_BYTES, sY = sX + TILE_BYTES;
+      const float* Ls = LsDs + stage * 2 * BN;
+      const float* Ds = Ls + BN;
+      const int k0 = t * BN, cnt = min(BN, total - k0);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {   // 32 streamed rows at a time (register pressure)
+        float sc[4][4], dp[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
+#pragma unroll
+        for (int j = 0; j < 4; j += 2) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            uint32_t b0, b1, c0, c1;
+            load_b_rows(sX, half * 4 + j, kk, lane, b0, b1, c0, c1);
+            mma16816(sc[j], fa[kk], b0, b1);
+            mma16816(sc[j + 1], fa[kk], c0, c1);
+            load_b_rows(sY, half * 4 + j, kk, lane, b0, b1, c0, c1);
+            mma16816(dp[j], fb[kk], b0, b1);
+            mma16816(dp[j + 1], fb[kk], c0, c1);
+          }
+        }
+        uint32_t pa[2][4], dsa[2][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float p[4], ds[4];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = 32 * half + 8 * j + 2 * t4 + e;      // streamed row index inside the tile
+            bool ok = col < cnt, ok0 = ok, ok1 = ok;
+            if (a.causal && ok) {
+              const int tok = streamed_token(s, k0 + col);
+              if (ROLE == 0) { ok0 = tok <= stok0; ok1 = tok <= stok1; }
+              else { ok0 = tok >= stok0; ok1 = tok >= stok1; }
+            }
+            const float la = ROLE == 0 ? lse0 : Ls[col], lb = ROLE == 0 ? lse1 : Ls[col];
+            const float da = ROLE == 0 ? dl0 : Ds[col], db = ROLE == 0 ? dl1 : Ds[col];
+            p[e] = ok0 ? exp2f(sc[j][e] * sl2 - la) : 0.f;
+            p[2 + e] = ok1 ? exp2f(sc[j][2 + e] * sl2 - lb) : 0.f;
+            ds[e] = p[e] * (dp[j][e] - da);
+            ds[2 + e] = p[2 + e] * (dp[j][2 + e] - db);
+          }
+          dsa[j >> 1][(j & 1) * 2] = pack_bf16x2(ds[0], ds[1]);
+          dsa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(ds[2], ds[3]);
+          if (ROLE == 1) {
+            pa[j >> 1][(j & 1) * 2] = pack_bf16x2(p[0], p[1]);
+            pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p[2], p[3]);
+          }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+          for (int jd = 0; jd < 8; jd += 2) {
+            uint32_t b0, b1, c0, c1;
+            load_b_cols(sX, half * 2 + kk, jd, lane, b0, b1, c0, c1);     // ROLE 0: K (dQ += dS K) ; ROLE 1: Q (dK += dS^T Q)
+            mma16816(acc0[jd], dsa[kk], b0, b1);
+            mma16816(acc0[jd + 1], dsa[kk], c0, c1);
+            if (ROLE == 1) {
+              load_b_cols(sY, half * 2 + kk, jd, lane, b0, b1, c0, c1);   // dO (dV += P^T dO)
+              mma16816(acc1[jd], pa[kk], b0, b1);
+              mma16816(acc1[jd + 1], pa[kk], c0, c1);
+            }
+          }
+        }
       }
     }
     __syncthreads();
-    for (int r = warp; r < s.st_count; r += kWarps) {
-      const int si = s.st_base + r * s.st_stride;
-      float av[HD], bv[HD];
-      if (ROLE == 0) {
-        load_row_f32(qb + (long long)si * rs, av, 1.0f);
-        load_row_f32(dob + (long long)si * ro, bv, 1.0f);
-      } else {
-        load_row_f32(kb + (long long)si * rs, av, 1.0f);
-        load_row_f32(vb + (long long)si * rs, bv, 1.0f);
-      }
-      float lse_s = 0.f, delta_s = 0.f;
-      if (ROLE == 0) { lse_s = lse_b[si]; delta_s = delta_b[si]; }
-      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-      if (t > t_begin) {
-        acc0 = st_acc[r][2 * lane]; acc1 = st_acc[r][2 * lane + 1];
-        if (ROLE == 1) { acc2 = st_acc[r][HD + 2 * lane]; acc3 = st_acc[r][HD + 2 * lane + 1]; }
-      }
-      float pv[KT / 32], dsv[KT / 32];
+  }
+  cp_async_wait<0>();
+  __syncthreads();   // all warps are past their last tile: tile 2/3 region is free for output staging
+  if (!warp_active) return;
+  // stage through this warp's private 16-row slice of tile 2 (and tile 3 for dV), then 16-byte row stores
+  uint8_t* stg = smem + 2 * TILE_BYTES;
 #pragma unroll
-      for (int kk = 0; kk < KT / 32; ++kk) {
-        const int row = kk * 32 + lane;
-        float p = 0.f, ds = 0.f;
-        if (row < cnt) {
-          const int tok = streamed_token(s, k0 + row);
-          const bool ok = !a.causal || (ROLE == 0 ? tok <= si : tok >= si);
-          if (ok) {
-            const float sdot = dot_row(av, Xs + row * PITCH) * a.scale;
-            const float dp = dot_row(bv, Ys + row * PITCH);
-            const float l_ = ROLE == 0 ? lse_s : Ls[row];
-            const float d_ = ROLE == 0 ? delta_s : Ds[row];
-            p = __expf(sdot - l_);
-            ds = p * (dp - d_);
-          }
-        }
-        pv[kk] = p;
-        dsv[kk] = ds;
-      }
+  for (int j = 0; j < 8; ++j) {
+    *reinterpret_cast<uint32_t*>(stg + swz(row0, j) + 4 * t4) = pack_bf16x2(acc0[j][0] * a.scale, acc0[j][1] * a.scale);
+    *reinterpret_cast<uint32_t*>(stg + swz(row1, j) + 4 * t4) = pack_bf16x2(acc0[j][2] * a.scale, acc0[j][3] * a.scale);
+    if (ROLE == 1) {
+      *reinterpret_cast<uint32_t*>(stg + TILE_BYTES + swz(row0, j) + 4 * t4) = pack_bf16x2(acc1[j][0], acc1[j][1]);
+      *reinterpret_cast<uint32_t*>(stg + TILE_BYTES + swz(row1, j) + 4 * t4) = pack_bf16x2(acc1[j][2], acc1[j][3]);
+    }
+  }
+  __syncwarp();
 #pragma unroll
-      for (int kk = 0; kk < KT / 32; ++kk) {
-        const int lim = min(32, cnt - kk * 32);
-        for (int j = 0; j < lim; ++j) {
-          const float ds = __shfl_sync(0xffffffffu, dsv[kk], j);
-          const float2 x = unpack_bf16x2(Xs[(kk * 32 + j) * PITCH + lane]);
-          acc0 = fmaf(ds, x.x, acc0);
-          acc1 = fmaf(ds, x.y, acc1);
-          if (ROLE == 1) {
-            const float p = __shfl_sync(0xffffffffu, pv[kk], j);
-            const float2 y = unpack_bf16x2(Ys[(kk * 32 + j) * PITCH + lane]);
-            acc2 = fmaf(p, y.x, acc2);
-            acc3 = fmaf(p, y.y, acc3);
-          }
-        }
-      }
-      if (t + 1 < t_end) {
-        st_acc[r][2 * lane] = acc0; st_acc[r][2 * lane + 1] = acc1;
-        if (ROLE == 1) { st_acc[r][HD + 2 * lane] = acc2; st_acc[r][HD + 2 * lane + 1] = acc3; }
-      } else {
-        bf16* o = dq_b + (long long)si * rs + (ROLE == 0 ? 0 : ro);
-        reinterpret_cast<uint32_t*>(o)[lane] = pack_bf16x2(acc0 * a.scale, acc1 * a.scale);
-        if (ROLE == 1) reinterpret_cast<uint32_t*>(o + ro)[lane] = pack_bf16x2(acc2, acc3);
+  for (int i = 0; i < 4; ++i) {
+    const int r = warp * 16 + i * 4 + (lane >> 3), c = lane & 7;
+    if (r < s.st_count) {
+      bf16* dst = dq_b + (long long)st_tok(r) * rs + (ROLE == 0 ? 0 : ro) + c * 8;
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(stg + swz(r, c));
+      if (ROLE == 1) *reinterpret_cast<uint4*>(dst + ro) = *reinterpret_cast<const uint4*>(stg + TILE_BYTES + swz(r, c));
+    }
+  }
+}
+
+// ================================================================================================ time mode: warp per slot
+// One warp owns (batch b, head h, slot j): queries = tokens 1 + f*n + j (f < T <= 16), keys = [CLS ; the same T tokens].
+// Per-warp shared memory: Q [16 rows] | K [32 rows] | V [32 rows] (| dO [16 rows] in backward), 128 B rows, swizzled.
+constexpr int TW = 4;                         // warps (slots) per CTA, forward
+constexpr int TWB = 3;                        // backward (48 KB static shared memory limit)
+constexpr int T_ROWS_FWD = 16 + 32 + 32;      // rows of 128 B per warp
+constexpr int T_ROWS_BWD = 16 + 32 + 32 + 16;
+
+template <bool BWD>
+__device__ __forceinline__ void time_load(uint32_t base, const bf16* qb, const bf16* dob, long long rs, long long ro, long long hd_off, int T,
+                                          int n, int slot, int lane) {
+  // rows: Q r<16 (token 1+r*n+slot, r<T) ; K 16+r (key r: 0 = CLS, else frame r-1) ; V 48+r ; dO 80+r
+  const int rows = BWD ? T_ROWS_BWD : T_ROWS_FWD;
+  for (int i = lane; i < rows * 8; i += 32) {
+    const int r = i >> 3, c = i & 7;
+    const bf16* src = qb;
+    bool ok;
+    if (r < 16) { ok = r < T; src = qb + (long long)(1 + (ok ? r : 0) * n + slot) * rs; }
+    else if (r < 80) {
+      const int kr = (r - 16) & 31, which = (r - 16) >> 5;   // 0 = K, 1 = V
+      ok = kr <= T;
+      const long long tok = (!ok || kr == 0) ? 0 : 1 + (long long)(kr - 1) * n + slot;
+      src = qb + tok * rs + (which + 1) * hd_off;
+    } else {
+      const int qr = r - 80;
+      ok = qr < T;
+      src = dob + (long long)(1 + (ok ? qr : 0) * n + slot) * ro;
+    }
+    cp_async16(base + swz(r, c), src + c * 8, ok);
+  }
+}
+
+__global__ void __launch_bounds__(TW * 32) attn_time_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse,
+                                                                AttnShape a) {
+  __shared__ __align__(128) uint8_t smem[TW * T_ROWS_FWD * 128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int slot = blockIdx.x * TW + warp;
+  if (slot >= a.n) return;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const long long rs = 3LL * a.H * HD, ro = (long long)a.H * HD;
+  const bf16* qb = qkv + (long long)b * a.N * rs + (long long)h * HD;
+  const uint32_t base = smem_u32(smem) + warp * T_ROWS_FWD * 128;
+  time_load<false>(base, qb, nullptr, rs, ro, ro, a.T, a.n, slot, lane);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncwarp();
+  const uint32_t sQ = base, sK = base + 16 * 128, sV = base + 48 * 128;
+  uint32_t qa[4][4];
+  load_a_frags(sQ, 0, lane, qa);
+  const int nk = a.T + 1;                      // keys
+  const int nkt = (nk + 7) >> 3;               // 8-key tiles: 2 (T <= 15) or 3 (T = 16); processed as pairs -> up to 4
+  float sc[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; j += 2) {
+    if (j < nkt) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t b0, b1, c0, c1;
+        load_b_rows(sK, j, kk, lane, b0, b1, c0, c1);
+        mma16816(sc[j], qa[kk], b0, b1);
+        mma16816(sc[j + 1], qa[kk], c0, c1);
       }
     }
+  }
+  const float sl2 = a.scale * LOG2E;
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const bool ok = 8 * j + 2 * t4 + e < nk;
+      if (!ok) { sc[j][e] = -INFINITY; sc[j][2 + e] = -INFINITY; }
+      mx0 = fmaxf(mx0, sc[j][e]); mx1 = fmaxf(mx1, sc[j][2 + e]);
+    }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  float l0 = 0.f, l1 = 0.f;
+  uint32_t pa[2][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float p00 = exp2f((sc[j][0] - mx0) * sl2), p01 = exp2f((sc[j][1] - mx0) * sl2);
+    const float p10 = exp2f((sc[j][2] - mx1) * sl2), p11 = exp2f((sc[j][3] - mx1) * sl2);
+    l0 += p00 + p01; l1 += p10 + p11;
+    pa[j >> 1][(j & 1) * 2] = pack_bf16x2(p00, p01);
+    pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p10, p11);
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk) {
+    if (kk * 16 < nk) {
+#pragma unroll
+      for (int jd = 0; jd < 8; jd += 2) {
+        uint32_t b0, b1, c0, c1;
+        load_b_cols(sV, kk, jd, lane, b0, b1, c0, c1);
+        mma16816(o[jd], pa[kk], b0, b1);
+        mma16816(o[jd + 1], pa[kk], c0, c1);
+      }
+    }
+  }
+  const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+  __syncwarp();
+  uint8_t* stg = smem + warp * T_ROWS_FWD * 128;   // reuse the Q rows
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    *reinterpret_cast<uint32_t*>(stg + swz(g, j) + 4 * t4) = pack_bf16x2(o[j][0] * inv0, o[j][1] * inv0);
+    *reinterpret_cast<uint32_t*>(stg + swz(g + 8, j) + 4 * t4) = pack_bf16x2(o[j][2] * inv1, o[j][3] * inv1);
+  }
+  __syncwarp();
+  bf16* ob = out + (long long)b * a.N * ro + (long long)h * HD;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 4 + (lane >> 3), c = lane & 7;
+    if (r < a.T) *reinterpret_cast<uint4*>(ob + (long long)(1 + r * a.n + slot) * ro + c * 8) = *reinterpret_cast<const uint4*>(stg + swz(r, c));
+  }
+  if (t4 == 0) {
+    float* lb = lse + ((long long)b * a.H + h) * a.N;
+    if (g < a.T) lb[1 + g * a.n + slot] = mx0 * a.scale + __logf(l0);
+    if (g + 8 < a.T) lb[1 + (g + 8) * a.n + slot] = mx1 * a.scale + __logf(l1);
+  }
+}
+
+// backward of one slot: dq (T rows), dk/dv of the slot's T patch keys.  The CLS key's dk/dv (and the CLS query's dq) sum over
+// ALL tokens and are produced by the streamed kernels launched with cls_only = 1.
+__global__ void __launch_bounds__(TWB * 32) attn_time_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+                                                                const float* __restrict__ lse, const float* __restrict__ delta,
+                                                                bf16* __restrict__ dqkv, AttnShape a) {
+  __shared__ __align__(128) uint8_t smem[TWB * T_ROWS_BWD * 128];
+  __shared__ float stat[TWB][2][16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int slot = blockIdx.x * TWB + warp;
+  if (slot >= a.n) return;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const long long rs = 3LL * a.H * HD, ro = (long long)a.H * HD;
+  const bf16* qb = qkv + (long long)b * a.N * rs + (long long)h * HD;
+  const bf16* dob = dout + (long long)b * a.N * ro + (long long)h * HD;
+  const float* lse_b = lse + ((long long)b * a.H + h) * a.N;
+  const float* delta_b = delta + ((long long)b * a.H + h) * a.N;
+  const uint32_t base = smem_u32(smem) + warp * T_ROWS_BWD * 128;
+  time_load<true>(base, qb, dob, rs, ro, ro, a.T, a.n, slot, lane);
+  cp_async_commit();
+  if (lane < 16) {
+    const bool ok = lane < a.T;
+    const int tok = 1 + (ok ? lane : 0) * a.n + slot;
+    stat[warp][0][lane] = ok ? lse_b[tok] * LOG2E : 0.f;
+    stat[warp][1][lane] = ok ? delta_b[tok] : 0.f;
+  }
+  cp_async_wait<0>();
+  __syncwarp();
+  const uint32_t sQ = base, sK = base + 16 * 128, sV = base + 48 * 128, sD = base + 80 * 128;
+  const int nk = a.T + 1;
+  const float sl2 = a.scale * LOG2E;
+  uint8_t* wsm = smem + warp * T_ROWS_BWD * 128;
+  bf16* dq_b = dqkv + (long long)b * a.N * rs + (long long)h * HD;
+
+  // ---------------- pass A: rows = queries (16), cols = keys (<= 32): dQ = scale * dS K
+  float dq[8][4];
+  {
+    uint32_t qa[4][4], da[4][4];
+    load_a_frags(sQ, 0, lane, qa);
+    load_a_frags(sD, 0, lane, da);
+    float sc[4][4], dp[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
+#pragma unroll
+    for (int j = 0; j < 4; j += 2) {
+      if (8 * j < nk) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          uint32_t b0, b1, c0, c1;
+          load_b_rows(sK, j, kk, lane, b0, b1, c0, c1);
+          mma16816(sc[j], qa[kk], b0, b1);
+          mma16816(sc[j + 1], qa[kk], c0, c1);
+          load_b_rows(sV, j, kk, lane, b0, b1, c0, c1);
+          mma16816(dp[j], da[kk], b0, b1);
+          mma16816(dp[j + 1], da[kk], c0, c1);
+        }
+      }
+    }
+    const float l0 = stat[warp][0][g], l1 = stat[warp][0][g + 8], d0 = stat[warp][1][g], d1 = stat[warp][1][g + 8];
+    uint32_t dsa[2][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float ds[4];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool ok = 8 * j + 2 * t4 + e < nk;
+        const float p0 = (ok && g < a.T) ? exp2f(sc[j][e] * sl2 - l0) : 0.f;
+        const float p1 = (ok && g + 8 < a.T) ? exp2f(sc[j][2 + e] * sl2 - l1) : 0.f;
+        ds[e] = p0 * (dp[j][e] - d0);
+        ds[2 + e] = p1 * (dp[j][2 + e] - d1);
+      }
+      dsa[j >> 1][(j & 1) * 2] = pack_bf16x2(ds[0], ds[1]);
+      dsa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(ds[2], ds[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      if (kk * 16 < nk) {
+#pragma unroll
+        for (int jd = 0; jd < 8; jd += 2) {
+          uint32_t b0, b1, c0, c1;
+          load_b_cols(sK, kk, jd, lane, b0, b1, c0, c1);
+          mma16816(dq[jd], dsa[kk], b0, b1);
+          mma16816(dq[jd + 1], dsa[kk], c0, c1);
+        }
+      }
+    }
+  }
+  // ---------------- pass B: rows = keys (2 m-tiles of 16), cols = queries (16): dK = scale * dS^T Q ; dV = P^T dO
+  // (each m-tile's results are staged straight into the K / V rows they correspond to: those rows are dead by then)
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    if (mt * 16 < nk) {
+      float dk[8][4], dv[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f;
+        dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f;
+      }
+      uint32_t ka[4][4], va[4][4];
+      load_a_frags(sK, mt * 16, lane, ka);
+      load_a_frags(sV, mt * 16, lane, va);
+      float sc[2][4], dp[2][4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t b0, b1, c0, c1;
+        load_b_rows(sQ, 0, kk, lane, b0, b1, c0, c1);
+        mma16816(sc[0], ka[kk], b0, b1);
+        mma16816(sc[1], ka[kk], c0, c1);
+        load_b_rows(sD, 0, kk, lane, b0, b1, c0, c1);
+        mma16816(dp[0], va[kk], b0, b1);
+        mma16816(dp[1], va[kk], c0, c1);
+      }
+      uint32_t pa[4], dsa[4];
+      const int key0 = mt * 16 + g, key1 = key0 + 8;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float p[4], ds[4];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int q = 8 * j + 2 * t4 + e;
+          const bool okq = q < a.T;
+          const float lq = stat[warp][0][q], dq_ = stat[warp][1][q];
+          p[e] = (okq && key0 < nk) ? exp2f(sc[j][e] * sl2 - lq) : 0.f;
+          p[2 + e] = (okq && key1 < nk) ? exp2f(sc[j][2 + e] * sl2 - lq) : 0.f;
+          ds[e] = p[e] * (dp[j][e] - dq_);
+          ds[2 + e] = p[2 + e] * (dp[j][2 + e] - dq_);
+        }
+        pa[j * 2] = pack_bf16x2(p[0], p[1]); pa[j * 2 + 1] = pack_bf16x2(p[2], p[3]);
+        dsa[j * 2] = pack_bf16x2(ds[0], ds[1]); dsa[j * 2 + 1] = pack_bf16x2(ds[2], ds[3]);
+      }
+#pragma unroll
+      for (int jd = 0; jd < 8; jd += 2) {
+        uint32_t b0, b1, c0, c1;
+        load_b_cols(sQ, 0, jd, lane, b0, b1, c0, c1);
+        mma16816(dk[jd], dsa, b0, b1);
+        mma16816(dk[jd + 1], dsa, c0, c1);
+        load_b_cols(sD, 0, jd, lane, b0, b1, c0, c1);
+        mma16816(dv[jd], pa, b0, b1);
+        mma16816(dv[jd + 1], pa, c0, c1);
+      }
+      __syncwarp();   // every lane has its K/V fragments of this m-tile in registers
+      const int r0 = 16 + mt * 16 + g, r1 = r0 + 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        *reinterpret_cast<uint32_t*>(wsm + swz(r0, j) + 4 * t4) = pack_bf16x2(dk[j][0] * a.scale, dk[j][1] * a.scale);
+        *reinterpret_cast<uint32_t*>(wsm + swz(r1, j) + 4 * t4) = pack_bf16x2(dk[j][2] * a.scale, dk[j][3] * a.scale);
+        *reinterpret_cast<uint32_t*>(wsm + swz(32 + r0, j) + 4 * t4) = pack_bf16x2(dv[j][0], dv[j][1]);
+        *reinterpret_cast<uint32_t*>(wsm + swz(32 + r1, j) + 4 * t4) = pack_bf16x2(dv[j][2], dv[j][3]);
+      }
+    }
+  }
+  // ---------------- dq goes into the (now dead) Q rows; then 16-byte row stores of everything
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    *reinterpret_cast<uint32_t*>(wsm + swz(g, j) + 4 * t4) = pack_bf16x2(dq[j][0] * a.scale, dq[j][1] * a.scale);
+    *reinterpret_cast<uint32_t*>(wsm + swz(g + 8, j) + 4 * t4) = pack_bf16x2(dq[j][2] * a.scale, dq[j][3] * a.scale);
+  }
+  __syncwarp();
+  for (int i = lane; i < 80 * 8; i += 32) {
+    const int r = i >> 3, c = i & 7;
+    long long tok; long long off;
+    if (r < 16) { if (r >= a.T) continue; tok = 1 + (long long)r * a.n + slot; off = 0; }
+    else {
+      const int kr = (r - 16) & 31, which = (r - 16) >> 5;
+      if (kr == 0 || kr > a.T) continue;                    // key 0 = CLS: written by the cls_only streamed launch
+      tok = 1 + (long long)(kr - 1) * a.n + slot; off = (which + 1) * ro;
+    }
+    *reinterpret_cast<uint4*>(dq_b + tok * rs + off + c * 8) = *reinterpret_cast<const uint4*>(wsm + swz(r, c));
   }
 }
 
@@ -340,17 +801,26 @@ int check_shape(const AttnShape& a, int64_t d) {
   return TVTS_OK;
 }
 
+inline bool use_time_kernels(const AttnShape& a) { return a.mode == 2 && a.T <= 16; }
+
 }  // namespace
 
 extern "C" int tvts_attn_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T,
                              int64_t n, int64_t causal, float scale, void* stream) {
-  AttnShape a{(int)B, (int)N, (int)H, (int)mode, (int)T, (int)n, (int)causal, scale};
+  AttnShape a{(int)B, (int)N, (int)H, (int)mode, (int)T, (int)n, (int)causal, scale, 0};
   if (B == 0) return TVTS_OK;
   int rc = check_shape(a, d);
   if (rc) return rc;
   TVTS_REQUIRE(qkv && out && lse, "attn_fwd: null pointer");
-  dim3 grid(num_blocks_x(a, SC_FWD), (unsigned)H, (unsigned)B);
-  attn_fwd_kernel<<<grid, kWarps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const bf16*)qkv, (bf16*)out, lse, a);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (use_time_kernels(a)) {
+    dim3 tg((unsigned)((a.n + TW - 1) / TW), (unsigned)H, (unsigned)B);
+    attn_time_fwd_kernel<<<tg, TW * 32, 0, st>>>((const bf16*)qkv, (bf16*)out, lse, a);
+    TVTS_LAUNCH_CHECK();
+    a.cls_only = 1;
+  }
+  dim3 grid(num_blocks_x(a), (unsigned)H, (unsigned)B);
+  attn_fwd_kernel<<<grid, kThreads, 0, st>>>((const bf16*)qkv, (bf16*)out, lse, a);
   TVTS_LAUNCH_CHECK();
   return TVTS_OK;
 }
@@ -358,7 +828,7 @@ extern "C" int tvts_attn_fwd(const void* qkv, void* out, float* lse, int64_t B, 
 extern "C" int tvts_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv, int64_t B,
                              int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal, float scale,
                              void* stream) {
-  AttnShape a{(int)B, (int)N, (int)H, (int)mode, (int)T, (int)n, (int)causal, scale};
+  AttnShape a{(int)B, (int)N, (int)H, (int)mode, (int)T, (int)n, (int)causal, scale, 0};
   if (B == 0) return TVTS_OK;
   int rc = check_shape(a, d);
   if (rc) return rc;
@@ -367,10 +837,16 @@ extern "C" int tvts_attn_bwd(const void* qkv, const void* out, const void* dout,
   const long long rows = (long long)B * N * H;
   attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta_ws, (int)B, (int)N, (int)H);
   TVTS_LAUNCH_CHECK();
-  dim3 grid(num_blocks_x(a, SC_BWD), (unsigned)H, (unsigned)B);
-  attn_bwd_kernel<0><<<grid, kWarps * 32, 0, st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, a);
+  if (use_time_kernels(a)) {
+    dim3 tg((unsigned)((a.n + TWB - 1) / TWB), (unsigned)H, (unsigned)B);
+    attn_time_bwd_kernel<<<tg, TWB * 32, 0, st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, a);
+    TVTS_LAUNCH_CHECK();
+    a.cls_only = 1;
+  }
+  dim3 grid(num_blocks_x(a), (unsigned)H, (unsigned)B);
+  attn_bwd_kernel<0><<<grid, kThreads, 0, st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, a);
   TVTS_LAUNCH_CHECK();
-  attn_bwd_kernel<1><<<grid, kWarps * 32, 0, st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, a);
+  attn_bwd_kernel<1><<<grid, kThreads, 0, st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, a);
   TVTS_LAUNCH_CHECK();
   return TVTS_OK;
 }
