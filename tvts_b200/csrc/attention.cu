@@ -15,8 +15,8 @@
 //     one (batch, head, group) and streams the group's other side through double-buffered 64-row tiles, flash-attention style:
 //         forward / dQ : stationary = queries, streamed = keys (+values)
 //         dK,dV        : stationary = keys,    streamed = queries (+dO)     (same index sets: the relation is symmetric)
-//   * "time" kernels: one WARP per (batch, head, slot): T <= 16 queries x (T+1) keys fit one MMA tile; forward and the whole
-//     backward (dq, dk, dv of the slot) each run in a single pass.
+//   * "time" kernels: one WARP per (batch, head, slot): T <= 15 queries x (T+1) keys fit one 16x16 MMA tile; forward and the
+//     whole backward (dq, dk, dv of the slot) each run in a single pass (more frames fall back to the streamed kernels).
 // fp32 softmax statistics (online max/sum in forward; saved log-sum-exp in backward), bf16 I/O.
 #include "common.cuh"
 #include "../../include/tvts_b200.h"
@@ -486,33 +486,33 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_kernel(const bf16* __restri
 }
 
 // ================================================================================================ time mode: warp per slot
-// One warp owns (batch b, head h, slot j): queries = tokens 1 + f*n + j (f < T <= 16), keys = [CLS ; the same T tokens].
-// Per-warp shared memory: Q [16 rows] | K [32 rows] | V [32 rows] (| dO [16 rows] in backward), 128 B rows, swizzled.
-constexpr int TW = 4;                         // warps (slots) per CTA, forward
-constexpr int TWB = 3;                        // backward (48 KB static shared memory limit)
-constexpr int T_ROWS_FWD = 16 + 32 + 32;      // rows of 128 B per warp
-constexpr int T_ROWS_BWD = 16 + 32 + 32 + 16;
+// One warp owns (batch b, head h, slot j): queries = tokens 1 + f*n + j (f < T <= 15), keys = [CLS ; the same T tokens]
+// (T+1 <= 16: one 16x16 score tile).  Per-warp shared memory, 128 B rows, swizzled:
+//   forward : Q [16] | K [16] | V [16]            backward: Q [16] | K [16] | V [16] | dO [16]
+// In backward, row T of the Q / dO tiles holds the CLS query: it also attends to the slot's keys, so it is one more
+// column of the transposed pass that produces dK / dV (its own dq is produced by the cls_only streamed launch).
+constexpr int TW = 4;                         // warps (slots) per CTA
+constexpr int T_ROWS_FWD = 48;
+constexpr int T_ROWS_BWD = 64;
+constexpr int T_MAX = 15;
 
 template <bool BWD>
-__device__ __forceinline__ void time_load(uint32_t base, const bf16* qb, const bf16* dob, long long rs, long long ro, long long hd_off, int T,
-                                          int n, int slot, int lane) {
-  // rows: Q r<16 (token 1+r*n+slot, r<T) ; K 16+r (key r: 0 = CLS, else frame r-1) ; V 48+r ; dO 80+r
+__device__ __forceinline__ void time_load(uint32_t base, const bf16* qb, const bf16* dob, long long rs, long long ro, int T, int n, int slot,
+                                          int lane) {
   const int rows = BWD ? T_ROWS_BWD : T_ROWS_FWD;
   for (int i = lane; i < rows * 8; i += 32) {
     const int r = i >> 3, c = i & 7;
-    const bf16* src = qb;
+    const int blk = r >> 4, rr = r & 15;       // blk 0 = Q, 1 = K, 2 = V, 3 = dO
     bool ok;
-    if (r < 16) { ok = r < T; src = qb + (long long)(1 + (ok ? r : 0) * n + slot) * rs; }
-    else if (r < 80) {
-      const int kr = (r - 16) & 31, which = (r - 16) >> 5;   // 0 = K, 1 = V
-      ok = kr <= T;
-      const long long tok = (!ok || kr == 0) ? 0 : 1 + (long long)(kr - 1) * n + slot;
-      src = qb + tok * rs + (which + 1) * hd_off;
-    } else {
-      const int qr = r - 80;
-      ok = qr < T;
-      src = dob + (long long)(1 + (ok ? qr : 0) * n + slot) * ro;
+    long long tok;
+    if (blk == 0 || blk == 3) {                // query-side rows: rr < T slot queries, rr == T the CLS query (backward only)
+      ok = rr < T || (BWD && rr == T);
+      tok = rr < T ? 1 + (long long)rr * n + slot : 0;
+    } else {                                   // key-side rows: rr == 0 CLS, rr <= T frame rr-1
+      ok = rr <= T;
+      tok = (rr == 0 || !ok) ? 0 : 1 + (long long)(rr - 1) * n + slot;
     }
+    const bf16* src = blk == 3 ? dob + tok * ro : qb + tok * rs + (blk == 3 ? 0 : blk) * ro;
     cp_async16(base + swz(r, c), src + c * 8, ok);
   }
 }
@@ -528,51 +528,44 @@ __global__ void __launch_bounds__(TW * 32) attn_time_fwd_kernel(const bf16* __re
   const long long rs = 3LL * a.H * HD, ro = (long long)a.H * HD;
   const bf16* qb = qkv + (long long)b * a.N * rs + (long long)h * HD;
   const uint32_t base = smem_u32(smem) + warp * T_ROWS_FWD * 128;
-  time_load<false>(base, qb, nullptr, rs, ro, ro, a.T, a.n, slot, lane);
+  time_load<false>(base, qb, nullptr, rs, ro, a.T, a.n, slot, lane);
   cp_async_commit();
   cp_async_wait<0>();
   __syncwarp();
-  const uint32_t sQ = base, sK = base + 16 * 128, sV = base + 48 * 128;
+  const uint32_t sQ = base, sK = base + 16 * 128, sV = base + 32 * 128;
+  const int nk = a.T + 1;
   uint32_t qa[4][4];
   load_a_frags(sQ, 0, lane, qa);
-  const int nk = a.T + 1;                      // keys
-  const int nkt = (nk + 7) >> 3;               // 8-key tiles: 2 (T <= 15) or 3 (T = 16); processed as pairs -> up to 4
-  float sc[4][4];
+  float sc[2][4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+  for (int j = 0; j < 2; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
 #pragma unroll
-  for (int j = 0; j < 4; j += 2) {
-    if (j < nkt) {
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        uint32_t b0, b1, c0, c1;
-        load_b_rows(sK, j, kk, lane, b0, b1, c0, c1);
-        mma16816(sc[j], qa[kk], b0, b1);
-        mma16816(sc[j + 1], qa[kk], c0, c1);
-      }
-    }
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t b0, b1, c0, c1;
+    load_b_rows(sK, 0, kk, lane, b0, b1, c0, c1);
+    mma16816(sc[0], qa[kk], b0, b1);
+    mma16816(sc[1], qa[kk], c0, c1);
   }
   const float sl2 = a.scale * LOG2E;
   float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
+  for (int j = 0; j < 2; ++j)
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const bool ok = 8 * j + 2 * t4 + e < nk;
-      if (!ok) { sc[j][e] = -INFINITY; sc[j][2 + e] = -INFINITY; }
+      if (8 * j + 2 * t4 + e >= nk) { sc[j][e] = -INFINITY; sc[j][2 + e] = -INFINITY; }
       mx0 = fmaxf(mx0, sc[j][e]); mx1 = fmaxf(mx1, sc[j][2 + e]);
     }
   mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
   mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
   float l0 = 0.f, l1 = 0.f;
-  uint32_t pa[2][4];
+  uint32_t pa[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < 2; ++j) {
     const float p00 = exp2f((sc[j][0] - mx0) * sl2), p01 = exp2f((sc[j][1] - mx0) * sl2);
     const float p10 = exp2f((sc[j][2] - mx1) * sl2), p11 = exp2f((sc[j][3] - mx1) * sl2);
     l0 += p00 + p01; l1 += p10 + p11;
-    pa[j >> 1][(j & 1) * 2] = pack_bf16x2(p00, p01);
-    pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p10, p11);
+    pa[j * 2] = pack_bf16x2(p00, p01);
+    pa[j * 2 + 1] = pack_bf16x2(p10, p11);
   }
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
@@ -580,16 +573,11 @@ __global__ void __launch_bounds__(TW * 32) attn_time_fwd_kernel(const bf16* __re
 #pragma unroll
   for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
 #pragma unroll
-  for (int kk = 0; kk < 2; ++kk) {
-    if (kk * 16 < nk) {
-#pragma unroll
-      for (int jd = 0; jd < 8; jd += 2) {
-        uint32_t b0, b1, c0, c1;
-        load_b_cols(sV, kk, jd, lane, b0, b1, c0, c1);
-        mma16816(o[jd], pa[kk], b0, b1);
-        mma16816(o[jd + 1], pa[kk], c0, c1);
-      }
-    }
+  for (int jd = 0; jd < 8; jd += 2) {
+    uint32_t b0, b1, c0, c1;
+    load_b_cols(sV, 0, jd, lane, b0, b1, c0, c1);
+    mma16816(o[jd], pa, b0, b1);
+    mma16816(o[jd + 1], pa, c0, c1);
   }
   const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
   __syncwarp();
@@ -613,16 +601,16 @@ __global__ void __launch_bounds__(TW * 32) attn_time_fwd_kernel(const bf16* __re
   }
 }
 
-// backward of one slot: dq (T rows), dk/dv of the slot's T patch keys.  The CLS key's dk/dv (and the CLS query's dq) sum over
-// ALL tokens and are produced by the streamed kernels launched with cls_only = 1.
-__global__ void __launch_bounds__(TWB * 32) attn_time_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+// backward of one slot: dq (T rows) and dk/dv of the slot's T patch keys (including the CLS query's contribution).  The CLS
+// key's dk/dv and the CLS query's dq sum over ALL tokens and are produced by the streamed kernels launched with cls_only = 1.
+__global__ void __launch_bounds__(TW * 32) attn_time_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                                                                 const float* __restrict__ lse, const float* __restrict__ delta,
                                                                 bf16* __restrict__ dqkv, AttnShape a) {
-  __shared__ __align__(128) uint8_t smem[TWB * T_ROWS_BWD * 128];
-  __shared__ float stat[TWB][2][16];
+  __shared__ __align__(128) uint8_t smem[TW * T_ROWS_BWD * 128];
+  __shared__ float stat[TW][2][16];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
-  const int slot = blockIdx.x * TWB + warp;
+  const int slot = blockIdx.x * TW + warp;
   if (slot >= a.n) return;
   const int h = blockIdx.y, b = blockIdx.z;
   const long long rs = 3LL * a.H * HD, ro = (long long)a.H * HD;
@@ -631,161 +619,139 @@ __global__ void __launch_bounds__(TWB * 32) attn_time_bwd_kernel(const bf16* __r
   const float* lse_b = lse + ((long long)b * a.H + h) * a.N;
   const float* delta_b = delta + ((long long)b * a.H + h) * a.N;
   const uint32_t base = smem_u32(smem) + warp * T_ROWS_BWD * 128;
-  time_load<true>(base, qb, dob, rs, ro, ro, a.T, a.n, slot, lane);
+  time_load<true>(base, qb, dob, rs, ro, a.T, a.n, slot, lane);
   cp_async_commit();
-  if (lane < 16) {
-    const bool ok = lane < a.T;
-    const int tok = 1 + (ok ? lane : 0) * a.n + slot;
+  if (lane < 16) {                       // lse / delta of query rows 0..T-1 (slot) and T (CLS)
+    const bool ok = lane <= a.T;
+    const int tok = lane < a.T ? 1 + lane * a.n + slot : 0;
     stat[warp][0][lane] = ok ? lse_b[tok] * LOG2E : 0.f;
     stat[warp][1][lane] = ok ? delta_b[tok] : 0.f;
   }
   cp_async_wait<0>();
   __syncwarp();
-  const uint32_t sQ = base, sK = base + 16 * 128, sV = base + 48 * 128, sD = base + 80 * 128;
+  const uint32_t sQ = base, sK = base + 16 * 128, sV = base + 32 * 128, sD = base + 48 * 128;
   const int nk = a.T + 1;
   const float sl2 = a.scale * LOG2E;
   uint8_t* wsm = smem + warp * T_ROWS_BWD * 128;
   bf16* dq_b = dqkv + (long long)b * a.N * rs + (long long)h * HD;
 
-  // ---------------- pass A: rows = queries (16), cols = keys (<= 32): dQ = scale * dS K
+  // ---------------- pass A: rows = queries, cols = keys: dQ = scale * dS K
   float dq[8][4];
   {
     uint32_t qa[4][4], da[4][4];
     load_a_frags(sQ, 0, lane, qa);
     load_a_frags(sD, 0, lane, da);
-    float sc[4][4], dp[4][4];
+    float sc[2][4], dp[2][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
+    for (int j = 0; j < 2; ++j) { sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
 #pragma unroll
-    for (int j = 0; j < 4; j += 2) {
-      if (8 * j < nk) {
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          uint32_t b0, b1, c0, c1;
-          load_b_rows(sK, j, kk, lane, b0, b1, c0, c1);
-          mma16816(sc[j], qa[kk], b0, b1);
-          mma16816(sc[j + 1], qa[kk], c0, c1);
-          load_b_rows(sV, j, kk, lane, b0, b1, c0, c1);
-          mma16816(dp[j], da[kk], b0, b1);
-          mma16816(dp[j + 1], da[kk], c0, c1);
-        }
-      }
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t b0, b1, c0, c1;
+      load_b_rows(sK, 0, kk, lane, b0, b1, c0, c1);
+      mma16816(sc[0], qa[kk], b0, b1);
+      mma16816(sc[1], qa[kk], c0, c1);
+      load_b_rows(sV, 0, kk, lane, b0, b1, c0, c1);
+      mma16816(dp[0], da[kk], b0, b1);
+      mma16816(dp[1], da[kk], c0, c1);
     }
     const float l0 = stat[warp][0][g], l1 = stat[warp][0][g + 8], d0 = stat[warp][1][g], d1 = stat[warp][1][g + 8];
-    uint32_t dsa[2][4];
+    uint32_t dsa[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 2; ++j) {
       float ds[4];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const bool ok = 8 * j + 2 * t4 + e < nk;
-        const float p0 = (ok && g < a.T) ? exp2f(sc[j][e] * sl2 - l0) : 0.f;
+        const float p0 = (ok && g < a.T) ? exp2f(sc[j][e] * sl2 - l0) : 0.f;          // row T (CLS) is not this kernel's
         const float p1 = (ok && g + 8 < a.T) ? exp2f(sc[j][2 + e] * sl2 - l1) : 0.f;
         ds[e] = p0 * (dp[j][e] - d0);
         ds[2 + e] = p1 * (dp[j][2 + e] - d1);
       }
-      dsa[j >> 1][(j & 1) * 2] = pack_bf16x2(ds[0], ds[1]);
-      dsa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(ds[2], ds[3]);
+      dsa[j * 2] = pack_bf16x2(ds[0], ds[1]);
+      dsa[j * 2 + 1] = pack_bf16x2(ds[2], ds[3]);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
 #pragma unroll
-    for (int kk = 0; kk < 2; ++kk) {
-      if (kk * 16 < nk) {
-#pragma unroll
-        for (int jd = 0; jd < 8; jd += 2) {
-          uint32_t b0, b1, c0, c1;
-          load_b_cols(sK, kk, jd, lane, b0, b1, c0, c1);
-          mma16816(dq[jd], dsa[kk], b0, b1);
-          mma16816(dq[jd + 1], dsa[kk], c0, c1);
-        }
-      }
+    for (int jd = 0; jd < 8; jd += 2) {
+      uint32_t b0, b1, c0, c1;
+      load_b_cols(sK, 0, jd, lane, b0, b1, c0, c1);
+      mma16816(dq[jd], dsa, b0, b1);
+      mma16816(dq[jd + 1], dsa, c0, c1);
     }
   }
-  // ---------------- pass B: rows = keys (2 m-tiles of 16), cols = queries (16): dK = scale * dS^T Q ; dV = P^T dO
-  // (each m-tile's results are staged straight into the K / V rows they correspond to: those rows are dead by then)
+  // ---------------- pass B: rows = keys, cols = queries (slot queries + CLS query): dK = scale * dS^T Q ; dV = P^T dO
+  float dk[8][4], dv[8][4];
+  {
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
-    if (mt * 16 < nk) {
-      float dk[8][4], dv[8][4];
+    for (int j = 0; j < 8; ++j) {
+      dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f;
+      dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f;
+    }
+    uint32_t ka[4][4], va[4][4];
+    load_a_frags(sK, 0, lane, ka);
+    load_a_frags(sV, 0, lane, va);
+    float sc[2][4], dp[2][4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f;
-        dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f;
+    for (int j = 0; j < 2; ++j) { sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t b0, b1, c0, c1;
+      load_b_rows(sQ, 0, kk, lane, b0, b1, c0, c1);
+      mma16816(sc[0], ka[kk], b0, b1);
+      mma16816(sc[1], ka[kk], c0, c1);
+      load_b_rows(sD, 0, kk, lane, b0, b1, c0, c1);
+      mma16816(dp[0], va[kk], b0, b1);
+      mma16816(dp[1], va[kk], c0, c1);
+    }
+    uint32_t pa[4], dsa[4];
+    const int key0 = g, key1 = g + 8;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float p[4], ds[4];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int q = 8 * j + 2 * t4 + e;
+        const bool okq = q <= a.T;           // q == T: the CLS query
+        const float lq = stat[warp][0][q], dq_ = stat[warp][1][q];
+        p[e] = (okq && key0 < nk) ? exp2f(sc[j][e] * sl2 - lq) : 0.f;
+        p[2 + e] = (okq && key1 < nk) ? exp2f(sc[j][2 + e] * sl2 - lq) : 0.f;
+        ds[e] = p[e] * (dp[j][e] - dq_);
+        ds[2 + e] = p[2 + e] * (dp[j][2 + e] - dq_);
       }
-      uint32_t ka[4][4], va[4][4];
-      load_a_frags(sK, mt * 16, lane, ka);
-      load_a_frags(sV, mt * 16, lane, va);
-      float sc[2][4], dp[2][4];
+      pa[j * 2] = pack_bf16x2(p[0], p[1]); pa[j * 2 + 1] = pack_bf16x2(p[2], p[3]);
+      dsa[j * 2] = pack_bf16x2(ds[0], ds[1]); dsa[j * 2 + 1] = pack_bf16x2(ds[2], ds[3]);
+    }
 #pragma unroll
-      for (int j = 0; j < 2; ++j) { sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        uint32_t b0, b1, c0, c1;
-        load_b_rows(sQ, 0, kk, lane, b0, b1, c0, c1);
-        mma16816(sc[0], ka[kk], b0, b1);
-        mma16816(sc[1], ka[kk], c0, c1);
-        load_b_rows(sD, 0, kk, lane, b0, b1, c0, c1);
-        mma16816(dp[0], va[kk], b0, b1);
-        mma16816(dp[1], va[kk], c0, c1);
-      }
-      uint32_t pa[4], dsa[4];
-      const int key0 = mt * 16 + g, key1 = key0 + 8;
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        float p[4], ds[4];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int q = 8 * j + 2 * t4 + e;
-          const bool okq = q < a.T;
-          const float lq = stat[warp][0][q], dq_ = stat[warp][1][q];
-          p[e] = (okq && key0 < nk) ? exp2f(sc[j][e] * sl2 - lq) : 0.f;
-          p[2 + e] = (okq && key1 < nk) ? exp2f(sc[j][2 + e] * sl2 - lq) : 0.f;
-          ds[e] = p[e] * (dp[j][e] - dq_);
-          ds[2 + e] = p[2 + e] * (dp[j][2 + e] - dq_);
-        }
-        pa[j * 2] = pack_bf16x2(p[0], p[1]); pa[j * 2 + 1] = pack_bf16x2(p[2], p[3]);
-        dsa[j * 2] = pack_bf16x2(ds[0], ds[1]); dsa[j * 2 + 1] = pack_bf16x2(ds[2], ds[3]);
-      }
-#pragma unroll
-      for (int jd = 0; jd < 8; jd += 2) {
-        uint32_t b0, b1, c0, c1;
-        load_b_cols(sQ, 0, jd, lane, b0, b1, c0, c1);
-        mma16816(dk[jd], dsa, b0, b1);
-        mma16816(dk[jd + 1], dsa, c0, c1);
-        load_b_cols(sD, 0, jd, lane, b0, b1, c0, c1);
-        mma16816(dv[jd], pa, b0, b1);
-        mma16816(dv[jd + 1], pa, c0, c1);
-      }
-      __syncwarp();   // every lane has its K/V fragments of this m-tile in registers
-      const int r0 = 16 + mt * 16 + g, r1 = r0 + 8;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        *reinterpret_cast<uint32_t*>(wsm + swz(r0, j) + 4 * t4) = pack_bf16x2(dk[j][0] * a.scale, dk[j][1] * a.scale);
-        *reinterpret_cast<uint32_t*>(wsm + swz(r1, j) + 4 * t4) = pack_bf16x2(dk[j][2] * a.scale, dk[j][3] * a.scale);
-        *reinterpret_cast<uint32_t*>(wsm + swz(32 + r0, j) + 4 * t4) = pack_bf16x2(dv[j][0], dv[j][1]);
-        *reinterpret_cast<uint32_t*>(wsm + swz(32 + r1, j) + 4 * t4) = pack_bf16x2(dv[j][2], dv[j][3]);
-      }
+    for (int jd = 0; jd < 8; jd += 2) {
+      uint32_t b0, b1, c0, c1;
+      load_b_cols(sQ, 0, jd, lane, b0, b1, c0, c1);
+      mma16816(dk[jd], dsa, b0, b1);
+      mma16816(dk[jd + 1], dsa, c0, c1);
+      load_b_cols(sD, 0, jd, lane, b0, b1, c0, c1);
+      mma16816(dv[jd], pa, b0, b1);
+      mma16816(dv[jd + 1], pa, c0, c1);
     }
   }
-  // ---------------- dq goes into the (now dead) Q rows; then 16-byte row stores of everything
+  // ---------------- outputs: stage in this warp's smem (all operand reads are done), 16-byte row stores
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     *reinterpret_cast<uint32_t*>(wsm + swz(g, j) + 4 * t4) = pack_bf16x2(dq[j][0] * a.scale, dq[j][1] * a.scale);
     *reinterpret_cast<uint32_t*>(wsm + swz(g + 8, j) + 4 * t4) = pack_bf16x2(dq[j][2] * a.scale, dq[j][3] * a.scale);
+    *reinterpret_cast<uint32_t*>(wsm + swz(16 + g, j) + 4 * t4) = pack_bf16x2(dk[j][0] * a.scale, dk[j][1] * a.scale);
+    *reinterpret_cast<uint32_t*>(wsm + swz(24 + g, j) + 4 * t4) = pack_bf16x2(dk[j][2] * a.scale, dk[j][3] * a.scale);
+    *reinterpret_cast<uint32_t*>(wsm + swz(32 + g, j) + 4 * t4) = pack_bf16x2(dv[j][0], dv[j][1]);
+    *reinterpret_cast<uint32_t*>(wsm + swz(40 + g, j) + 4 * t4) = pack_bf16x2(dv[j][2], dv[j][3]);
   }
   __syncwarp();
-  for (int i = lane; i < 80 * 8; i += 32) {
+  for (int i = lane; i < 48 * 8; i += 32) {
     const int r = i >> 3, c = i & 7;
-    long long tok; long long off;
-    if (r < 16) { if (r >= a.T) continue; tok = 1 + (long long)r * a.n + slot; off = 0; }
-    else {
-      const int kr = (r - 16) & 31, which = (r - 16) >> 5;
-      if (kr == 0 || kr > a.T) continue;                    // key 0 = CLS: written by the cls_only streamed launch
-      tok = 1 + (long long)(kr - 1) * a.n + slot; off = (which + 1) * ro;
-    }
-    *reinterpret_cast<uint4*>(dq_b + tok * rs + off + c * 8) = *reinterpret_cast<const uint4*>(wsm + swz(r, c));
+    const int blk = r >> 4, rr = r & 15;     // 0 = dq, 1 = dk, 2 = dv
+    long long tok;
+    if (blk == 0) { if (rr >= a.T) continue; tok = 1 + (long long)rr * a.n + slot; }
+    else { if (rr == 0 || rr > a.T) continue; tok = 1 + (long long)(rr - 1) * a.n + slot; }   // key 0 = CLS: cls_only launch
+    *reinterpret_cast<uint4*>(dq_b + tok * rs + blk * ro + c * 8) = *reinterpret_cast<const uint4*>(wsm + swz(r, c));
   }
 }
 
@@ -801,7 +767,7 @@ int check_shape(const AttnShape& a, int64_t d) {
   return TVTS_OK;
 }
 
-inline bool use_time_kernels(const AttnShape& a) { return a.mode == 2 && a.T <= 16; }
+inline bool use_time_kernels(const AttnShape& a) { return a.mode == 2 && a.T <= T_MAX; }
 
 }  // namespace
 
@@ -838,8 +804,8 @@ extern "C" int tvts_attn_bwd(const void* qkv, const void* out, const void* dout,
   attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta_ws, (int)B, (int)N, (int)H);
   TVTS_LAUNCH_CHECK();
   if (use_time_kernels(a)) {
-    dim3 tg((unsigned)((a.n + TWB - 1) / TWB), (unsigned)H, (unsigned)B);
-    attn_time_bwd_kernel<<<tg, TWB * 32, 0, st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, a);
+    dim3 tg((unsigned)((a.n + TW - 1) / TW), (unsigned)H, (unsigned)B);
+    attn_time_bwd_kernel<<<tg, TW * 32, 0, st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, a);
     TVTS_LAUNCH_CHECK();
     a.cls_only = 1;
   }
