@@ -66,6 +66,8 @@ typedef struct tvts_gemm_args {
 int tvts_gemm(const tvts_gemm_args* args, void* stream);
 /* debug knob for bring-up of the MN-major shared-memory descriptors (0 = built-in defaults) */
 int tvts_gemm_debug_set(int lbo_bytes, int sbo_bytes, int k_advance_bytes);
+/* tile policy: -1 auto (CTA pairs / cta_group::2 with 256x256 tiles for large problems), 0 single-CTA 128x256 tiles only, 1 pairs always */
+int tvts_gemm_set_pair_mode(int mode);
 /* debug knob: 0 normal epilogue, 1 no global stores, 2 direct row-per-thread bf16 stores, 3 skip epilogue (timing experiments) */
 int tvts_gemm_debug_epi(int mode);
 

@@ -18,6 +18,8 @@ def run_case(spec):
     dev = "cuda"
     M, N, K = spec["M"], spec["N"], spec["K"]
     a_mn, b_mn = spec.get("a_mn", 0), spec.get("b_mn", 0)
+    if "pair" in spec:
+        L.lib().tvts_gemm_set_pair_mode(spec["pair"])
     if spec.get("epi"):
         L.lib().tvts_gemm_debug_epi(spec["epi"])
     if spec.get("dbg"):
@@ -111,6 +113,25 @@ CASES = [
     dict(name="mn_ab_alt_swapped", M=256, N=512, K=256, a_mn=1, b_mn=1, dbg=(1024, 8192, 2048)),
     dict(name="mn_ab_alt_adv", M=256, N=512, K=256, a_mn=1, b_mn=1, dbg=(8192, 1024, 32)),
 ]
+PAIR = [
+    dict(name="pair_256x256x64", M=256, N=256, K=64, pair=1),
+    dict(name="pair_512x512x256", M=512, N=512, K=256, pair=1),
+    dict(name="pair_ragged", M=1000, N=384, K=128, pair=1),
+    dict(name="pair_bias_act_res", M=1000, N=768, K=768, mode="bias_act_res", pair=1),
+    dict(name="pair_dact_mnB", M=515, N=512, K=2048, b_mn=1, mode="dact", bf16_out=True, pair=1),
+    dict(name="pair_mn_ab", M=512, N=512, K=256, a_mn=1, b_mn=1, pair=1),
+    dict(name="pair_wgrad", M=768, N=2304, K=25152, a_mn=1, b_mn=1, mode="splitk", pair=1),
+    dict(name="pair_perf_qkv", M=25152, N=2304, K=768, bf16_out=True, perf=True, pair=1),
+    dict(name="solo_perf_qkv", M=25152, N=2304, K=768, bf16_out=True, perf=True, pair=0),
+    dict(name="pair_perf_proj_res", M=25152, N=768, K=768, mode="bias_act_res", perf=True, pair=1),
+    dict(name="pair_perf_fc", M=25152, N=3072, K=768, bf16_out=True, perf=True, pair=1),
+    dict(name="pair_perf_cproj", M=25152, N=768, K=3072, perf=True, pair=1),
+    dict(name="solo_perf_cproj", M=25152, N=768, K=3072, perf=True, pair=0),
+    dict(name="pair_perf_wgrad", M=768, N=3072, K=25152, a_mn=1, b_mn=1, mode="splitk", perf=True, pair=1),
+    dict(name="solo_perf_wgrad", M=768, N=3072, K=25152, a_mn=1, b_mn=1, mode="splitk", perf=True, pair=0),
+    dict(name="pair_perf_8192", M=8192, N=8192, K=8192, bf16_out=True, perf=True, pair=1),
+    dict(name="solo_perf_8192", M=8192, N=8192, K=8192, bf16_out=True, perf=True, pair=0),
+]
 EPI = [
     dict(name="epi0_qkv", M=25152, N=2304, K=768, bf16_out=True, perf=True),
     dict(name="epi1_qkv_nostore", M=25152, N=2304, K=768, bf16_out=True, perf=True, epi=1),
@@ -138,9 +159,11 @@ def main():
         cases += PERF
     if "--epi" in sys.argv:
         cases = list(EPI)
+    if "--pair" in sys.argv:
+        cases = list(PAIR)
     if "--one" in sys.argv:
         name = sys.argv[sys.argv.index("--one") + 1]
-        spec = [c for c in CASES + PERF + EPI if c["name"] == name][0]
+        spec = [c for c in CASES + PERF + EPI + PAIR if c["name"] == name][0]
         print(run_case(spec))
         return
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

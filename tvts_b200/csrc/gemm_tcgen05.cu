@@ -27,16 +27,20 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kStages = 4;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 128 + kEpiWarps * 32;
 
-template <int BN>
+// CTAS = 1: one CTA per 128 x BN tile.  CTAS = 2: a CTA pair (cluster of 2, cta_group::2) per 256 x BN tile -- each CTA stages its
+// own 128 rows of A and HALF of the B tile (BN/2 rows), so operand shared-memory traffic per SM drops from 96 to 64 B/clk and the
+// smaller stage buys a deeper TMA pipeline.
+template <int BN, int CTAS>
 struct SmemLayout {
+  static constexpr int STAGES = CTAS == 2 ? 6 : 4;
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int B_ROWS = BN / CTAS;
+  static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = kStages * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + tmem ptr + alignment slack
 };
 
@@ -59,11 +63,15 @@ struct GemmShape {
   int m_tiles, n_tiles, k_blocks, splits, kb_per_split;
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int CTAS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             GemmShape s, EpiParams ep, int dbg_lbo, int dbg_sbo, int dbg_kadv, int dbg_epi) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, CTAS>;
+  constexpr int kStages = L::STAGES;
+  const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;   // rank inside the pair; rank 0 = leader (issues the MMAs)
+  const int worker = CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_workers = CTAS == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -90,13 +98,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar(i), 1);
-      mbar_init(tempty_bar(i), kEpiWarps * 32);
+      mbar_init(tempty_bar(i), CTAS * kEpiWarps);   // one elected lane per epilogue warp (of both CTAs of a pair)
     }
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc(tmem_holder, 2 * BN);
+  if (warp == 2) {
+    if (CTAS == 2) tmem_alloc_pair(tmem_holder, 2 * BN);
+    else tmem_alloc(tmem_holder, 2 * BN);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();   // the peer's barriers must be initialised before anything is signalled remotely
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder_gen;
 
@@ -106,40 +118,46 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+    for (int unit = worker; unit < total_units; unit += n_workers) {
       const int split = unit % s.splits;
       const int tile = unit / s.splits;
       const int n_blk = tile % s.n_tiles;
       const int m_blk = tile / s.n_tiles;
       const int kb0 = split * s.kb_per_split;
       const int kb1 = min(kb0 + s.kb_per_split, s.k_blocks);
+      const int m0 = m_blk * (BLOCK_M * CTAS) + (int)cta_rank * BLOCK_M;   // this CTA's rows of A
+      const int n0 = n_blk * BN + (int)cta_rank * L::B_ROWS;               // this CTA's rows of B
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
-        mbar_arrive_expect_tx(full_bar(stage), L::STAGE_BYTES);
+        // pair: both CTAs' bytes complete on the LEADER's barrier (its MMA thread consumes both halves)
+        const uint32_t fb = CTAS == 2 ? mapa_shared(full_bar(stage), 0) : full_bar(stage);
+        if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), CTAS * L::STAGE_BYTES);
         const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
         const uint32_t sb = sa + L::A_BYTES;
+        auto load = [&](uint32_t dst, const CUtensorMap* tm, int c0, int c1) {
+          if (CTAS == 2) tma_load_2d_pair(dst, tm, fb, c0, c1);
+          else tma_load_2d(dst, tm, fb, c0, c1);
+        };
         if (!A_MN) {
-          tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M);
+          load(sa, &tmap_a, kb * BLOCK_K, m0);
         } else {
 #pragma unroll
-          for (int j = 0; j < BLOCK_M / 64; ++j)
-            tma_load_2d(sa + j * (64 * BLOCK_K * 2), &tmap_a, full_bar(stage), m_blk * BLOCK_M + j * 64, kb * BLOCK_K);
+          for (int j = 0; j < BLOCK_M / 64; ++j) load(sa + j * (64 * BLOCK_K * 2), &tmap_a, m0 + j * 64, kb * BLOCK_K);
         }
         if (!B_MN) {
-          tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BLOCK_K, n_blk * BN);
+          load(sb, &tmap_b, kb * BLOCK_K, n0);
         } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            tma_load_2d(sb + j * (64 * BLOCK_K * 2), &tmap_b, full_bar(stage), n_blk * BN + j * 64, kb * BLOCK_K);
+          for (int j = 0; j < L::B_ROWS / 64; ++j) load(sb + j * (64 * BLOCK_K * 2), &tmap_b, n0 + j * 64, kb * BLOCK_K);
         }
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer (single thread) =====================
+  } else if (warp == 1 && lane == 0 && cta_rank == 0) {
+    // ===================== MMA issuer (single thread; the leader CTA of a pair) =====================
     // instruction descriptor: D=f32 (bit4), A=B=bf16 (bits 7,10), major bits 15/16, N>>3 at 17, M>>4 at 24
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BLOCK_M * CTAS) >> 4) << 24);
     // K-major SW128: 8-row groups are 1024 B apart (SBO); LBO unused.  Advance 32 B per UMMA_K inside the row.
     // MN-major SW128: 64-element MN groups are one TMA box (8192 B) apart (LBO); 8-k-row groups 1024 B apart (SBO);
     //                 UMMA_K = 16 k-rows = 2 groups -> advance 2048 B.
@@ -152,7 +170,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
+    for (int unit = worker; unit < total_units; unit += n_workers, ++it) {
       const int split = unit % s.splits;
       const int kb0 = split * s.kb_per_split;
       const int kb1 = min(kb0 + s.kb_per_split, s.k_blocks);
@@ -170,12 +188,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
           const uint64_t da = umma_smem_desc(sa + k * a_adv, a_lbo, a_sbo);
           const uint64_t db = umma_smem_desc(sb + k * b_adv, b_lbo, b_sbo);
-          umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          if (CTAS == 2) umma_bf16_pair(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          else umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(empty_bar(stage));
+        if (CTAS == 2) umma_commit_pair(empty_bar(stage));   // frees the stage in BOTH CTAs
+        else umma_commit(empty_bar(stage));
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(tfull_bar(acc));
+      if (CTAS == 2) umma_commit_pair(tfull_bar(acc));
+      else umma_commit(tfull_bar(acc));
     }
   } else if (warp >= 4) {
     // ===================== epilogue: 8 warps, row-per-thread, direct 128-bit global I/O =====================
@@ -184,7 +205,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int half = (warp - 4) >> 2;
     constexpr int COLS_PER_WARP = BN / 2;
     int it = 0;
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
+    const uint32_t tempty_leader0 = CTAS == 2 ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
+    for (int unit = worker; unit < total_units; unit += n_workers, ++it) {
       const int tile = unit / s.splits;
       const bool first_split = (unit % s.splits) == 0;  // bias / residual are added by one split only
       const int n_blk = tile % s.n_tiles;
@@ -193,7 +215,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const long long grow = (long long)m_blk * BLOCK_M + q * 32 + lane;
+      const long long grow = (long long)m_blk * (BLOCK_M * CTAS) + cta_rank * BLOCK_M + q * 32 + lane;
       const bool row_ok = grow < s.M;
       const int col_base = n_blk * BN + half * COLS_PER_WARP;
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * COLS_PER_WARP;
@@ -287,15 +309,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
+      __syncwarp();
+      if (lane == 0) {
+        if (CTAS == 2) mbar_arrive_cluster(tempty_leader0 + 8u * acc);   // the leader's MMA thread waits for both CTAs
+        else mbar_arrive(tempty_bar(acc));
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();   // neither CTA may free TMEM / exit while the pair's MMAs or remote arrives are in flight
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    if (CTAS == 2) tmem_dealloc_pair(tmem_base, 2 * BN);
+    else tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -336,35 +364,53 @@ int make_tmap(CUtensorMap* m, const void* ptr, long long d0, long long d1, long 
 }
 
 int g_dbg_lbo = 0, g_dbg_sbo = 0, g_dbg_kadv = 0, g_dbg_epi = 0;
+int g_pair_mode = -1;   // -1 auto, 0 never use CTA pairs, 1 always when the shape allows
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int CTAS>
 int launch(const tvts_gemm_args* g, const GemmShape& s, const EpiParams& ep, cudaStream_t stream) {
+  using L = SmemLayout<BN, CTAS>;
   CUtensorMap ta, tb;
   int rc;
   if (!A_MN) rc = make_tmap(&ta, g->a, g->K, g->M, g->lda, BLOCK_K, BLOCK_M);
   else rc = make_tmap(&ta, g->a, g->M, g->K, g->lda, 64, BLOCK_K);
   if (rc) return rc;
-  if (!B_MN) rc = make_tmap(&tb, g->b, g->K, g->N, g->ldb, BLOCK_K, BN);
+  if (!B_MN) rc = make_tmap(&tb, g->b, g->K, g->N, g->ldb, BLOCK_K, L::B_ROWS);
   else rc = make_tmap(&tb, g->b, g->N, g->K, g->ldb, 64, BLOCK_K);
   if (rc) return rc;
-  auto kern = gemm_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, CTAS>;
   static bool attr_set = false;
   if (!attr_set) {
-    TVTS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BN>::TOTAL));
+    TVTS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
   const int units = s.m_tiles * s.n_tiles * s.splits;
-  const int grid = units < tvts_num_sms() ? units : tvts_num_sms();
+  const int workers = tvts_num_sms() / CTAS;
+  const int grid = (units < workers ? units : workers) * CTAS;
   int prof_slot;
   tvts_prof_begin(stream, 2.0 * (double)s.M * (double)s.N * (double)s.K, 0.0, &prof_slot);
-  kern<<<grid, kThreads, SmemLayout<BN>::TOTAL, stream>>>(ta, tb, s, ep, g_dbg_lbo, g_dbg_sbo, g_dbg_kadv, g_dbg_epi);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ta, tb, s, ep, g_dbg_lbo, g_dbg_sbo, g_dbg_kadv, g_dbg_epi);
   tvts_prof_end(stream, prof_slot);
-  TVTS_LAUNCH_CHECK();
+  tvts_count_launch(1);
+  if (le != cudaSuccess) return tvts_set_error(TVTS_ERR_CUDA, "gemm launch failed: %s", cudaGetErrorString(le));
   return TVTS_OK;
 }
 
 }  // namespace
 
+extern "C" int tvts_gemm_set_pair_mode(int mode) {
+  g_pair_mode = mode;
+  return TVTS_OK;
+}
 extern "C" int tvts_gemm_debug_epi(int mode) {
   g_dbg_epi = mode;
   return TVTS_OK;
@@ -406,9 +452,14 @@ extern "C" int tvts_gemm(const tvts_gemm_args* g, void* stream_) {
 
   const bool small_n = g->N <= 128;
   const int BN = small_n ? 128 : 256;
+  // CTA pairs (256 x 256 tiles) when there are enough rows to fill the machine with them
+  bool pair = !small_n && g->M >= 2048 && g->N >= 256;
+  if (g_pair_mode == 0) pair = false;
+  if (g_pair_mode == 1) pair = !small_n;
+  const int tile_m = pair ? 2 * BLOCK_M : BLOCK_M;
   GemmShape s;
   s.M = (int)g->M; s.N = (int)g->N; s.K = (int)g->K;
-  s.m_tiles = (s.M + BLOCK_M - 1) / BLOCK_M;
+  s.m_tiles = (s.M + tile_m - 1) / tile_m;
   s.n_tiles = (s.N + BN - 1) / BN;
   s.k_blocks = (s.K + BLOCK_K - 1) / BLOCK_K;
   int splits = g->splits;
@@ -427,11 +478,11 @@ extern "C" int tvts_gemm(const tvts_gemm_args* g, void* stream_) {
   s.kb_per_split = (s.k_blocks + splits - 1) / splits;
   s.splits = (s.k_blocks + s.kb_per_split - 1) / s.kb_per_split;
 
-#define TVTS_DISPATCH(BN_)                                                          \
-  if (!g->a_mn && !g->b_mn) return launch<BN_, false, false>(g, s, ep, stream);     \
-  if (g->a_mn && g->b_mn) return launch<BN_, true, true>(g, s, ep, stream);         \
-  if (!g->a_mn && g->b_mn) return launch<BN_, false, true>(g, s, ep, stream);       \
-  return launch<BN_, true, false>(g, s, ep, stream);
-  if (small_n) { TVTS_DISPATCH(128) } else { TVTS_DISPATCH(256) }
+#define TVTS_DISPATCH(BN_, C_)                                                          \
+  if (!g->a_mn && !g->b_mn) return launch<BN_, false, false, C_>(g, s, ep, stream);     \
+  if (g->a_mn && g->b_mn) return launch<BN_, true, true, C_>(g, s, ep, stream);         \
+  if (!g->a_mn && g->b_mn) return launch<BN_, false, true, C_>(g, s, ep, stream);       \
+  return launch<BN_, true, false, C_>(g, s, ep, stream);
+  if (small_n) { TVTS_DISPATCH(128, 1) } else if (pair) { TVTS_DISPATCH(256, 2) } else { TVTS_DISPATCH(256, 1) }
 #undef TVTS_DISPATCH
 }
