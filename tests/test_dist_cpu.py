@@ -1,0 +1,90 @@
+"""Multi-rank semantics of the step on 2 gloo ranks (CPU, kernels replaced by tests/emu.py): the fused embedding gather has
+AllGather_multi's forward / local-slice backward (v2/trainer/trainer.py:41-57), the global loss equals the single-process loss on
+the concatenated batch, and averaged parameter gradients are exactly 1/W of the single-process ones."""
+import os
+import sys
+import types
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out):
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import emu
+        import tvts_oracle as O
+        from tvts_b200 import config as C
+        from tvts_b200 import engine as E
+        from tvts_b200 import modules as M
+        from tvts_b200 import optim
+        from tvts_b200.synthetic import make_batch, make_state_dict
+        from tvts_b200.trainer import AllGather_multi, TrainStep, gather_embeddings
+        emu.install()
+        torch.set_num_threads(2)
+        # --- AllGather_multi: forward concatenates in rank order, backward returns the local slice
+        x = (torch.arange(6, dtype=torch.float32).view(3, 2) + 100 * rank).requires_grad_(True)
+        y = AllGather_multi.apply(x, world, types.SimpleNamespace(rank=rank))
+        assert y.shape == (3 * world, 2) and torch.equal(y[3 * rank: 3 * rank + 3], x.detach())
+        w = torch.arange(3 * world * 2, dtype=torch.float32).view(3 * world, 2)
+        (y * w).sum().backward()
+        assert torch.equal(x.grad, w[3 * rank: 3 * rank + 3])
+        # --- one step on a 2-rank global batch vs the oracle on the concatenated batch
+        cfg = C.TINY_B
+        Bl, T, nt = 2, 2, 4
+        sd = make_state_dict(cfg, seed=1234)
+        m = M.TVTSv2Base(types.SimpleNamespace(local_rank=0, rank=rank), arch=cfg)
+        m.load_state_dict(sd, strict=True)
+        opt = optim.build_reference_optimizer(m)
+        E.WEIGHTS.clear()
+        step = TrainStep(m, None, cfg.temperature, torch.device("cpu"))
+        step.optimizer = types.SimpleNamespace(flat=opt.flat, zero_grad=opt.zero_grad, step=lambda: None)   # keep the weights fixed
+        local = make_batch(cfg, Bl, T, n_trans=nt, seed=3, rank=rank)
+        l1, l2 = step(local)
+        grads = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+        if rank == 0:
+            parts = [make_batch(cfg, Bl, T, n_trans=nt, seed=3, rank=r) for r in range(world)]
+            video = torch.cat([p["video"] for p in parts])
+            keep = torch.cat([p["keep_ind"] for p in parts])
+            label = torch.cat([p["label"] for p in parts])
+            # clip-major text rows: index t*B + b over the GLOBAL batch
+            text = torch.cat([torch.stack([p["text"][t * Bl:(t + 1) * Bl] for p in parts]).reshape(-1, cfg.context) for t in range(nt)])
+            trainable = {k for k, p in m.named_parameters() if p.requires_grad}
+            o1, o2, _, og = O.step_with_grads(sd, text, video, keep, label, cfg, trainable=trainable)
+            out["loss1"] = (l1.item(), o1.item())
+            worst = 0.0
+            for k, g in og.items():
+                if k.startswith("pred_model") or k not in grads:
+                    continue
+                # InfoNCE part: local-slice backward + averaging => 1/W of the global gradient; the video/text towers also carry the
+                # LOCAL sort-loss gradient averaged over ranks = the global mean-CE gradient, so the whole thing is 1/W * global for
+                # the contrastive part and exactly global for the sort part; compare on parameters only the contrastive loss reaches
+                if not k.startswith("text_"):
+                    continue
+                ref = g / world
+                rel = (grads[k] - ref).norm().item() / (ref.norm().item() + 1e-12)
+                worst = max(worst, rel)
+            out["worst_text_grad_rel"] = worst
+        opt.flat.release()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_rank_step_matches_single_process_oracle():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    a, b = out["loss1"]
+    assert abs(a - b) < 5e-2, (a, b)
+    assert out["worst_text_grad_rel"] < 0.08, out["worst_text_grad_rel"]

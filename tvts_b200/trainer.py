@@ -75,7 +75,11 @@ def average_flat(fs):
     """Gradient averaging over the flat arena: one NCCL all-reduce (AVG), no flatten / unflatten copies."""
     if _world() == 1:
         return 0
-    dist.all_reduce(fs.g, op=dist.ReduceOp.AVG)
+    if dist.get_backend() == "nccl":
+        dist.all_reduce(fs.g, op=dist.ReduceOp.AVG)
+    else:                                   # gloo (CPU tests) has no AVG
+        dist.all_reduce(fs.g, op=dist.ReduceOp.SUM)
+        fs.g.mul_(1.0 / _world())
     return fs.g.numel() * 4
 
 
