@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
+    ap.add_argument("--gemm-breakdown", action="store_true", help="print a per-shape table of the GEMM launches (stderr)")
+    ap.add_argument("--pair-mode", type=int, default=-1, help="GEMM tile policy override (tvts_gemm_set_pair_mode)")
     return ap.parse_args()
 
 
@@ -112,17 +114,19 @@ def workload(args):
 
 
 def algorithmic_flops_per_pair(cfg, T, n_trans):
-    """2*MAC FLOPs of fwd+bwd for one video-text pair (bwd = 2x fwd for trainable parts, 1x for the
-    frozen text layers; here every layer is trained, matching what the timed step computes)."""
+    """2*MAC FLOPs of fwd+bwd for one video-text pair (bwd = 2x fwd for trainable parts, 1x = dgrad only
+    for the frozen text layers 0..3L/4-1, as in the reference script's freeze policy)."""
     p, D, L, E = cfg.patch, cfg.width, cfg.layers, cfg.embed_dim
     n = cfg.kept_per_frame
     N = 1 + T * n
     f_video = 2 * T * n * (3 * p * p) * D + L * (32 * N * D * D + 4 * n * T * (T + 1) * D + 4 * T * n * (n + 1) * D + 8 * N * D) + 2 * N * D * E
     W = cfg.text_width
-    f_text = cfg.text_layers * (24 * 77 * W * W + 4 * 77 * 77 * W) + 2 * W * E
+    f_layer = 24 * 77 * W * W + 4 * 77 * 77 * W
+    frozen = (cfg.text_layers * 3) // 4
+    f_text3 = 3.0 * ((cfg.text_layers - frozen) * f_layer + 2 * W * E) + 2.0 * frozen * f_layer
     S = N + n_trans
     f_sort = cfg.sort_depth * (24 * S * E * E + 4 * S * S * E) if n_trans > 1 else 0
-    return 3.0 * (f_video + n_trans * f_text + f_sort)
+    return 3.0 * (f_video + f_sort) + n_trans * f_text3
 
 
 # ---------------------------------------------------------------------------------------------------------------- CPU legs
@@ -135,12 +139,14 @@ def cpu_oracle_steps(cfg, batch, frames, n_trans, steps, warmup, max_seconds=1e9
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = make_state_dict(cfg, seed=1234)
+    frozen = (cfg.text_layers * 3) // 4       # the reference script freezes text layers 0..8 (train_dist_TVTSv2_ViT_B_16.py:69,96)
+    trainable = {k for k in sd if not (k.startswith("text_model.resblocks.") and int(k.split(".")[2]) < frozen)}
     data = make_batch(cfg, batch, frames, n_trans=n_trans, seed=0)
     times = []
     t_begin = time.perf_counter()
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.step_with_grads(sd, data["text"], data["video"], data["keep_ind"], data["label"], cfg)
+        O.step_with_grads(sd, data["text"], data["video"], data["keep_ind"], data["label"], cfg, trainable=trainable)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
@@ -194,6 +200,8 @@ def run_ours(args):
     if world != args.gpus and rank == 0:
         print(f"bench.py: WORLD_SIZE={world} but --gpus {args.gpus}; using {world}", file=sys.stderr)
     _lib.lib()   # fail loudly if the CUDA library is missing
+    if args.pair_mode >= 0:
+        _lib.lib().tvts_gemm_set_pair_mode(args.pair_mode)
 
     cfg, batch, frames, n_trans = workload(args)
     model = M.TVTSv2Base(types.SimpleNamespace(local_rank=local_rank), arch=cfg)
@@ -248,6 +256,16 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
 
     import ctypes
+    breakdown = None
+    if args.gemm_breakdown and rank == 0:
+        import collections
+        agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
+        ms_, fl_, tg_ = ctypes.c_double(), ctypes.c_double(), (ctypes.c_longlong * 4)()
+        for i in range(_lib.lib().tvts_prof_count()):
+            if _lib.lib().tvts_prof_record(i, ctypes.byref(ms_), ctypes.byref(fl_), tg_) == 0:
+                a = agg[(tg_[0], tg_[1], tg_[2], tg_[3] & 255, tg_[3] >> 8)]
+                a[0] += 1; a[1] += ms_.value; a[2] += fl_.value
+        breakdown = sorted(((k, v) for k, v in agg.items()), key=lambda kv: -kv[1][1])
     t_ms, t_fl, t_by = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
     _lib.lib().tvts_prof_collect.restype = ctypes.c_longlong
     n_gemm = _lib.lib().tvts_prof_collect(ctypes.byref(t_ms), ctypes.byref(t_fl), ctypes.byref(t_by))
@@ -289,6 +307,11 @@ def run_ours(args):
                          "launches": int(n_gemm), "gemm_ms_per_step": t_ms.value / args.steps,
                          "gemm_share_of_step": (t_ms.value / args.steps) / ms_step, "peak_source": pk["source"] + " (sustained figure: kernel timed inside a long step)"},
         }
+        if breakdown:
+            print("GEMM breakdown over the timed region: M N K flags(1 a_mn,2 b_mn,4 pair,8 bf16out,16 res,32 pre,64 dact,128 acc) splits | launches, ms/step, TFLOP/s",
+                  file=sys.stderr)
+            for k, v in breakdown:
+                print(f"  {k[0]:6d} {k[1]:5d} {k[2]:6d} f={k[3]:3d} s={k[4]:2d} | {v[0] // args.steps:4d} {v[1] / args.steps:8.3f} {v[2] / v[1] / 1e9:8.1f}", file=sys.stderr)
         if e2e:
             line["e2e"] = e2e
         if cpu:

@@ -32,6 +32,9 @@ long long tvts_launch_count(void);
  * device time (ms), algorithmic FLOPs (2*M*N*K) and bytes. */
 int tvts_prof_enable(int on);
 long long tvts_prof_collect(double* total_ms, double* total_flops, double* total_bytes);
+/* per-launch readout before collect(): tags = {M, N, K, flags: 1 a_mn, 2 b_mn, 4 CTA pair, 8 bf16 out, 16 residual, 32 out_pre, 64 dact, 128 accumulate, splits<<8} */
+int tvts_prof_count(void);
+int tvts_prof_record(int i, double* ms, double* flops, long long* tags);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM:  out[M,N] = epilogue(alpha * sum_k A[m,k]*B[n,k])      (tcgen05 + TMA, bf16 in / fp32 accumulate)
@@ -68,6 +71,8 @@ int tvts_gemm(const tvts_gemm_args* args, void* stream);
 int tvts_gemm_debug_set(int lbo_bytes, int sbo_bytes, int k_advance_bytes);
 /* tile policy: -1 auto (CTA pairs / cta_group::2 with 256x256 tiles for large problems), 0 single-CTA 128x256 tiles only, 1 pairs always */
 int tvts_gemm_set_pair_mode(int mode);
+/* debug: co-resident clusters of the pair kernel for a given cluster size (cudaOccupancyMaxActiveClusters) */
+int tvts_gemm_debug_max_clusters(int cluster_size);
 /* debug knob: 0 normal epilogue, 1 no global stores, 2 direct row-per-thread bf16 stores, 3 skip epilogue (timing experiments) */
 int tvts_gemm_debug_epi(int mode);
 

@@ -39,7 +39,7 @@ extern "C" long long tvts_launch_count(void) { return g_launches.load(std::memor
 // with two CUDA events recorded on the launching stream; tvts_prof_collect sums the elapsed times afterwards.
 // ------------------------------------------------------------------------------------------------
 namespace {
-struct ProfRec { cudaEvent_t e0, e1; double flops; double bytes; };
+struct ProfRec { cudaEvent_t e0, e1; double flops; double bytes; long long tag[4]; };
 constexpr int kProfMax = 16384;
 ProfRec g_prof[kProfMax];
 int g_prof_created = 0;
@@ -48,6 +48,9 @@ bool g_prof_on = false;
 long long g_prof_dropped = 0;
 }  // namespace
 
+void tvts_prof_tag(int slot, long long a, long long b, long long c, long long d) {
+  if (slot >= 0) { g_prof[slot].tag[0] = a; g_prof[slot].tag[1] = b; g_prof[slot].tag[2] = c; g_prof[slot].tag[3] = d; }
+}
 bool tvts_prof_begin(cudaStream_t stream, double flops, double bytes, int* slot) {
   *slot = -1;
   if (!g_prof_on) return false;
@@ -73,6 +76,16 @@ extern "C" int tvts_prof_enable(int on) {
   if (on) { g_prof_used = 0; g_prof_dropped = 0; }
   return TVTS_OK;
 }
+// Per-record readout (call after synchronising, before tvts_prof_collect): elapsed ms, flops and the 4 tags (M, N, K, flags).
+extern "C" int tvts_prof_record(int i, double* ms, double* flops, long long* tags) {
+  if (i < 0 || i >= g_prof_used) return TVTS_ERR_INVALID;
+  float t = 0.f;
+  if (cudaEventElapsedTime(&t, g_prof[i].e0, g_prof[i].e1) != cudaSuccess) return TVTS_ERR_CUDA;
+  *ms = t; *flops = g_prof[i].flops;
+  for (int k = 0; k < 4; ++k) tags[k] = g_prof[i].tag[k];
+  return TVTS_OK;
+}
+extern "C" int tvts_prof_count(void) { return g_prof_used; }
 // Call after the stream has been synchronised.  Sums over the recorded launches; returns the number of records.
 extern "C" long long tvts_prof_collect(double* total_ms, double* total_flops, double* total_bytes) {
   double ms = 0.0, fl = 0.0, by = 0.0;

@@ -42,6 +42,7 @@ void tvts_count_launch(int n);
 int tvts_num_sms();  // cached SM count of the current device
 bool tvts_prof_begin(cudaStream_t stream, double flops, double bytes, int* slot);  // live launch timing (api.cu)
 void tvts_prof_end(cudaStream_t stream, int slot);
+void tvts_prof_tag(int slot, long long a, long long b, long long c, long long d);
 
 typedef __nv_bfloat16 bf16;
 

@@ -12,10 +12,14 @@
 // Structure: persistent CTAs (one per SM), warp-specialised:
 //   warp 0  TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1  MMA issuer    (one thread, tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16 per instruction)
+//   work units = output tiles x K splits, ordered tile-fastest: units running concurrently cover all output tiles of one K range and
+//           share its operand slices through L2 (wgrad: small output, K = 25k tokens)
 //   warp 2  TMEM allocator (2 x BN fp32 columns: double-buffered accumulator so the epilogue of tile i
 //           overlaps the MMAs of tile i+1)
-//   warps 4-11 epilogue   (tcgen05.ld 32x32b -> per-warp swizzled smem transpose -> coalesced global I/O with fused
-//           bias / QuickGELU|GELU / residual add / activation-derivative / split-K reduction)
+//   warps 4-11 epilogue   (tcgen05.ld 32x32b: one accumulator row per thread -> 128-bit global I/O with fused
+//           bias / QuickGELU|GELU / residual add / activation-derivative / split-K reduction.  A per-warp swizzled
+//           shared-memory transpose for coalesced stores was measured SLOWER on B200 for the short-K shapes of this path
+//           (qkv 937 -> 735, fc 981 -> 761 TFLOP/s; profiles/r1_gemm_experiments.md), so rows are stored directly.)
 #include <cuda.h>
 #include "common.cuh"
 #include "../../include/tvts_b200.h"
@@ -38,8 +42,7 @@ struct SmemLayout {
   static constexpr int B_ROWS = BN / CTAS;
   static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;          // epilogue staging: 8 warps x 4 KB
-  static constexpr int BAR_OFFSET = STG_OFFSET + kEpiWarps * 4096;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + tmem ptr + alignment slack
 };
 
@@ -59,7 +62,7 @@ struct EpiParams {
 
 struct GemmShape {
   int M, N, K;
-  int m_tiles, n_tiles, k_blocks, splits, kb_per_split;
+  int m_tiles, n_tiles, k_blocks, splits, kb_per_split, tiles;
 };
 
 template <int BN, bool A_MN, bool B_MN, int CTAS>
@@ -118,8 +121,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     int stage = 0;
     uint32_t phase = 0;
     for (int unit = worker; unit < total_units; unit += n_workers) {
-      const int split = unit % s.splits;
-      const int tile = unit / s.splits;
+      const int split = unit / s.tiles;
+      const int tile = unit % s.tiles;
       const int n_blk = tile % s.n_tiles;
       const int m_blk = tile / s.n_tiles;
       const int kb0 = split * s.kb_per_split;
@@ -170,7 +173,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     uint32_t phase = 0;
     int it = 0;
     for (int unit = worker; unit < total_units; unit += n_workers, ++it) {
-      const int split = unit % s.splits;
+      const int split = unit / s.tiles;
       const int kb0 = split * s.kb_per_split;
       const int kb1 = min(kb0 + s.kb_per_split, s.k_blocks);
       const int acc = it & 1;
@@ -198,29 +201,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       else umma_commit(tfull_bar(acc));
     }
   } else if (warp >= 4) {
-    // ===================== epilogue: 8 warps =====================
+    // ===================== epilogue: 8 warps, row-per-thread, direct 128-bit global I/O =====================
     // TMEM lane quadrant q = warp % 4 (hardware restriction); the two warps of a quadrant split the tile's columns.
-    // tcgen05.ld hands every thread one accumulator ROW (32 consecutive columns); storing that layout directly makes each 16-byte
-    // access of a warp touch 32 different 128-byte lines (LSU-bound: the fp32+residual epilogues ran at ~300 TFLOP/s).  So each
-    // warp transposes its 32x32 fp32 block through a private XOR-swizzled 4 KB shared-memory buffer (conflict-free both ways) and
-    // does all global I/O -- bias, residual, aux, stores -- with 8 lanes covering 128 contiguous bytes of a row (4 rows / instruction).
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
     constexpr int COLS_PER_WARP = BN / 2;
-    const uint32_t stg = smem_base + L::STG_OFFSET + (uint32_t)(warp - 4) * 4096u;
-    const int rsub = lane >> 3, cc = lane & 7;
-    const uint32_t tempty_leader0 = CTAS == 2 ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
     int it = 0;
+    const uint32_t tempty_leader0 = CTAS == 2 ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
     for (int unit = worker; unit < total_units; unit += n_workers, ++it) {
-      const int tile = unit / s.splits;
-      const bool first_split = (unit % s.splits) == 0;  // bias / residual are added by one split only
+      const int tile = unit % s.tiles;
+      const bool first_split = (unit / s.tiles) == 0;  // bias / residual are added by one split only
       const int n_blk = tile % s.n_tiles;
       const int m_blk = tile / s.n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const long long row_base = (long long)m_blk * (BLOCK_M * CTAS) + cta_rank * BLOCK_M + q * 32;
+      const long long grow = (long long)m_blk * (BLOCK_M * CTAS) + cta_rank * BLOCK_M + q * 32 + lane;
+      const bool row_ok = grow < s.M;
       const int col_base = n_blk * BN + half * COLS_PER_WARP;
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * COLS_PER_WARP;
       const bool use_res = ep.residual != nullptr && first_split;
@@ -229,70 +227,88 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
         const int col0 = col_base + c * 32;
         if (col0 >= s.N || dbg_epi == 3) break;  // warp-uniform
+        // issue the independent global loads first so their latency overlaps the TMEM load
+        float4 r4[8];
+        uint4 x4[4];
+        if (use_res && row_ok) {
+          const float* rp = ep.residual + grow * ep.ldr + col0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            r4[j] = (col0 + 4 * j < s.N) ? *reinterpret_cast<const float4*>(rp + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (ep.dact != TVTS_ACT_NONE && row_ok) {
+          const bf16* ap = ep.aux + grow * ep.ldaux + col0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            x4[j] = (col0 + 8 * j < s.N) ? *reinterpret_cast<const uint4*>(ap + 8 * j) : make_uint4(0, 0, 0, 0);
+        }
         uint32_t v[32];
         tmem_ld_32x32(t_base + c * 32, v);
         tmem_ld_wait();
+        if (!row_ok) continue;
+        float f[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t addr = stg + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]),
-                       "r"(v[4 * j + 3])
-                       : "memory");
-        }
-        __syncwarp();
-        const int col = col0 + 4 * cc;         // this lane's 4 columns
-        const bool col_ok = col < s.N;
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (use_bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
-        // issue the independent global loads of all 8 row groups first
-        float4 r4[8];
-        uint2 x2[8];
-        if (use_res) {
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * ep.alpha;
+        if (use_bias) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const long long grow = row_base + i * 4 + rsub;
-            r4[i] = (col_ok && grow < s.M) ? *reinterpret_cast<const float4*>(ep.residual + grow * ep.ldr + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < 8; ++j) {
+            if (col0 + 4 * j < s.N) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + j);
+              f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+            }
           }
+        }
+        if (ep.out_pre != nullptr) {
+          bf16* o = reinterpret_cast<bf16*>(ep.out_pre) + grow * ep.ldo + col0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (col0 + 8 * j < s.N)
+              *reinterpret_cast<uint4*>(o + 8 * j) =
+                  make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                             pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+        }
+        if (ep.act != TVTS_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], ep.act);
         }
         if (ep.dact != TVTS_ACT_NONE) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const long long grow = row_base + i * 4 + rsub;
-            x2[i] = (col_ok && grow < s.M) ? *reinterpret_cast<const uint2*>(ep.aux + grow * ep.ldaux + col) : make_uint2(0, 0);
+          for (int j = 0; j < 4; ++j) {
+            const float2 p0 = unpack_bf16x2(x4[j].x), p1 = unpack_bf16x2(x4[j].y), p2 = unpack_bf16x2(x4[j].z), p3 = unpack_bf16x2(x4[j].w);
+            f[8 * j] *= act_bwd(p0.x, ep.dact); f[8 * j + 1] *= act_bwd(p0.y, ep.dact);
+            f[8 * j + 2] *= act_bwd(p1.x, ep.dact); f[8 * j + 3] *= act_bwd(p1.y, ep.dact);
+            f[8 * j + 4] *= act_bwd(p2.x, ep.dact); f[8 * j + 5] *= act_bwd(p2.y, ep.dact);
+            f[8 * j + 6] *= act_bwd(p3.x, ep.dact); f[8 * j + 7] *= act_bwd(p3.y, ep.dact);
           }
         }
+        if (use_res) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 4 + rsub;
-          const long long grow = row_base + r;
-          float4 f;
-          {
-            const uint32_t addr = stg + (uint32_t)r * 128u + (uint32_t)((cc ^ (r & 7)) << 4);
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w) : "r"(addr));
-          }
-          if (!col_ok || grow >= s.M) continue;
-          f.x = f.x * ep.alpha + b4.x; f.y = f.y * ep.alpha + b4.y; f.z = f.z * ep.alpha + b4.z; f.w = f.w * ep.alpha + b4.w;
-          if (ep.out_pre != nullptr)
-            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out_pre) + grow * ep.ldo + col) =
-                make_uint2(pack_bf16x2(f.x, f.y), pack_bf16x2(f.z, f.w));
-          if (ep.act != TVTS_ACT_NONE) { f.x = act_fwd(f.x, ep.act); f.y = act_fwd(f.y, ep.act); f.z = act_fwd(f.z, ep.act); f.w = act_fwd(f.w, ep.act); }
-          if (ep.dact != TVTS_ACT_NONE) {
-            const float2 p0 = unpack_bf16x2(x2[i].x), p1 = unpack_bf16x2(x2[i].y);
-            f.x *= act_bwd(p0.x, ep.dact); f.y *= act_bwd(p0.y, ep.dact); f.z *= act_bwd(p1.x, ep.dact); f.w *= act_bwd(p1.y, ep.dact);
-          }
-          if (use_res) { f.x += r4[i].x; f.y += r4[i].y; f.z += r4[i].z; f.w += r4[i].w; }
-          if (dbg_epi == 1) continue;
-          if (ep.out_dtype == 1) {
-            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + grow * ep.ldo + col) = make_uint2(pack_bf16x2(f.x, f.y), pack_bf16x2(f.z, f.w));
+          for (int j = 0; j < 8; ++j) { f[4 * j] += r4[j].x; f[4 * j + 1] += r4[j].y; f[4 * j + 2] += r4[j].z; f[4 * j + 3] += r4[j].w; }
+        }
+        if (dbg_epi == 1) continue;
+        if (ep.out_dtype == 1) {
+          bf16* o = reinterpret_cast<bf16*>(ep.out) + grow * ep.ldo + col0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (col0 + 8 * j < s.N)
+              *reinterpret_cast<uint4*>(o + 8 * j) =
+                  make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                             pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+        } else {
+          float* o = reinterpret_cast<float*>(ep.out) + grow * ep.ldo + col0;
+          if (ep.accumulate) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (col0 + 4 * j < s.N)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * j), "f"(f[4 * j]), "f"(f[4 * j + 1]),
+                             "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
+                             : "memory");
           } else {
-            float* o = reinterpret_cast<float*>(ep.out) + grow * ep.ldo + col;
-            if (ep.accumulate)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(f.x), "f"(f.y), "f"(f.z), "f"(f.w) : "memory");
-            else
-              *reinterpret_cast<float4*>(o) = f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (col0 + 4 * j < s.N) *reinterpret_cast<float4*>(o + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
           }
         }
-        __syncwarp();   // the staging buffer is rewritten by the next chunk
       }
       tc_fence_before();
       __syncwarp();
@@ -374,6 +390,9 @@ int launch(const tvts_gemm_args* g, const GemmShape& s, const EpiParams& ep, cud
   const int grid = (units < workers ? units : workers) * CTAS;
   int prof_slot;
   tvts_prof_begin(stream, 2.0 * (double)s.M * (double)s.N * (double)s.K, 0.0, &prof_slot);
+  tvts_prof_tag(prof_slot, s.M, s.N, s.K,
+                (A_MN ? 1 : 0) | (B_MN ? 2 : 0) | (CTAS == 2 ? 4 : 0) | (ep.out_dtype ? 8 : 0) | (ep.residual ? 16 : 0) | (ep.out_pre ? 32 : 0) |
+                    (ep.dact ? 64 : 0) | (ep.accumulate ? 128 : 0) | (s.splits << 8));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kThreads);
@@ -393,6 +412,26 @@ int launch(const tvts_gemm_args* g, const GemmShape& s, const EpiParams& ep, cud
 
 }  // namespace
 
+// how many clusters of `cluster_size` CTAs of the pair kernel can be co-resident (GPC packing check for multicast designs)
+extern "C" int tvts_gemm_debug_max_clusters(int cluster_size) {
+  auto kern = gemm_kernel<256, false, false, 2>;
+  using L = SmemLayout<256, 2>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+  cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(148 * 4);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = -1;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+  if (e != cudaSuccess) { cudaGetLastError(); return -1; }
+  return n;
+}
 extern "C" int tvts_gemm_set_pair_mode(int mode) {
   g_pair_mode = mode;
   return TVTS_OK;
@@ -463,6 +502,7 @@ extern "C" int tvts_gemm(const tvts_gemm_args* g, void* stream_) {
   if (splits > s.k_blocks) splits = s.k_blocks;
   s.kb_per_split = (s.k_blocks + splits - 1) / splits;
   s.splits = (s.k_blocks + s.kb_per_split - 1) / s.kb_per_split;
+  s.tiles = s.m_tiles * s.n_tiles;
 
 #define TVTS_DISPATCH(BN_, C_)                                                          \
   if (!g->a_mn && !g->b_mn) return launch<BN_, false, false, C_>(g, s, ep, stream);     \
