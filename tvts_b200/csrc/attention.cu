@@ -192,12 +192,14 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_kernel(const bf16* __restri
       for (int j = 0; j < 8; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; j += 2) {
+        if (8 * j < cnt) {     // CTA-uniform: key tiles past the end of a short group are never computed
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          uint32_t b0, b1, c0, c1;
-          load_b_rows(sK, j, kk, lane, b0, b1, c0, c1);
-          mma16816(sc[j], qa[kk], b0, b1);
-          mma16816(sc[j + 1], qa[kk], c0, c1);
+          for (int kk = 0; kk < 4; ++kk) {
+            uint32_t b0, b1, c0, c1;
+            load_b_rows(sK, j, kk, lane, b0, b1, c0, c1);
+            mma16816(sc[j], qa[kk], b0, b1);
+            mma16816(sc[j + 1], qa[kk], c0, c1);
+          }
         }
       }
       // mask + row max
@@ -240,12 +242,14 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_kernel(const bf16* __restri
       for (int j = 0; j < 8; ++j) { o[j][0] *= corr0; o[j][1] *= corr0; o[j][2] *= corr1; o[j][3] *= corr1; }
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
+        if (16 * kk < cnt) {
 #pragma unroll
-        for (int jd = 0; jd < 8; jd += 2) {
-          uint32_t b0, b1, c0, c1;
-          load_b_cols(sV, kk, jd, lane, b0, b1, c0, c1);
-          mma16816(o[jd], pa[kk], b0, b1);
-          mma16816(o[jd + 1], pa[kk], c0, c1);
+          for (int jd = 0; jd < 8; jd += 2) {
+            uint32_t b0, b1, c0, c1;
+            load_b_cols(sV, kk, jd, lane, b0, b1, c0, c1);
+            mma16816(o[jd], pa[kk], b0, b1);
+            mma16816(o[jd + 1], pa[kk], c0, c1);
+          }
         }
       }
     }
@@ -283,19 +287,34 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_kernel(const bf16* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ delta = rowsum(dO * O)
-__global__ void attn_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, float* __restrict__ delta, int B, int N,
-                                  int H) {
-  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (w >= (long long)B * N * H) return;
-  const int h = (int)(w % H);
-  const long long bn = w / H;
-  const int i = (int)(bn % N);
-  const int b = (int)(bn / N);
-  const float2 o = unpack_bf16x2(reinterpret_cast<const uint32_t*>(out + w * HD)[lane]);
-  const float2 d = unpack_bf16x2(reinterpret_cast<const uint32_t*>(dout + w * HD)[lane]);
-  const float s = warp_sum(o.x * d.x + o.y * d.y);
-  if (lane == 0) delta[((long long)b * H + h) * N + i] = s;
+__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, float* __restrict__ delta,
+                                                         int B, int N, int H) {
+  // 8 lanes per (token, head) row of 64 bf16: one 16-byte load of O and of dO per lane, reduce inside the octet
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int sub = threadIdx.x & 7;
+  const bool ok = w < (long long)B * N * H;
+  float s = 0.f;
+  if (ok) {
+    const uint4 o = reinterpret_cast<const uint4*>(out + w * HD)[sub];
+    const uint4 d = reinterpret_cast<const uint4*>(dout + w * HD)[sub];
+    const uint32_t ov[4] = {o.x, o.y, o.z, o.w}, dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 a = unpack_bf16x2(ov[i]), c = unpack_bf16x2(dv[i]);
+      s = fmaf(a.x, c.x, s);
+      s = fmaf(a.y, c.y, s);
+    }
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (ok && sub == 0) {
+    const int h = (int)(w % H);
+    const long long bn = w / H;
+    const int i = (int)(bn % N);
+    const int b = (int)(bn / N);
+    delta[((long long)b * H + h) * N + i] = s;
+  }
 }
 
 // ================================================================================================ streamed backward
@@ -397,20 +416,23 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_kernel(const bf16* __restri
       const int k0 = t * BN, cnt = min(BN, total - k0);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {   // 32 streamed rows at a time (register pressure)
+        if (32 * half >= cnt) break;           // CTA-uniform
         float sc[4][4], dp[4][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) { sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
 #pragma unroll
         for (int j = 0; j < 4; j += 2) {
+          if (32 * half + 8 * j < cnt) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            uint32_t b0, b1, c0, c1;
-            load_b_rows(sX, half * 4 + j, kk, lane, b0, b1, c0, c1);
-            mma16816(sc[j], fa[kk], b0, b1);
-            mma16816(sc[j + 1], fa[kk], c0, c1);
-            load_b_rows(sY, half * 4 + j, kk, lane, b0, b1, c0, c1);
-            mma16816(dp[j], fb[kk], b0, b1);
-            mma16816(dp[j + 1], fb[kk], c0, c1);
+            for (int kk = 0; kk < 4; ++kk) {
+              uint32_t b0, b1, c0, c1;
+              load_b_rows(sX, half * 4 + j, kk, lane, b0, b1, c0, c1);
+              mma16816(sc[j], fa[kk], b0, b1);
+              mma16816(sc[j + 1], fa[kk], c0, c1);
+              load_b_rows(sY, half * 4 + j, kk, lane, b0, b1, c0, c1);
+              mma16816(dp[j], fb[kk], b0, b1);
+              mma16816(dp[j + 1], fb[kk], c0, c1);
+            }
           }
         }
         uint32_t pa[2][4], dsa[2][4];
@@ -442,6 +464,7 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_kernel(const bf16* __restri
         }
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk) {
+          if (32 * half + 16 * kk >= cnt) break;
 #pragma unroll
           for (int jd = 0; jd < 8; jd += 2) {
             uint32_t b0, b1, c0, c1;
@@ -801,7 +824,7 @@ extern "C" int tvts_attn_bwd(const void* qkv, const void* out, const void* dout,
   TVTS_REQUIRE(qkv && out && dout && lse && delta_ws && dqkv, "attn_bwd: null pointer");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long rows = (long long)B * N * H;
-  attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta_ws, (int)B, (int)N, (int)H);
+  attn_delta_kernel<<<(unsigned)((rows + 31) / 32), 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta_ws, (int)B, (int)N, (int)H);
   TVTS_LAUNCH_CHECK();
   if (use_time_kernels(a)) {
     dim3 tg((unsigned)((a.n + TW - 1) / TW), (unsigned)H, (unsigned)B);
