@@ -16,10 +16,9 @@
 //           share its operand slices through L2 (wgrad: small output, K = 25k tokens)
 //   warp 2  TMEM allocator (2 x BN fp32 columns: double-buffered accumulator so the epilogue of tile i
 //           overlaps the MMAs of tile i+1)
-//   warps 4-11 epilogue   (tcgen05.ld 32x32b: one accumulator row per thread -> 128-bit global I/O with fused
-//           bias / QuickGELU|GELU / residual add / activation-derivative / split-K reduction.  A per-warp swizzled
-//           shared-memory transpose for coalesced stores was measured SLOWER on B200 for the short-K shapes of this path
-//           (qkv 937 -> 735, fc 981 -> 761 TFLOP/s; profiles/r1_gemm_experiments.md), so rows are stored directly.)
+//   warps 4-11 epilogue   (tcgen05.ld 32x32b: one accumulator row per thread; fused bias / QuickGELU|GELU / activation-derivative /
+//           residual add in registers; the warp's [32 rows x 128 B] block goes through a 128B-swizzled shared-memory box to the TMA
+//           engine: cp.async.bulk.tensor store, or cp.reduce.async.bulk .add for split-K / gradient accumulation)
 #include <cuda.h>
 #include "common.cuh"
 #include "../../include/tvts_b200.h"
@@ -37,12 +36,17 @@ constexpr int kThreads = 128 + kEpiWarps * 32;
 // smaller stage buys a deeper TMA pipeline.
 template <int BN, int CTAS>
 struct SmemLayout {
-  static constexpr int STAGES = CTAS == 2 ? 6 : 4;
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_ROWS = BN / CTAS;
   static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int EPI_BYTES = kEpiWarps * 2 * 4096;          // per epilogue warp: ring of two [32 rows x 128 B] TMA-store boxes
+  static constexpr int BIAS_BYTES = BN * 4;                       // the tile's bias slice
+  static constexpr int STAGES = (227 * 1024 - EPI_BYTES - BIAS_BYTES - 256 - 1024) / STAGE_BYTES > 6
+                                    ? 6 : (227 * 1024 - EPI_BYTES - BIAS_BYTES - 256 - 1024) / STAGE_BYTES;   // pair: 5, solo: 3 (BN=256) / 5 (BN=128)
+  static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BIAS_OFFSET = EPI_OFFSET + EPI_BYTES;
+  static constexpr int BAR_OFFSET = BIAS_OFFSET + BIAS_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + tmem ptr + alignment slack
 };
 
@@ -68,6 +72,7 @@ struct GemmShape {
 template <int BN, bool A_MN, bool B_MN, int CTAS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_pre,
             GemmShape s, EpiParams ep, int dbg_lbo, int dbg_sbo, int dbg_kadv, int dbg_epi) {
   using L = SmemLayout<BN, CTAS>;
   constexpr int kStages = L::STAGES;
@@ -92,6 +97,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_out);
+    if (ep.out_pre != nullptr) tma_prefetch_desc(&tmap_pre);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -201,13 +208,51 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       else umma_commit(tfull_bar(acc));
     }
   } else if (warp >= 4) {
-    // ===================== epilogue: 8 warps, row-per-thread, direct 128-bit global I/O =====================
+    // ===================== epilogue: 8 warps =====================
     // TMEM lane quadrant q = warp % 4 (hardware restriction); the two warps of a quadrant split the tile's columns.
+    // tcgen05.ld gives every thread one accumulator ROW; the fused math (alpha, bias, activation, act', residual) runs in that
+    // layout, then the warp writes its [32 rows x 128 B] block (64 bf16 or 32 fp32 columns) into a 128B-swizzled shared-memory
+    // box (conflict-free 16-byte stores) and ONE lane hands it to the TMA engine: cp.async.bulk.tensor store (or
+    // cp.reduce.async.bulk .add for split-K / gradient accumulation).  Stores are asynchronous, fully coalesced, clipped at the
+    // matrix edges by the tensor map, and double-buffered per warp.
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
+    const int ew = warp - 4;
     constexpr int COLS_PER_WARP = BN / 2;
-    int it = 0;
+    const uint32_t ring = smem_base + L::EPI_OFFSET + (uint32_t)ew * 8192u;
+    const float* bias_s = reinterpret_cast<const float*>(smem_gen + L::BIAS_OFFSET);
     const uint32_t tempty_leader0 = CTAS == 2 ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
+    const bool out_bf16 = ep.out_dtype == 1;
+    const int CH = out_bf16 ? 64 : 32;                 // columns per 128-byte box row
+    uint32_t nstore = 0;                               // boxes issued by this warp (ring index; lane 0 owns the bulk groups)
+    // wait until this warp's ring buffer(s) have been read out by the TMA engine (lane 0 issued them)
+    auto box_acquire = [&](bool both) {
+      if (lane == 0) { if (both) bulk_wait_read<0>(); else bulk_wait_read<1>(); }
+      __syncwarp();
+    };
+    // write `nchunks` 16-byte chunks (starting at chunk0) of this thread's 128-byte row into a 128B-swizzled box
+    auto box_write = [&](uint32_t buf, int chunk0, const uint32_t* w, int nchunks) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < nchunks) {
+          const uint32_t addr = buf + (uint32_t)lane * 128u + (uint32_t)(((chunk0 + j) ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[4 * j]), "r"(w[4 * j + 1]), "r"(w[4 * j + 2]),
+                       "r"(w[4 * j + 3])
+                       : "memory");
+        }
+      }
+    };
+    auto box_issue = [&](const CUtensorMap* tm, uint32_t buf, int col0, int row0, bool reduce) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (reduce) tma_reduce_add_2d(tm, buf, col0, row0);
+        else tma_store_2d(tm, buf, col0, row0);
+        bulk_commit();
+      }
+    };
+    const bool has_pre = ep.out_pre != nullptr;
+    int it = 0;
     for (int unit = worker; unit < total_units; unit += n_workers, ++it) {
       const int tile = unit % s.tiles;
       const bool first_split = (unit / s.tiles) == 0;  // bias / residual are added by one split only
@@ -215,99 +260,100 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int m_blk = tile / s.n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      const bool use_res = ep.residual != nullptr && first_split;
+      const bool use_bias = ep.bias != nullptr && first_split;
+      // stage the tile's bias slice (all 8 epilogue warps = 256 threads, one column each); named barrier 1 = epilogue warps only
+      if (ep.bias != nullptr) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // the previous tile's readers are done
+        const int t = (int)threadIdx.x - 128;
+        if (use_bias && t < BN) {
+          const int col = n_blk * BN + t;
+          reinterpret_cast<float*>(smem_gen + L::BIAS_OFFSET)[t] = col < s.N ? __ldg(ep.bias + col) : 0.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const long long grow = (long long)m_blk * (BLOCK_M * CTAS) + cta_rank * BLOCK_M + q * 32 + lane;
+      const int row0 = m_blk * (BLOCK_M * CTAS) + (int)cta_rank * BLOCK_M + q * 32;
+      const long long grow = (long long)row0 + lane;
       const bool row_ok = grow < s.M;
       const int col_base = n_blk * BN + half * COLS_PER_WARP;
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * COLS_PER_WARP;
-      const bool use_res = ep.residual != nullptr && first_split;
-      const bool use_bias = ep.bias != nullptr && first_split;
 #pragma unroll 1
-      for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
-        const int col0 = col_base + c * 32;
+      for (int c0 = 0; c0 < COLS_PER_WARP; c0 += CH) {
+        const int col0 = col_base + c0;
         if (col0 >= s.N || dbg_epi == 3) break;  // warp-uniform
-        // issue the independent global loads first so their latency overlaps the TMEM load
-        float4 r4[8];
-        uint4 x4[4];
-        if (use_res && row_ok) {
-          const float* rp = ep.residual + grow * ep.ldr + col0;
+        uint32_t buf_o, buf_p = 0;
+        if (has_pre) { box_acquire(true); buf_p = ring; buf_o = ring + 4096u; }
+        else { box_acquire(false); buf_o = ring + (nstore & 1u) * 4096u; ++nstore; }
+#pragma unroll 1
+        for (int sub = 0; sub < CH; sub += 32) {   // 32 accumulator columns per pass
+          const int cs = col0 + sub;
+          uint32_t v[32];
+          tmem_ld_32x32(t_base + c0 + sub, v);
+          // independent global loads first (row-per-thread: a row's 128-byte line is fetched once and then served by L1)
+          float4 r4[8];
+          uint4 x4[4];
+          if (use_res && row_ok) {
+            const float* rp = ep.residual + grow * ep.ldr + cs;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            r4[j] = (col0 + 4 * j < s.N) ? *reinterpret_cast<const float4*>(rp + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (ep.dact != TVTS_ACT_NONE && row_ok) {
-          const bf16* ap = ep.aux + grow * ep.ldaux + col0;
+            for (int j = 0; j < 8; ++j)
+              r4[j] = (cs + 4 * j < s.N) ? *reinterpret_cast<const float4*>(rp + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          if (ep.dact != TVTS_ACT_NONE && row_ok) {
+            const bf16* ap = ep.aux + grow * ep.ldaux + cs;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            x4[j] = (col0 + 8 * j < s.N) ? *reinterpret_cast<const uint4*>(ap + 8 * j) : make_uint4(0, 0, 0, 0);
-        }
-        uint32_t v[32];
-        tmem_ld_32x32(t_base + c * 32, v);
-        tmem_ld_wait();
-        if (!row_ok) continue;
-        float f[32];
+            for (int j = 0; j < 4; ++j)
+              x4[j] = (cs + 8 * j < s.N) ? *reinterpret_cast<const uint4*>(ap + 8 * j) : make_uint4(0, 0, 0, 0);
+          }
+          tmem_ld_wait();
+          float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * ep.alpha;
-        if (use_bias) {
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * ep.alpha;
+          if (use_bias) {
+            const float* bp = bias_s + half * COLS_PER_WARP + c0 + sub;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (col0 + 4 * j < s.N) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + j);
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bp + 4 * j);   // shared-memory broadcast
               f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
             }
           }
-        }
-        if (ep.out_pre != nullptr) {
-          bf16* o = reinterpret_cast<bf16*>(ep.out_pre) + grow * ep.ldo + col0;
+          if (has_pre) {                               // bf16 copy of the pre-activation
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (col0 + 8 * j < s.N)
-              *reinterpret_cast<uint4*>(o + 8 * j) =
-                  make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                             pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-        }
-        if (ep.act != TVTS_ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], ep.act);
-        }
-        if (ep.dact != TVTS_ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 p0 = unpack_bf16x2(x4[j].x), p1 = unpack_bf16x2(x4[j].y), p2 = unpack_bf16x2(x4[j].z), p3 = unpack_bf16x2(x4[j].w);
-            f[8 * j] *= act_bwd(p0.x, ep.dact); f[8 * j + 1] *= act_bwd(p0.y, ep.dact);
-            f[8 * j + 2] *= act_bwd(p1.x, ep.dact); f[8 * j + 3] *= act_bwd(p1.y, ep.dact);
-            f[8 * j + 4] *= act_bwd(p2.x, ep.dact); f[8 * j + 5] *= act_bwd(p2.y, ep.dact);
-            f[8 * j + 6] *= act_bwd(p3.x, ep.dact); f[8 * j + 7] *= act_bwd(p3.y, ep.dact);
+            for (int j = 0; j < 16; ++j) v[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+            box_write(buf_p, sub >> 3, v, 4);
           }
-        }
-        if (use_res) {
+          if (ep.act != TVTS_ACT_NONE) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { f[4 * j] += r4[j].x; f[4 * j + 1] += r4[j].y; f[4 * j + 2] += r4[j].z; f[4 * j + 3] += r4[j].w; }
-        }
-        if (dbg_epi == 1) continue;
-        if (ep.out_dtype == 1) {
-          bf16* o = reinterpret_cast<bf16*>(ep.out) + grow * ep.ldo + col0;
+            for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], ep.act);
+          }
+          if (ep.dact != TVTS_ACT_NONE && row_ok) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (col0 + 8 * j < s.N)
-              *reinterpret_cast<uint4*>(o + 8 * j) =
-                  make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                             pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-        } else {
-          float* o = reinterpret_cast<float*>(ep.out) + grow * ep.ldo + col0;
-          if (ep.accumulate) {
+            for (int j = 0; j < 4; ++j) {
+              const float2 p0 = unpack_bf16x2(x4[j].x), p1 = unpack_bf16x2(x4[j].y), p2 = unpack_bf16x2(x4[j].z), p3 = unpack_bf16x2(x4[j].w);
+              f[8 * j] *= act_bwd(p0.x, ep.dact); f[8 * j + 1] *= act_bwd(p0.y, ep.dact);
+              f[8 * j + 2] *= act_bwd(p1.x, ep.dact); f[8 * j + 3] *= act_bwd(p1.y, ep.dact);
+              f[8 * j + 4] *= act_bwd(p2.x, ep.dact); f[8 * j + 5] *= act_bwd(p2.y, ep.dact);
+              f[8 * j + 6] *= act_bwd(p3.x, ep.dact); f[8 * j + 7] *= act_bwd(p3.y, ep.dact);
+            }
+          }
+          if (use_res && row_ok) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (col0 + 4 * j < s.N)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * j), "f"(f[4 * j]), "f"(f[4 * j + 1]),
-                             "f"(f[4 * j + 2]), "f"(f[4 * j + 3])
-                             : "memory");
+            for (int j = 0; j < 8; ++j) { f[4 * j] += r4[j].x; f[4 * j + 1] += r4[j].y; f[4 * j + 2] += r4[j].z; f[4 * j + 3] += r4[j].w; }
+          }
+          if (out_bf16) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+            box_write(buf_o, sub >> 3, v, 4);          // 32 bf16 columns = 64 bytes = 4 chunks
           } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (col0 + 4 * j < s.N) *reinterpret_cast<float4*>(o + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(f[j]);
+            box_write(buf_o, 0, v, 8);                 // 32 fp32 columns = the whole 128-byte row
           }
+        }
+        if (dbg_epi != 1) {
+          if (has_pre) box_issue(&tmap_pre, buf_p, col0, row0, false);
+          box_issue(&tmap_out, buf_o, col0, row0, ep.accumulate != 0);
         }
       }
       tc_fence_before();
@@ -317,6 +363,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         else mbar_arrive(tempty_bar(acc));
       }
     }
+    if (lane == 0) bulk_wait_all();   // every box has left shared memory and been written before the CTA may exit
   }
 
   tc_fence_before();
@@ -348,20 +395,20 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor map: inner (contiguous) extent d0, outer extent d1, outer stride ld elements.
-int make_tmap(CUtensorMap* m, const void* ptr, long long d0, long long d1, long long ld, int box0, int box1) {
+// 2-D tensor map: inner (contiguous) extent d0, outer extent d1, outer stride ld elements of `esize` bytes; 128B swizzle.
+int make_tmap(CUtensorMap* m, const void* ptr, long long d0, long long d1, long long ld, int box0, int box1, int esize = 2) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return tvts_set_error(TVTS_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   cuuint64_t dims[2] = {(cuuint64_t)d0, (cuuint64_t)d1};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (cuuint64_t)esize};
   cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = fn(m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
-    return tvts_set_error(TVTS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): ptr=%p dims=%lld,%lld ld=%lld box=%d,%d", (int)r, ptr,
-                          d0, d1, ld, box0, box1);
+    return tvts_set_error(TVTS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): ptr=%p dims=%lld,%lld ld=%lld box=%d,%d esize=%d", (int)r, ptr,
+                          d0, d1, ld, box0, box1, esize);
   return TVTS_OK;
 }
 
@@ -379,6 +426,17 @@ int launch(const tvts_gemm_args* g, const GemmShape& s, const EpiParams& ep, cud
   if (!B_MN) rc = make_tmap(&tb, g->b, g->K, g->N, g->ldb, BLOCK_K, L::B_ROWS);
   else rc = make_tmap(&tb, g->b, g->N, g->K, g->ldb, 64, BLOCK_K);
   if (rc) return rc;
+  // epilogue boxes: [32 rows x 128 bytes] of the output (and of the optional bf16 pre-activation copy)
+  CUtensorMap tout, tpre;
+  const int oes = g->out_dtype == 1 ? 2 : 4;
+  rc = make_tmap(&tout, g->out, g->N, g->M, g->ldo, 128 / oes, 32, oes);
+  if (rc) return rc;
+  if (g->out_pre) {
+    rc = make_tmap(&tpre, g->out_pre, g->N, g->M, g->ldo, 64, 32, 2);
+    if (rc) return rc;
+  } else {
+    tpre = tout;
+  }
   auto kern = gemm_kernel<BN, A_MN, B_MN, CTAS>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -403,7 +461,7 @@ int launch(const tvts_gemm_args* g, const GemmShape& s, const EpiParams& ep, cud
   attr[0].val.clusterDim.x = CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ta, tb, s, ep, g_dbg_lbo, g_dbg_sbo, g_dbg_kadv, g_dbg_epi);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, tpre, s, ep, g_dbg_lbo, g_dbg_sbo, g_dbg_kadv, g_dbg_epi);
   tvts_prof_end(stream, prof_slot);
   tvts_count_launch(1);
   if (le != cudaSuccess) return tvts_set_error(TVTS_ERR_CUDA, "gemm launch failed: %s", cudaGetErrorString(le));
@@ -463,6 +521,7 @@ extern "C" int tvts_gemm(const tvts_gemm_args* g, void* stream_) {
   TVTS_REQUIRE(!(g->splits > 1 && !g->accumulate), "tvts_gemm: split-K requires accumulate=1 into a pre-initialised fp32 output");
   TVTS_REQUIRE(!(g->dact && !g->aux), "tvts_gemm: dact needs aux");
   TVTS_REQUIRE(!(g->splits > 1 && (g->act || g->dact || g->out_pre)), "tvts_gemm: split-K cannot be combined with act/dact/out_pre");
+  TVTS_REQUIRE(!(g->out_pre && g->out_dtype != 1), "tvts_gemm: out_pre requires a bf16 output");
   if (g->residual) TVTS_REQUIRE(g->ldr % 4 == 0 && (uintptr_t)g->residual % 16 == 0, "tvts_gemm: residual alignment");
   if (g->bias) TVTS_REQUIRE((uintptr_t)g->bias % 16 == 0, "tvts_gemm: bias alignment");
   if (g->aux) TVTS_REQUIRE((uintptr_t)g->aux % 16 == 0, "tvts_gemm: aux alignment");
@@ -478,7 +537,7 @@ extern "C" int tvts_gemm(const tvts_gemm_args* g, void* stream_) {
   const bool small_n = g->N <= 128;
   const int BN = small_n ? 128 : 256;
   // CTA pairs (256 x 256 tiles) when there are enough rows to fill the machine with them
-  bool pair = !small_n && g->M >= 2048 && g->N >= 256;
+  bool pair = !small_n && g->M > 128;
   if (g_pair_mode == 0) pair = false;
   if (g_pair_mode == 1) pair = !small_n;
   const int tile_m = pair ? 2 * BLOCK_M : BLOCK_M;
