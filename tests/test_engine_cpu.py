@@ -64,3 +64,20 @@ def test_unused_sort_head_gets_no_grad(emu_backend):
     run_step(m, data, cfg)
     assert all(p.grad is None for k, p in m.named_parameters() if k.startswith("pred_model"))
     assert all(p.grad is not None for k, p in m.named_parameters() if not k.startswith("pred_model"))
+
+
+def test_weight_cache_rejects_recycled_parameter_ids(emu_backend):
+    """id() values are recycled after a model is garbage-collected: a cache entry keyed by a dead parameter's id must not be
+    served for a new parameter that happens to get the same id / storage / version (this produced NaNs between GPU tests)."""
+    import weakref
+    cache = E._WeightCache()
+    old = torch.nn.Parameter(torch.randn(4, 4))
+    stale = cache.get(old)
+    new = torch.nn.Parameter(torch.randn(8, 8))
+    cache._c[id(new)] = (new._version, new.data_ptr(), stale, weakref.ref(old))     # what id reuse leaves behind
+    got = cache.get(new)
+    assert got.shape == new.shape and torch.equal(got, new.detach().to(torch.bfloat16))
+    assert cache.get(new) is got                                                       # now a genuine hit
+    with torch.no_grad():
+        new.add_(1.0)                                                                   # version bump -> re-cast
+    assert torch.equal(cache.get(new), new.detach().to(torch.bfloat16))

@@ -28,7 +28,10 @@ GEMM_CASES = [
     (297, 384, 128, 0, 0, "plain", False),           # ragged M (TMA OOB rows), N not a multiple of the tile
     (300, 128, 512, 0, 0, "plain", True),            # BN=128 path
     (64, 4, 128, 0, 0, "plain", False),              # tiny N
-    (1000, 768, 768, 0, 0, "bias_act_res", False),
+    (1000, 768, 768, 0, 0, "bias_act_res", False),     # fp32 out: bias + QuickGELU + residual
+    (1000, 768, 768, 0, 0, "bias_act_pre", True),      # bf16 out + bf16 pre-activation copy (the c_fc GEMM)
+    (598, 384, 128, 0, 0, "bias", True),               # pair tiles whose second CTA is entirely out of range
+    (598, 128, 512, 0, 0, "bias_act_res", False),
     (1000, 2304, 768, 0, 0, "bias", True),
     (515, 512, 2048, 0, 1, "dact", True),            # dgrad form: B read MN-major
     (768, 2304, 8192, 0, 0, "splitk", False),
@@ -53,10 +56,12 @@ def test_gemm(M, N, K, a_mn, b_mn, mode, out_bf16):
     lda, ldb = (M if a_mn else K), (N if b_mn else K)
     kw = {}
     out = torch.zeros(M, N, device=DEV, dtype=BF16 if out_bf16 else F32)
-    if mode in ("bias", "bias_act_res"):
+    if mode in ("bias", "bias_act_res", "bias_act_pre"):
         kw["bias"] = rnd(N)
     if mode == "bias_act_res":
-        kw.update(residual=rnd(M, N), act="quick_gelu", out_pre=torch.empty(M, N, device=DEV, dtype=BF16))
+        kw.update(residual=rnd(M, N), act="quick_gelu")
+    if mode == "bias_act_pre":
+        kw.update(act="gelu", out_pre=torch.empty(M, N, device=DEV, dtype=BF16))
     if mode == "dact":
         kw.update(aux=rnd(M, N).to(BF16), dact="gelu")
     if mode == "splitk":

@@ -14,6 +14,8 @@ Reference semantics restated here (paths relative to /root/reference):
   sort head    v2/model/sort_transformer.py:124-142
   losses       v2/model/loss.py:13-25, model_dist_TVTSv2_ViT_B_16.py:119-127, v2/trainer/trainer.py:481-494
 """
+import weakref
+
 import torch
 
 from . import _lib as L
@@ -28,6 +30,10 @@ MODE_FULL, MODE_SPACE, MODE_TIME = 0, 1, 2
 # bf16 operand cache for the fp32 master weights (re-cast only when the parameter changed)
 # --------------------------------------------------------------------------------------------------
 class _WeightCache:
+    """bf16 operand copies of fp32 parameters that are not in a FlatState arena (frozen weights, optimizer-less runs).
+    An entry is valid only for the very same Parameter object (weak reference: `id()` values are recycled once a model is
+    garbage-collected), the same storage and the same version counter."""
+
     def __init__(self):
         self._c = {}
 
@@ -38,15 +44,18 @@ class _WeightCache:
         key = id(p)
         ent = self._c.get(key)
         ver = p._version
-        if ent is not None and ent[0] == ver and ent[1] == p.data_ptr() and ent[2].device == p.device:
+        if ent is not None and ent[3]() is p and ent[0] == ver and ent[1] == p.data_ptr() and ent[2].shape == p.shape \
+                and ent[2].device == p.device:
             return ent[2]
         src = p.detach()
         if not src.is_contiguous():
             src = src.contiguous()
-        dst = ent[2] if (ent is not None and ent[2].numel() == src.numel() and ent[2].device == p.device) else \
-            torch.empty(src.shape, dtype=BF16, device=p.device)
+        reuse = ent is not None and ent[3]() is p and ent[2].shape == p.shape and ent[2].device == p.device
+        dst = ent[2] if reuse else torch.empty(src.shape, dtype=BF16, device=p.device)
         L.call("cast_bf16", src, dst, src.numel())
-        self._c[key] = (ver, p.data_ptr(), dst)
+        if len(self._c) > 4096:             # drop entries of dead parameters
+            self._c = {k: v for k, v in self._c.items() if v[3]() is not None}
+        self._c[key] = (ver, p.data_ptr(), dst, weakref.ref(p))
         return dst
 
     def clear(self):

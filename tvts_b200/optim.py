@@ -73,7 +73,7 @@ class FlatState:
 
     # ---- views -------------------------------------------------------------------------------------------------
     def has(self, p):
-        i = self.index.get(id(p))
+        i = self.index.get(id(p))           # the arena keeps its parameters alive, so a matching id is the same object
         return i is not None and self.params[i] is p
 
     def _view(self, arena, p):
