@@ -142,7 +142,7 @@ __device__ __forceinline__ void load_tile(uint32_t tile, const bf16* base, long 
 }
 
 // ================================================================================================ streamed forward
-__global__ void __launch_bounds__(kThreads) attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse,
+__global__ void __launch_bounds__(kThreads, 4) attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse,
                                                             AttnShape a) {
   __shared__ __align__(128) uint8_t smem[5 * TILE_BYTES];   // Q | K0 | V0 | K1 | V1
   const uint32_t sQ = smem_u32(smem);
@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_kernel(const bf16* __restri
       float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
+        if (8 * j >= cnt) { sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = -INFINITY; continue; }   // CTA-uniform
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int key = 8 * j + 2 * t4 + e;
@@ -231,6 +232,7 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_kernel(const bf16* __restri
       uint32_t pa[4][4];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
+        if (8 * j >= cnt) { pa[j >> 1][(j & 1) * 2] = 0u; pa[j >> 1][(j & 1) * 2 + 1] = 0u; continue; }
         const float p00 = exp2f((sc[j][0] - mu0) * sl2), p01 = exp2f((sc[j][1] - mu0) * sl2);
         const float p10 = exp2f((sc[j][2] - mu1) * sl2), p11 = exp2f((sc[j][3] - mu1) * sl2);
         ps0 += p00 + p01; ps1 += p10 + p11;
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
 // with p_ij = exp(scale q_i.k_j - lse_i), ds_ij = p_ij (do_i.v_j - delta_i).  In ROLE 1 the register tiles hold the TRANSPOSED
 // score matrix (rows = keys), so P^T / dS^T are directly the A operands of the dV / dK products.
 template <int ROLE>
-__global__ void __launch_bounds__(kThreads) attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+__global__ void __launch_bounds__(kThreads, 4) attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                                                             const float* __restrict__ lse, const float* __restrict__ delta,
                                                             bf16* __restrict__ dqkv, AttnShape a) {
   __shared__ __align__(128) uint8_t smem[4 * TILE_BYTES + 2 * 2 * BN * 4];   // A-side(2 tiles; reused as stages) | X0 Y0 | ... see below
@@ -438,6 +440,11 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_kernel(const bf16* __restri
         uint32_t pa[2][4], dsa[2][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
+          if (32 * half + 8 * j >= cnt) {                        // CTA-uniform: nothing streamed there
+            dsa[j >> 1][(j & 1) * 2] = 0u; dsa[j >> 1][(j & 1) * 2 + 1] = 0u;
+            if (ROLE == 1) { pa[j >> 1][(j & 1) * 2] = 0u; pa[j >> 1][(j & 1) * 2 + 1] = 0u; }
+            continue;
+          }
           float p[4], ds[4];
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
