@@ -529,21 +529,25 @@ constexpr int T_MAX = 15;
 template <bool BWD>
 __device__ __forceinline__ void time_load(uint32_t base, const bf16* qb, const bf16* dob, long long rs, long long ro, int T, int n, int slot,
                                           int lane) {
-  const int rows = BWD ? T_ROWS_BWD : T_ROWS_FWD;
-  for (int i = lane; i < rows * 8; i += 32) {
-    const int r = i >> 3, c = i & 7;
-    const int blk = r >> 4, rr = r & 15;       // blk 0 = Q, 1 = K, 2 = V, 3 = dO
-    bool ok;
-    long long tok;
-    if (blk == 0 || blk == 3) {                // query-side rows: rr < T slot queries, rr == T the CLS query (backward only)
-      ok = rr < T || (BWD && rr == T);
-      tok = rr < T ? 1 + (long long)rr * n + slot : 0;
-    } else {                                   // key-side rows: rr == 0 CLS, rr <= T frame rr-1
-      ok = rr <= T;
-      tok = (rr == 0 || !ok) ? 0 : 1 + (long long)(rr - 1) * n + slot;
-    }
-    const bf16* src = blk == 3 ? dob + tok * ro : qb + tok * rs + (blk == 3 ? 0 : blk) * ro;
-    cp_async16(base + swz(r, c), src + c * 8, ok);
+  // lane -> (16-byte chunk c, row r0 + 4*it) of each 16-row block; token pointers advance by a constant 4*n rows per iteration
+  const int c = lane & 7, r0 = lane >> 3;
+  const long long step_q = 4LL * n * rs, step_o = 4LL * n * ro;
+  const bf16* pq = qb + (1LL + slot + (long long)r0 * n) * rs + c * 8;          // query-side row rr: token 1 + rr*n + slot
+  const bf16* pk = qb + (1LL + slot + (long long)(r0 - 1) * n) * rs + ro + c * 8;  // key-side row rr >= 1: token 1 + (rr-1)*n + slot
+  const bf16* pd = BWD ? dob + (1LL + slot + (long long)r0 * n) * ro + c * 8 : nullptr;
+  const bf16* cls = qb + c * 8;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int rr = r0 + 4 * it;
+    const uint32_t so = (uint32_t)(rr * 128 + (((c ^ rr) & 7) << 4));         // block bases are multiples of 8 rows: same swizzle
+    const bool okq = rr < T, okc = BWD && rr == T, okk = rr <= T;
+    // (rows that are not loaded are zero-filled; they are still given a valid address)
+    cp_async16(base + so, okq ? pq : cls, okq || okc);                                        // Q   (row T: the CLS query, backward)
+    cp_async16(base + 16 * 128 + so, (rr == 0 || !okk) ? cls + ro : pk, okk);                 // K   (row 0: the CLS key)
+    cp_async16(base + 32 * 128 + so, (rr == 0 || !okk) ? cls + 2 * ro : pk + ro, okk);        // V
+    if (BWD) cp_async16(base + 48 * 128 + so, okq ? pd : dob + c * 8, okq || okc);            // dO
+    pq += step_q; pk += step_q;
+    if (BWD) pd += step_o;
   }
 }
 

@@ -547,15 +547,20 @@ extern "C" int tvts_gemm(const tvts_gemm_args* g, void* stream_) {
   s.n_tiles = (s.N + BN - 1) / BN;
   s.k_blocks = (s.K + BLOCK_K - 1) / BLOCK_K;
   int splits = g->splits;
-  if (splits <= 0) {  // auto: fill the machine when the output grid alone cannot (wgrad: small output, very deep K)
+  if (splits <= 0) {  // auto (only when the caller accumulates): pick the split count whose units fill whole waves of workers
     splits = 1;
     if (g->accumulate) {
       const int tiles = s.m_tiles * s.n_tiles;
-      const int sms = tvts_num_sms();
-      if (tiles < sms) splits = (2 * sms + tiles - 1) / tiles;
-      const int max_splits = (s.k_blocks + 3) / 4;  // keep >= 4 k-blocks per unit
-      if (splits > max_splits) splits = max_splits;
-      if (splits < 1) splits = 1;
+      const int workers = tvts_num_sms() / (pair ? 2 : 1);
+      const int max_splits = (s.k_blocks + 7) / 8;  // keep >= 8 k-blocks per unit
+      double best = 0.0;
+      for (int cand = 1; cand <= max_splits && cand * tiles <= 3 * workers + tiles; ++cand) {
+        const int units = cand * tiles;
+        const int waves = (units + workers - 1) / workers;
+        // efficiency of the wave packing, slightly penalising more splits (each adds a tile-sized reduce-add pass)
+        const double eff = (double)units / ((double)waves * workers) - 0.004 * cand;
+        if (eff > best + 1e-9) { best = eff; splits = cand; }
+      }
     }
   }
   if (splits > s.k_blocks) splits = s.k_blocks;

@@ -167,7 +167,9 @@ class AdamW:
     def zero_grad(self, set_to_none=True):
         self.flat.zero_grad()
 
-    def step(self, grad_scale=1.0):
+    def prepare(self):
+        """Host half of step(): advance the step counters of the parameters that have a gradient, refresh the per-tensor
+        hyper-parameter table and upload it (async, pinned ring).  Stream-ordered before launch()."""
         fs = self.flat
         slot = self._slot
         self._slot = (slot + 1) % len(self._ring)
@@ -194,12 +196,20 @@ class AdamW:
             ev = torch.cuda.Event()
             ev.record()
             self._ring_ev[slot] = ev
+
+    def launch(self, grad_scale=1.0):
+        """Device half of step(): ONE kernel over the arena (capturable in a CUDA graph: it only reads device-resident state)."""
+        fs = self.flat
         b1, b2 = self.param_groups[0]["betas"]
         L.call("adamw_flat", fs.p, fs.g, fs.m, fs.v, fs.bf, self.chunk_tensor_arg(), self.table, fs.n_chunks, fs.chunk, float(b1), float(b2),
                float(self.param_groups[0]["eps"]), float(grad_scale))
         for i, p in enumerate(fs.params):
             if p.grad is not None:
                 fs.synced[i] = p._version      # the kernel refreshed the bf16 copy of every active tensor
+
+    def step(self, grad_scale=1.0):
+        self.prepare()
+        self.launch(grad_scale)
 
     def chunk_tensor_arg(self):
         return self.flat.chunk_tensor

@@ -10,6 +10,8 @@ Mirrors (paths relative to /root/reference):
 The two embedding gathers of the reference are fused into ONE NCCL all-gather of the concatenated [B_local, 2E] buffer;
 the gradient all-reduce runs over a flat fp32 arena (one NCCL call per arena chunk), averaged by 1/W like DDP.
 """
+import types
+
 import torch
 import torch.distributed as dist
 
@@ -109,14 +111,21 @@ class TrainStep:
 
     data: {'video' [B,T,3,R,R] f32, 'text' [n_trans*B, ctx] int (clip-major), 'keep_ind' [B,n] int64, 'label' [B,n_trans] int64}
     (host or device tensors; host tensors are copied like trainer.py:474-475,489).
-    Returns (loss1, loss2) as 0-d device tensors (no host sync here; the caller decides when to .item())."""
+    Returns (loss1, loss2) as 0-d device tensors (no host sync here; the caller decides when to .item()).
 
-    def __init__(self, model, optimizer=None, temperature=0.05, device=None):
+    use_graph=True captures the whole step (memset, ~850 kernel launches, NCCL collectives, AdamW) into ONE CUDA graph per input
+    signature and replays it: the Python / launch cost of a step (~30 ms of host time) collapses to a graph launch.  Inputs are
+    copied into static device buffers; the optimizer's small host-side table upload stays outside the graph."""
+
+    def __init__(self, model, optimizer=None, temperature=0.05, device=None, use_graph=False):
         self.model = model
         self.optimizer = optimizer
         self.loss = M.NormSoftmaxLoss(temperature)
         self.device = device if device is not None else next(model.parameters()).device
         self.params = [p for p in model.parameters() if p.requires_grad]   # after the optimizer applied the freeze policy
+        self.use_graph = use_graph
+        self._graphs = {}
+        self.launches_per_graph = 0
 
     def to_device(self, data):
         out = {}
@@ -124,8 +133,7 @@ class TrainStep:
             out[k] = v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v
         return out
 
-    def __call__(self, data):
-        data = self.to_device(data)
+    def _body(self, data, optimizer_launch_only=False, skip_optimizer=False):
         flat = getattr(self.optimizer, "flat", None)
         if flat is not None:
             self.optimizer.zero_grad()              # one memset over the gradient arena
@@ -146,6 +154,44 @@ class TrainStep:
             average_flat(flat)
         else:
             average_gradients(self.params)
-        if self.optimizer is not None:
-            self.optimizer.step()
+        if self.optimizer is not None and not skip_optimizer:
+            if optimizer_launch_only:
+                self.optimizer.launch()
+            else:
+                self.optimizer.step()
         return loss1.detach(), loss2.detach()
+
+    def _capture(self, key, data):
+        from . import _lib as L
+        if not (self.optimizer is None or hasattr(self.optimizer, "launch")):
+            raise RuntimeError("TrainStep(use_graph=True) needs tvts_b200.optim.AdamW (or no optimizer)")
+        static = {k: v.to(self.device, copy=True) for k, v in data.items() if torch.is_tensor(v)}
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):               # warm-up outside capture: allocator pools, bf16 weight casts, NCCL, func attributes
+            self._body(static, skip_optimizer=True)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        n0 = L.launch_count()
+        with torch.cuda.graph(graph):
+            l1, l2 = self._body(static, optimizer_launch_only=True)
+        self.launches_per_graph = L.launch_count() - n0
+        ent = types.SimpleNamespace(graph=graph, static=static, l1=l1, l2=l2)
+        self._graphs[key] = ent
+        return ent
+
+    def __call__(self, data):
+        if not self.use_graph:
+            return self._body(self.to_device(data))
+        key = tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(data.items()) if torch.is_tensor(v))
+        ent = self._graphs.get(key)
+        if ent is None:
+            ent = self._capture(key, data)
+        for k, v in ent.static.items():
+            v.copy_(data[k], non_blocking=True)
+        if self.optimizer is not None:
+            self.optimizer.prepare()                # host table -> device, stream-ordered before the replay
+        ent.graph.replay()
+        return ent.l1, ent.l2
