@@ -71,6 +71,8 @@ int tvts_gemm(const tvts_gemm_args* args, void* stream);
 int tvts_gemm_debug_set(int lbo_bytes, int sbo_bytes, int k_advance_bytes);
 /* tile policy: -1 auto (CTA pairs / cta_group::2 with 256x256 tiles for large problems), 0 single-CTA 128x256 tiles only, 1 pairs always */
 int tvts_gemm_set_pair_mode(int mode);
+/* 1 (default): the residual / aux epilogue operand is prefetched by TMA into the store ring; 0: read straight from global memory */
+int tvts_gemm_set_operand_prefetch(int on);
 /* debug: co-resident clusters of the pair kernel for a given cluster size (cudaOccupancyMaxActiveClusters) */
 int tvts_gemm_debug_max_clusters(int cluster_size);
 /* debug knob: 0 normal epilogue, 1 no global stores, 2 direct row-per-thread bf16 stores, 3 skip epilogue (timing experiments) */

@@ -42,12 +42,12 @@ struct SmemLayout {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_BYTES = kEpiWarps * 2 * 4096;          // per epilogue warp: ring of two [32 rows x 128 B] TMA-store boxes
   static constexpr int BIAS_BYTES = BN * 4;                       // the tile's bias slice
-  static constexpr int STAGES = (227 * 1024 - EPI_BYTES - BIAS_BYTES - 256 - 1024) / STAGE_BYTES > 6
-                                    ? 6 : (227 * 1024 - EPI_BYTES - BIAS_BYTES - 256 - 1024) / STAGE_BYTES;   // pair: 5, solo: 3 (BN=256) / 5 (BN=128)
+  static constexpr int STAGES = (227 * 1024 - EPI_BYTES - BIAS_BYTES - 512 - 1024) / STAGE_BYTES > 6
+                                    ? 6 : (227 * 1024 - EPI_BYTES - BIAS_BYTES - 512 - 1024) / STAGE_BYTES;   // pair: 5, solo: 3 (BN=256) / 5 (BN=128)
   static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int BIAS_OFFSET = EPI_OFFSET + EPI_BYTES;
   static constexpr int BAR_OFFSET = BIAS_OFFSET + BIAS_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + tmem ptr + alignment slack
+  static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;  // barriers + tmem ptr + alignment slack
 };
 
 struct EpiParams {
@@ -61,6 +61,7 @@ struct EpiParams {
   int act;         // applied to acc + bias
   int dact;        // multiply by act'(aux) (dgrad through an activation)
   int accumulate;  // 0 store, 1 red.add into fp32 out (split-K / grad accumulation)
+  int opnd_mode;   // 0: residual / aux read straight from global memory; 1: residual, 2: aux prefetched by TMA into the store ring
   float alpha;
 };
 
@@ -73,7 +74,7 @@ template <int BN, bool A_MN, bool B_MN, int CTAS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_pre,
-            GemmShape s, EpiParams ep, int dbg_lbo, int dbg_sbo, int dbg_kadv, int dbg_epi) {
+            const __grid_constant__ CUtensorMap tmap_opnd, GemmShape s, EpiParams ep, int dbg_lbo, int dbg_sbo, int dbg_kadv, int dbg_epi) {
   using L = SmemLayout<BN, CTAS>;
   constexpr int kStages = L::STAGES;
   const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;   // rank inside the pair; rank 0 = leader (issues the MMAs)
@@ -93,11 +94,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * kStages + 2 + i); };
   const uint32_t tmem_holder = bar_base + 8u * (2 * kStages + 4);
   volatile uint32_t* tmem_holder_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFFSET + 8 * (2 * kStages + 4));
+  auto opnd_bar = [&](int ew, int b) { return bar_base + 8u * (2 * kStages + 6 + 2 * ew + b); };   // epilogue-operand boxes (2 per warp)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     tma_prefetch_desc(&tmap_out);
+    if (ep.opnd_mode != 0) tma_prefetch_desc(&tmap_opnd);
     if (ep.out_pre != nullptr) tma_prefetch_desc(&tmap_pre);
   }
   if (warp == 1 && lane == 0) {
@@ -109,6 +112,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       mbar_init(tfull_bar(i), 1);
       mbar_init(tempty_bar(i), CTAS * kEpiWarps);   // one elected lane per epilogue warp (of both CTAs of a pair)
     }
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(opnd_bar(i >> 1, i & 1), 1);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -252,6 +256,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
     };
     const bool has_pre = ep.out_pre != nullptr;
+    // Epilogue operand (the fp32 residual, or the bf16 pre-activation whose act' multiplies a dgrad) is PREFETCHED by TMA into
+    // the very ring box the result will be stored from ([32 rows x 128 B] = 32 fp32 / 64 bf16 columns, same shape as the output
+    // box): the first two boxes of a tile are requested before the accumulator is even ready, the following ones as soon as the
+    // box two chunks back has been read out.  The thread reads its row from the swizzled box, combines, and overwrites it in place.
+    const bool has_opnd = ep.opnd_mode != 0;
+    uint32_t nload = 0;                                 // operand boxes requested / consumed by this warp (ring + phase index)
+    uint32_t nuse = 0;
+    auto opnd_request = [&](int col0, int row0) {       // lane 0 only
+      const uint32_t b = nload & 1u;
+      mbar_arrive_expect_tx(opnd_bar(ew, b), 4096u);
+      tma_load_2d(ring + b * 4096u, &tmap_opnd, opnd_bar(ew, b), col0, row0);
+    };
+    const int nchunks = COLS_PER_WARP / CH;
     int it = 0;
     for (int unit = worker; unit < total_units; unit += n_workers, ++it) {
       const int tile = unit % s.tiles;
@@ -262,6 +279,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const uint32_t acc_phase = (it >> 1) & 1;
       const bool use_res = ep.residual != nullptr && first_split;
       const bool use_bias = ep.bias != nullptr && first_split;
+      const int row0 = m_blk * (BLOCK_M * CTAS) + (int)cta_rank * BLOCK_M + q * 32;
+      const long long grow = (long long)row0 + lane;
+      const bool row_ok = grow < s.M;
+      const int col_base = n_blk * BN + half * COLS_PER_WARP;
+      const bool tile_opnd = has_opnd && (ep.opnd_mode == 2 || use_res);
+      // operand boxes of the first two chunks: requested while the MMAs of this tile are still running
+      if (tile_opnd) {
+        if (lane == 0) {
+          bulk_wait_read<0>();                           // both ring boxes have been read out by earlier stores
+          for (int c = 0; c < 2 && c < nchunks; ++c)
+            if (col_base + c * CH < s.N) { opnd_request(col_base + c * CH, row0); ++nload; }
+        }
+        nload = __shfl_sync(0xffffffffu, nload, 0);
+      }
       // stage the tile's bias slice (all 8 epilogue warps = 256 threads, one column each); named barrier 1 = epilogue warps only
       if (ep.bias != nullptr) {
         asm volatile("bar.sync 1, 256;" ::: "memory");   // the previous tile's readers are done
@@ -274,37 +305,53 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row0 = m_blk * (BLOCK_M * CTAS) + (int)cta_rank * BLOCK_M + q * 32;
-      const long long grow = (long long)row0 + lane;
-      const bool row_ok = grow < s.M;
-      const int col_base = n_blk * BN + half * COLS_PER_WARP;
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * COLS_PER_WARP;
 #pragma unroll 1
       for (int c0 = 0; c0 < COLS_PER_WARP; c0 += CH) {
         const int col0 = col_base + c0;
         if (col0 >= s.N || dbg_epi == 3) break;  // warp-uniform
         uint32_t buf_o, buf_p = 0;
-        if (has_pre) { box_acquire(true); buf_p = ring; buf_o = ring + 4096u; }
+        if (tile_opnd) {
+          buf_o = ring + (nuse & 1u) * 4096u;            // the operand box of this chunk; the result overwrites it
+          mbar_wait(opnd_bar(ew, nuse & 1u), (nuse >> 1) & 1u);
+          ++nuse;
+        } else if (has_pre) { box_acquire(true); buf_p = ring; buf_o = ring + 4096u; }
         else { box_acquire(false); buf_o = ring + (nstore & 1u) * 4096u; ++nstore; }
 #pragma unroll 1
         for (int sub = 0; sub < CH; sub += 32) {   // 32 accumulator columns per pass
           const int cs = col0 + sub;
           uint32_t v[32];
           tmem_ld_32x32(t_base + c0 + sub, v);
-          // independent global loads first (row-per-thread: a row's 128-byte line is fetched once and then served by L1)
+          // operand of this pass: from the prefetched box (swizzled, conflict-free), else straight from global memory
           float4 r4[8];
           uint4 x4[4];
-          if (use_res && row_ok) {
-            const float* rp = ep.residual + grow * ep.ldr + cs;
+          if (tile_opnd) {
+            if (ep.opnd_mode == 1) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              r4[j] = (cs + 4 * j < s.N) ? *reinterpret_cast<const float4*>(rp + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          if (ep.dact != TVTS_ACT_NONE && row_ok) {
-            const bf16* ap = ep.aux + grow * ep.ldaux + cs;
+              for (int j = 0; j < 8; ++j) {
+                const uint32_t addr = buf_o + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r4[j].x), "=f"(r4[j].y), "=f"(r4[j].z), "=f"(r4[j].w) : "r"(addr));
+              }
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              x4[j] = (cs + 8 * j < s.N) ? *reinterpret_cast<const uint4*>(ap + 8 * j) : make_uint4(0, 0, 0, 0);
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t addr = buf_o + (uint32_t)lane * 128u + (uint32_t)((((sub >> 3) + j) ^ (lane & 7)) << 4);
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x4[j].x), "=r"(x4[j].y), "=r"(x4[j].z), "=r"(x4[j].w) : "r"(addr));
+              }
+            }
+          } else {
+            if (use_res && row_ok) {
+              const float* rp = ep.residual + grow * ep.ldr + cs;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                r4[j] = (cs + 4 * j < s.N) ? *reinterpret_cast<const float4*>(rp + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (ep.dact != TVTS_ACT_NONE && row_ok) {
+              const bf16* ap = ep.aux + grow * ep.ldaux + cs;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                x4[j] = (cs + 8 * j < s.N) ? *reinterpret_cast<const uint4*>(ap + 8 * j) : make_uint4(0, 0, 0, 0);
+            }
           }
           tmem_ld_wait();
           float f[32];
@@ -327,7 +374,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], ep.act);
           }
-          if (ep.dact != TVTS_ACT_NONE && row_ok) {
+          if (ep.dact != TVTS_ACT_NONE && (row_ok || tile_opnd)) {     // (out-of-range rows of a prefetched box are zero-filled)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float2 p0 = unpack_bf16x2(x4[j].x), p1 = unpack_bf16x2(x4[j].y), p2 = unpack_bf16x2(x4[j].z), p3 = unpack_bf16x2(x4[j].w);
@@ -337,7 +384,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               f[8 * j + 6] *= act_bwd(p3.x, ep.dact); f[8 * j + 7] *= act_bwd(p3.y, ep.dact);
             }
           }
-          if (use_res && row_ok) {
+          if (use_res && (row_ok || tile_opnd)) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) { f[4 * j] += r4[j].x; f[4 * j + 1] += r4[j].y; f[4 * j + 2] += r4[j].z; f[4 * j + 3] += r4[j].w; }
           }
@@ -354,6 +401,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (dbg_epi != 1) {
           if (has_pre) box_issue(&tmap_pre, buf_p, col0, row0, false);
           box_issue(&tmap_out, buf_o, col0, row0, ep.accumulate != 0);
+        }
+        if (tile_opnd) {
+          // request the operand box two chunks ahead: it reuses THIS chunk's box once the store just issued has been read out
+          const int cn = c0 + 2 * CH;
+          const bool more = cn < COLS_PER_WARP && col_base + cn < s.N;     // warp-uniform
+          if (more) {
+            if (lane == 0) { bulk_wait_read<0>(); opnd_request(col_base + cn, row0); }   // chunk c0's box has been read out
+            ++nload;
+          }
         }
       }
       tc_fence_before();
@@ -414,6 +470,7 @@ int make_tmap(CUtensorMap* m, const void* ptr, long long d0, long long d1, long 
 
 int g_dbg_lbo = 0, g_dbg_sbo = 0, g_dbg_kadv = 0, g_dbg_epi = 0;
 int g_pair_mode = -1;   // -1 auto, 0 never use CTA pairs, 1 always when the shape allows
+int g_opnd_prefetch = 1; // TMA prefetch of the residual / aux epilogue operand
 
 template <int BN, bool A_MN, bool B_MN, int CTAS>
 int launch(const tvts_gemm_args* g, const GemmShape& s, const EpiParams& ep, cudaStream_t stream) {
@@ -436,6 +493,21 @@ int launch(const tvts_gemm_args* g, const GemmShape& s, const EpiParams& ep, cud
     if (rc) return rc;
   } else {
     tpre = tout;
+  }
+  // epilogue operand prefetch (see the kernel): residual with an fp32 output, or act'(aux) with a bf16 output
+  CUtensorMap topnd = tout;
+  EpiParams ep2 = ep;
+  ep2.opnd_mode = 0;
+  if (g_opnd_prefetch && !g->out_pre) {
+    if (g->residual && !g->dact && g->out_dtype == 0) {
+      rc = make_tmap(&topnd, g->residual, g->N, g->M, g->ldr, 32, 32, 4);
+      if (rc) return rc;
+      ep2.opnd_mode = 1;
+    } else if (g->dact && !g->residual && g->out_dtype == 1) {
+      rc = make_tmap(&topnd, g->aux, g->N, g->M, g->ldaux, 64, 32, 2);
+      if (rc) return rc;
+      ep2.opnd_mode = 2;
+    }
   }
   auto kern = gemm_kernel<BN, A_MN, B_MN, CTAS>;
   static bool attr_set = false;
@@ -461,7 +533,7 @@ int launch(const tvts_gemm_args* g, const GemmShape& s, const EpiParams& ep, cud
   attr[0].val.clusterDim.x = CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, tpre, s, ep, g_dbg_lbo, g_dbg_sbo, g_dbg_kadv, g_dbg_epi);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, tpre, topnd, s, ep2, g_dbg_lbo, g_dbg_sbo, g_dbg_kadv, g_dbg_epi);
   tvts_prof_end(stream, prof_slot);
   tvts_count_launch(1);
   if (le != cudaSuccess) return tvts_set_error(TVTS_ERR_CUDA, "gemm launch failed: %s", cudaGetErrorString(le));
@@ -492,6 +564,10 @@ extern "C" int tvts_gemm_debug_max_clusters(int cluster_size) {
 }
 extern "C" int tvts_gemm_set_pair_mode(int mode) {
   g_pair_mode = mode;
+  return TVTS_OK;
+}
+extern "C" int tvts_gemm_set_operand_prefetch(int on) {
+  g_opnd_prefetch = on;
   return TVTS_OK;
 }
 extern "C" int tvts_gemm_debug_epi(int mode) {
