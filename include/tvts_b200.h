@@ -101,6 +101,9 @@ int tvts_layernorm_bwd(const void* dy, int64_t dy_is_bf16, const float* x, const
  */
 int tvts_attn_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n,
                   int64_t causal, float scale, void* stream);
+/* 1 (default): the CLS row/column launches of the divided modes run on an internal side stream forked from / joined into `stream`
+ * with events (graph-capture safe); 0: everything on `stream` */
+int tvts_attn_set_side_stream(int on);
 int tvts_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv, int64_t B, int64_t N,
                   int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal, float scale, void* stream);
 

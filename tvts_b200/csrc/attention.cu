@@ -1152,9 +1152,36 @@ int check_shape(const AttnShape& a, int64_t d) {
   return TVTS_OK;
 }
 
+// The CLS row / column of the divided modes (one query over all N keys, one key under all N queries: 384 tiny CTAs that stream
+// 13 tiles each) is latency-bound and independent of the group kernels (disjoint outputs), so it runs on a side stream forked
+// from / joined back into the caller's stream with events -- also legal inside a CUDA-graph capture, where it becomes a parallel
+// branch of the graph.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+SideStream* side_stream() {
+  static SideStream per_dev[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& s = per_dev[dev];
+  if (s.stream == nullptr) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return &s;
+}
+int g_attn_side = 1;
+
 inline bool use_time_kernels(const AttnShape& a) { return a.mode == 2 && a.T <= T_MAX; }
 
 }  // namespace
+
+extern "C" int tvts_attn_set_side_stream(int on) {
+  g_attn_side = on;
+  return TVTS_OK;
+}
 
 extern "C" int tvts_attn_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T,
                              int64_t n, int64_t causal, float scale, void* stream) {
@@ -1164,14 +1191,28 @@ extern "C" int tvts_attn_fwd(const void* qkv, void* out, float* lse, int64_t B, 
   if (rc) return rc;
   TVTS_REQUIRE(qkv && out && lse, "attn_fwd: null pointer");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (use_time_kernels(a)) {
+  const int gw = group_warps(a);
+  const bool time_k = use_time_kernels(a);
+  const bool split = a.mode != 0 && (time_k || gw);       // group/time kernel + separate CLS launch
+  SideStream* sd = (split && g_attn_side) ? side_stream() : nullptr;
+  cudaStream_t cls_st = st;
+  if (sd) {
+    TVTS_CHECK_CUDA(cudaEventRecord(sd->fork, st));
+    TVTS_CHECK_CUDA(cudaStreamWaitEvent(sd->stream, sd->fork, 0));
+    cls_st = sd->stream;
+  }
+  if (split) {                                             // CLS query over all tokens
+    AttnShape c = a;
+    c.cls_only = 1;
+    dim3 grid(num_blocks_x(c), (unsigned)H, (unsigned)B);
+    attn_fwd_kernel<<<grid, kThreads, 0, cls_st>>>((const bf16*)qkv, (bf16*)out, lse, c);
+    TVTS_LAUNCH_CHECK();
+  }
+  if (time_k) {
     dim3 tg((unsigned)((a.n + TW - 1) / TW), (unsigned)H, (unsigned)B);
     attn_time_fwd_kernel<<<tg, TW * 32, 0, st>>>((const bf16*)qkv, (bf16*)out, lse, a);
     TVTS_LAUNCH_CHECK();
-    a.cls_only = 1;
-  }
-  const int gw = group_warps(a);
-  if (gw) {
+  } else if (gw) {
     dim3 gg((unsigned)(a.mode == 0 ? 1 : a.T), (unsigned)H, (unsigned)B);
     switch (gw) {
 #define TVTS_GF(NW_) case NW_: attn_group_fwd_kernel<NW_><<<gg, NW_ * 32, 0, st>>>((const bf16*)qkv, (bf16*)out, lse, a); break;
@@ -1179,12 +1220,15 @@ extern "C" int tvts_attn_fwd(const void* qkv, void* out, float* lse, int64_t B, 
 #undef TVTS_GF
     }
     TVTS_LAUNCH_CHECK();
-    if (a.mode == 0) return TVTS_OK;
-    a.cls_only = 1;
+  } else {
+    dim3 grid(num_blocks_x(a), (unsigned)H, (unsigned)B);
+    attn_fwd_kernel<<<grid, kThreads, 0, st>>>((const bf16*)qkv, (bf16*)out, lse, a);
+    TVTS_LAUNCH_CHECK();
   }
-  dim3 grid(num_blocks_x(a), (unsigned)H, (unsigned)B);
-  attn_fwd_kernel<<<grid, kThreads, 0, st>>>((const bf16*)qkv, (bf16*)out, lse, a);
-  TVTS_LAUNCH_CHECK();
+  if (sd) {
+    TVTS_CHECK_CUDA(cudaEventRecord(sd->join, sd->stream));
+    TVTS_CHECK_CUDA(cudaStreamWaitEvent(st, sd->join, 0));
+  }
   return TVTS_OK;
 }
 
@@ -1200,14 +1244,30 @@ extern "C" int tvts_attn_bwd(const void* qkv, const void* out, const void* dout,
   const long long rows = (long long)B * N * H;
   attn_delta_kernel<<<(unsigned)((rows + 31) / 32), 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta_ws, (int)B, (int)N, (int)H);
   TVTS_LAUNCH_CHECK();
-  if (use_time_kernels(a)) {
+  const int gw = group_warps(a);
+  const bool time_k = use_time_kernels(a);
+  const bool split = a.mode != 0 && (time_k || gw);
+  SideStream* sd = (split && g_attn_side) ? side_stream() : nullptr;
+  cudaStream_t cls_st = st;
+  if (sd) {
+    TVTS_CHECK_CUDA(cudaEventRecord(sd->fork, st));      // after delta
+    TVTS_CHECK_CUDA(cudaStreamWaitEvent(sd->stream, sd->fork, 0));
+    cls_st = sd->stream;
+  }
+  if (split) {                                             // dq of the CLS query, dk/dv of the CLS key
+    AttnShape c = a;
+    c.cls_only = 1;
+    dim3 grid(num_blocks_x(c), (unsigned)H, (unsigned)B);
+    attn_bwd_kernel<0><<<grid, kThreads, 0, cls_st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, c);
+    TVTS_LAUNCH_CHECK();
+    attn_bwd_kernel<1><<<grid, kThreads, 0, cls_st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, c);
+    TVTS_LAUNCH_CHECK();
+  }
+  if (time_k) {
     dim3 tg((unsigned)((a.n + TW - 1) / TW), (unsigned)H, (unsigned)B);
     attn_time_bwd_kernel<<<tg, TW * 32, 0, st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, a);
     TVTS_LAUNCH_CHECK();
-    a.cls_only = 1;
-  }
-  const int gw = group_warps(a);
-  if (gw) {
+  } else if (gw) {
     dim3 gg((unsigned)(a.mode == 0 ? 1 : a.T), (unsigned)H, (unsigned)B);
     const int smem_bytes = 5 * gw * 16 * 128 + 2 * gw * 16 * 4;
     switch (gw) {
@@ -1224,13 +1284,16 @@ extern "C" int tvts_attn_bwd(const void* qkv, const void* out, const void* dout,
 #undef TVTS_GB
     }
     TVTS_LAUNCH_CHECK();
-    if (a.mode == 0) return TVTS_OK;
-    a.cls_only = 1;
+  } else {
+    dim3 grid(num_blocks_x(a), (unsigned)H, (unsigned)B);
+    attn_bwd_kernel<0><<<grid, kThreads, 0, st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, a);
+    TVTS_LAUNCH_CHECK();
+    attn_bwd_kernel<1><<<grid, kThreads, 0, st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, a);
+    TVTS_LAUNCH_CHECK();
   }
-  dim3 grid(num_blocks_x(a), (unsigned)H, (unsigned)B);
-  attn_bwd_kernel<0><<<grid, kThreads, 0, st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, a);
-  TVTS_LAUNCH_CHECK();
-  attn_bwd_kernel<1><<<grid, kThreads, 0, st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, a);
-  TVTS_LAUNCH_CHECK();
+  if (sd) {
+    TVTS_CHECK_CUDA(cudaEventRecord(sd->join, sd->stream));
+    TVTS_CHECK_CUDA(cudaStreamWaitEvent(st, sd->join, 0));
+  }
   return TVTS_OK;
 }

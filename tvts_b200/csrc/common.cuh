@@ -79,14 +79,21 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 #define TVTS_ACT_QUICK_GELU 1
 #define TVTS_ACT_GELU 2
 
+// sigmoid(z) = 0.5 * (1 + tanh(z / 2)): ONE MUFU op (tanh.approx, rel. error 2^-11) instead of ex2 + rcp -- the c_fc / c_proj-dgrad
+// GEMM epilogues evaluate 32768 activations per tile and were MUFU-bound; their results are rounded to bf16 (2^-9) anyway.
+__device__ __forceinline__ float fast_sigmoid(float z) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
+  return fmaf(0.5f, t, 0.5f);
+}
 __device__ __forceinline__ float act_fwd(float x, int act) {
-  if (act == TVTS_ACT_QUICK_GELU) return x / (1.0f + __expf(-1.702f * x));
+  if (act == TVTS_ACT_QUICK_GELU) return x * fast_sigmoid(1.702f * x);
   if (act == TVTS_ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
   return x;
 }
 __device__ __forceinline__ float act_bwd(float x, int act) {
   if (act == TVTS_ACT_QUICK_GELU) {
-    float s = 1.0f / (1.0f + __expf(-1.702f * x));
+    const float s = fast_sigmoid(1.702f * x);
     return s * (1.0f + 1.702f * x * (1.0f - s));
   }
   if (act == TVTS_ACT_GELU) {
