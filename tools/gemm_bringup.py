@@ -135,11 +135,17 @@ PAIR = [
     dict(name="solo_perf_8192", M=8192, N=8192, K=8192, bf16_out=True, perf=True, pair=0),
 ]
 EPI = [
-    dict(name="epi0_qkv", M=25152, N=2304, K=768, bf16_out=True, perf=True),
-    dict(name="epi1_qkv_nostore", M=25152, N=2304, K=768, bf16_out=True, perf=True, epi=1),
-    dict(name="epi2_qkv_direct", M=25152, N=2304, K=768, bf16_out=True, perf=True, epi=2),
-    dict(name="epi3_qkv_skip", M=25152, N=2304, K=768, bf16_out=True, perf=True, epi=3),
-    dict(name="epi3_8192_skip", M=8192, N=8192, K=8192, bf16_out=True, perf=True, epi=3),
+    dict(name="epi0_qkv", M=25120, N=2304, K=768, bf16_out=True, perf=True, pair=1),
+    dict(name="epi1_qkv_nostore", M=25120, N=2304, K=768, bf16_out=True, perf=True, epi=1, pair=1),
+    dict(name="epi3_qkv_skip", M=25120, N=2304, K=768, bf16_out=True, perf=True, epi=3, pair=1),
+    dict(name="epi0_qkv_f32", M=25120, N=2304, K=768, perf=True, pair=1),
+    dict(name="epi0_text_qkv", M=9856, N=1536, K=512, bf16_out=True, perf=True, pair=1),
+    dict(name="epi3_text_qkv_skip", M=9856, N=1536, K=512, bf16_out=True, perf=True, epi=3, pair=1),
+    dict(name="epi0_text_out", M=9856, N=512, K=512, perf=True, pair=1),
+    dict(name="epi3_text_out_skip", M=9856, N=512, K=512, perf=True, epi=3, pair=1),
+    dict(name="epi0_k3072", M=25120, N=768, K=3072, perf=True, pair=1),
+    dict(name="epi3_k3072_skip", M=25120, N=768, K=3072, perf=True, epi=3, pair=1),
+    dict(name="epi3_8192_skip", M=8192, N=8192, K=8192, bf16_out=True, perf=True, epi=3, pair=1),
 ]
 PERF = [
     dict(name="perf_qkv", M=25152, N=2304, K=768, bf16_out=True, perf=True),

@@ -6,7 +6,8 @@ returns the parameter gradients in reference-parameter order, so nn.Module / DDP
 nn.Parameters with ordinary .grad tensors.
 
 Numerics: fp32 master weights, fp32 residual stream / LayerNorm statistics / softmax / losses; bf16 GEMM operands with
-fp32 accumulation (tcgen05, TMEM); bf16 qkv / attention-output / MLP-hidden activations.
+fp32 accumulation (tcgen05, TMEM); bf16 qkv / attention-output / MLP-hidden activations and bf16 branch gradients (the fp32
+residual-gradient stream is kept in fp32).
 
 Reference semantics restated here (paths relative to /root/reference):
   video tower  v2/model/video_encoder_ViT_B_16.py:176-235 (+ block :113-124, VarAttention :38-76)
@@ -272,7 +273,7 @@ def st_block_bwd(P, p, saved, d_out, d_out_bf, B, N, T, n, H, act):
     _linear_bwd(P, p + "mlp.c_proj.weight", p + "mlp.c_proj.bias", d_out_bf, g)
     dh = lin_dgrad(d_out_bf, P.bf(p + "mlp.c_proj.weight"), BF16, dact=act, aux=h)
     _linear_bwd(P, p + "mlp.c_fc.weight", p + "mlp.c_fc.bias", dh, a2)
-    da2 = lin_dgrad(dh, P.bf(p + "mlp.c_fc.weight"), F32)
+    da2 = lin_dgrad(dh, P.bf(p + "mlp.c_fc.weight"), BF16)   # LN backward reads its dy as bf16: half the traffic of this stream
     dw, db = _ln_grads(P, p, "ln_2")
     d_sr, d_sr_bf = ln_bwd(da2, sr, mu2, rs2, P[p + "ln_2.weight"], res1=d_out, dw=dw, db=db)
     # space attention
@@ -280,7 +281,7 @@ def st_block_bwd(P, p, saved, d_out, d_out_bf, B, N, T, n, H, act):
     do_s = lin_dgrad(d_sr_bf, P.bf(p + "attn.proj.weight"), BF16)
     dqkv_s = attn_bwd(qkv_s, o_s, do_s, lse_s, B, N, H, MODE_SPACE, T, n)
     _linear_bwd(P, p + "attn.qkv.weight", p + "attn.qkv.bias", dqkv_s, a1)
-    da1 = lin_dgrad(dqkv_s, P.bf(p + "attn.qkv.weight"), F32)
+    da1 = lin_dgrad(dqkv_s, P.bf(p + "attn.qkv.weight"), BF16)   # LN backward reads its dy as bf16: half the traffic of this stream
     dw, db = _ln_grads(P, p, "ln_1")
     d_tr, d_tr_bf = ln_bwd(da1, tr, mu1, rs1, P[p + "ln_1.weight"], dw=dw, db=db)     # tr only feeds ln_1
     # time attention
@@ -288,7 +289,7 @@ def st_block_bwd(P, p, saved, d_out, d_out_bf, B, N, T, n, H, act):
     do_t = lin_dgrad(d_tr_bf, P.bf(p + "timeattn.proj.weight"), BF16)
     dqkv_t = attn_bwd(qkv_t, o_t, do_t, lse_t, B, N, H, MODE_TIME, T, n)
     _linear_bwd(P, p + "timeattn.qkv.weight", p + "timeattn.qkv.bias", dqkv_t, a3)
-    da3 = lin_dgrad(dqkv_t, P.bf(p + "timeattn.qkv.weight"), F32)
+    da3 = lin_dgrad(dqkv_t, P.bf(p + "timeattn.qkv.weight"), BF16)   # LN backward reads its dy as bf16: half the traffic of this stream
     dw, db = _ln_grads(P, p, "ln_3")
     d_x, d_x_bf = ln_bwd(da3, x, mu3, rs3, P[p + "ln_3.weight"], res1=d_sr, res2=d_tr, dw=dw, db=db)
     return d_x, d_x_bf
@@ -330,7 +331,7 @@ def block_bwd(P, nm, saved, d_out, d_out_bf, B, S, H, act, causal):
     _linear_bwd(P, nm.proj_w, nm.proj_b, d_out_bf, g)
     dh = lin_dgrad(d_out_bf, P.bf(nm.proj_w), BF16, dact=act, aux=h)
     _linear_bwd(P, nm.fc_w, nm.fc_b, dh, a2)
-    da2 = lin_dgrad(dh, P.bf(nm.fc_w), F32)
+    da2 = lin_dgrad(dh, P.bf(nm.fc_w), BF16)   # LN backward reads its dy as bf16: half the traffic of this stream
     need2 = P.need(nm.ln2 + ".weight") or P.need(nm.ln2 + ".bias")
     d_x1, d_x1_bf = ln_bwd(da2, x1, mu2, rs2, P[nm.ln2 + ".weight"], res1=d_out,
                            dw=P.gbuf(nm.ln2 + ".weight") if need2 else None, db=P.gbuf(nm.ln2 + ".bias") if need2 else None)
@@ -338,7 +339,7 @@ def block_bwd(P, nm, saved, d_out, d_out_bf, B, S, H, act, causal):
     do = lin_dgrad(d_x1_bf, P.bf(nm.out_w), BF16)
     dqkv = attn_bwd(qkv, o, do, lse, B, S, H, MODE_FULL, causal=causal)
     _linear_bwd(P, nm.qkv_w, nm.qkv_b, dqkv, a1)
-    da1 = lin_dgrad(dqkv, P.bf(nm.qkv_w), F32)
+    da1 = lin_dgrad(dqkv, P.bf(nm.qkv_w), BF16)   # LN backward reads its dy as bf16: half the traffic of this stream
     need1 = P.need(nm.ln1 + ".weight") or P.need(nm.ln1 + ".bias")
     d_x, d_x_bf = ln_bwd(da1, x, mu1, rs1, P[nm.ln1 + ".weight"], res1=d_x1,
                          dw=P.gbuf(nm.ln1 + ".weight") if need1 else None, db=P.gbuf(nm.ln1 + ".bias") if need1 else None)

@@ -126,6 +126,8 @@ class TrainStep:
         self.use_graph = use_graph
         self._graphs = {}
         self.launches_per_graph = 0
+        self._copy_stream = None
+        self._staged = None
 
     def to_device(self, data):
         out = {}
@@ -182,7 +184,47 @@ class TrainStep:
         self._graphs[key] = ent
         return ent
 
-    def __call__(self, data):
+    def prefetch(self, data):
+        """Start the host->device copy of the NEXT batch on a dedicated copy stream so that it overlaps the step that is running
+        (what a pipelined data loader does); the following __call__(None) consumes it.  Pinned host tensors copy asynchronously."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._stage_bufs = {}
+        cs = self._copy_stream
+        if self._staged is not None:
+            cs.wait_event(self._staged[2])           # the previous consumer has finished reading the staging buffers
+        with torch.cuda.stream(cs):
+            staged = {}
+            for k, v in data.items():
+                if not torch.is_tensor(v):
+                    continue
+                buf = self._stage_bufs.get(k)
+                if buf is None or buf.shape != v.shape or buf.dtype != v.dtype:
+                    buf = torch.empty(v.shape, dtype=v.dtype, device=self.device)
+                    self._stage_bufs[k] = buf
+                buf.copy_(v, non_blocking=True)
+                staged[k] = buf
+            ready = torch.cuda.Event()
+            ready.record(cs)
+        self._staged = (staged, ready, torch.cuda.Event())
+
+    def _take_staged(self):
+        staged, ready, consumed = self._staged
+        torch.cuda.current_stream().wait_event(ready)
+        return staged, consumed
+
+    def __call__(self, data=None):
+        consumed = None
+        if data is None:
+            if self._staged is None:
+                raise ValueError("TrainStep(None) needs a batch staged with prefetch()")
+            data, consumed = self._take_staged()
+        out = self._run(data)
+        if consumed is not None:
+            consumed.record(torch.cuda.current_stream())   # (graph mode: the static copies are enqueued before this point)
+        return out
+
+    def _run(self, data):
         if not self.use_graph:
             return self._body(self.to_device(data))
         key = tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(data.items()) if torch.is_tensor(v))
