@@ -1152,6 +1152,166 @@ int check_shape(const AttnShape& a, int64_t d) {
   return TVTS_OK;
 }
 
+// ================================================================================================ CLS row / column kernels
+// In the divided modes the CLS token attends to (and is attended by) ALL N tokens: one query row and one key column per (batch,
+// head) -- matrix-vector work.  One CTA per (batch, head): thread-per-token dot products over 16-byte row chunks (the vectors
+// q0 / dO0 / k0 / v0 are broadcast from shared memory), block reductions for the softmax, then warp-split weighted row sums.
+constexpr int CLS_THREADS = 256;
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ float dot8(const uint4& u, const float* v) {
+  float f[8];
+  unpack8(u, f);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s = fmaf(f[i], v[i], s);
+  return s;
+}
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {   // red: >= 9 floats; result broadcast to all
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float r = red[0];
+    for (int w = 1; w < CLS_THREADS / 32; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
+    red[8] = r;
+  }
+  __syncthreads();
+  return red[8];
+}
+
+// out[b, 0, h, :] = softmax(scale * q0 . K^T) V  over all N tokens; lse[b, h, 0]
+__global__ void __launch_bounds__(CLS_THREADS) attn_cls_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse,
+                                                                   AttnShape a) {
+  extern __shared__ __align__(16) float csm[];           // q0 [64] | red [16] | acc [8][64] | p [N]
+  float* q0 = csm;
+  float* red = csm + 64;
+  float* accs = csm + 80;
+  float* p = csm + 80 + 8 * 64;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long rs = 3LL * a.H * HD, ro = (long long)a.H * HD;
+  const bf16* qb = qkv + (long long)b * a.N * rs + (long long)h * HD;
+  const bf16* kb = qb + ro;
+  const bf16* vb = kb + ro;
+  if (threadIdx.x < 64) q0[threadIdx.x] = __bfloat162float(qb[threadIdx.x]) * a.scale;
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < a.N; j += CLS_THREADS) {
+    const uint4* kr = reinterpret_cast<const uint4*>(kb + (long long)j * rs);
+    float sj = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sj += dot8(kr[c], q0 + 8 * c);
+    p[j] = sj;
+    mx = fmaxf(mx, sj);
+  }
+  mx = block_reduce(mx, red, true);
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < a.N; j += CLS_THREADS) {
+    const float e = __expf(p[j] - mx);
+    p[j] = e;
+    sum += e;
+  }
+  sum = block_reduce(sum, red, false);                    // (its barriers also publish p[])
+  float a0 = 0.f, a1 = 0.f;
+  for (int j = warp; j < a.N; j += CLS_THREADS / 32) {
+    const float2 v = unpack_bf16x2(reinterpret_cast<const uint32_t*>(vb + (long long)j * rs)[lane]);
+    const float pj = p[j];
+    a0 = fmaf(pj, v.x, a0);
+    a1 = fmaf(pj, v.y, a1);
+  }
+  accs[warp * 64 + 2 * lane] = a0;
+  accs[warp * 64 + 2 * lane + 1] = a1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float o = 0.f;
+#pragma unroll
+    for (int w = 0; w < CLS_THREADS / 32; ++w) o += accs[w * 64 + threadIdx.x];
+    out[(long long)b * a.N * ro + (long long)h * HD + threadIdx.x] = __float2bfloat16(o / sum);
+  }
+  if (threadIdx.x == 0) lse[((long long)b * a.H + h) * a.N] = mx + __logf(sum);
+}
+
+// dq of the CLS query (row 0 of the probability matrix) and dk / dv of the CLS key (column 0), all of token 0
+__global__ void __launch_bounds__(CLS_THREADS) attn_cls_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+                                                                   const float* __restrict__ lse, const float* __restrict__ delta,
+                                                                   bf16* __restrict__ dqkv, AttnShape a) {
+  extern __shared__ __align__(16) float csm[];           // q0 | do0 | k0 | v0 [64 each] | acc [8][192] | dsA [N] | pB [N] | dsB [N]
+  float* q0 = csm;
+  float* do0 = csm + 64;
+  float* k0 = csm + 128;
+  float* v0 = csm + 192;
+  float* accs = csm + 256;
+  float* dsA = csm + 256 + 8 * 192;
+  float* pB = dsA + a.N;
+  float* dsB = pB + a.N;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long rs = 3LL * a.H * HD, ro = (long long)a.H * HD;
+  const bf16* qb = qkv + (long long)b * a.N * rs + (long long)h * HD;
+  const bf16* kb = qb + ro;
+  const bf16* vb = kb + ro;
+  const bf16* dob = dout + (long long)b * a.N * ro + (long long)h * HD;
+  const float* lse_b = lse + ((long long)b * a.H + h) * a.N;
+  const float* delta_b = delta + ((long long)b * a.H + h) * a.N;
+  if (threadIdx.x < 64) {
+    q0[threadIdx.x] = __bfloat162float(qb[threadIdx.x]) * a.scale;      // scaled: s = (scale q) . k
+    do0[threadIdx.x] = __bfloat162float(dob[threadIdx.x]);
+    k0[threadIdx.x] = __bfloat162float(kb[threadIdx.x]) * a.scale;
+    v0[threadIdx.x] = __bfloat162float(vb[threadIdx.x]);
+  }
+  __syncthreads();
+  const float lse0 = lse_b[0], delta0 = delta_b[0];
+  for (int j = threadIdx.x; j < a.N; j += CLS_THREADS) {
+    const uint4* kr = reinterpret_cast<const uint4*>(kb + (long long)j * rs);
+    const uint4* vr = reinterpret_cast<const uint4*>(vb + (long long)j * rs);
+    const uint4* qr = reinterpret_cast<const uint4*>(qb + (long long)j * rs);
+    const uint4* dr = reinterpret_cast<const uint4*>(dob + (long long)j * ro);
+    float sA = 0.f, dpA = 0.f, sB = 0.f, dpB = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      sA += dot8(kr[c], q0 + 8 * c);
+      dpA += dot8(vr[c], do0 + 8 * c);
+      sB += dot8(qr[c], k0 + 8 * c);
+      dpB += dot8(dr[c], v0 + 8 * c);
+    }
+    const float pa = __expf(sA - lse0);
+    dsA[j] = pa * (dpA - delta0);
+    const float pb = __expf(sB - lse_b[j]);
+    pB[j] = pb;
+    dsB[j] = pb * (dpB - delta_b[j]);
+  }
+  __syncthreads();
+  float dq0 = 0.f, dq1 = 0.f, dk0 = 0.f, dk1 = 0.f, dv0 = 0.f, dv1 = 0.f;
+  for (int j = warp; j < a.N; j += CLS_THREADS / 32) {
+    const float2 k = unpack_bf16x2(reinterpret_cast<const uint32_t*>(kb + (long long)j * rs)[lane]);
+    const float2 q = unpack_bf16x2(reinterpret_cast<const uint32_t*>(qb + (long long)j * rs)[lane]);
+    const float2 d = unpack_bf16x2(reinterpret_cast<const uint32_t*>(dob + (long long)j * ro)[lane]);
+    const float da = dsA[j], db = dsB[j], pb = pB[j];
+    dq0 = fmaf(da, k.x, dq0); dq1 = fmaf(da, k.y, dq1);
+    dk0 = fmaf(db, q.x, dk0); dk1 = fmaf(db, q.y, dk1);
+    dv0 = fmaf(pb, d.x, dv0); dv1 = fmaf(pb, d.y, dv1);
+  }
+  float* ar = accs + warp * 192;
+  ar[2 * lane] = dq0; ar[2 * lane + 1] = dq1;
+  ar[64 + 2 * lane] = dk0; ar[64 + 2 * lane + 1] = dk1;
+  ar[128 + 2 * lane] = dv0; ar[128 + 2 * lane + 1] = dv1;
+  __syncthreads();
+  if (threadIdx.x < 192) {
+    float o = 0.f;
+#pragma unroll
+    for (int w = 0; w < CLS_THREADS / 32; ++w) o += accs[w * 192 + threadIdx.x];
+    const int which = threadIdx.x >> 6, dim = threadIdx.x & 63;       // 0 dq, 1 dk, 2 dv
+    if (which < 2) o *= a.scale;
+    dqkv[(long long)b * a.N * rs + (long long)which * ro + (long long)h * HD + dim] = __float2bfloat16(o);
+  }
+}
+
 // The CLS row / column of the divided modes (one query over all N keys, one key under all N queries: 384 tiny CTAs that stream
 // 13 tiles each) is latency-bound and independent of the group kernels (disjoint outputs), so it runs on a side stream forked
 // from / joined back into the caller's stream with events -- also legal inside a CUDA-graph capture, where it becomes a parallel
@@ -1202,10 +1362,15 @@ extern "C" int tvts_attn_fwd(const void* qkv, void* out, float* lse, int64_t B, 
     cls_st = sd->stream;
   }
   if (split) {                                             // CLS query over all tokens
-    AttnShape c = a;
-    c.cls_only = 1;
-    dim3 grid(num_blocks_x(c), (unsigned)H, (unsigned)B);
-    attn_fwd_kernel<<<grid, kThreads, 0, cls_st>>>((const bf16*)qkv, (bf16*)out, lse, c);
+    const int smem_bytes = (80 + 8 * 64 + a.N) * 4;
+    if (smem_bytes <= 48 * 1024) {
+      attn_cls_fwd_kernel<<<dim3((unsigned)H, (unsigned)B), CLS_THREADS, smem_bytes, cls_st>>>((const bf16*)qkv, (bf16*)out, lse, a);
+    } else {
+      AttnShape c = a;
+      c.cls_only = 1;
+      dim3 grid(num_blocks_x(c), (unsigned)H, (unsigned)B);
+      attn_fwd_kernel<<<grid, kThreads, 0, cls_st>>>((const bf16*)qkv, (bf16*)out, lse, c);
+    }
     TVTS_LAUNCH_CHECK();
   }
   if (time_k) {
@@ -1255,13 +1420,20 @@ extern "C" int tvts_attn_bwd(const void* qkv, const void* out, const void* dout,
     cls_st = sd->stream;
   }
   if (split) {                                             // dq of the CLS query, dk/dv of the CLS key
-    AttnShape c = a;
-    c.cls_only = 1;
-    dim3 grid(num_blocks_x(c), (unsigned)H, (unsigned)B);
-    attn_bwd_kernel<0><<<grid, kThreads, 0, cls_st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, c);
-    TVTS_LAUNCH_CHECK();
-    attn_bwd_kernel<1><<<grid, kThreads, 0, cls_st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, c);
-    TVTS_LAUNCH_CHECK();
+    const int smem_bytes = (256 + 8 * 192 + 3 * a.N) * 4;
+    if (smem_bytes <= 48 * 1024) {
+      attn_cls_bwd_kernel<<<dim3((unsigned)H, (unsigned)B), CLS_THREADS, smem_bytes, cls_st>>>((const bf16*)qkv, (const bf16*)dout, lse,
+                                                                                                delta_ws, (bf16*)dqkv, a);
+      TVTS_LAUNCH_CHECK();
+    } else {
+      AttnShape c = a;
+      c.cls_only = 1;
+      dim3 grid(num_blocks_x(c), (unsigned)H, (unsigned)B);
+      attn_bwd_kernel<0><<<grid, kThreads, 0, cls_st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, c);
+      TVTS_LAUNCH_CHECK();
+      attn_bwd_kernel<1><<<grid, kThreads, 0, cls_st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, c);
+      TVTS_LAUNCH_CHECK();
+    }
   }
   if (time_k) {
     dim3 tg((unsigned)((a.n + TW - 1) / TW), (unsigned)H, (unsigned)B);

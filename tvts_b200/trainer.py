@@ -219,20 +219,19 @@ class TrainStep:
             if self._staged is None:
                 raise ValueError("TrainStep(None) needs a batch staged with prefetch()")
             data, consumed = self._take_staged()
-        out = self._run(data)
-        if consumed is not None:
-            consumed.record(torch.cuda.current_stream())   # (graph mode: the static copies are enqueued before this point)
-        return out
-
-    def _run(self, data):
         if not self.use_graph:
-            return self._body(self.to_device(data))
+            out = self._body(self.to_device(data))
+            if consumed is not None:
+                consumed.record(torch.cuda.current_stream())
+            return out
         key = tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(data.items()) if torch.is_tensor(v))
         ent = self._graphs.get(key)
         if ent is None:
             ent = self._capture(key, data)
         for k, v in ent.static.items():
             v.copy_(data[k], non_blocking=True)
+        if consumed is not None:
+            consumed.record(torch.cuda.current_stream())   # staging buffers are free again: the next H2D copy may start now
         if self.optimizer is not None:
             self.optimizer.prepare()                # host table -> device, stream-ordered before the replay
         ent.graph.replay()
