@@ -1199,16 +1199,28 @@ __global__ void __launch_bounds__(CLS_THREADS) attn_cls_fwd_kernel(const bf16* _
   const bf16* qb = qkv + (long long)b * a.N * rs + (long long)h * HD;
   const bf16* kb = qb + ro;
   const bf16* vb = kb + ro;
-  if (threadIdx.x < 64) q0[threadIdx.x] = __bfloat162float(qb[threadIdx.x]) * a.scale;
-  __syncthreads();
-  float mx = -INFINITY;
-  for (int j = threadIdx.x; j < a.N; j += CLS_THREADS) {
-    const uint4* kr = reinterpret_cast<const uint4*>(kb + (long long)j * rs);
-    float sj = 0.f;
+  // scores: 8 lanes per token (one 16-byte chunk each -> a warp reads 4 whole 128-byte rows per instruction), octet reduction
+  const int sub = threadIdx.x & 7;
+  float q0c[8];
+  {
+    const uint4 u = reinterpret_cast<const uint4*>(qb)[sub];
+    unpack8(u, q0c);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) sj += dot8(kr[c], q0 + 8 * c);
-    p[j] = sj;
-    mx = fmaxf(mx, sj);
+    for (int i = 0; i < 8; ++i) q0c[i] *= a.scale;
+  }
+  (void)q0;
+  float mx = -INFINITY;
+  for (int j0 = 0; j0 < a.N; j0 += CLS_THREADS / 8) {
+    const int j = j0 + (threadIdx.x >> 3);
+    float sj = 0.f;
+    if (j < a.N) sj = dot8(reinterpret_cast<const uint4*>(kb + (long long)j * rs)[sub], q0c);
+    sj += __shfl_xor_sync(0xffffffffu, sj, 1);
+    sj += __shfl_xor_sync(0xffffffffu, sj, 2);
+    sj += __shfl_xor_sync(0xffffffffu, sj, 4);
+    if (j < a.N) {
+      if (sub == 0) p[j] = sj;
+      mx = fmaxf(mx, sj);
+    }
   }
   mx = block_reduce(mx, red, true);
   float sum = 0.f;
@@ -1259,32 +1271,40 @@ __global__ void __launch_bounds__(CLS_THREADS) attn_cls_bwd_kernel(const bf16* _
   const bf16* dob = dout + (long long)b * a.N * ro + (long long)h * HD;
   const float* lse_b = lse + ((long long)b * a.H + h) * a.N;
   const float* delta_b = delta + ((long long)b * a.H + h) * a.N;
-  if (threadIdx.x < 64) {
-    q0[threadIdx.x] = __bfloat162float(qb[threadIdx.x]) * a.scale;      // scaled: s = (scale q) . k
-    do0[threadIdx.x] = __bfloat162float(dob[threadIdx.x]);
-    k0[threadIdx.x] = __bfloat162float(kb[threadIdx.x]) * a.scale;
-    v0[threadIdx.x] = __bfloat162float(vb[threadIdx.x]);
-  }
-  __syncthreads();
-  const float lse0 = lse_b[0], delta0 = delta_b[0];
-  for (int j = threadIdx.x; j < a.N; j += CLS_THREADS) {
-    const uint4* kr = reinterpret_cast<const uint4*>(kb + (long long)j * rs);
-    const uint4* vr = reinterpret_cast<const uint4*>(vb + (long long)j * rs);
-    const uint4* qr = reinterpret_cast<const uint4*>(qb + (long long)j * rs);
-    const uint4* dr = reinterpret_cast<const uint4*>(dob + (long long)j * ro);
-    float sA = 0.f, dpA = 0.f, sB = 0.f, dpB = 0.f;
+  // pass 1: 8 lanes per token (16-byte chunks: a warp reads 4 whole rows per instruction), the four vectors live in registers
+  const int sub = threadIdx.x & 7;
+  float q0c[8], do0c[8], k0c[8], v0c[8];
+  unpack8(reinterpret_cast<const uint4*>(qb)[sub], q0c);
+  unpack8(reinterpret_cast<const uint4*>(dob)[sub], do0c);
+  unpack8(reinterpret_cast<const uint4*>(kb)[sub], k0c);
+  unpack8(reinterpret_cast<const uint4*>(vb)[sub], v0c);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      sA += dot8(kr[c], q0 + 8 * c);
-      dpA += dot8(vr[c], do0 + 8 * c);
-      sB += dot8(qr[c], k0 + 8 * c);
-      dpB += dot8(dr[c], v0 + 8 * c);
+  for (int i = 0; i < 8; ++i) { q0c[i] *= a.scale; k0c[i] *= a.scale; }   // s = (scale q) . k
+  (void)q0; (void)do0; (void)k0; (void)v0;
+  const float lse0 = lse_b[0], delta0 = delta_b[0];
+  for (int j0 = 0; j0 < a.N; j0 += CLS_THREADS / 8) {
+    const int j = j0 + (threadIdx.x >> 3);
+    float sA = 0.f, dpA = 0.f, sB = 0.f, dpB = 0.f;
+    if (j < a.N) {
+      sA = dot8(reinterpret_cast<const uint4*>(kb + (long long)j * rs)[sub], q0c);
+      dpA = dot8(reinterpret_cast<const uint4*>(vb + (long long)j * rs)[sub], do0c);
+      sB = dot8(reinterpret_cast<const uint4*>(qb + (long long)j * rs)[sub], k0c);
+      dpB = dot8(reinterpret_cast<const uint4*>(dob + (long long)j * ro)[sub], v0c);
     }
-    const float pa = __expf(sA - lse0);
-    dsA[j] = pa * (dpA - delta0);
-    const float pb = __expf(sB - lse_b[j]);
-    pB[j] = pb;
-    dsB[j] = pb * (dpB - delta_b[j]);
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      sA += __shfl_xor_sync(0xffffffffu, sA, o);
+      dpA += __shfl_xor_sync(0xffffffffu, dpA, o);
+      sB += __shfl_xor_sync(0xffffffffu, sB, o);
+      dpB += __shfl_xor_sync(0xffffffffu, dpB, o);
+    }
+    if (j < a.N && sub == 0) {
+      const float pa = __expf(sA - lse0);
+      dsA[j] = pa * (dpA - delta0);
+      const float pb = __expf(sB - lse_b[j]);
+      pB[j] = pb;
+      dsB[j] = pb * (dpB - delta_b[j]);
+    }
   }
   __syncthreads();
   float dq0 = 0.f, dq1 = 0.f, dk0 = 0.f, dk1 = 0.f, dv0 = 0.f, dv1 = 0.f;
