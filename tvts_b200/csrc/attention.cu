@@ -1210,16 +1210,25 @@ __global__ void __launch_bounds__(CLS_THREADS) attn_cls_fwd_kernel(const bf16* _
   }
   (void)q0;
   float mx = -INFINITY;
-  for (int j0 = 0; j0 < a.N; j0 += CLS_THREADS / 8) {
-    const int j = j0 + (threadIdx.x >> 3);
-    float sj = 0.f;
-    if (j < a.N) sj = dot8(reinterpret_cast<const uint4*>(kb + (long long)j * rs)[sub], q0c);
-    sj += __shfl_xor_sync(0xffffffffu, sj, 1);
-    sj += __shfl_xor_sync(0xffffffffu, sj, 2);
-    sj += __shfl_xor_sync(0xffffffffu, sj, 4);
-    if (j < a.N) {
-      if (sub == 0) p[j] = sj;
-      mx = fmaxf(mx, sj);
+  constexpr int TPI = CLS_THREADS / 8;                   // tokens per CTA iteration
+  for (int j0 = 0; j0 < a.N; j0 += 4 * TPI) {            // 4 independent row loads in flight per thread
+    uint4 kr[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * TPI + (threadIdx.x >> 3);
+      kr[u] = j < a.N ? reinterpret_cast<const uint4*>(kb + (long long)j * rs)[sub] : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * TPI + (threadIdx.x >> 3);
+      float sj = dot8(kr[u], q0c);
+      sj += __shfl_xor_sync(0xffffffffu, sj, 1);
+      sj += __shfl_xor_sync(0xffffffffu, sj, 2);
+      sj += __shfl_xor_sync(0xffffffffu, sj, 4);
+      if (j < a.N) {
+        if (sub == 0) p[j] = sj;
+        mx = fmaxf(mx, sj);
+      }
     }
   }
   mx = block_reduce(mx, red, true);
@@ -1231,11 +1240,23 @@ __global__ void __launch_bounds__(CLS_THREADS) attn_cls_fwd_kernel(const bf16* _
   }
   sum = block_reduce(sum, red, false);                    // (its barriers also publish p[])
   float a0 = 0.f, a1 = 0.f;
-  for (int j = warp; j < a.N; j += CLS_THREADS / 32) {
-    const float2 v = unpack_bf16x2(reinterpret_cast<const uint32_t*>(vb + (long long)j * rs)[lane]);
-    const float pj = p[j];
-    a0 = fmaf(pj, v.x, a0);
-    a1 = fmaf(pj, v.y, a1);
+  constexpr int NWARP = CLS_THREADS / 32;
+  for (int j0 = warp; j0 < a.N; j0 += 8 * NWARP) {       // 8 independent row loads in flight per warp
+    uint32_t vr[8];
+    float pj[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + u * NWARP;
+      const bool ok = j < a.N;
+      vr[u] = ok ? reinterpret_cast<const uint32_t*>(vb + (long long)j * rs)[lane] : 0u;
+      pj[u] = ok ? p[j] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float2 v = unpack_bf16x2(vr[u]);
+      a0 = fmaf(pj[u], v.x, a0);
+      a1 = fmaf(pj[u], v.y, a1);
+    }
   }
   accs[warp * 64 + 2 * lane] = a0;
   accs[warp * 64 + 2 * lane + 1] = a1;
@@ -1282,40 +1303,64 @@ __global__ void __launch_bounds__(CLS_THREADS) attn_cls_bwd_kernel(const bf16* _
   for (int i = 0; i < 8; ++i) { q0c[i] *= a.scale; k0c[i] *= a.scale; }   // s = (scale q) . k
   (void)q0; (void)do0; (void)k0; (void)v0;
   const float lse0 = lse_b[0], delta0 = delta_b[0];
-  for (int j0 = 0; j0 < a.N; j0 += CLS_THREADS / 8) {
-    const int j = j0 + (threadIdx.x >> 3);
-    float sA = 0.f, dpA = 0.f, sB = 0.f, dpB = 0.f;
-    if (j < a.N) {
-      sA = dot8(reinterpret_cast<const uint4*>(kb + (long long)j * rs)[sub], q0c);
-      dpA = dot8(reinterpret_cast<const uint4*>(vb + (long long)j * rs)[sub], do0c);
-      sB = dot8(reinterpret_cast<const uint4*>(qb + (long long)j * rs)[sub], k0c);
-      dpB = dot8(reinterpret_cast<const uint4*>(dob + (long long)j * ro)[sub], v0c);
+  constexpr int TPI = CLS_THREADS / 8;
+  for (int j0 = 0; j0 < a.N; j0 += 2 * TPI) {            // 8 independent 16-byte loads in flight per thread
+    uint4 rk[2], rv[2], rq[2], rd[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int j = j0 + u * TPI + (threadIdx.x >> 3);
+      const bool ok = j < a.N;
+      const long long jj = ok ? j : 0;
+      rk[u] = reinterpret_cast<const uint4*>(kb + jj * rs)[sub];
+      rv[u] = reinterpret_cast<const uint4*>(vb + jj * rs)[sub];
+      rq[u] = reinterpret_cast<const uint4*>(qb + jj * rs)[sub];
+      rd[u] = reinterpret_cast<const uint4*>(dob + jj * ro)[sub];
     }
 #pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-      sA += __shfl_xor_sync(0xffffffffu, sA, o);
-      dpA += __shfl_xor_sync(0xffffffffu, dpA, o);
-      sB += __shfl_xor_sync(0xffffffffu, sB, o);
-      dpB += __shfl_xor_sync(0xffffffffu, dpB, o);
-    }
-    if (j < a.N && sub == 0) {
-      const float pa = __expf(sA - lse0);
-      dsA[j] = pa * (dpA - delta0);
-      const float pb = __expf(sB - lse_b[j]);
-      pB[j] = pb;
-      dsB[j] = pb * (dpB - delta_b[j]);
+    for (int u = 0; u < 2; ++u) {
+      const int j = j0 + u * TPI + (threadIdx.x >> 3);
+      float sA = dot8(rk[u], q0c), dpA = dot8(rv[u], do0c), sB = dot8(rq[u], k0c), dpB = dot8(rd[u], v0c);
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        sA += __shfl_xor_sync(0xffffffffu, sA, o);
+        dpA += __shfl_xor_sync(0xffffffffu, dpA, o);
+        sB += __shfl_xor_sync(0xffffffffu, sB, o);
+        dpB += __shfl_xor_sync(0xffffffffu, dpB, o);
+      }
+      if (j < a.N && sub == 0) {
+        const float pa = __expf(sA - lse0);
+        dsA[j] = pa * (dpA - delta0);
+        const float pb = __expf(sB - lse_b[j]);
+        pB[j] = pb;
+        dsB[j] = pb * (dpB - delta_b[j]);
+      }
     }
   }
   __syncthreads();
   float dq0 = 0.f, dq1 = 0.f, dk0 = 0.f, dk1 = 0.f, dv0 = 0.f, dv1 = 0.f;
-  for (int j = warp; j < a.N; j += CLS_THREADS / 32) {
-    const float2 k = unpack_bf16x2(reinterpret_cast<const uint32_t*>(kb + (long long)j * rs)[lane]);
-    const float2 q = unpack_bf16x2(reinterpret_cast<const uint32_t*>(qb + (long long)j * rs)[lane]);
-    const float2 d = unpack_bf16x2(reinterpret_cast<const uint32_t*>(dob + (long long)j * ro)[lane]);
-    const float da = dsA[j], db = dsB[j], pb = pB[j];
-    dq0 = fmaf(da, k.x, dq0); dq1 = fmaf(da, k.y, dq1);
-    dk0 = fmaf(db, q.x, dk0); dk1 = fmaf(db, q.y, dk1);
-    dv0 = fmaf(pb, d.x, dv0); dv1 = fmaf(pb, d.y, dv1);
+  constexpr int NWARP = CLS_THREADS / 32;
+  for (int j0 = warp; j0 < a.N; j0 += 4 * NWARP) {       // 12 independent row loads in flight per warp
+    uint32_t rk[4], rq[4], rd[4];
+    float da[4], db[4], pb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * NWARP;
+      const bool ok = j < a.N;
+      const long long jj = ok ? j : 0;
+      rk[u] = reinterpret_cast<const uint32_t*>(kb + jj * rs)[lane];
+      rq[u] = reinterpret_cast<const uint32_t*>(qb + jj * rs)[lane];
+      rd[u] = reinterpret_cast<const uint32_t*>(dob + jj * ro)[lane];
+      da[u] = ok ? dsA[j] : 0.f;
+      db[u] = ok ? dsB[j] : 0.f;
+      pb[u] = ok ? pB[j] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2 k = unpack_bf16x2(rk[u]), q = unpack_bf16x2(rq[u]), d = unpack_bf16x2(rd[u]);
+      dq0 = fmaf(da[u], k.x, dq0); dq1 = fmaf(da[u], k.y, dq1);
+      dk0 = fmaf(db[u], q.x, dk0); dk1 = fmaf(db[u], q.y, dk1);
+      dv0 = fmaf(pb[u], d.x, dv0); dv1 = fmaf(pb[u], d.y, dv1);
+    }
   }
   float* ar = accs + warp * 192;
   ar[2 * lane] = dq0; ar[2 * lane + 1] = dq1;

@@ -162,7 +162,9 @@ __global__ void text_embed_bwd_kernel(const float* __restrict__ dx, const TokT* 
     for (long long r = blockIdx.y; r < rows; r += gridDim.y) {
       float4 d = reinterpret_cast<const float4*>(dx)[(r * L + l) * W4 + c];
       acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
-      if (dtable) {
+      // positions after the EOT token receive an exactly-zero gradient (causal attention, EOT pooling); skipping them removes
+      // thousands of contended atomics on the padding row (id 0) without changing the sum
+      if (dtable && (d.x != 0.f || d.y != 0.f || d.z != 0.f || d.w != 0.f)) {
         const long long id = (long long)tok[r * L + l];
         float* pt = dtable + (id * W4 + c) * 4;
         atomicAdd(pt + 0, d.x); atomicAdd(pt + 1, d.y); atomicAdd(pt + 2, d.z); atomicAdd(pt + 3, d.w);
