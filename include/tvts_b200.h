@@ -107,6 +107,15 @@ int tvts_attn_set_side_stream(int on);
 int tvts_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv, int64_t B, int64_t N,
                   int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal, float scale, void* stream);
 
+/* Query-window attention (mode FULL, non-causal): only rows [q0, q0+qn) of every sample are queries, all N tokens are keys/values.
+ * Used for the LAST block of the sort head, whose only consumed outputs are its n_trans transcript rows
+ * (v2/model/sort_transformer.py:134-142).  fwd writes out / lse for the window rows only.  bwd writes dq for the window rows only
+ * (the caller zero-fills dqkv first) and dk / dv for every token; rows of out / dout outside the window must be finite (zero). */
+int tvts_attn_window_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t N, int64_t H, int64_t d, int64_t q0, int64_t qn,
+                         float scale, void* stream);
+int tvts_attn_window_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv, int64_t B,
+                         int64_t N, int64_t H, int64_t d, int64_t q0, int64_t qn, float scale, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Video token front end (v2/model/video_encoder_ViT_B_16.py:176-216).
  *   patch_gather: video [B,T,3,R,R] f32 + keep_ind [B,n] int64 -> im2col rows of the KEPT patches only,

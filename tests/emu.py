@@ -116,6 +116,25 @@ def attn_bwd(qkv, out, dout, lse, delta, dqkv, B, N, H, d, mode, T, n, causal, s
     dqkv.view(B, N, 3, H, d).copy_(r.to(BF16))
 
 
+def attn_window_fwd(qkv, out, lse, B, N, H, d, q0, qn, scale):
+    o = torch.empty(B * N, H * d, dtype=BF16, device=qkv.device)
+    l = torch.empty(B, H, N, device=qkv.device)
+    attn_fwd(qkv, o, l, B, N, H, d, 0, 0, 0, 0, scale)
+    out.view(B, N, H * d)[:, q0:q0 + qn].copy_(o.view(B, N, H * d)[:, q0:q0 + qn])
+    lse.view(B, H, N)[:, :, q0:q0 + qn].copy_(l[:, :, q0:q0 + qn])
+
+
+def attn_window_bwd(qkv, out, dout, lse, delta, dqkv, B, N, H, d, q0, qn, scale):
+    # queries outside the window do not exist: mask their probabilities by zeroing dout / out there and using a huge lse
+    o = torch.zeros(B, N, H * d, dtype=out.dtype, device=out.device)
+    do = torch.zeros_like(o)
+    l = torch.full((B, H, N), 1e30, device=lse.device)
+    o[:, q0:q0 + qn] = out.view(B, N, H * d)[:, q0:q0 + qn]
+    do[:, q0:q0 + qn] = dout.view(B, N, H * d)[:, q0:q0 + qn]
+    l[:, :, q0:q0 + qn] = lse.view(B, H, N)[:, :, q0:q0 + qn]
+    attn_bwd(qkv, o.view(B * N, H * d), do.view(B * N, H * d), l, delta, dqkv, B, N, H, d, 0, 0, 0, 0, scale)
+
+
 def layernorm_fwd(x, g, b, y, y_bf16, mean, rstd, M, D, eps):
     x = x.view(M, D)
     mu = x.mean(-1, keepdim=True)

@@ -157,6 +157,33 @@ def test_attention(B, H, mode, T, n, N, causal):
     close(grads[0], grads[1], atol=3e-2, rtol=3e-2, what="attn dqkv")
 
 
+@pytest.mark.parametrize("B,H,N,q0,qn", [(2, 2, 103, 99, 4), (2, 8, 789, 785, 4), (1, 2, 300, 100, 70)])
+def test_attention_query_window(B, H, N, q0, qn):
+    """Only rows [q0, q0+qn) are queries (last sort-head block): fwd rows, dq of the window, dk/dv of every token."""
+    torch.manual_seed(N)
+    d = 64
+    qkv = rnd(B, N, 3 * H * d, scale=1.0).to(BF16)
+    scale = d ** -0.5
+    res = []
+    for fn in (L.call, lambda nme, *a: emu.OPS[nme](*a)):
+        out = torch.zeros(B * N, H * d, device=DEV, dtype=BF16)
+        lse = torch.zeros(B, H, N, device=DEV)
+        fn("attn_window_fwd", qkv, out, lse, B, N, H, d, q0, qn, scale)
+        res.append((out, lse))
+    close(res[0][0], res[1][0], atol=2e-2, what="window out")
+    close(res[0][1], res[1][1], atol=1e-3, what="window lse")
+    out, lse = res[1]
+    dout = torch.zeros(B, N, H * d, device=DEV, dtype=BF16)
+    dout[:, q0:q0 + qn] = rnd(B, qn, H * d).to(BF16)
+    grads = []
+    for fn in (L.call, lambda nme, *a: emu.OPS[nme](*a)):
+        dqkv = torch.zeros_like(qkv)
+        delta = torch.empty_like(lse)
+        fn("attn_window_bwd", qkv, out, dout.view(B * N, H * d), lse, delta, dqkv, B, N, H, d, q0, qn, scale)
+        grads.append(dqkv)
+    close(grads[0], grads[1], atol=3e-2, rtol=3e-2, what="window dqkv")
+
+
 # ------------------------------------------------------------------------------------------------ glue kernels
 def both(name, make):
     """run op `name` with the real kernel and the restatement on identical fresh argument lists; return the two lists"""

@@ -38,6 +38,7 @@ struct AttnShape {
   int causal;  // mode 0 only
   float scale;
   int cls_only;  // modes 1/2: launch covers only the CLS group (used next to the time kernels)
+  int q0, qn;    // mode 0 only: QUERY WINDOW [q0, q0+qn) (qn = 0: all N rows are queries); keys are always all N tokens
 };
 
 struct Sets {
@@ -50,18 +51,27 @@ __host__ __device__ inline int chunks_per_group(const AttnShape& a) {
   const int len = a.mode == 1 ? a.n : a.T;
   return (len + BM - 1) / BM;
 }
-__host__ __device__ inline int num_blocks_x(const AttnShape& a) {
-  if (a.mode == 0) return chunks_per_group(a);
+// grid.x of a streamed launch; `transposed` = the dK/dV role (stationary rows are keys)
+__host__ __device__ inline int num_blocks_x(const AttnShape& a, bool transposed = false) {
+  if (a.mode == 0) return (a.qn > 0 && !transposed) ? (a.qn + BM - 1) / BM : chunks_per_group(a);
   if (a.cls_only) return 1;
   const int groups = a.mode == 1 ? a.T : a.n;
   return groups * chunks_per_group(a) + 1;  // + the CLS group
 }
 
-__device__ inline Sets decode_sets(const AttnShape& a, int bx) {
+__device__ inline Sets decode_sets(const AttnShape& a, int bx, bool transposed = false) {
   Sets s;
   if (a.mode == 0) {
-    s.st_base = bx * BM; s.st_stride = 1; s.st_count = min(BM, a.N - s.st_base);
-    s.sm_has0 = 0; s.sm_base = 0; s.sm_stride = 1; s.sm_count = a.N;
+    if (a.qn > 0 && !transposed) {        // stationary = the query window, streamed = every key
+      s.st_base = a.q0 + bx * BM; s.st_stride = 1; s.st_count = min(BM, a.q0 + a.qn - s.st_base);
+      s.sm_has0 = 0; s.sm_base = 0; s.sm_stride = 1; s.sm_count = a.N;
+    } else if (a.qn > 0) {                // stationary = every key, streamed = the query window
+      s.st_base = bx * BM; s.st_stride = 1; s.st_count = min(BM, a.N - s.st_base);
+      s.sm_has0 = 0; s.sm_base = a.q0; s.sm_stride = 1; s.sm_count = a.qn;
+    } else {
+      s.st_base = bx * BM; s.st_stride = 1; s.st_count = min(BM, a.N - s.st_base);
+      s.sm_has0 = 0; s.sm_base = 0; s.sm_stride = 1; s.sm_count = a.N;
+    }
     return s;
   }
   const int cpg = chunks_per_group(a);
@@ -337,7 +347,7 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_kernel(const bf16* __restri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const int h = blockIdx.y, b = blockIdx.z;
-  const Sets s = decode_sets(a, blockIdx.x);
+  const Sets s = decode_sets(a, blockIdx.x, ROLE == 1);
   const long long rs = 3LL * a.H * HD, ro = (long long)a.H * HD;
   const bf16* qb = qkv + (long long)b * a.N * rs + (long long)h * HD;
   const bf16* kb = qb + ro;
@@ -1239,27 +1249,38 @@ __global__ void __launch_bounds__(CLS_THREADS) attn_cls_fwd_kernel(const bf16* _
     sum += e;
   }
   sum = block_reduce(sum, red, false);                    // (its barriers also publish p[])
-  float a0 = 0.f, a1 = 0.f;
-  constexpr int NWARP = CLS_THREADS / 32;
-  for (int j0 = warp; j0 < a.N; j0 += 8 * NWARP) {       // 8 independent row loads in flight per warp
-    uint32_t vr[8];
+  // weighted row sum: 8 lanes per token again (16-byte loads, 8 rows in flight per lane); lane (octet group g8, chunk sub)
+  // accumulates dims 8*sub..8*sub+7 over tokens j = g8 (mod 32); groups are reduced by shuffles, warps through shared memory
+  float acc8[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc8[i] = 0.f;
+  for (int j0 = 0; j0 < a.N; j0 += 8 * TPI) {
+    uint4 vr[8];
     float pj[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int j = j0 + u * NWARP;
+      const int j = j0 + u * TPI + (threadIdx.x >> 3);
       const bool ok = j < a.N;
-      vr[u] = ok ? reinterpret_cast<const uint32_t*>(vb + (long long)j * rs)[lane] : 0u;
+      vr[u] = ok ? reinterpret_cast<const uint4*>(vb + (long long)j * rs)[sub] : make_uint4(0, 0, 0, 0);
       pj[u] = ok ? p[j] : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const float2 v = unpack_bf16x2(vr[u]);
-      a0 = fmaf(pj[u], v.x, a0);
-      a1 = fmaf(pj[u], v.y, a1);
+      float f[8];
+      unpack8(vr[u], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc8[i] = fmaf(pj[u], f[i], acc8[i]);
     }
   }
-  accs[warp * 64 + 2 * lane] = a0;
-  accs[warp * 64 + 2 * lane + 1] = a1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc8[i] += __shfl_xor_sync(0xffffffffu, acc8[i], 8);
+    acc8[i] += __shfl_xor_sync(0xffffffffu, acc8[i], 16);
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) accs[warp * 64 + 8 * lane + i] = acc8[i];
+  }
   __syncthreads();
   if (threadIdx.x < 64) {
     float o = 0.f;
@@ -1337,35 +1358,52 @@ __global__ void __launch_bounds__(CLS_THREADS) attn_cls_bwd_kernel(const bf16* _
     }
   }
   __syncthreads();
-  float dq0 = 0.f, dq1 = 0.f, dk0 = 0.f, dk1 = 0.f, dv0 = 0.f, dv1 = 0.f;
-  constexpr int NWARP = CLS_THREADS / 32;
-  for (int j0 = warp; j0 < a.N; j0 += 4 * NWARP) {       // 12 independent row loads in flight per warp
-    uint32_t rk[4], rq[4], rd[4];
+  // pass 2: weighted row sums in the same octet layout (12 independent 16-byte loads in flight per lane)
+  float dq8[8], dk8[8], dv8[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dq8[i] = dk8[i] = dv8[i] = 0.f;
+  for (int j0 = 0; j0 < a.N; j0 += 4 * TPI) {
+    uint4 rk[4], rq[4], rd[4];
     float da[4], db[4], pb[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int j = j0 + u * NWARP;
+      const int j = j0 + u * TPI + (threadIdx.x >> 3);
       const bool ok = j < a.N;
       const long long jj = ok ? j : 0;
-      rk[u] = reinterpret_cast<const uint32_t*>(kb + jj * rs)[lane];
-      rq[u] = reinterpret_cast<const uint32_t*>(qb + jj * rs)[lane];
-      rd[u] = reinterpret_cast<const uint32_t*>(dob + jj * ro)[lane];
+      rk[u] = reinterpret_cast<const uint4*>(kb + jj * rs)[sub];
+      rq[u] = reinterpret_cast<const uint4*>(qb + jj * rs)[sub];
+      rd[u] = reinterpret_cast<const uint4*>(dob + jj * ro)[sub];
       da[u] = ok ? dsA[j] : 0.f;
       db[u] = ok ? dsB[j] : 0.f;
       pb[u] = ok ? pB[j] : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const float2 k = unpack_bf16x2(rk[u]), q = unpack_bf16x2(rq[u]), d = unpack_bf16x2(rd[u]);
-      dq0 = fmaf(da[u], k.x, dq0); dq1 = fmaf(da[u], k.y, dq1);
-      dk0 = fmaf(db[u], q.x, dk0); dk1 = fmaf(db[u], q.y, dk1);
-      dv0 = fmaf(pb[u], d.x, dv0); dv1 = fmaf(pb[u], d.y, dv1);
+      float fk[8], fq[8], fd[8];
+      unpack8(rk[u], fk); unpack8(rq[u], fq); unpack8(rd[u], fd);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        dq8[i] = fmaf(da[u], fk[i], dq8[i]);
+        dk8[i] = fmaf(db[u], fq[i], dk8[i]);
+        dv8[i] = fmaf(pb[u], fd[i], dv8[i]);
+      }
     }
   }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    dq8[i] += __shfl_xor_sync(0xffffffffu, dq8[i], 8); dq8[i] += __shfl_xor_sync(0xffffffffu, dq8[i], 16);
+    dk8[i] += __shfl_xor_sync(0xffffffffu, dk8[i], 8); dk8[i] += __shfl_xor_sync(0xffffffffu, dk8[i], 16);
+    dv8[i] += __shfl_xor_sync(0xffffffffu, dv8[i], 8); dv8[i] += __shfl_xor_sync(0xffffffffu, dv8[i], 16);
+  }
   float* ar = accs + warp * 192;
-  ar[2 * lane] = dq0; ar[2 * lane + 1] = dq1;
-  ar[64 + 2 * lane] = dk0; ar[64 + 2 * lane + 1] = dk1;
-  ar[128 + 2 * lane] = dv0; ar[128 + 2 * lane + 1] = dv1;
+  if (lane < 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      ar[8 * lane + i] = dq8[i];
+      ar[64 + 8 * lane + i] = dk8[i];
+      ar[128 + 8 * lane + i] = dv8[i];
+    }
+  }
   __syncthreads();
   if (threadIdx.x < 192) {
     float o = 0.f;
@@ -1410,7 +1448,7 @@ extern "C" int tvts_attn_set_side_stream(int on) {
 
 extern "C" int tvts_attn_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T,
                              int64_t n, int64_t causal, float scale, void* stream) {
-  AttnShape a{(int)B, (int)N, (int)H, (int)mode, (int)T, (int)n, (int)causal, scale, 0};
+  AttnShape a{(int)B, (int)N, (int)H, (int)mode, (int)T, (int)n, (int)causal, scale, 0, 0, 0};
   if (B == 0) return TVTS_OK;
   int rc = check_shape(a, d);
   if (rc) return rc;
@@ -1465,7 +1503,7 @@ extern "C" int tvts_attn_fwd(const void* qkv, void* out, float* lse, int64_t B, 
 extern "C" int tvts_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv, int64_t B,
                              int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal, float scale,
                              void* stream) {
-  AttnShape a{(int)B, (int)N, (int)H, (int)mode, (int)T, (int)n, (int)causal, scale, 0};
+  AttnShape a{(int)B, (int)N, (int)H, (int)mode, (int)T, (int)n, (int)causal, scale, 0, 0, 0};
   if (B == 0) return TVTS_OK;
   int rc = check_shape(a, d);
   if (rc) return rc;
@@ -1532,5 +1570,44 @@ extern "C" int tvts_attn_bwd(const void* qkv, const void* out, const void* dout,
     TVTS_CHECK_CUDA(cudaEventRecord(sd->join, sd->stream));
     TVTS_CHECK_CUDA(cudaStreamWaitEvent(st, sd->join, 0));
   }
+  return TVTS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ query-window attention
+// Full (non-causal) attention where only rows [q0, q0+qn) of every sample act as QUERIES while all N tokens are keys / values:
+// the last block of the sort head feeds the loss through its n_trans transcript rows only (v2/model/sort_transformer.py:134-142),
+// so its attention, projection and MLP are evaluated for those rows alone (identical results, ~S/n_trans times less work).
+extern "C" int tvts_attn_window_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t N, int64_t H, int64_t d, int64_t q0,
+                                    int64_t qn, float scale, void* stream) {
+  AttnShape a{(int)B, (int)N, (int)H, 0, 0, 0, 0, scale, 0, (int)q0, (int)qn};
+  if (B == 0 || qn == 0) return TVTS_OK;
+  int rc = check_shape(a, d);
+  if (rc) return rc;
+  TVTS_REQUIRE(qkv && out && lse && q0 >= 0 && qn > 0 && q0 + qn <= N, "attn_window_fwd: bad arguments");
+  dim3 grid(num_blocks_x(a), (unsigned)H, (unsigned)B);
+  attn_fwd_kernel<<<grid, kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const bf16*)qkv, (bf16*)out, lse, a);
+  TVTS_LAUNCH_CHECK();
+  return TVTS_OK;
+}
+
+// dq is written for the window rows only (the caller zero-fills dqkv first); dk / dv are written for every token.
+// `out` / `dout` rows outside the window are never read by the dQ / dK,dV kernels (delta_ws is filled for all rows).
+extern "C" int tvts_attn_window_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv,
+                                    int64_t B, int64_t N, int64_t H, int64_t d, int64_t q0, int64_t qn, float scale, void* stream) {
+  AttnShape a{(int)B, (int)N, (int)H, 0, 0, 0, 0, scale, 0, (int)q0, (int)qn};
+  if (B == 0 || qn == 0) return TVTS_OK;
+  int rc = check_shape(a, d);
+  if (rc) return rc;
+  TVTS_REQUIRE(qkv && out && dout && lse && delta_ws && dqkv && q0 >= 0 && qn > 0 && q0 + qn <= N, "attn_window_bwd: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long rows = (long long)B * N * H;
+  attn_delta_kernel<<<(unsigned)((rows + 31) / 32), 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta_ws, (int)B, (int)N, (int)H);
+  TVTS_LAUNCH_CHECK();
+  dim3 g0(num_blocks_x(a, false), (unsigned)H, (unsigned)B);
+  attn_bwd_kernel<0><<<g0, kThreads, 0, st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, a);
+  TVTS_LAUNCH_CHECK();
+  dim3 g1(num_blocks_x(a, true), (unsigned)H, (unsigned)B);
+  attn_bwd_kernel<1><<<g1, kThreads, 0, st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, a);
+  TVTS_LAUNCH_CHECK();
   return TVTS_OK;
 }

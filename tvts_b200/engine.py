@@ -180,6 +180,28 @@ def attn_bwd(qkv, out, dout, lse, B, N, H, mode, T=0, n=0, causal=False):
     return dqkv
 
 
+def gather_rows_any(src, idx, rows):
+    """dst[r] = src[idx[r]] for fp32 or bf16 row-major matrices (bf16 rows are moved as fp32 words)."""
+    D = src.shape[1]
+    dst = torch.empty((rows, D), dtype=src.dtype, device=src.device)
+    if src.dtype == BF16:
+        L.call("gather_rows", src.view(F32), idx, dst.view(F32), rows, D // 2)
+    else:
+        L.call("gather_rows", src, idx, dst, rows, D)
+    return dst
+
+
+def scatter_rows_into_zeros(src, idx, total_rows):
+    """zeros[total_rows, D] with dst[idx[r]] = src[r] (fp32 or bf16)."""
+    rows, D = src.shape
+    dst = torch.zeros((total_rows, D), dtype=src.dtype, device=src.device)
+    if src.dtype == BF16:
+        L.call("scatter_rows", src.view(F32), idx, dst.view(F32), rows, D // 2, 0)
+    else:
+        L.call("scatter_rows", src, idx, dst, rows, D, 0)
+    return dst
+
+
 # --------------------------------------------------------------------------------------------------
 # parameter access helpers
 # --------------------------------------------------------------------------------------------------
@@ -344,6 +366,55 @@ def block_bwd(P, nm, saved, d_out, d_out_bf, B, S, H, act, causal):
     d_x, d_x_bf = ln_bwd(da1, x, mu1, rs1, P[nm.ln1 + ".weight"], res1=d_x1,
                          dw=P.gbuf(nm.ln1 + ".weight") if need1 else None, db=P.gbuf(nm.ln1 + ".bias") if need1 else None)
     return d_x, d_x_bf
+
+
+# --------------------------------------------------------------------------------------------------
+# LAST block of the sort head: only its n_trans transcript rows are consumed (norm + head, sort_transformer.py:134-142), so the
+# attention queries, the projection and the MLP are evaluated for those rows alone; K / V (hence LN1 + the qkv GEMM) still cover
+# every token.  Identical results, ~S / n_trans times less attention / MLP work in this block (forward and backward).
+# --------------------------------------------------------------------------------------------------
+def window_block_fwd(P, nm, z, idx, B, S, q0, qn, H, act, eps):
+    E_ = z.shape[1]
+    d = E_ // H
+    a1, mu1, rs1 = ln_fwd(z, P[nm.ln1 + ".weight"], P[nm.ln1 + ".bias"], eps)
+    qkv = lin_fwd(a1, P.bf(nm.qkv_w), P[nm.qkv_b], BF16)
+    o = _zeros((B * S, E_), BF16, z)
+    lse = _zeros((B, H, S), F32, z)
+    L.call("attn_window_fwd", qkv, o, lse, B, S, H, d, q0, qn, float(d ** -0.5))
+    o_t = gather_rows_any(o, idx, B * qn)
+    z_t = gather_rows_any(z, idx, B * qn)
+    x1 = lin_fwd(o_t, P.bf(nm.out_w), P[nm.out_b], F32, residual=z_t)
+    a2, mu2, rs2 = ln_fwd(x1, P[nm.ln2 + ".weight"], P[nm.ln2 + ".bias"], eps)
+    g, h = lin_fwd(a2, P.bf(nm.fc_w), P[nm.fc_b], BF16, act=act, want_pre=True)
+    out = lin_fwd(g, P.bf(nm.proj_w), P[nm.proj_b], F32, residual=x1)
+    return out, (z, a1, mu1, rs1, qkv, o, lse, o_t, x1, a2, mu2, rs2, h, g)
+
+
+def window_block_bwd(P, nm, saved, d_out, idx, B, S, q0, qn, H, act):
+    (z, a1, mu1, rs1, qkv, o, lse, o_t, x1, a2, mu2, rs2, h, g) = saved
+    E_ = z.shape[1]
+    d = E_ // H
+    d_out_bf = cast_bf16(d_out)
+    _linear_bwd(P, nm.proj_w, nm.proj_b, d_out_bf, g)
+    dh = lin_dgrad(d_out_bf, P.bf(nm.proj_w), BF16, dact=act, aux=h)
+    _linear_bwd(P, nm.fc_w, nm.fc_b, dh, a2)
+    da2 = lin_dgrad(dh, P.bf(nm.fc_w), BF16)
+    need2 = P.need(nm.ln2 + ".weight") or P.need(nm.ln2 + ".bias")
+    d_x1, d_x1_bf = ln_bwd(da2, x1, mu2, rs2, P[nm.ln2 + ".weight"], res1=d_out,
+                           dw=P.gbuf(nm.ln2 + ".weight") if need2 else None, db=P.gbuf(nm.ln2 + ".bias") if need2 else None)
+    _linear_bwd(P, nm.out_w, nm.out_b, d_x1_bf, o_t)
+    do_t = lin_dgrad(d_x1_bf, P.bf(nm.out_w), BF16)
+    do = scatter_rows_into_zeros(do_t, idx, B * S)
+    dqkv = torch.zeros_like(qkv)                       # dq outside the query window is exactly zero
+    delta = torch.empty_like(lse)
+    L.call("attn_window_bwd", qkv, o, do, lse, delta, dqkv, B, S, H, d, q0, qn, float(d ** -0.5))
+    _linear_bwd(P, nm.qkv_w, nm.qkv_b, dqkv, a1)
+    da1 = lin_dgrad(dqkv, P.bf(nm.qkv_w), BF16)
+    d_res = scatter_rows_into_zeros(d_x1, idx, B * S)  # the residual path reaches the window rows only
+    need1 = P.need(nm.ln1 + ".weight") or P.need(nm.ln1 + ".bias")
+    d_z, d_z_bf = ln_bwd(da1, z, mu1, rs1, P[nm.ln1 + ".weight"], res1=d_res,
+                         dw=P.gbuf(nm.ln1 + ".weight") if need1 else None, db=P.gbuf(nm.ln1 + ".bias") if need1 else None)
+    return d_z, d_z_bf
 
 
 # --------------------------------------------------------------------------------------------------
@@ -530,14 +601,15 @@ def sort_forward(P, text, vtok, cfg):
     text = text.contiguous()
     z = _empty((B * S, E), F32, vtok)
     L.call("sort_concat", vtok, text, P["type_embed"], z, B, N, nt, E)
-    blocks = []
-    for i in range(cfg.sort_depth):
-        z, sv = block_fwd(P, sort_block_names(f"blocks.{i}."), z, B, S, H, "gelu", cfg.sort_ln_eps, False)
-        blocks.append(sv)
     idx = (torch.arange(B, device=z.device, dtype=torch.int64)[:, None] * S + N +
            torch.arange(nt, device=z.device, dtype=torch.int64)[None, :]).reshape(-1).contiguous()
-    zt = _empty((B * nt, E), F32, z)
-    L.call("gather_rows", z, idx, zt, B * nt, E)
+    blocks = []
+    for i in range(cfg.sort_depth - 1):
+        z, sv = block_fwd(P, sort_block_names(f"blocks.{i}."), z, B, S, H, "gelu", cfg.sort_ln_eps, False)
+        blocks.append(sv)
+    # the last block: transcript rows only
+    zt, sv = window_block_fwd(P, sort_block_names(f"blocks.{cfg.sort_depth - 1}."), z, idx, B, S, N, nt, H, "gelu", cfg.sort_ln_eps)
+    blocks.append(sv)
     y, mu, rs = ln_fwd(zt, P["norm.weight"], P["norm.bias"], cfg.sort_ln_eps, out_dtype=F32)
     C = P["head.weight"].shape[0]
     logits = _empty((B * nt, C), F32, z)
@@ -554,10 +626,10 @@ def sort_backward(P, saved, d_logits, cfg):
     L.call("small_linear_bwd", d_logits, saved["y"], P["head.weight"], dy, P.gbuf("head.weight"), P.gbuf("head.bias"), B * nt, E, C)
     d_zt, _ = ln_bwd(dy, saved["zt"], saved["mu"], saved["rs"], P["norm.weight"], want_bf16=False,
                      dw=P.gbuf("norm.weight"), db=P.gbuf("norm.bias"))
-    d_z = _zeros((B * S, E), F32, d_zt)
-    L.call("scatter_rows", d_zt, saved["idx"], d_z, B * nt, E, 0)
-    d_z_bf = cast_bf16(d_z)
-    for i in reversed(range(cfg.sort_depth)):
+    last = cfg.sort_depth - 1
+    d_z, d_z_bf = window_block_bwd(P, sort_block_names(f"blocks.{last}."), saved["blocks"][last], d_zt, saved["idx"], B, S, N, nt, H, "gelu")
+    saved["blocks"][last] = None
+    for i in reversed(range(last)):
         d_z, d_z_bf = block_bwd(P, sort_block_names(f"blocks.{i}."), saved["blocks"][i], d_z, d_z_bf, B, S, H, "gelu", False)
         saved["blocks"][i] = None
     d_vtok = _empty((B, N, E), F32, d_z)
