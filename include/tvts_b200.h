@@ -91,6 +91,12 @@ int tvts_layernorm_bwd(const void* dy, int64_t dy_is_bf16, const float* x, const
                        const float* res1, const float* res2, float* dx, void* dx_bf16, float* dgamma, float* dbeta, int64_t M,
                        int64_t D, void* stream);
 
+/* layernorm_bwd that also ACCUMULATES dxsum[D] += column sums of dx: dx is the output gradient of the Linear that produced this
+ * LayerNorm's input branch (attn.proj / mlp.c_proj), so its column sums are that Linear's bias gradient -- no separate pass. */
+int tvts_layernorm_bwd_colsum(const void* dy, int64_t dy_is_bf16, const float* x, const float* mean, const float* rstd, const float* gamma,
+                              const float* res1, const float* res2, float* dx, void* dx_bf16, float* dgamma, float* dbeta, float* dxsum,
+                              int64_t M, int64_t D, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Grouped multi-head attention, head dim 64, on the packed qkv buffer [B, N, 3, H, 64] (bf16) written by the qkv GEMM.
  *   mode 0 FULL  (+causal): v2/CLIP/clip/model.py:185-188 (nn.MultiheadAttention + mask :330-336),

@@ -167,6 +167,13 @@ def layernorm_bwd(dy, dy_bf16, x, mean, rstd, g, res1, res2, dx, dxb, dg, db, M,
         db.add_(d.sum(0))
 
 
+def layernorm_bwd_colsum(dy, dy_bf16, x, mean, rstd, g, res1, res2, dx, dxb, dg, db, dxsum, M, D):
+    tmp = dx if dx is not None else torch.empty(M, D, dtype=torch.float32, device=x.device)
+    layernorm_bwd(dy, dy_bf16, x, mean, rstd, g, res1, res2, tmp, dxb, dg, db, M, D)
+    if dxsum is not None:
+        dxsum += tmp.view(M, D).sum(0)
+
+
 def cast_bf16(src, dst, n):
     dst.view(-1).copy_(src.reshape(-1).to(BF16))
 

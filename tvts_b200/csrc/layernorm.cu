@@ -65,17 +65,18 @@ __global__ void __launch_bounds__(kWarps * 32) ln_bwd_kernel(const void* __restr
                                                              const float* __restrict__ gamma, const float* __restrict__ res1,
                                                              const float* __restrict__ res2, float* __restrict__ dx,
                                                              bf16* __restrict__ dx_bf16, float* __restrict__ dgamma,
-                                                             float* __restrict__ dbeta, long long M) {
+                                                             float* __restrict__ dbeta, float* __restrict__ dxsum, long long M) {
   constexpr int D = NV * 128;
   __shared__ float red[kWarps][128];  // one float4-column group at a time
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  float4 g4[NV], dg[NV], db[NV];
+  float4 g4[NV], dg[NV], db[NV], dxs[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     g4[i] = reinterpret_cast<const float4*>(gamma)[lane + 32 * i];
     dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    dxs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (long long row = (long long)blockIdx.x * kWarps + warp; row < M; row += (long long)gridDim.x * kWarps) {
     const float mean = mean_in[row], rstd = rstd_in[row];
@@ -115,18 +116,21 @@ __global__ void __launch_bounds__(kWarps * 32) ln_bwd_kernel(const void* __restr
         float4 r = reinterpret_cast<const float4*>(res2 + row * D)[lane + 32 * i];
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
+      if (dxsum) { dxs[i].x += o.x; dxs[i].y += o.y; dxs[i].z += o.z; dxs[i].w += o.w; }
       if (dx) reinterpret_cast<float4*>(dx + row * D)[lane + 32 * i] = o;
       if (dx_bf16)
         reinterpret_cast<uint2*>(dx_bf16 + row * D)[lane + 32 * i] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
     }
   }
   // column reductions: per float4 group i, columns (lane + 32 i)*4 .. +3
-  if (dgamma == nullptr) return;
+  //   pass 0 dgamma, 1 dbeta, 2 dxsum = column sums of dx (the bias gradient of the Linear whose output gradient dx is)
 #pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = 0; pass < 3; ++pass) {
+    float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dxsum);
+    if (dst == nullptr) continue;   // block-uniform
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const float4 v = pass == 0 ? dg[i] : db[i];
+      const float4 v = pass == 0 ? dg[i] : (pass == 1 ? db[i] : dxs[i]);
       __syncthreads();
       *reinterpret_cast<float4*>(&red[warp][lane * 4]) = v;
       __syncthreads();
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(kWarps * 32) ln_bwd_kernel(const void* __restr
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) s += red[w][threadIdx.x];
-        atomicAdd((pass == 0 ? dgamma : dbeta) + i * 128 + threadIdx.x, s);
+        atomicAdd(dst + i * 128 + threadIdx.x, s);
       }
     }
   }
@@ -169,9 +173,9 @@ extern "C" int tvts_layernorm_fwd(const float* x, const float* gamma, const floa
   return TVTS_OK;
 }
 
-extern "C" int tvts_layernorm_bwd(const void* dy, int64_t dy_is_bf16, const float* x, const float* mean, const float* rstd,
-                                  const float* gamma, const float* res1, const float* res2, float* dx, void* dx_bf16, float* dgamma,
-                                  float* dbeta, int64_t M, int64_t D, void* stream_) {
+extern "C" int tvts_layernorm_bwd_colsum(const void* dy, int64_t dy_is_bf16, const float* x, const float* mean, const float* rstd,
+                                         const float* gamma, const float* res1, const float* res2, float* dx, void* dx_bf16,
+                                         float* dgamma, float* dbeta, float* dxsum, int64_t M, int64_t D, void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   if (M == 0) return TVTS_OK;
   TVTS_REQUIRE(dy && x && mean && rstd && gamma && M > 0, "layernorm_bwd: bad arguments");
@@ -183,12 +187,18 @@ extern "C" int tvts_layernorm_bwd(const void* dy, int64_t dy_is_bf16, const floa
 #define LAUNCH(NV_)                                                                                                          \
   if (dy_is_bf16)                                                                                                            \
     ln_bwd_kernel<NV_, true><<<grid, kWarps * 32, 0, st>>>(dy, x, mean, rstd, gamma, res1, res2, dx, (bf16*)dx_bf16, dgamma, \
-                                                           dbeta, M);                                                        \
+                                                           dbeta, dxsum, M);                                                 \
   else                                                                                                                       \
     ln_bwd_kernel<NV_, false><<<grid, kWarps * 32, 0, st>>>(dy, x, mean, rstd, gamma, res1, res2, dx, (bf16*)dx_bf16, dgamma, \
-                                                            dbeta, M);
+                                                            dbeta, dxsum, M);
   LN_DISPATCH_NV(D, LAUNCH)
 #undef LAUNCH
   TVTS_LAUNCH_CHECK();
   return TVTS_OK;
+}
+
+extern "C" int tvts_layernorm_bwd(const void* dy, int64_t dy_is_bf16, const float* x, const float* mean, const float* rstd,
+                                  const float* gamma, const float* res1, const float* res2, float* dx, void* dx_bf16, float* dgamma,
+                                  float* dbeta, int64_t M, int64_t D, void* stream_) {
+  return tvts_layernorm_bwd_colsum(dy, dy_is_bf16, x, mean, rstd, gamma, res1, res2, dx, dx_bf16, dgamma, dbeta, nullptr, M, D, stream_);
 }

@@ -91,11 +91,15 @@ def ln_fwd(x, w, b, eps, out_dtype=BF16):
     return y, mean, rstd
 
 
-def ln_bwd(dy, x, mean, rstd, w, res1=None, res2=None, want_f32=True, want_bf16=True, dw=None, db=None):
+def ln_bwd(dy, x, mean, rstd, w, res1=None, res2=None, want_f32=True, want_bf16=True, dw=None, db=None, dxsum=None):
+    """dxsum (optional, ACCUMULATED): column sums of dx = the bias gradient of the Linear whose output gradient dx is."""
     M, D = x.shape
     dx = _empty((M, D), F32, x) if want_f32 else None
     dxb = _empty((M, D), BF16, x) if want_bf16 else None
-    L.call("layernorm_bwd", dy, int(dy.dtype == BF16), x, mean, rstd, w, res1, res2, dx, dxb, dw, db, M, D)
+    if dxsum is None:
+        L.call("layernorm_bwd", dy, int(dy.dtype == BF16), x, mean, rstd, w, res1, res2, dx, dxb, dw, db, M, D)
+    else:
+        L.call("layernorm_bwd_colsum", dy, int(dy.dtype == BF16), x, mean, rstd, w, res1, res2, dx, dxb, dw, db, dxsum, M, D)
     return dx, dxb
 
 
@@ -289,31 +293,39 @@ def _ln_grads(P, p, name):
     return P.gbuf(p + name + ".weight"), P.gbuf(p + name + ".bias")
 
 
-def st_block_bwd(P, p, saved, d_out, d_out_bf, B, N, T, n, H, act):
+def _bias_buf(P, name):
+    return P.gbuf(name) if (name is not None and P.need(name)) else None
+
+
+def st_block_bwd(P, p, saved, d_out, d_out_bf, B, N, T, n, H, act, prev_cproj_bias=None):
+    """Bias gradients of the three projections that feed the residual stream are column sums of a gradient that a LayerNorm
+    backward produces anyway, so they are accumulated there (ln_bwd dxsum): attn.proj <- ln_2, timeattn.proj <- ln_1, and the
+    PREVIOUS block's mlp.c_proj <- this block's ln_3 (this block's own c_proj bias was filled by the producer of d_out)."""
     (x, a3, mu3, rs3, qkv_t, o_t, lse_t, tr, a1, mu1, rs1, qkv_s, o_s, lse_s, sr, a2, mu2, rs2, h, g) = saved
     # MLP
-    _linear_bwd(P, p + "mlp.c_proj.weight", p + "mlp.c_proj.bias", d_out_bf, g)
+    _linear_bwd(P, p + "mlp.c_proj.weight", None, d_out_bf, g)
     dh = lin_dgrad(d_out_bf, P.bf(p + "mlp.c_proj.weight"), BF16, dact=act, aux=h)
     _linear_bwd(P, p + "mlp.c_fc.weight", p + "mlp.c_fc.bias", dh, a2)
     da2 = lin_dgrad(dh, P.bf(p + "mlp.c_fc.weight"), BF16)   # LN backward reads its dy as bf16: half the traffic of this stream
     dw, db = _ln_grads(P, p, "ln_2")
-    d_sr, d_sr_bf = ln_bwd(da2, sr, mu2, rs2, P[p + "ln_2.weight"], res1=d_out, dw=dw, db=db)
+    d_sr, d_sr_bf = ln_bwd(da2, sr, mu2, rs2, P[p + "ln_2.weight"], res1=d_out, dw=dw, db=db, dxsum=_bias_buf(P, p + "attn.proj.bias"))
     # space attention
-    _linear_bwd(P, p + "attn.proj.weight", p + "attn.proj.bias", d_sr_bf, o_s)
+    _linear_bwd(P, p + "attn.proj.weight", None, d_sr_bf, o_s)
     do_s = lin_dgrad(d_sr_bf, P.bf(p + "attn.proj.weight"), BF16)
     dqkv_s = attn_bwd(qkv_s, o_s, do_s, lse_s, B, N, H, MODE_SPACE, T, n)
     _linear_bwd(P, p + "attn.qkv.weight", p + "attn.qkv.bias", dqkv_s, a1)
-    da1 = lin_dgrad(dqkv_s, P.bf(p + "attn.qkv.weight"), BF16)   # LN backward reads its dy as bf16: half the traffic of this stream
+    da1 = lin_dgrad(dqkv_s, P.bf(p + "attn.qkv.weight"), BF16)
     dw, db = _ln_grads(P, p, "ln_1")
-    d_tr, d_tr_bf = ln_bwd(da1, tr, mu1, rs1, P[p + "ln_1.weight"], dw=dw, db=db)     # tr only feeds ln_1
+    d_tr, d_tr_bf = ln_bwd(da1, tr, mu1, rs1, P[p + "ln_1.weight"], dw=dw, db=db,
+                           dxsum=_bias_buf(P, p + "timeattn.proj.bias"))     # tr only feeds ln_1
     # time attention
-    _linear_bwd(P, p + "timeattn.proj.weight", p + "timeattn.proj.bias", d_tr_bf, o_t)
+    _linear_bwd(P, p + "timeattn.proj.weight", None, d_tr_bf, o_t)
     do_t = lin_dgrad(d_tr_bf, P.bf(p + "timeattn.proj.weight"), BF16)
     dqkv_t = attn_bwd(qkv_t, o_t, do_t, lse_t, B, N, H, MODE_TIME, T, n)
     _linear_bwd(P, p + "timeattn.qkv.weight", p + "timeattn.qkv.bias", dqkv_t, a3)
-    da3 = lin_dgrad(dqkv_t, P.bf(p + "timeattn.qkv.weight"), BF16)   # LN backward reads its dy as bf16: half the traffic of this stream
+    da3 = lin_dgrad(dqkv_t, P.bf(p + "timeattn.qkv.weight"), BF16)
     dw, db = _ln_grads(P, p, "ln_3")
-    d_x, d_x_bf = ln_bwd(da3, x, mu3, rs3, P[p + "ln_3.weight"], res1=d_sr, res2=d_tr, dw=dw, db=db)
+    d_x, d_x_bf = ln_bwd(da3, x, mu3, rs3, P[p + "ln_3.weight"], res1=d_sr, res2=d_tr, dw=dw, db=db, dxsum=_bias_buf(P, prev_cproj_bias))
     return d_x, d_x_bf
 
 
@@ -356,8 +368,9 @@ def block_bwd(P, nm, saved, d_out, d_out_bf, B, S, H, act, causal):
     da2 = lin_dgrad(dh, P.bf(nm.fc_w), BF16)   # LN backward reads its dy as bf16: half the traffic of this stream
     need2 = P.need(nm.ln2 + ".weight") or P.need(nm.ln2 + ".bias")
     d_x1, d_x1_bf = ln_bwd(da2, x1, mu2, rs2, P[nm.ln2 + ".weight"], res1=d_out,
-                           dw=P.gbuf(nm.ln2 + ".weight") if need2 else None, db=P.gbuf(nm.ln2 + ".bias") if need2 else None)
-    _linear_bwd(P, nm.out_w, nm.out_b, d_x1_bf, o)
+                           dw=P.gbuf(nm.ln2 + ".weight") if need2 else None, db=P.gbuf(nm.ln2 + ".bias") if need2 else None,
+                           dxsum=_bias_buf(P, nm.out_b))           # out-projection bias gradient = column sums of d_x1
+    _linear_bwd(P, nm.out_w, None, d_x1_bf, o)
     do = lin_dgrad(d_x1_bf, P.bf(nm.out_w), BF16)
     dqkv = attn_bwd(qkv, o, do, lse, B, S, H, MODE_FULL, causal=causal)
     _linear_bwd(P, nm.qkv_w, nm.qkv_b, dqkv, a1)
@@ -479,9 +492,11 @@ def video_backward(P, saved, d_vtok, cfg):
     da = mat_dgrad(d_vtok_bf, P.bf("proj"), F32)
     needp = P.need("ln_post.weight") or P.need("ln_post.bias")
     d_x, d_x_bf = ln_bwd(da, saved["x_last"], saved["mup"], saved["rsp"], P["ln_post.weight"],
-                         dw=P.gbuf("ln_post.weight") if needp else None, db=P.gbuf("ln_post.bias") if needp else None)
+                         dw=P.gbuf("ln_post.weight") if needp else None, db=P.gbuf("ln_post.bias") if needp else None,
+                         dxsum=_bias_buf(P, f"transformer.resblocks.{cfg.layers - 1}.mlp.c_proj.bias") if cfg.layers > 0 else None)
     for i in reversed(range(cfg.layers)):
-        d_x, d_x_bf = st_block_bwd(P, f"transformer.resblocks.{i}.", saved["blocks"][i], d_x, d_x_bf, B, N, T, n, H, cfg.act)
+        prev_bias = f"transformer.resblocks.{i - 1}.mlp.c_proj.bias" if i > 0 else None
+        d_x, d_x_bf = st_block_bwd(P, f"transformer.resblocks.{i}.", saved["blocks"][i], d_x, d_x_bf, B, N, T, n, H, cfg.act, prev_bias)
         saved["blocks"][i] = None
     need0 = P.need("ln_pre.weight") or P.need("ln_pre.bias")
     d_x0, _ = ln_bwd(d_x, saved["x0"], saved["mu0"], saved["rs0"], P["ln_pre.weight"], want_bf16=False,
