@@ -81,3 +81,14 @@ def test_weight_cache_rejects_recycled_parameter_ids(emu_backend):
     with torch.no_grad():
         new.add_(1.0)                                                                   # version bump -> re-cast
     assert torch.equal(cache.get(new), new.detach().to(torch.bfloat16))
+
+
+def test_validate_runs_forward_only(emu_backend):
+    from tvts_b200.trainer import validate
+    cfg = C.TINY_B
+    m, sd = build(cfg)
+    batches = [make_batch(cfg, 6, 2, n_trans=4, seed=9)]
+    res = validate(m, batches, device=torch.device("cpu"))
+    assert set(res) == {"t2v_metrics", "v2t_metrics", "order_acc"}
+    assert 0.0 <= res["t2v_metrics"]["R1"] <= 100.0 and res["order_acc"] is not None
+    assert all(p.grad is None for p in m.parameters())

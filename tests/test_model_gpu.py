@@ -92,3 +92,25 @@ def test_missing_library_is_loud(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libtvts_b200.so")
     with pytest.raises(RuntimeError, match="no CPU / PyTorch fallback"):
         _lib.lib()
+
+
+def test_validation_metrics_match_oracle():
+    """R@k / MedR of the validation path (forward only) on a 24-pair synthetic batch: CUDA towers vs the CPU oracle."""
+    from tvts_b200 import metrics as MT
+    from tvts_b200.trainer import validate
+    cfg = C.TINY_B
+    m, sd = build(cfg)
+    batches = [make_batch(cfg, 12, 2, n_trans=4, seed=40 + i) for i in range(2)]
+    res = validate(m, [to_cuda(b) for b in batches])
+    te, ve = [], []
+    with torch.no_grad():
+        for b in batches:
+            t, v, _ = O.model_forward(sd, b["text"], b["video"], b["keep_ind"], cfg)
+            te.append(t); ve.append(v)
+    sims = O.sim_matrix(torch.cat(te), torch.cat(ve)).numpy()
+    ref = {"t2v_metrics": MT.t2v_metrics(sims), "v2t_metrics": MT.v2t_metrics(sims)}
+    for k in ("t2v_metrics", "v2t_metrics"):
+        # ranks can only differ where two similarities are within bf16 noise of each other: allow one swapped query out of 24
+        assert abs(res[k]["R1"] - ref[k]["R1"]) <= 100 / 24 + 1e-6, (k, res[k], ref[k])
+        assert abs(res[k]["MedR"] - ref[k]["MedR"]) <= 1.0, (k, res[k], ref[k])
+    assert res["order_acc"] is not None

@@ -236,3 +236,43 @@ class TrainStep:
             self.optimizer.prepare()                # host table -> device, stream-ordered before the replay
         ent.graph.replay()
         return ent.l1, ent.l2
+
+
+def validate(model, batches, device=None, metrics=None):
+    """The retrieval / order-accuracy core of Trainer_TVTSv2_*._valid_epoch (v2/trainer/trainer.py:527-635) for tokenised
+    batches: forward without grad, all-gather of the embeddings (and of argmax(pred_order) / labels), then
+    sim_matrix(text, video) (note the transposed order of validation, :605) -> t2v / v2t metrics and the exact-order accuracy.
+    Returns {'t2v_metrics': {...}, 'v2t_metrics': {...}, 'order_acc': float | None}."""
+    from . import metrics as MT
+    metrics = metrics or [MT.t2v_metrics, MT.v2t_metrics]
+    device = device if device is not None else next(model.parameters()).device
+    W = _world()
+    was_training = model.training
+    model.eval()
+    text_arr, vid_arr = [], []
+    hits = total = 0
+
+    def gather(t):
+        if W == 1:
+            return t
+        out = torch.empty((W * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous())
+        return out
+
+    with torch.no_grad():
+        for data in batches:
+            data = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in data.items()}
+            text_embed, vid_embed, preds = model(data, return_embeds=True)
+            vid_arr.append(gather(vid_embed).cpu())
+            text_arr.append(gather(text_embed).cpu())
+            if preds is not None:
+                labels = gather(data["label"].to(device)).cpu().numpy()
+                order = gather(torch.argmax(preds, dim=-1)).cpu().numpy()
+                hits += int((order == labels).all(axis=1).sum())
+                total += order.shape[0]
+    sims = M.sim_matrix(torch.cat(text_arr).to(device), torch.cat(vid_arr).to(device)).detach().cpu().numpy()
+    if was_training:
+        model.train()
+    res = {m.__name__: m(sims) for m in metrics}
+    res["order_acc"] = (hits / total) if total else None
+    return res
