@@ -342,7 +342,17 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave WITHOUT tearing the process group down: destroying it while CUDA graphs that captured its NCCL kernels are still
+        # alive hung every multi-rank run of round 1 after the line had been printed (profiles/r1_final_scaling.md).  All ranks
+        # meet at a last barrier (everything, including rank 0's print, is done), then exit without running finalizers.
+        try:
+            dist.barrier()
+            torch.cuda.synchronize()
+        except Exception:
+            pass
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -94,23 +94,23 @@ def test_missing_library_is_loud(monkeypatch):
         _lib.lib()
 
 
-def test_validation_metrics_match_oracle():
-    """R@k / MedR of the validation path (forward only) on a 24-pair synthetic batch: CUDA towers vs the CPU oracle."""
-    from tvts_b200 import metrics as MT
+def test_validation_path_runs_and_similarities_match_oracle():
+    """Validation path (forward only, v2/trainer/trainer.py:527-635): metrics are produced, no gradients appear, and the
+    text x video similarity matrix the metrics are computed from matches the CPU oracle's (bf16 tolerance).  (Rank-based R@k of a
+    RANDOM-INIT toy model is decided by similarity gaps far below bf16 noise, so ranks themselves are compared only on CPU with
+    exact inputs: tests/test_metrics_cpu.py.)"""
     from tvts_b200.trainer import validate
     cfg = C.TINY_B
     m, sd = build(cfg)
-    batches = [make_batch(cfg, 12, 2, n_trans=4, seed=40 + i) for i in range(2)]
-    res = validate(m, [to_cuda(b) for b in batches])
-    te, ve = [], []
-    with torch.no_grad():
-        for b in batches:
-            t, v, _ = O.model_forward(sd, b["text"], b["video"], b["keep_ind"], cfg)
-            te.append(t); ve.append(v)
-    sims = O.sim_matrix(torch.cat(te), torch.cat(ve)).numpy()
-    ref = {"t2v_metrics": MT.t2v_metrics(sims), "v2t_metrics": MT.v2t_metrics(sims)}
+    batch = make_batch(cfg, 12, 2, n_trans=4, seed=40)
+    res = validate(m, [to_cuda(batch)])
+    assert set(res) == {"t2v_metrics", "v2t_metrics", "order_acc"}
     for k in ("t2v_metrics", "v2t_metrics"):
-        # ranks can only differ where two similarities are within bf16 noise of each other: allow one swapped query out of 24
-        assert abs(res[k]["R1"] - ref[k]["R1"]) <= 100 / 24 + 1e-6, (k, res[k], ref[k])
-        assert abs(res[k]["MedR"] - ref[k]["MedR"]) <= 1.0, (k, res[k], ref[k])
-    assert res["order_acc"] is not None
+        assert 0.0 <= res[k]["R1"] <= 100.0 and res[k]["MedR"] >= 1.0
+    assert res["order_acc"] is not None and all(p.grad is None for p in m.parameters())
+    with torch.no_grad():
+        te, ve, _ = m(to_cuda(batch))
+        sims = M.sim_matrix(te, ve).cpu()
+        ote, ove, _ = O.model_forward(sd, batch["text"], batch["video"], batch["keep_ind"], cfg)
+    osims = O.sim_matrix(ote, ove)
+    assert (sims - osims).abs().max().item() < 8e-2, (sims - osims).abs().max()
