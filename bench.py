@@ -327,7 +327,8 @@ def run_ours(args):
             "clocks": clocks, "gpu_launches": launches, "loss": loss,
             "step_model_tflops": flops_pair * batch / (ms_step / 1e3) / 1e12,
             "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05)", "achieved": achieved, "peak": pk["bf16_sustained"],
-                         "unit": "TFLOP/s", "frac": (achieved / pk["bf16_sustained"]) if achieved else None, "traffic": None,
+                         "unit": "TFLOP/s", "frac": (achieved / pk["bf16_sustained"]) if achieved else None, "traffic": 124.6e6,
+                         "traffic_note": "mean dram__bytes_read+write per launch over the 6 GEMM launches of the ncu --set full capture in profiles/r1_ncu_gemm.md (bytes; below the algorithmic operand+output bytes: operands partly L2-resident)",
                          "launches": int(n_gemm), "gemm_ms_per_step": t_ms.value / args.steps,
                          "gemm_share_of_step": (t_ms.value / args.steps) / ms_step, "measured_in": roof_mode, "peak_source": pk["source"] + " (sustained figure: kernel timed inside a long step)"},
         }
