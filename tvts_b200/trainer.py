@@ -276,3 +276,143 @@ def validate(model, batches, device=None, metrics=None):
     res = {m.__name__: m(sims) for m in metrics}
     res["order_acc"] = (hits / total) if total else None
     return res
+
+
+class Trainer_TVTSv2:
+    """Epoch loop of `Trainer_TVTSv2_{B_16,B_32,H_14}` (v2/trainer/trainer.py:361-525) on top of `TrainStep` / `validate`:
+    same constructor signature, `train()`, `_train_epoch`, `_valid_epoch`, `_adjust_learning_rate`.
+
+    What it keeps from the reference: the loader interleaving (the loader whose length equals `len_epoch` drives, the others are
+    cycled, :440-461), clip-major flattening of the caption lists + tokenisation (:465-473), one optimizer step per loader batch,
+    per-loader running losses, per-epoch x0.1 decay at `args.schedule` milestones (:402-411).  What it does differently: the step
+    itself runs through `TrainStep` (CUDA graph, arena all-reduce, fused AdamW) instead of DDP + `optimizer.step()`, and losses are
+    read back once per `log_step` instead of 3-4 `.item()` syncs per step.  Checkpointing / monitoring stay with the reference's
+    `base.Multi_BaseTrainer_dist` (out of scope): pass `on_epoch_end` to hook them in."""
+
+    def __init__(self, args, model, loss, metrics, optimizer, config, data_loader, valid_data_loader=None, lr_scheduler=None,
+                 len_epoch=None, writer=None, visualizer=None, tokenizer=None, max_samples_per_epoch=50000, use_graph=True,
+                 on_epoch_end=None):
+        self.args, self.model, self.loss, self.metrics, self.optimizer, self.config = args, model, loss, metrics, optimizer, config
+        self.data_loader = list(data_loader)
+        self.valid_data_loader = valid_data_loader
+        self.do_validation = valid_data_loader is not None
+        self.lr_scheduler, self.writer, self.visualizer, self.tokenizer = lr_scheduler, writer, visualizer, tokenizer
+        self.max_samples_per_epoch = max_samples_per_epoch
+        if len_epoch is None:
+            self.len_epoch = None
+            for x in self.data_loader:
+                if getattr(x, "dataset_name", "").startswith("YT"):
+                    self.len_epoch = len(x)
+            if self.len_epoch is None:
+                self.len_epoch = len(self.data_loader[0])
+        else:
+            self.len_epoch = len_epoch
+        self.batch_size = getattr(self.data_loader[0], "batch_size", 1)
+        self.log_step = max(1, int(self.batch_size ** 0.5))
+        self.n_gpu = getattr(args, "world_size", _world())
+        self.allgather = AllGather_multi.apply
+        self.num_clips = 4
+        self.n_trans = 4
+        trainer_cfg = (config["trainer"] if config is not None and "trainer" in config else {})
+        self.epochs = trainer_cfg.get("epochs", 1)
+        self.start_epoch = 1
+        self.init_val = trainer_cfg.get("init_val", False)
+        self.device = next(model.parameters()).device
+        temperature = getattr(loss, "temperature", 0.05)
+        self.step = TrainStep(model, optimizer, temperature, self.device, use_graph=use_graph and self.device.type == "cuda")
+        self.on_epoch_end = on_epoch_end
+        self.history = []
+
+    # ---- helpers ------------------------------------------------------------------------------------------------
+    def _tokenize(self, data):
+        """caption lists [clip][sample] -> flat clip-major list (index t*B + b) -> token tensor (:465-473)."""
+        if self.tokenizer is not None and not torch.is_tensor(data["text"]):
+            text_all = []
+            for clip in data["text"]:
+                text_all = text_all + list(clip)
+            data = dict(data)
+            data["text"] = self.tokenizer(text_all, truncate=True)
+        return data
+
+    def _adjust_learning_rate(self, optimizer, epoch, args):
+        lr_rate = 1.0
+        for milestone in getattr(args, "schedule", []):
+            if epoch == milestone:
+                lr_rate = 0.1
+        for group in optimizer.param_groups:
+            group["lr"] = group["lr"] * lr_rate
+        return lr_rate
+
+    # ---- epoch ----------------------------------------------------------------------------------------------------
+    def _train_epoch(self, epoch):
+        self.model.train()
+        total_loss = [None] * len(self.data_loader)
+        for loader in self.data_loader:
+            sampler = getattr(loader, "train_sampler", None)
+            if sampler is not None:
+                sampler.set_epoch(epoch)
+        iter_dl = [None] * len(self.data_loader)
+        loop_dl, loop_dl_idx = None, None
+        for dl_idx, dl in enumerate(self.data_loader):
+            if loop_dl is None and len(dl) == self.len_epoch:
+                loop_dl, loop_dl_idx = dl, dl_idx
+            else:
+                iter_dl[dl_idx] = iter(dl)
+        if loop_dl is None:
+            loop_dl, loop_dl_idx = self.data_loader[0], 0
+            iter_dl[0] = None
+        for batch_idx, loop_dl_data in enumerate(loop_dl):
+            data_li = [None] * len(self.data_loader)
+            for dl_idx in range(len(iter_dl)):
+                if dl_idx != loop_dl_idx:
+                    try:
+                        data_li[dl_idx] = next(iter_dl[dl_idx])
+                    except StopIteration:
+                        iter_dl[dl_idx] = iter(self.data_loader[dl_idx])
+                        data_li[dl_idx] = next(iter_dl[dl_idx])
+            data_li[loop_dl_idx] = loop_dl_data
+            for dl_idx, data in enumerate(data_li):
+                data = self._tokenize(data)
+                batch = {k: data[k] for k in ("text", "video", "keep_ind", "label") if k in data}
+                loss1, loss2 = self.step(batch)
+                step_loss = (loss1 + loss2).reshape(())
+                total_loss[dl_idx] = step_loss.clone() if total_loss[dl_idx] is None else total_loss[dl_idx] + step_loss
+                if batch_idx % self.log_step == 0 and getattr(self.args, "local_rank", 0) == 0:
+                    print("Train Epoch: {} dl{} [{}/{}] Loss_ct: {:.6f} Loss_ce: {:.6f} Loss: {:.6f}".format(
+                        epoch, dl_idx, batch_idx, self.len_epoch, loss1.item(), loss2.item(), step_loss.item()))
+        log = {f"loss_{i}": (float(t.item()) / self.len_epoch if t is not None else 0.0) for i, t in enumerate(total_loss)}
+        if self.do_validation:
+            val_log = self._valid_epoch(epoch)
+            if getattr(self.args, "rank", 0) == 0:
+                log.update(val_log)
+        self._adjust_learning_rate(self.optimizer, epoch, self.args)
+        return log
+
+    def _valid_epoch(self, epoch):
+        out = {}
+        for dl_idx, dl in enumerate(self.valid_data_loader):
+            res = validate(self.model, (self._tokenize(d) for d in dl), device=self.device, metrics=self.metrics or None)
+            for name, vals in res.items():
+                if isinstance(vals, dict):
+                    for k, v in vals.items():
+                        out[f"val_{dl_idx}_{name}_{k}"] = v
+            out[f"val_loss_{dl_idx}"] = res["order_acc"] if res["order_acc"] is not None else 1.0
+        return out
+
+    def train(self):
+        if self.init_val and self.do_validation:
+            self._valid_epoch(-1)
+        for epoch in range(self.start_epoch, self.epochs + 1):
+            log = {"epoch": epoch}
+            log.update(self._train_epoch(epoch))
+            self.history.append(log)
+            if getattr(self.args, "rank", 0) == 0:
+                for k, v in log.items():
+                    print("    {:15s}: {}".format(str(k), v))
+            if self.on_epoch_end is not None:
+                self.on_epoch_end(self, epoch, log)
+        return self.history
+
+
+Trainer_TVTSv2_B_16 = Trainer_TVTSv2
+Trainer_TVTSv2_B_32 = Trainer_TVTSv2
