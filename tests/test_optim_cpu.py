@@ -65,3 +65,22 @@ def test_flat_adamw_steps_match_oracle(emu_backend):
         assert any(v == 2 for k, v in nsteps.items() if k.startswith("pred_model")) and nsteps["video_model.proj"] == 3
     finally:
         opt.flat.release()
+
+
+def test_flatstate_active_mask_roundtrip():
+    ps = [torch.nn.Parameter(torch.randn(10)), torch.nn.Parameter(torch.randn(3, 3)), torch.nn.Parameter(torch.randn(5))]
+    opt = optim.AdamW([{"params": ps, "lr": 1e-3}])
+    try:
+        fs = opt.flat
+        ps[0].grad = fs.grad_view(ps[0])
+        ps[2].grad = fs.grad_view(ps[2])
+        mask = fs.active_mask()
+        assert mask == [True, False, True]
+        fs.zero_grad()
+        assert fs.active_mask() == [False, False, False]
+        fs.set_active(mask)
+        assert fs.active_mask() == mask and ps[0].grad.data_ptr() == fs.grad_view(ps[0]).data_ptr()
+        fs.set_active([False, True, False])
+        assert ps[0].grad is None and ps[1].grad is not None and ps[2].grad is None
+    finally:
+        opt.flat.release()

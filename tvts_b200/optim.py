@@ -101,6 +101,21 @@ class FlatState:
             self.params[i].grad = None
         self.touched.clear()
 
+    def active_mask(self):
+        """Which parameters currently carry a gradient (what AdamW.prepare() keys on)."""
+        return [p.grad is not None for p in self.params]
+
+    def set_active(self, mask):
+        """Re-create the .grad attachment pattern of an earlier step (CUDA-graph replay: the Python-side bookkeeping of the step
+        that was captured -- which parameters received a gradient -- has to be restored before the optimizer looks at it)."""
+        self.touched = set()
+        for i, (p, on) in enumerate(zip(self.params, mask)):
+            if on:
+                p.grad = self._view(self.g, p)
+                self.touched.add(i)
+            else:
+                p.grad = None
+
     def publish_grads(self, params=None):
         """Attach arena views as .grad of every parameter the backward wrote (what autograd's AccumulateGrad would do)."""
         for i in self.touched:

@@ -180,8 +180,10 @@ class TrainStep:
         with torch.cuda.graph(graph):
             l1, l2 = self._body(static, optimizer_launch_only=True)
         self.launches_per_graph = L.launch_count() - n0
-        ent = types.SimpleNamespace(graph=graph, static=static, l1=l1, l2=l2)
+        flat = getattr(self.optimizer, "flat", None)
+        ent = types.SimpleNamespace(graph=graph, static=static, l1=l1, l2=l2, active=flat.active_mask() if flat is not None else None)
         self._graphs[key] = ent
+        self._last_key = key
         return ent
 
     def prefetch(self, data):
@@ -228,6 +230,13 @@ class TrainStep:
         ent = self._graphs.get(key)
         if ent is None:
             ent = self._capture(key, data)
+        if getattr(self, "_last_key", None) != key:
+            # another graph (e.g. the caption-batch graph, which leaves the sort head without gradients) ran last: restore the
+            # gradient-attachment pattern this graph was captured with, so that AdamW.prepare() skips / steps the right tensors
+            flat = getattr(self.optimizer, "flat", None)
+            if flat is not None and ent.active is not None:
+                flat.set_active(ent.active)
+            self._last_key = key
         for k, v in ent.static.items():
             v.copy_(data[k], non_blocking=True)
         if consumed is not None:
