@@ -28,3 +28,43 @@ def test_argument_errors_are_reported_not_crashing():
     g = _lib.GemmArgs()
     assert lib.tvts_gemm(ctypes.byref(g), None) < 0
     assert b"empty problem" in lib.tvts_last_error()
+
+
+def _err(lib):
+    return lib.tvts_last_error().decode()
+
+
+def test_entry_points_validate_arguments_before_touching_the_device():
+    """Error convention of the C ABI (include/tvts_b200.h): negative return code + thread-local message, no launch, no crash --
+    checked without a GPU because every entry point validates its arguments first."""
+    from tvts_b200 import _lib
+    lib = _lib.lib()
+    i64, f32, vp = ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+    dummy = ctypes.create_string_buffer(256)
+    p = ctypes.cast(dummy, vp)
+    # attention: only head dim 64
+    rc = lib.tvts_attn_fwd(p, p, p, i64(1), i64(16), i64(2), i64(80), i64(0), i64(0), i64(0), i64(0), f32(0.1), None)
+    assert rc < 0 and "head dim" in _err(lib)
+    # divided modes need N == 1 + T*n
+    rc = lib.tvts_attn_fwd(p, p, p, i64(1), i64(16), i64(2), i64(64), i64(1), i64(2), i64(5), i64(0), f32(0.1), None)
+    assert rc < 0 and "1 + T*n" in _err(lib)
+    # query window must lie inside the sequence
+    rc = lib.tvts_attn_window_fwd(p, p, p, i64(1), i64(16), i64(2), i64(64), i64(14), i64(4), f32(0.1), None)
+    assert rc < 0 and "attn_window_fwd" in _err(lib)
+    # LayerNorm width must be a multiple of 128
+    rc = lib.tvts_layernorm_fwd(p, p, p, p, i64(1), p, p, i64(4), i64(100), f32(1e-5), None)
+    assert rc < 0 and "multiple of 128" in _err(lib)
+    # GEMM: bf16 output needs N % 8 == 0; split-K needs accumulate
+    g = _lib.GemmArgs()
+    g.a = g.b = g.out = ctypes.addressof(dummy) & ~0xF
+    g.M, g.N, g.K, g.lda, g.ldb, g.ldo, g.ldr, g.ldaux = 128, 12, 64, 64, 64, 16, 16, 16
+    g.out_dtype = 1
+    assert lib.tvts_gemm(ctypes.byref(g), None) < 0 and "multiples of 8" in _err(lib)
+    g.N, g.out_dtype, g.splits = 16, 0, 4
+    assert lib.tvts_gemm(ctypes.byref(g), None) < 0 and "split-K requires accumulate" in _err(lib)
+    # optimizer: null arena
+    rc = lib.tvts_adamw_flat(None, None, None, None, None, None, None, i64(4), i64(4096), f32(0.9), f32(0.999), f32(1e-6), f32(1.0), None)
+    assert rc < 0 and "adamw_flat" in _err(lib)
+    # empty problems are no-ops, not errors
+    assert lib.tvts_attn_fwd(p, p, p, i64(0), i64(16), i64(2), i64(64), i64(0), i64(0), i64(0), i64(0), f32(0.1), None) == 0
+    assert lib.tvts_layernorm_fwd(p, p, p, p, i64(1), p, p, i64(0), i64(128), f32(1e-5), None) == 0
