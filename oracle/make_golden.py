@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz by EXECUTING THE UNMODIFIED REFERENCE (build container only).
 
-    python oracle/make_golden.py            # writes tests/golden/{c1_b32,tiny_B,tiny_B_mask,tiny_B_cap}.npz
+    python oracle/make_golden.py            # writes tests/golden/{c1_b32,tiny_B,tiny_B_mask,tiny_B_cap,tiny_H}.npz
 
 For each case: seeded state_dict (tvts_b200.synthetic.make_state_dict) is loaded strict=True into the
 reference modules, the reference forward + the trainer's loss lines (v2/trainer/trainer.py:479-496)
@@ -53,9 +53,39 @@ def build_reference_model(cfg):
     return m, ref_model.sim_matrix
 
 
+def build_reference_model_h14(cfg):
+    """A reference TVTSv2_H_14 instance with cfg's (tiny) dims: the modified-OpenCLIP video encoder
+    (v2/model/video_encoder_ViT_H_14.py), the OpenCLIP text Transformer with its causal attn_mask
+    (v2/OpenCLIP/transformer.py), the SortTransformer; forward()/compute_text()/compute_video() are the reference's own."""
+    from torch import nn
+    import model.model_dist_TVTSv2_ViT_H_14 as ref_model
+    from model.video_encoder_ViT_H_14 import VisionTransformer, LayerNorm
+    from model.sort_transformer import SortTransformer
+    from OpenCLIP.transformer import Transformer as TextTransformer, LayerNorm as TextLayerNorm
+
+    m = ref_model.TVTSv2_H_14.__new__(ref_model.TVTSv2_H_14)
+    nn.Module.__init__(m)
+    W = cfg.text_width
+    m.text_model = TextTransformer(width=W, layers=cfg.text_layers, heads=cfg.text_heads, act_layer=nn.GELU)
+    m.text_token_embedding = nn.Embedding(cfg.vocab, W)
+    m.text_positional_embedding = nn.Parameter(torch.empty(cfg.context, W))
+    m.text_ln_final = TextLayerNorm(W)
+    m.text_projection = nn.Parameter(torch.empty(W, cfg.embed_dim))
+    mask = torch.empty(cfg.context, cfg.context)
+    mask.fill_(float("-inf"))
+    mask.triu_(1)                                               # OpenCLIP CLIP.build_attention_mask (v2/OpenCLIP/model.py)
+    m.text_attn_mask = mask
+    m.video_model = VisionTransformer(image_size=cfg.resolution, patch_size=cfg.patch, width=cfg.width, layers=cfg.layers,
+                                      heads=cfg.heads, mlp_ratio=4.0, output_dim=cfg.embed_dim, act_layer=nn.GELU,
+                                      norm_layer=LayerNorm, num_frames=cfg.num_frames, mask_ratio=cfg.mask_ratio)
+    m.n_trans = cfg.n_trans
+    m.pred_model = SortTransformer(num_classes=cfg.n_trans, embed_dim=cfg.embed_dim, num_heads=cfg.sort_heads)
+    return m, ref_model.sim_matrix
+
+
 def run_case(name, cfg, batch, frames, n_trans, seed):
     from model.loss import NormSoftmaxLoss
-    m, sim_matrix = build_reference_model(cfg)
+    m, sim_matrix = build_reference_model_h14(cfg) if cfg.post_mode == "h14" else build_reference_model(cfg)
     sd = make_state_dict(cfg, seed=1234)
     m.load_state_dict(sd, strict=True)
     m.train()
@@ -111,6 +141,7 @@ def main():
     run_case("tiny_B_mask", C.TINY_B_MASK, batch=2, frames=3, n_trans=4, seed=12)
     run_case("tiny_B_cap", C.TINY_B, batch=4, frames=2, n_trans=1, seed=13)       # caption mode: pred_order None
     run_case("c1_b32", C.TVTSV2_B_32, batch=4, frames=2, n_trans=4, seed=0)       # BASELINE.json configs[0]
+    run_case("tiny_H", C.TINY_H, batch=2, frames=3, n_trans=4, seed=14)           # H/14 semantics (configs[3]) at toy dims
 
 
 if __name__ == "__main__":

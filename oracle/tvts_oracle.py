@@ -138,7 +138,9 @@ def video_embed(video, keep_ind, sd, cfg, prefix="video_model."):
 
 
 def video_tower(video, keep_ind, sd, cfg, prefix="video_model."):
-    """VisionTransformer.forward, v2/model/video_encoder_ViT_B_16.py:176-235 -> [B,N,E]."""
+    """VisionTransformer.forward, v2/model/video_encoder_ViT_B_16.py:176-235 -> [B,N,E].
+    cfg.post_mode == 'h14' (v2/model/video_encoder_ViT_H_14.py:419-484, exact-GELU blocks via cfg.act): returns
+    (pooled [B,E] = ln_post(x[:,0]) @ proj, tokens [B,N-1,E] = x[:,1:] @ proj -- no ln_post, no CLS; :472-482)."""
     T = 1 if video.dim() == 4 else video.shape[1]
     n = keep_ind.shape[1]
     assert n == cfg.kept_per_frame, (n, cfg.kept_per_frame)            # :220 time_n must equal kept count
@@ -146,6 +148,9 @@ def video_tower(video, keep_ind, sd, cfg, prefix="video_model."):
     x = layer_norm(x, sd[prefix + "ln_pre.weight"], sd[prefix + "ln_pre.bias"], cfg.ln_eps)
     for i in range(cfg.layers):
         x = st_block(x, sd, f"{prefix}transformer.resblocks.{i}.", cfg.heads, T, n, cfg.act, cfg.ln_eps)
+    if getattr(cfg, "post_mode", "all") == "h14":
+        pooled = layer_norm(x[:, 0], sd[prefix + "ln_post.weight"], sd[prefix + "ln_post.bias"], cfg.ln_eps) @ sd[prefix + "proj"]
+        return pooled, x[:, 1:] @ sd[prefix + "proj"]
     x = layer_norm(x, sd[prefix + "ln_post.weight"], sd[prefix + "ln_post.bias"], cfg.ln_eps)
     return x @ sd[prefix + "proj"]
 
@@ -221,8 +226,13 @@ def model_forward(sd, text, video, keep_ind, cfg):
     n_trans = t.shape[0]
     transcripts = t.detach().permute(1, 0, 2)                      # :69-70 no grad into text from the sort head
     text_emb = t.mean(0)                                           # :74-76
-    vtok = video_tower(video, keep_ind, sd, cfg)
-    video_emb = vtok[:, 0]
+    if getattr(cfg, "post_mode", "all") == "h14":
+        # TVTSv2_H_14.forward, model_dist_TVTSv2_ViT_H_14.py:97-131: the sort head sees the projected patch tokens only
+        # (the reference runs this under fp16 autocast; the oracle restates the fp32 semantics)
+        video_emb, vtok = video_tower(video, keep_ind, sd, cfg)
+    else:
+        vtok = video_tower(video, keep_ind, sd, cfg)
+        video_emb = vtok[:, 0]
     pred = sort_head(transcripts, vtok, sd, cfg) if n_trans != 1 else None
     return text_emb, video_emb, pred
 

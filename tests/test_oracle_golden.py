@@ -11,10 +11,10 @@ from tvts_b200 import config as C
 from tvts_b200.synthetic import make_batch, make_state_dict
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-CASES = {"tiny_B": C.TINY_B, "tiny_B_mask": C.TINY_B_MASK, "tiny_B_cap": C.TINY_B, "c1_b32": C.TVTSV2_B_32}
+CASES = {"tiny_B": C.TINY_B, "tiny_B_mask": C.TINY_B_MASK, "tiny_B_cap": C.TINY_B, "c1_b32": C.TVTSV2_B_32, "tiny_H": C.TINY_H}
 
 
-@pytest.mark.parametrize("name", ["tiny_B", "tiny_B_mask", "tiny_B_cap", "c1_b32"])
+@pytest.mark.parametrize("name", ["tiny_B", "tiny_B_mask", "tiny_B_cap", "c1_b32", "tiny_H"])
 def test_oracle_matches_reference_golden(name):
     cfg = CASES[name]
     g = np.load(os.path.join(GOLD, name + ".npz"), allow_pickle=False)

@@ -67,6 +67,10 @@ ARCHS = {c.name: c for c in (TVTSV2_B_32, TVTSV2_B_16, TVTSV2_H_14)}
 TINY_B = ArchConfig("tiny_B", patch=32, width=128, layers=2, heads=2, embed_dim=128, mask_ratio=0.0,
                     text_width=128, text_heads=2, text_layers=2, vocab=512, sort_heads=2)
 TINY_B_MASK = TINY_B.small(name="tiny_B_mask", patch=16, mask_ratio=0.5)
+# H/14-shaped toy (oracle / golden only for now: the CUDA attention kernels are head-dim-64): patch 14, mask 0.7 (int(256*0.3) = 76
+# kept patches), head dim 80, exact GELU in both towers, ln_post on CLS only, sort head on the patch tokens
+TINY_H = ArchConfig("tiny_H", patch=14, width=160, layers=2, heads=2, embed_dim=128, mask_ratio=0.7, act="gelu", post_mode="h14",
+                    text_width=128, text_heads=2, text_layers=2, vocab=512, text_act="gelu", sort_heads=2)
 
 
 @dataclass(frozen=True)
