@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz by EXECUTING THE UNMODIFIED REFERENCE (build container only).
 
-    python oracle/make_golden.py            # writes tests/golden/{c1_b32,tiny_B,tiny_B_mask,tiny_B_cap,tiny_H}.npz
+    python oracle/make_golden.py            # writes tests/golden/{c1_b32,tiny_B,tiny_B_mask,tiny_B_cap,tiny_H,tiny_v1}.npz
 
 For each case: seeded state_dict (tvts_b200.synthetic.make_state_dict) is loaded strict=True into the
 reference modules, the reference forward + the trainer's loss lines (v2/trainer/trainer.py:479-496)
@@ -142,7 +142,78 @@ def main():
     run_case("tiny_B_cap", C.TINY_B, batch=4, frames=2, n_trans=1, seed=13)       # caption mode: pred_order None
     run_case("c1_b32", C.TVTSV2_B_32, batch=4, frames=2, n_trans=4, seed=0)       # BASELINE.json configs[0]
     run_case("tiny_H", C.TINY_H, batch=2, frames=3, n_trans=4, seed=14)           # H/14 semantics (configs[3]) at toy dims
+    run_case_v1()                                                                 # TVTS v1 semantics (configs[4]) at toy dims
 
 
 if __name__ == "__main__":
     main()
+
+
+# ------------------------------------------------------------------------------------------------------------------ TVTS v1
+from make_golden_spec import spec_state_dict  # noqa: E402
+
+
+def run_case_v1(name="tiny_v1", seed=15):
+    """TVTS v1 at toy dims through the UNMODIFIED reference classes (v1/model/model_dist_TVTS.py, video_encoder.py): a randomly
+    initialised 1-layer DistilBERT from the installed `transformers` stands in for 'distilbert-base-uncased'; its [CLS] vectors are
+    stored in the fixture because the oracle takes them as input (the text encoder is an un-vendored dependency)."""
+    from functools import partial
+    from torch import nn
+    import transformers
+    ref_shims.install("v1")
+    import model.model_dist_TVTS as ref_model
+    from model.video_encoder import VisionTransformer
+    from model.sort_transformer import SortTransformer
+    from model.loss import NormSoftmaxLoss
+
+    D, heads, depth, patch, res, frames, nt, B, proj = 96, 2, 2, 16, 64, 8, 4, 2, 32
+    torch.manual_seed(seed)
+    m = ref_model.TVTS.__new__(ref_model.TVTS)
+    nn.Module.__init__(m)
+    m.text_params = {"model": "distilbert-base-uncased", "pretrained": True}
+    m.text_model = transformers.DistilBertModel(transformers.DistilBertConfig(vocab_size=128, dim=D, n_layers=1, n_heads=2, hidden_dim=2 * D,
+                                                                              max_position_embeddings=32, dropout=0.0, attention_dropout=0.0))
+    m.video_model = VisionTransformer(img_size=res, patch_size=patch, embed_dim=D, depth=depth, num_heads=heads, mlp_ratio=4, qkv_bias=True,
+                                      norm_layer=partial(nn.LayerNorm, eps=1e-6), num_frames=frames)
+    m.video_model.pre_logits = nn.Identity()
+    m.txt_proj = nn.Sequential(nn.ReLU(), nn.Linear(D, proj))
+    m.vid_proj = nn.Sequential(nn.Linear(D, proj))
+    m.n_trans = nt
+    m.pred_model = SortTransformer(num_classes=nt, embed_dim=D, num_heads=heads)
+    names = [k for k, _ in m.named_parameters() if not k.startswith("text_model.")]
+    shapes = [tuple(p.shape) for k, p in m.named_parameters() if not k.startswith("text_model.")]
+    sd = spec_state_dict(names, shapes, 4321)
+    m.load_state_dict(sd, strict=False)
+    m.train()
+    g = torch.Generator().manual_seed(seed)
+    P = (res // patch) ** 2
+    n_keep = P // 2
+    video = torch.randn(B, frames, 3, res, res, generator=torch.Generator().manual_seed(seed + 1))   # regenerated from the seed by the test
+    keep = torch.stack([torch.stack([torch.randperm(P, generator=g)[:n_keep] for _ in range(frames // 2)]) for _ in range(B)])
+    ids = torch.randint(1, 128, (nt * B, 12), generator=g)
+    text = {"input_ids": ids, "attention_mask": torch.ones_like(ids)}
+    labels = torch.arange(nt).repeat(B, 1)
+    text_cls = m.text_model(**text).last_hidden_state[:, 0, :].detach()
+    te, ve, pred = m({"text": text, "video": video, "keep_ind": keep})
+    loss1 = NormSoftmaxLoss(0.05)(ref_model.sim_matrix(ve, te))
+    loss2 = torch.nn.CrossEntropyLoss()(pred.reshape(-1, nt), labels.reshape(-1)) * 2
+    (loss1 + loss2).backward()
+    gn = {k: p.grad.double().norm().item() for k, p in m.named_parameters() if p.grad is not None and not k.startswith("text_model.")}
+    out = dict(names=np.array(names), shapes=np.array([",".join(map(str, s)) for s in shapes]), wseed=4321, text_cls=text_cls.numpy(),
+               video_seed=seed + 1, keep_ind=keep.numpy(), text_emb=te.detach().numpy(), video_emb=ve.detach().numpy(),
+               pred_order=pred.detach().numpy(), loss1=np.float64(loss1.item()), loss2=np.float64(loss2.item()),
+               grad_names=np.array(list(gn)), grad_norms=np.array(list(gn.values())),
+               dims=np.array([D, heads, depth, patch, res, frames, nt, B, proj]))
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, **out)
+    import tvts_oracle as O
+    cfg = types.SimpleNamespace(patch=patch, width=D, heads=heads, layers=depth, sort_heads=heads, sort_depth=2, sort_ln_eps=1e-6)
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ote, ove, opr = O.v1_model_forward(sdr, text_cls, video, keep, cfg)
+    l1 = O.norm_softmax_loss(O.sim_matrix(ove, ote), 0.05)
+    l2 = O.sort_ce(opr, labels)
+    (l1 + l2).backward()
+    worst = max(abs(sdr[k].grad.double().norm().item() - v) / (v + 1e-12) for k, v in gn.items() if k != "txt_proj.1.weight" or True)
+    print(f"[{name}] loss1 ref {loss1.item():.7f} oracle {l1.item():.7f} | loss2 ref {loss2.item():.7f} oracle {l2.item():.7f}")
+    print(f"   max|d text_emb| {(ote - te).abs().max().item():.2e} max|d video_emb| {(ove - ve).abs().max().item():.2e} "
+          f"max|d pred| {(opr - pred).abs().max().item():.2e}  worst rel grad-norm dev over {len(gn)} params {worst:.2e} -> {path} ({os.path.getsize(path)} B)")

@@ -281,6 +281,59 @@ def step_with_grads(sd_tensors, text, video, keep_ind, labels, cfg, trainable=No
 
 
 # --------------------------------------------------------------------------------------------------
+# TVTS v1 (BASELINE.json configs[4]): VideoMAE-style ViT with Conv3d tubelets + joint space-time attention, projection heads,
+# the same sort head and losses.  The text encoder is HuggingFace DistilBERT (un-vendored dependency, `transformers` pin 4.10.2,
+# parity unpinned): its [CLS] vectors are an INPUT of this restatement (`text_cls`), everything downstream is restated.
+# --------------------------------------------------------------------------------------------------
+def v1_video_tower(video, keep_ind, sd, cfg, prefix="video_model."):
+    """VisionTransformer.forward_features, v1/model/video_encoder.py:178-217.
+    video [B,T,3,H,W]; keep_ind [B, T/2, n] int64 (an independent subset per tube, v1/data_loader/YTTemporal_dataset.py:206-215).
+    Conv3d(3, D, k=s=(2,p,p)) WITH bias (:89-91) on the [B,3,T,H,W] permutation == per-tubelet linear map over (c, dt, u, v)."""
+    B, T, C, H, W = video.shape
+    p, D = cfg.patch, cfg.width
+    g = H // p
+    nt = T // 2
+    w = sd[prefix + "patch_embed.proj.weight"].reshape(D, -1)                # [D, 3*2*p*p], (c, dt, u, v) order
+    x = video.reshape(B, nt, 2, C, g, p, g, p).permute(0, 1, 4, 6, 3, 2, 5, 7).reshape(B, nt, g * g, C * 2 * p * p)
+    keep = keep_ind[:, :nt].to(torch.long)
+    idx = keep[..., None].expand(B, nt, keep.shape[-1], x.shape[-1])
+    tok = torch.gather(x, 2, idx) @ w.t() + sd[prefix + "patch_embed.proj.bias"]          # gather before the (per-patch) linear map
+    pos = sd[prefix + "pos_embed"][0]                                          # [P+1, D]
+    tem = sd[prefix + "temporal_embed"][0]                                     # [num_tubes, D]
+    tok = tok + pos[1:][keep] + tem[:nt][None, :, None, :]                     # (:193-199) added before the mask gather
+    cls = (sd[prefix + "cls_token"][0, 0] + pos[0]).expand(B, 1, D)
+    x = torch.cat([cls, tok.reshape(B, -1, D)], 1)
+    h = cfg.heads
+    d = D // h
+    for i in range(cfg.layers):                                               # Block (:59-75): pre-LN, joint attention over all tokens
+        q_ = f"{prefix}blocks.{i}."
+        y = layer_norm(x, sd[q_ + "norm1.weight"], sd[q_ + "norm1.bias"], 1e-6)
+        qkv = linear(y, sd[q_ + "attn.qkv.weight"], sd[q_ + "attn.qkv.bias"]).reshape(B, -1, 3, h, d)
+        q = qkv[:, :, 0].transpose(1, 2) * (d ** -0.5)
+        k = qkv[:, :, 1].transpose(1, 2)
+        v = qkv[:, :, 2].transpose(1, 2)
+        o = _softmax_av(q, k, v).transpose(1, 2).reshape(B, -1, D)
+        x = x + linear(o, sd[q_ + "attn.proj.weight"], sd[q_ + "attn.proj.bias"])
+        y = layer_norm(x, sd[q_ + "norm2.weight"], sd[q_ + "norm2.bias"], 1e-6)
+        x = x + linear(gelu_erf(linear(y, sd[q_ + "mlp.fc1.weight"], sd[q_ + "mlp.fc1.bias"])), sd[q_ + "mlp.fc2.weight"], sd[q_ + "mlp.fc2.bias"])
+    return layer_norm(x, sd[prefix + "norm.weight"], sd[prefix + "norm.bias"], 1e-6)
+
+
+def v1_model_forward(sd, text_cls, video, keep_ind, cfg):
+    """TVTS.forward, v1/model/model_dist_TVTS.py:95-141, from the DistilBERT [CLS] vectors `text_cls` [n_trans*B, Dt] (clip-major).
+    -> (text_emb [B,proj], video_emb [B,proj], pred_order [B,nt,nt] | None)."""
+    B = video.shape[0]
+    t = linear(torch.relu(text_cls), sd["txt_proj.1.weight"], sd["txt_proj.1.bias"])       # 'minimal' projection (:66-74)
+    n_trans = text_cls.shape[0] // B
+    transcripts = text_cls.detach().reshape(n_trans, B, -1).permute(1, 0, 2)
+    text_emb = t.reshape(n_trans, B, -1).mean(0)
+    vtok = v1_video_tower(video, keep_ind, sd, cfg)
+    video_emb = linear(vtok[:, 0], sd["vid_proj.0.weight"], sd["vid_proj.0.bias"])
+    pred = sort_head(transcripts, vtok, sd, cfg) if n_trans != 1 else None                 # raw 768-d tokens incl. CLS (:113-116)
+    return text_emb, video_emb, pred
+
+
+# --------------------------------------------------------------------------------------------------
 # optimiser: transformers==4.10.2 AdamW (un-vendored; parity unpinned by the reference -- restated from its
 # published algorithm: Adam with bias correction, eps added to sqrt(v) BEFORE bias correction is folded
 # into the step size, decoupled weight decay applied AFTER the Adam update with the un-corrected lr).

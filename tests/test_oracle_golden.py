@@ -1,6 +1,7 @@
 """The CPU oracle (oracle/tvts_oracle.py) must reproduce the outputs of the UNMODIFIED reference recorded in
 tests/golden/*.npz by oracle/make_golden.py (the reference ships no fixtures of its own for this path)."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -37,3 +38,30 @@ def test_oracle_matches_reference_golden(name):
         assert abs(gn - nrm) <= 1e-3 * nrm + 1e-7, (k, gn, nrm)
         h = grads[k].reshape(-1)[:8].double().numpy()
         np.testing.assert_allclose(h, head[: h.size], atol=1e-5 + 1e-3 * np.abs(head[: h.size]).max())
+
+
+def test_v1_oracle_matches_reference_golden():
+    """TVTS v1 (Conv3d tubelets, joint attention, per-tube mask, projection heads, sort head on raw tokens): oracle vs the fixture
+    written by executing v1/model/model_dist_TVTS.py; the DistilBERT [CLS] vectors are an input (un-vendored text encoder)."""
+    import types
+    sys_path_oracle = os.path.join(os.path.dirname(GOLD), "..", "oracle")
+    g = np.load(os.path.join(GOLD, "tiny_v1.npz"), allow_pickle=False)
+    sys.path.insert(0, os.path.abspath(sys_path_oracle))
+    from make_golden_spec import spec_state_dict
+    D, heads, depth, patch, res, frames, nt, B, proj = [int(v) for v in g["dims"]]
+    names = [str(s) for s in g["names"]]
+    shapes = [tuple(int(x) for x in str(s).split(",")) for s in g["shapes"]]
+    sd = {k: v.requires_grad_(True) for k, v in spec_state_dict(names, shapes, int(g["wseed"])).items()}
+    video = torch.randn(B, frames, 3, res, res, generator=torch.Generator().manual_seed(int(g["video_seed"])))
+    cfg = types.SimpleNamespace(patch=patch, width=D, heads=heads, layers=depth, sort_heads=heads, sort_depth=2, sort_ln_eps=1e-6)
+    te, ve, pr = O.v1_model_forward(sd, torch.from_numpy(g["text_cls"]), video, torch.from_numpy(g["keep_ind"]), cfg)
+    l1 = O.norm_softmax_loss(O.sim_matrix(ve, te), 0.05)
+    l2 = O.sort_ce(pr, torch.arange(nt).repeat(B, 1))
+    (l1 + l2).backward()
+    assert abs(l1.item() - float(g["loss1"])) < 2e-5 and abs(l2.item() - float(g["loss2"])) < 2e-5
+    np.testing.assert_allclose(te.detach().numpy(), g["text_emb"], atol=2e-5, rtol=1e-4)
+    np.testing.assert_allclose(ve.detach().numpy(), g["video_emb"], atol=2e-5, rtol=1e-4)
+    np.testing.assert_allclose(pr.detach().numpy(), g["pred_order"], atol=5e-5, rtol=1e-4)
+    for k, nrm in zip([str(s) for s in g["grad_names"]], g["grad_norms"]):
+        gn = sd[k].grad.double().norm().item()
+        assert abs(gn - nrm) <= 1e-3 * nrm + 1e-7, (k, gn, nrm)
