@@ -29,7 +29,9 @@ def run_step(m, data, cfg):
     return loss1.detach(), loss2.detach(), te.detach(), ve.detach(), None if pred is None else pred.detach()
 
 
-@pytest.mark.parametrize("cfg,batch,frames,n_trans", [(C.TINY_B, 3, 2, 4), (C.TINY_B_MASK, 2, 3, 4), (C.TINY_B, 4, 2, 1)])
+@pytest.mark.parametrize("cfg,batch,frames,n_trans", [(C.TINY_B, 3, 2, 4), (C.TINY_B_MASK, 2, 3, 4), (C.TINY_B, 4, 2, 1),
+                                                      (C.TINY_B_MASK, 1, 12, 2),      # the shipped 12-frame clips, 2 transcripts
+                                                      (C.TINY_B, 2, 1, 3)])           # single frame (4-D video path: T = 1)
 def test_engine_matches_oracle(emu_backend, cfg, batch, frames, n_trans):
     torch.manual_seed(0)
     m, sd = build(cfg)
