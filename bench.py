@@ -120,7 +120,8 @@ def algorithmic_flops_per_pair(cfg, T, n_trans):
     p, D, L, E = cfg.patch, cfg.width, cfg.layers, cfg.embed_dim
     n = cfg.kept_per_frame
     N = 1 + T * n
-    f_video = 2 * T * n * (3 * p * p) * D + L * (32 * N * D * D + 4 * n * T * (T + 1) * D + 4 * T * n * (n + 1) * D + 8 * N * D) + 2 * N * D * E
+    P_all = cfg.patches_per_frame     # SURVEY counts the reference's patch-embed over ALL patches (this repo embeds the kept ones only)
+    f_video = 2 * T * P_all * (3 * p * p) * D + L * (32 * N * D * D + 4 * n * T * (T + 1) * D + 4 * T * n * (n + 1) * D + 8 * N * D) + 2 * N * D * E
     W = cfg.text_width
     f_layer = 24 * 77 * W * W + 4 * 77 * 77 * W
     frozen = (cfg.text_layers * 3) // 4

@@ -17,3 +17,14 @@ def test_reference_arm_prints_contract_line():
         assert k in line, k
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_flop_model_reproduces_survey_table():
+    """bench.algorithmic_flops_per_pair == SURVEY.md section 8d table (fwd+bwd GFLOP per pair, modes A / B)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from tvts_b200 import config as C
+    table = {("c1", C.TVTSV2_B_32, 2): (82.9, 127.1), ("c2", C.TVTSV2_B_32, 8): (289.6, 346.7), ("c3", C.TVTSV2_B_16, 8): (563.7, 641.4)}
+    for (name, cfg, T), (a, b) in table.items():
+        assert abs(bench.algorithmic_flops_per_pair(cfg, T, 1) / 1e9 - a) < 0.15, name
+        assert abs(bench.algorithmic_flops_per_pair(cfg, T, 4) / 1e9 - b) < 0.15, name
