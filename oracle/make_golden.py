@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz by EXECUTING THE UNMODIFIED REFERENCE (build container only).
 
-    python oracle/make_golden.py            # writes tests/golden/{c1_b32,tiny_B,tiny_B_mask,tiny_B_cap,tiny_H,tiny_v1}.npz
+    python oracle/make_golden.py            # writes tests/golden/{c1_b32,tiny_B,tiny_B_mask,tiny_B_cap,tiny_H,tiny_ds,tiny_v1}.npz
 
 For each case: seeded state_dict (tvts_b200.synthetic.make_state_dict) is loaded strict=True into the
 reference modules, the reference forward + the trainer's loss lines (v2/trainer/trainer.py:479-496)
@@ -142,11 +142,8 @@ def main():
     run_case("tiny_B_cap", C.TINY_B, batch=4, frames=2, n_trans=1, seed=13)       # caption mode: pred_order None
     run_case("c1_b32", C.TVTSV2_B_32, batch=4, frames=2, n_trans=4, seed=0)       # BASELINE.json configs[0]
     run_case("tiny_H", C.TINY_H, batch=2, frames=3, n_trans=4, seed=14)           # H/14 semantics (configs[3]) at toy dims
+    run_case_downstream()                                                         # v2/downstream towers (mask 0, no sort head), forward only
     run_case_v1()                                                                 # TVTS v1 semantics (configs[4]) at toy dims
-
-
-if __name__ == "__main__":
-    main()
 
 
 # ------------------------------------------------------------------------------------------------------------------ TVTS v1
@@ -217,3 +214,55 @@ def run_case_v1(name="tiny_v1", seed=15):
     print(f"[{name}] loss1 ref {loss1.item():.7f} oracle {l1.item():.7f} | loss2 ref {loss2.item():.7f} oracle {l2.item():.7f}")
     print(f"   max|d text_emb| {(ote - te).abs().max().item():.2e} max|d video_emb| {(ove - ve).abs().max().item():.2e} "
           f"max|d pred| {(opr - pred).abs().max().item():.2e}  worst rel grad-norm dev over {len(gn)} params {worst:.2e} -> {path} ({os.path.getsize(path)} B)")
+
+
+# ------------------------------------------------------------------------------------------------------------------ downstream
+def run_case_downstream(name="tiny_ds", seed=16):
+    """v2/downstream/model_TVTSv2_ViT_B_32.py (+ _mc) at toy dims through the UNMODIFIED reference classes: the towers of TINY_B with
+    mask_ratio 0 and no sort head, forward only (eval, no_grad), n_trans 3.  Weights = the pre-training seeded state_dict minus
+    pred_model.* (what a released downstream checkpoint holds)."""
+    from torch import nn
+    ref_shims.install("v2")
+    import downstream.model_TVTSv2_ViT_B_32 as ds
+    import downstream.model_TVTSv2_ViT_B_32_mc as ds_mc
+    from model.video_encoder_ViT_B_32 import VisionTransformer
+    from CLIP.clip.model import CLIP
+
+    cfg = C.TINY_B
+    sd = {k: v for k, v in make_state_dict(cfg, seed=1234).items() if not k.startswith("pred_model.")}
+    B, T, nt = 3, 2, 3
+    data = make_batch(cfg, B, T, n_trans=nt, seed=seed)
+    out = {"batch": B, "frames": T, "n_trans": nt, "seed": seed}
+    for tag, mod in (("", ds), ("_mc", ds_mc)):
+        m = mod.TVTSv2_B_32.__new__(mod.TVTSv2_B_32)
+        nn.Module.__init__(m)
+        clip_model = CLIP(cfg.embed_dim, cfg.resolution, 1, 64, cfg.patch, cfg.context, cfg.vocab, cfg.text_width, cfg.text_heads, cfg.text_layers)
+        m.text_model = clip_model.transformer
+        m.text_token_embedding = clip_model.token_embedding
+        m.text_positional_embedding = clip_model.positional_embedding
+        m.text_ln_final = clip_model.ln_final
+        m.text_projection = clip_model.text_projection
+        m.video_model = VisionTransformer(input_resolution=cfg.resolution, patch_size=cfg.patch, width=cfg.width, layers=cfg.layers,
+                                          heads=cfg.heads, output_dim=cfg.embed_dim, num_frames=cfg.num_frames, mask_ratio=0.)
+        m.load_state_dict(sd, strict=True)
+        m.eval()
+        with torch.no_grad():
+            te, ve = m(data, return_embeds=True)
+            out["text_emb" + tag], out["video_emb" + tag] = te.numpy(), ve.numpy()
+            if tag == "":
+                out["sims"] = m(data, return_embeds=False).numpy()
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, **out)
+    import tvts_oracle as O
+    full = make_state_dict(cfg, seed=1234)
+    ote, ove, _ = O.model_forward(full, data["text"], data["video"], data["keep_ind"], cfg)
+    print(f"[{name}] max|d text_emb| {(ote - torch.from_numpy(out['text_emb'])).abs().max().item():.2e} "
+          f"max|d video_emb| {(ove - torch.from_numpy(out['video_emb'])).abs().max().item():.2e}  text_emb_mc {out['text_emb_mc'].shape} -> {path} ({os.path.getsize(path)} B)")
+
+
+if __name__ == "__main__":
+    if "--downstream" in sys.argv:      # regenerate only tests/golden/tiny_ds.npz
+        torch.manual_seed(0)
+        run_case_downstream()
+    else:
+        main()

@@ -78,3 +78,81 @@ def test_epoch_loop_interleaves_loaders_and_decays_lr(emu_backend):
         assert steps[id(m.pred_model.head.weight)] == 6                    # transcript (YT) batches only: WebVid steps skip the sort head
     finally:
         opt.flat.release()
+
+
+def _mini_trainer(cfg, seed_sd=1234, config=None):
+    m = M.TVTSv2Base(types.SimpleNamespace(local_rank=0), arch=cfg)
+    m.load_state_dict(make_state_dict(cfg, seed=seed_sd), strict=True)
+    opt = optim.build_reference_optimizer(m)
+    for g in opt.param_groups:
+        g["lr"] *= 50.0                                   # make 2 steps move the weights visibly
+    batches = [make_batch(cfg, 2, 2, n_trans=4, seed=70 + i) for i in range(4)]
+    loader = FakeLoader("YTTemporal", batches, 2)
+    args = types.SimpleNamespace(rank=0, local_rank=0, world_size=1, schedule=[])
+    tr = Trainer_TVTSv2_B_16(args, m, M.NormSoftmaxLoss(0.05), [], opt, config or {"trainer": {"epochs": 1}, "optimizer": {"type": "AdamW"}},
+                             [loader], use_graph=False)
+    return tr, m, opt, batches
+
+
+def test_checkpoint_file_has_the_reference_layout_and_resumes_exactly(emu_backend, tmp_path):
+    """v2/base/base_trainer.py:165-247: {'arch','epoch','state_dict' (module.-prefixed, as saved from the DDP wrapper),'optimizer'
+    (torch Optimizer.state_dict layout of transformers.AdamW),'monitor_best','config'}; resuming continues bit-identically."""
+    cfg = C.TINY_B
+    tr, m, opt, batches = _mini_trainer(cfg)
+    try:
+        for b in batches[:2]:
+            tr.step(b)
+        path = tr.save_checkpoint(str(tmp_path / "checkpoint-epoch1.pth"), epoch=1)
+        ref_losses = [tuple(x.item() for x in tr.step(b)) for b in batches[2:]]
+        ref_w = m.video_model.proj.detach().clone()
+    finally:
+        opt.flat.release()
+    ck = torch.load(path, weights_only=False)
+    assert set(ck) == {"arch", "epoch", "state_dict", "optimizer", "monitor_best", "config"} and ck["arch"] == "TVTSv2Base" and ck["epoch"] == 1
+    assert all(k.startswith("module.") for k in ck["state_dict"])
+    assert {k[7:] for k in ck["state_dict"]} == set(make_state_dict(cfg).keys())
+    osd = ck["optimizer"]
+    assert set(osd) == {"state", "param_groups"} and len(osd["param_groups"]) == 4
+    assert [g["params"][0] for g in osd["param_groups"] if g["params"]][0] == 0
+    n_params = sum(len(g["params"]) for g in osd["param_groups"])
+    assert sorted(i for g in osd["param_groups"] for i in g["params"]) == list(range(n_params))
+    g0 = osd["param_groups"][0]
+    assert g0["betas"] == (0.9, 0.999) and g0["eps"] == 1e-6 and g0["correct_bias"] is True and g0["weight_decay"] == 0.05
+    st = osd["state"][0]
+    assert set(st) == {"step", "exp_avg", "exp_avg_sq"} and st["step"] == 2
+    # a stock torch optimizer over the same groups accepts the file's optimizer entry (same layout as transformers.AdamW's)
+    shadow = [[torch.nn.Parameter(p.detach().clone()) for p in g["params"]] for g in opt.param_groups]
+    topt = torch.optim.AdamW([{"params": ps} for ps in shadow])
+    topt.load_state_dict(osd)
+    assert torch.equal(topt.state[shadow[0][0]]["exp_avg"], st["exp_avg"])
+
+    # resume into a fresh model / optimizer through the constructor's config.resume hook (base_trainer.py:60-61)
+    class Cfg(dict):
+        resume = path
+    tr2, m2, opt2, _ = _mini_trainer(cfg, seed_sd=99, config=Cfg({"trainer": {"epochs": 1}, "optimizer": {"type": "AdamW"}}))
+    try:
+        assert tr2.start_epoch == 2
+        assert opt2.steps[0] == 2 and opt2.param_groups[0]["lr"] == opt.param_groups[0]["lr"]
+        assert m2.video_model.proj.data_ptr() == opt2.flat._view(opt2.flat.p, m2.video_model.proj).data_ptr()   # still arena views
+        got = [tuple(x.item() for x in tr2.step(b)) for b in batches[2:]]
+        assert got == ref_losses, (got, ref_losses)
+        assert torch.equal(m2.video_model.proj.detach(), ref_w)
+    finally:
+        opt2.flat.release()
+    # ... and the model constructors' load_checkpoint= path takes the same file (model_dist_TVTSv2_ViT_B_16.py:51-56)
+    m3 = M.TVTSv2Base(types.SimpleNamespace(local_rank=0), arch=cfg)
+    from tvts_b200.compat import state_dict_data_parallel_fix
+    m3.load_state_dict(state_dict_data_parallel_fix(ck["state_dict"], m3.state_dict()), strict=True)
+
+
+def test_parameter_order_matches_the_reference(emu_backend):
+    """Optimizer state in the reference's checkpoints is keyed by POSITION in the param groups, which are filled in
+    named_parameters() order: ours must enumerate parameters in the reference's order (fixture: names in the order the executed
+    reference listed them, oracle/make_golden.py)."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "tiny_B.npz"))
+    ref_order = [str(s) for s in g["grad_names"]]
+    m = M.TVTSv2Base(types.SimpleNamespace(local_rank=0), arch=C.TINY_B)
+    ours = [k for k, _ in m.named_parameters() if k in set(ref_order)]
+    assert len(ref_order) > 50 and ours == ref_order

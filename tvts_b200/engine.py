@@ -59,6 +59,19 @@ class _WeightCache:
         self._c[key] = (ver, p.data_ptr(), dst, weakref.ref(p))
         return dst
 
+    def refresh(self):
+        """Re-cast, into the SAME buffers, the copies of parameters that were modified since they were cast (checkpoint resume,
+        manual edits): a captured CUDA graph reads those buffers directly and never comes back through get()."""
+        n = 0
+        for key, (ver, ptr, dst, ref) in list(self._c.items()):
+            p = ref()
+            if p is None or p._version == ver or p.data_ptr() != ptr or p.shape != dst.shape:
+                continue
+            L.call("cast_bf16", p.detach().contiguous(), dst, p.numel())
+            self._c[key] = (p._version, ptr, dst, ref)
+            n += 1
+        return n
+
     def clear(self):
         self._c.clear()
 

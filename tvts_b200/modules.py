@@ -69,8 +69,8 @@ class ResidualSpaceTimeAttentionBlock(nn.Module):
         super().__init__()
         self.attn = VarAttention(d_model, num_heads=n_head, qkv_bias=True)
         self.timeattn = VarAttention(d_model, num_heads=n_head, qkv_bias=True, initialize=time_init)
-        self.ln_1 = LayerNorm(d_model)
-        self.ln_3 = LayerNorm(d_model)
+        self.ln_3 = LayerNorm(d_model)          # registration order = the reference's (:99-108): optimizer state in its
+        self.ln_1 = LayerNorm(d_model)          # checkpoints is keyed by position in named_parameters() order
         self.mlp = nn.Sequential(OrderedDict([
             ("c_fc", nn.Linear(d_model, d_model * 4)),
             ("gelu", QuickGELU()),
@@ -258,6 +258,7 @@ class TVTSv2Base(BaseModel):
     PATCH = 16
     MASK_RATIO = 0.5
     CLIP_FILE = "CLIP/models/ViT-B-16.pt"
+    SORT_HEAD = True
 
     def __init__(self, args, load_checkpoint=None, arch=None):
         super().__init__()
@@ -282,15 +283,19 @@ class TVTSv2Base(BaseModel):
                 new_sd[k] = v
             self.video_model.load_state_dict(new_sd, strict=False)
             print("ViT initialized with CLIP weights.")
-        self.n_trans = arch.n_trans
-        self.pred_model = SortTransformer(num_classes=self.n_trans, embed_dim=arch.embed_dim, num_heads=arch.sort_heads)
+        if self.SORT_HEAD:
+            self.n_trans = arch.n_trans
+            self.pred_model = SortTransformer(num_classes=self.n_trans, embed_dim=arch.embed_dim, num_heads=arch.sort_heads)
         if load_checkpoint not in ["", None]:
-            checkpoint = torch.load(load_checkpoint, map_location="cuda:{}".format(self.args.local_rank))
+            checkpoint = torch.load(load_checkpoint, map_location=self._checkpoint_location())
             state_dict = checkpoint["state_dict"]
             from .compat import state_dict_data_parallel_fix
             self.load_state_dict(state_dict_data_parallel_fix(state_dict, self.state_dict()), strict=True)
             print("loading checkpoint from {}".format(load_checkpoint))
         self._text_named = None
+
+    def _checkpoint_location(self):
+        return "cuda:{}".format(self.args.local_rank)
 
     def set_device(self, device):
         self.device = device
@@ -309,19 +314,22 @@ class TVTSv2Base(BaseModel):
         return E.text_tower(self.arch, self._text_params(), text)
 
     def compute_text(self, text):
-        return self.compute_text_all(text)
+        """-> (text_before_embeddings, text_embeddings): the same [n_txt, E] tensor twice, like the reference (:108-111)."""
+        t = self.compute_text_all(text)
+        return t, t
 
     def compute_video(self, video, keep_ind):
+        """-> (video_before_embeddings [B, N, E], video_embeddings [B, E] = the CLS row)   (:113-116)"""
         out = self.video_model(video, keep_ind)
-        return out[:, 0, :], out
+        return out, out[:, 0, :]
 
     def forward(self, data, return_embeds=True):
         text, video, keep_ind = data["text"], data["video"], data["keep_ind"]
         B = video.shape[0]
-        t = self.compute_text(text)                                   # [n_trans*B, E] clip-major
+        t, _ = self.compute_text(text)                                # [n_trans*B, E] clip-major
         n_trans = t.shape[0] // B
         text_embeddings = E.group_mean(t, n_trans)                    # :74-76
-        video_embeddings, video_order_embeddings = self.compute_video(video, keep_ind)
+        video_order_embeddings, video_embeddings = self.compute_video(video, keep_ind)
         if n_trans != 1:
             predict_order = self.pred_model.forward_clip_major(t, video_order_embeddings)   # :69-70 text is detached
         else:
@@ -337,3 +345,50 @@ class TVTSv2_B_16(TVTSv2Base):
 
 class TVTSv2_B_32(TVTSv2Base):
     PATCH, MASK_RATIO, CLIP_FILE = 32, 0.0, "CLIP/models/ViT-B-32.pt"
+
+
+# ------------------------------------------------------------------------------------------------ downstream (zero-shot / feature extraction)
+class TVTSv2Downstream(TVTSv2Base):
+    """v2/downstream/model_TVTSv2_ViT_B_16.py:10-98 (and _B_32): the pre-training towers with mask_ratio 0 and no sort head, used
+    forward-only by zero_ret_* / zero_recognition_* / feature_extraction_*.  Constructor takes only `load_checkpoint`; the
+    state_dict has no `pred_model.*` keys; forward returns (text_embeddings, video_embeddings)."""
+
+    SORT_HEAD = False
+    MEAN_OVER_CLIPS = True        # False in the *_mc variants (model_TVTSv2_ViT_B_16_mc.py:64: the mean over n_trans is commented out)
+
+    def __init__(self, load_checkpoint=None, arch=None):
+        base = arch or (C.TVTSV2_B_16 if self.PATCH == 16 else C.TVTSV2_B_32)
+        super().__init__(None, load_checkpoint, arch=base.small(mask_ratio=0.0))
+
+    def _checkpoint_location(self):
+        return None               # downstream/model_TVTSv2_ViT_B_16.py:42 torch.load(load_checkpoint)
+
+    def forward(self, data, return_embeds=True):
+        text, video, keep_ind = data["text"], data["video"], data["keep_ind"]
+        B = video.shape[0]
+        t, _ = self.compute_text(text)
+        n_trans = t.shape[0] // B
+        if self.MEAN_OVER_CLIPS:
+            text_embeddings = E.group_mean(t, n_trans)                # :62-64
+        else:
+            text_embeddings = t.reshape(n_trans, B, t.shape[-1])      # _mc: [n_choices, B, E]
+        _, video_embeddings = self.compute_video(video, keep_ind)
+        if return_embeds:
+            return text_embeddings, video_embeddings
+        return sim_matrix(text_embeddings, video_embeddings)
+
+
+class TVTSv2_B_16_downstream(TVTSv2Downstream):
+    PATCH, CLIP_FILE = 16, "CLIP/models/ViT-B-16.pt"
+
+
+class TVTSv2_B_32_downstream(TVTSv2Downstream):
+    PATCH, CLIP_FILE = 32, "CLIP/models/ViT-B-32.pt"
+
+
+class TVTSv2_B_16_downstream_mc(TVTSv2_B_16_downstream):
+    MEAN_OVER_CLIPS = False
+
+
+class TVTSv2_B_32_downstream_mc(TVTSv2_B_32_downstream):
+    MEAN_OVER_CLIPS = False

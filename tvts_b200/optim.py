@@ -93,6 +93,18 @@ class FlatState:
             self.synced[i] = p._version
         return view
 
+    def refresh_bf16(self):
+        """Re-cast the bf16 copy of every operand that changed outside the fused optimizer (load_state_dict, manual edits).  Eager
+        steps get this lazily through bf16_view(); a captured CUDA graph reads the arena copy directly, so TrainStep calls this
+        before every replay (a few hundred integer compares when nothing changed)."""
+        n = 0
+        for i, p in enumerate(self.params):
+            if self.synced[i] != -1 and self.synced[i] != p._version:
+                L.call("cast_bf16", p.detach(), self._view(self.bf, p), p.numel())
+                self.synced[i] = p._version
+                n += 1
+        return n
+
     # ---- step bookkeeping ----------------------------------------------------------------------------------------
     def zero_grad(self):
         """One memset over the gradient arena; every parameter's .grad becomes None (torch 2.x zero_grad semantics)."""
@@ -230,16 +242,47 @@ class AdamW:
         return self.flat.chunk_tensor
 
     def state_dict(self):
+        """The `torch.optim.Optimizer.state_dict()` layout `transformers.AdamW` (4.10.2) writes into the reference's checkpoints
+        (v2/base/base_trainer.py:173-181): param ids = positions in group order; per stepped parameter {'step' (int), 'exp_avg',
+        'exp_avg_sq'} shaped like the parameter; groups carry lr / betas / eps / weight_decay / correct_bias."""
         fs = self.flat
-        return {"steps": list(self.steps), "exp_avg": fs.m.clone(), "exp_avg_sq": fs.v.clone(),
-                "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
+        groups, idx = [], 0
+        for g in self.param_groups:
+            d = {k: v for k, v in g.items() if k != "params"}
+            d["params"] = list(range(idx, idx + len(g["params"])))
+            idx += len(g["params"])
+            groups.append(d)
+        state = {}
+        for i, p in enumerate(fs.params):
+            if self.steps[i] > 0:
+                state[i] = {"step": self.steps[i], "exp_avg": fs._view(fs.m, p).clone(), "exp_avg_sq": fs._view(fs.v, p).clone()}
+        return {"state": state, "param_groups": groups}
 
     def load_state_dict(self, sd):
-        self.steps = list(sd["steps"])
-        self.flat.m.copy_(sd["exp_avg"])
-        self.flat.v.copy_(sd["exp_avg_sq"])
-        for g, s in zip(self.param_groups, sd["param_groups"]):
-            g.update(s)
+        """Inverse of state_dict(); also accepts a checkpoint the reference's own optimizer wrote for the same model (same group
+        sizes: the groups are built from named_parameters() in the same order)."""
+        fs = self.flat
+        sizes = [len(g["params"]) for g in sd["param_groups"]]
+        if sizes != [len(g["params"]) for g in self.param_groups]:
+            raise ValueError("loaded state dict has parameter groups of sizes %s, optimizer has %s"
+                             % (sizes, [len(g["params"]) for g in self.param_groups]))
+        ids = [i for g in sd["param_groups"] for i in g["params"]]
+        self.steps = [0] * len(fs.params)
+        fs.m.zero_()
+        fs.v.zero_()
+        with torch.no_grad():
+            for pos, pid in enumerate(ids):
+                st = sd["state"].get(pid)
+                if st is None:
+                    continue
+                p = fs.params[pos]
+                if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                    raise ValueError("optimizer state %d has shape %s, parameter has %s" % (pid, tuple(st["exp_avg"].shape), tuple(p.shape)))
+                self.steps[pos] = int(st["step"])
+                fs._view(fs.m, p).copy_(st["exp_avg"])
+                fs._view(fs.v, p).copy_(st["exp_avg_sq"])
+        for g, s_ in zip(self.param_groups, sd["param_groups"]):
+            g.update({k: (tuple(v) if k == "betas" else v) for k, v in s_.items() if k != "params"})
 
 
 def build_reference_optimizer(model, text_layers=None, tune_from=None):

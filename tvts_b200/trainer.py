@@ -237,6 +237,10 @@ class TrainStep:
             if flat is not None and ent.active is not None:
                 flat.set_active(ent.active)
             self._last_key = key
+        flat = getattr(self.optimizer, "flat", None)
+        if flat is not None:
+            flat.refresh_bf16()                     # weights edited outside the optimizer (checkpoint resume): the graph reads the
+        E.WEIGHTS.refresh()                         # bf16 operand copies directly, so bring them up to date first
         for k, v in ent.static.items():
             v.copy_(data[k], non_blocking=True)
         if consumed is not None:
@@ -331,6 +335,10 @@ class Trainer_TVTSv2:
         self.step = TrainStep(model, optimizer, temperature, self.device, use_graph=use_graph and self.device.type == "cuda")
         self.on_epoch_end = on_epoch_end
         self.history = []
+        self.mnt_best = float("inf")
+        resume = getattr(config, "resume", None)
+        if resume is not None:                                   # base_trainer.py:60-61
+            self.resume_checkpoint(resume)
 
     # ---- helpers ------------------------------------------------------------------------------------------------
     def _tokenize(self, data):
@@ -351,6 +359,41 @@ class Trainer_TVTSv2:
         for group in optimizer.param_groups:
             group["lr"] = group["lr"] * lr_rate
         return lr_rate
+
+    # ---- checkpoints (file format of v2/base/base_trainer.py:165-247) -----------------------------------------------------------
+    def save_checkpoint(self, path, epoch, ddp_prefix=True):
+        """Write what `_save_checkpoint` writes: {'arch', 'epoch', 'state_dict', 'optimizer', 'monitor_best', 'config'}.  The reference
+        saves the DDP-wrapped model, so its keys carry a `module.` prefix; `ddp_prefix=True` reproduces that (both the reference's
+        `_resume_checkpoint` and the model constructors' `load_checkpoint=` accept either form)."""
+        sd = self.model.state_dict()
+        if ddp_prefix and not next(iter(sd)).startswith("module."):
+            sd = type(sd)(("module." + k, v) for k, v in sd.items())
+        state = {"arch": type(self.model).__name__, "epoch": epoch, "state_dict": sd, "optimizer": self.optimizer.state_dict(),
+                 "monitor_best": self.mnt_best, "config": self.config}
+        torch.save(state, path)
+        return path
+
+    def resume_checkpoint(self, path):
+        """`_resume_checkpoint` (:196-247): model weights (with or without the `module.` prefix), optimizer state when the optimizer
+        type is unchanged, start epoch = saved epoch + 1."""
+        from .compat import state_dict_data_parallel_fix
+        checkpoint = torch.load(str(path), map_location=self.device, weights_only=False)
+        self.start_epoch = checkpoint["epoch"] + 1
+        self.mnt_best = checkpoint["monitor_best"]
+        with torch.no_grad():
+            # in-place copy: the parameters are views of the optimizer's flat arena and must stay so
+            self.model.load_state_dict(state_dict_data_parallel_fix(checkpoint["state_dict"], self.model.state_dict()))
+        saved_cfg, cfg = checkpoint.get("config"), self.config
+        same_opt = True
+        try:
+            same_opt = saved_cfg["optimizer"]["type"] == cfg["optimizer"]["type"]
+        except (KeyError, TypeError):
+            pass
+        if same_opt:
+            self.optimizer.load_state_dict(checkpoint["optimizer"])
+        else:
+            print("Warning: Optimizer type given in config file is different from that of checkpoint. Optimizer parameters not being resumed.")
+        return checkpoint
 
     # ---- epoch ----------------------------------------------------------------------------------------------------
     def _train_epoch(self, epoch):
