@@ -98,11 +98,12 @@ int tvts_layernorm_bwd_colsum(const void* dy, int64_t dy_is_bf16, const float* x
                               int64_t M, int64_t D, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Grouped multi-head attention, head dim 64, on the packed qkv buffer [B, N, 3, H, 64] (bf16) written by the qkv GEMM.
+ * Grouped multi-head attention on the packed qkv buffer [B, N, 3, H, d] (bf16) written by the qkv GEMM; head dim d = 64 (B/16, B/32,
+ * text towers, sort head: specialised kernels) or 80 (ViT-H/14 video tower, v2/model/model_dist_TVTSv2_ViT_H_14.py:43-45: generic kernels).
  *   mode 0 FULL  (+causal): v2/CLIP/clip/model.py:185-188 (nn.MultiheadAttention + mask :330-336),
  *                           v2/model/sort_transformer.py:9-13,43-57
  *   mode 1 SPACE / mode 2 TIME: VarAttention, v2/model/video_encoder_ViT_B_16.py:38-76 (N = 1 + T*n, token 0 = CLS)
- * out [B, N, H, 64] bf16; lse [B, H, N] f32 (saved for backward); scale multiplies q.k (reference: q * d^-0.5, :45).
+ * out [B, N, H, d] bf16; lse [B, H, N] f32 (saved for backward); scale multiplies q.k (reference: q * d^-0.5, :45).
  * bwd writes every element of dqkv (same layout as qkv); delta_ws is a [B, H, N] f32 workspace.
  */
 int tvts_attn_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n,
@@ -112,6 +113,13 @@ int tvts_attn_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t N, 
 int tvts_attn_set_side_stream(int on);
 int tvts_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv, int64_t B, int64_t N,
                   int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal, float scale, void* stream);
+
+/* The head-dim generic streamed kernels behind tvts_attn_fwd / tvts_attn_bwd for d != 64, callable directly (d = 64 or 80; same
+ * arguments and results): with d = 64 they cross-check the generic code against the specialised kernels. */
+int tvts_attn_generic_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T,
+                          int64_t n, int64_t causal, float scale, void* stream);
+int tvts_attn_generic_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv, int64_t B,
+                          int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal, float scale, void* stream);
 
 /* Query-window attention (mode FULL, non-causal): only rows [q0, q0+qn) of every sample are queries, all N tokens are keys/values.
  * Used for the LAST block of the sort head, whose only consumed outputs are its n_trans transcript rows
@@ -132,6 +140,13 @@ int tvts_attn_window_bwd(const void* qkv, const void* out, const void* dout, con
  */
 int tvts_patch_gather(const float* video, const int64_t* keep_ind, void* cols, int64_t B, int64_t T, int64_t R, int64_t p, int64_t n,
                       void* stream);
+/* Patch sizes that are not a multiple of 4 (ViT-H/14: 14x14 patches, v2/model/video_encoder_ViT_H_14.py:419-441): 3*p*p = 588 bf16 is
+ * not a whole number of 16-byte units, so the im2col rows are written at a pitch of `ld` elements (a multiple of 8, >= 3*p*p) with a
+ * zero tail, and the conv1 weight is cast to bf16 rows of the same pitch (cast_bf16_pad: src [rows, cols] f32 contiguous ->
+ * dst [rows, ld] bf16, tail zero): the patch-embed GEMM then runs with K = ld, exactly. */
+int tvts_patch_gather_ld(const float* video, const int64_t* keep_ind, void* cols, int64_t B, int64_t T, int64_t R, int64_t p, int64_t n,
+                         int64_t ld, void* stream);
+int tvts_cast_bf16_pad(const float* src, void* dst, int64_t rows, int64_t cols, int64_t ld, void* stream);
 int tvts_video_assemble(const float* tok, const float* cls, const float* pos, const float* tem, const int64_t* keep_ind, float* x0,
                         int64_t B, int64_t T, int64_t n, int64_t D, void* stream);
 int tvts_video_assemble_bwd(const float* dx0, const int64_t* keep_ind, float* dcls, float* dpos, float* dtem, void* dtok_bf16, int64_t B,

@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz by EXECUTING THE UNMODIFIED REFERENCE (build container only).
 
-    python oracle/make_golden.py            # writes tests/golden/{c1_b32,tiny_B,tiny_B_mask,tiny_B_cap,tiny_H,tiny_ds,tiny_v1}.npz
+    python oracle/make_golden.py            # writes tests/golden/{c1_b32,tiny_B,tiny_B_mask,tiny_B_cap,tiny_H,tiny_H640,tiny_ds,tiny_v1}.npz
 
 For each case: seeded state_dict (tvts_b200.synthetic.make_state_dict) is loaded strict=True into the
 reference modules, the reference forward + the trainer's loss lines (v2/trainer/trainer.py:479-496)
@@ -142,6 +142,7 @@ def main():
     run_case("tiny_B_cap", C.TINY_B, batch=4, frames=2, n_trans=1, seed=13)       # caption mode: pred_order None
     run_case("c1_b32", C.TVTSV2_B_32, batch=4, frames=2, n_trans=4, seed=0)       # BASELINE.json configs[0]
     run_case("tiny_H", C.TINY_H, batch=2, frames=3, n_trans=4, seed=14)           # H/14 semantics (configs[3]) at toy dims
+    run_case("tiny_H640", C.TINY_H640, batch=2, frames=3, n_trans=4, seed=17)     # ... at the smallest width the CUDA kernels take
     run_case_downstream()                                                         # v2/downstream towers (mask 0, no sort head), forward only
     run_case_v1()                                                                 # TVTS v1 semantics (configs[4]) at toy dims
 
@@ -264,5 +265,10 @@ if __name__ == "__main__":
     if "--downstream" in sys.argv:      # regenerate only tests/golden/tiny_ds.npz
         torch.manual_seed(0)
         run_case_downstream()
+    elif "--h640" in sys.argv:          # regenerate only tests/golden/tiny_H640.npz
+        torch.manual_seed(0)
+        torch.set_num_threads(os.cpu_count())
+        ref_shims.install("v2")
+        run_case("tiny_H640", C.TINY_H640, batch=2, frames=3, n_trans=4, seed=17)
     else:
         main()

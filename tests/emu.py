@@ -189,6 +189,29 @@ def patch_gather(video, keep, cols, B, T, R, p, n):
     cols.view(B, T, n, -1).copy_(torch.gather(v, 2, idx).to(BF16))
 
 
+def patch_gather_ld(video, keep, cols, B, T, R, p, n, ld):
+    K = 3 * p * p
+    tmp = torch.empty(B * T * n, K, dtype=BF16, device=video.device)
+    patch_gather(video, keep, tmp, B, T, R, p, n)
+    c = cols.view(B * T * n, ld)
+    c.zero_()
+    c[:, :K].copy_(tmp)
+
+
+def cast_bf16_pad(src, dst, rows, cols, ld):
+    d = dst.view(rows, ld)
+    d.zero_()
+    d[:, :cols].copy_(src.reshape(rows, cols).to(BF16))
+
+
+def attn_generic_fwd(*a):
+    attn_fwd(*a)
+
+
+def attn_generic_bwd(*a):
+    attn_bwd(*a)
+
+
 def video_assemble(tok, cls, pos, tem, keep, x0, B, T, n, D):
     t = tok.view(B, T, n, D) + pos[1:][keep.view(B, n)][:, None] + tem[:T][None, :, None, :]
     x = x0.view(B, 1 + T * n, D)

@@ -42,8 +42,8 @@ def test_entry_points_validate_arguments_before_touching_the_device():
     i64, f32, vp = ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
     dummy = ctypes.create_string_buffer(256)
     p = ctypes.cast(dummy, vp)
-    # attention: only head dim 64
-    rc = lib.tvts_attn_fwd(p, p, p, i64(1), i64(16), i64(2), i64(80), i64(0), i64(0), i64(0), i64(0), f32(0.1), None)
+    # attention: head dims 64 (specialised kernels) and 80 (generic kernels, H/14) only
+    rc = lib.tvts_attn_fwd(p, p, p, i64(1), i64(16), i64(2), i64(96), i64(0), i64(0), i64(0), i64(0), f32(0.1), None)
     assert rc < 0 and "head dim" in _err(lib)
     # divided modes need N == 1 + T*n
     rc = lib.tvts_attn_fwd(p, p, p, i64(1), i64(16), i64(2), i64(64), i64(1), i64(2), i64(5), i64(0), f32(0.1), None)

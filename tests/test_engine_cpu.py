@@ -94,3 +94,33 @@ def test_validate_runs_forward_only(emu_backend):
     assert set(res) == {"t2v_metrics", "v2t_metrics", "order_acc"}
     assert 0.0 <= res["t2v_metrics"]["R1"] <= 100.0 and res["order_acc"] is not None
     assert all(p.grad is None for p in m.parameters())
+
+
+@pytest.mark.parametrize("cfg,name", [(C.TINY_H, "tiny_H"), (C.TINY_H640, "tiny_H640")])
+def test_h14_engine_matches_reference_golden_and_oracle(emu_backend, cfg, name):
+    """TVTSv2_H_14 semantics (model_dist_TVTSv2_ViT_H_14.py, video_encoder_ViT_H_14.py): 14x14 patches through the padded patch-embed
+    GEMM, head dim 80, exact GELU, ln_post on the CLS row only, sort head over the patch tokens -- against the fixture written by the
+    executed reference and the oracle's gradients; parameter enumeration order = the reference's."""
+    import os
+    import numpy as np
+    E.WEIGHTS.clear()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    m = M.TVTSv2_H_14(types.SimpleNamespace(local_rank=0), arch=cfg)
+    sd = make_state_dict(cfg, seed=1234)
+    m.load_state_dict(sd, strict=True)
+    data = make_batch(cfg, int(g["batch"]), int(g["frames"]), n_trans=int(g["n_trans"]), seed=int(g["seed"]))
+    l1, l2, te, ve, pred = run_step(m, data, cfg)
+    assert abs(l1.item() - float(g["loss1"])) < 2e-2 and abs(l2.item() - float(g["loss2"])) < 2e-2
+    np.testing.assert_allclose(te.numpy(), g["text_emb"], atol=3e-2, rtol=3e-2)
+    np.testing.assert_allclose(ve.numpy(), g["video_emb"], atol=3e-2, rtol=3e-2)
+    np.testing.assert_allclose(pred.numpy(), g["pred_order"], atol=5e-2, rtol=5e-2)
+    tokens, pooled = m.compute_video(data["video"], data["keep_ind"])
+    assert tokens.shape == (int(g["batch"]), cfg.tokens(int(g["frames"])) - 1, cfg.embed_dim) and pooled.shape == ve.shape
+    _, _, _, ograds = O.step_with_grads(sd, data["text"], data["video"], data["keep_ind"], data["label"], cfg)
+    got = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+    assert set(got) == set(ograds)
+    for k, gr in ograds.items():
+        rel = (got[k].double() - gr.double()).norm().item() / (gr.double().norm().item() + 1e-8)
+        assert rel < 0.08, (k, rel)
+    ref_order = [str(s) for s in g["grad_names"]]
+    assert [k for k, _ in m.named_parameters() if k in set(ref_order)] == ref_order

@@ -23,10 +23,11 @@ def _read_state_dict(path):
         return sd.get("state_dict", sd) if isinstance(sd, dict) else sd.state_dict()
 
 
-def load(name, arch, device="cpu"):
-    """-> (CLIPTextParts, visual_state_dict | None)"""
+def load(name, arch, device="cpu", open_clip=False):
+    """-> (CLIPTextParts, visual_state_dict | None).  open_clip=True: the text blocks register their parameters in OpenCLIP's order
+    (v2/OpenCLIP/transformer.py:189-214); an OpenCLIP `open_clip_pytorch_model.bin` has the same key layout as an OpenAI state_dict."""
     parts = M.CLIPTextParts(embed_dim=arch.embed_dim, context_length=arch.context, vocab_size=arch.vocab,
-                            width=arch.text_width, heads=arch.text_heads, layers=arch.text_layers)
+                            width=arch.text_width, heads=arch.text_heads, layers=arch.text_layers, open_clip=open_clip)
     visual_sd = None
     if name and os.path.isfile(name):
         sd = {k: v.float() for k, v in _read_state_dict(name).items() if torch.is_tensor(v)}

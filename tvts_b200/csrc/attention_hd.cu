@@ -1,0 +1,509 @@
+// Streamed grouped attention for head dims other than 64 (TVTSv2 ViT-H/14: D 1280 / 16 heads = 80,
+// v2/model/model_dist_TVTSv2_ViT_H_14.py:43-45 + v2/OpenCLIP/model_configs/ViT-H-14.json), forward + backward.
+//
+// Same algorithm, index sets (attention_common.cuh: FULL / SPACE / TIME with the CLS row and column) and launch geometry as the
+// streamed kernels of attention.cu, templated on the head dim HD (a multiple of 16, <= 128):
+//   * a token's head slice is HD/8 16-byte chunks; shared-memory tiles keep 64 rows at a pitch of 128 B (HD <= 64) or 256 B, with the
+//     16-byte chunk index XOR-ed with (row & 7) so that ldmatrix stays bank-conflict free; chunks past HD/8 are never touched
+//   * S = Q K^T runs HD/16 k-steps, O = P V / dQ / dK / dV produce HD/8 8-wide n-tiles per warp
+// tvts_attn_fwd / tvts_attn_bwd (attention.cu) forward here whenever d != 64; the HD = 64 instantiation exists only so that the
+// generic code can be checked against the specialised kernels (tests call tvts_attn_generic_* with d = 64 directly).
+#include "attention_common.cuh"
+#include "../../include/tvts_b200.h"
+
+namespace {
+
+template <int HD>
+struct Geo {
+  static_assert(HD % 16 == 0 && HD >= 16 && HD <= 128, "head dim must be a multiple of 16, at most 128");
+  static constexpr int CH = HD / 8;                    // 16-byte chunks per row
+  static constexpr int KS = HD / 16;                   // k-steps of a product that contracts over the head dim
+  static constexpr int ND = HD / 8;                    // 8-wide n-tiles of a product whose columns are the head dim
+  static constexpr int PITCH = HD <= 64 ? 128 : 256;   // shared-memory row pitch in bytes
+  static constexpr int TILE = 64 * PITCH;              // one 64-row tile
+};
+
+// byte offset of 16-byte chunk `c` of row `r` in a tile of pitch P (c ^ (r & 7) stays inside c's group of 8 chunks = 128 B)
+template <int P>
+__device__ __forceinline__ uint32_t swzp(int r, int c) { return (uint32_t)(r * P + ((c ^ (r & 7)) << 4)); }
+
+// A fragments: 16 rows starting at row0, all HD dims
+template <int HD>
+__device__ __forceinline__ void g_load_a(uint32_t tile, int row0, int lane, uint32_t (&a)[Geo<HD>::KS][4]) {
+  const int r = row0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+  for (int kk = 0; kk < Geo<HD>::KS; ++kk)
+    ldsm_x4(tile + swzp<Geo<HD>::PITCH>(r, 2 * kk + (lane >> 4)), a[kk][0], a[kk][1], a[kk][2], a[kk][3]);
+}
+// B fragments, tile ROWS as the n index (S = A . tile^T): n-tiles j, j+1 (rows 8j .. 8j+15), k-step kk (dims 16kk ..)
+template <int HD>
+__device__ __forceinline__ void g_load_b_rows(uint32_t tile, int j, int kk, int lane, uint32_t& b0, uint32_t& b1, uint32_t& c0, uint32_t& c1) {
+  const int r = 8 * j + (lane & 7) + ((lane >> 4) & 1) * 8;
+  ldsm_x4(tile + swzp<Geo<HD>::PITCH>(r, 2 * kk + ((lane >> 3) & 1)), b0, b1, c0, c1);
+}
+// B fragments, tile ROWS as the k index (O = P . tile): k-step kk (rows 16kk .. 16kk+15), n-tiles jd, jd+1 (dims 8jd ..)
+template <int HD>
+__device__ __forceinline__ void g_load_b_cols(uint32_t tile, int kk, int jd, int lane, uint32_t& b0, uint32_t& b1, uint32_t& c0, uint32_t& c1) {
+  const int r = 16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8;
+  ldsm_x4_t(tile + swzp<Geo<HD>::PITCH>(r, jd + (lane >> 4)), b0, b1, c0, c1);
+}
+// cooperative 64-row tile load (rows >= cnt are zero-filled); token(r) gives the token index of tile row r
+template <int HD, typename TokFn>
+__device__ __forceinline__ void g_load_tile(uint32_t tile, const bf16* base, long long row_stride, int cnt, TokFn token) {
+  constexpr int CH = Geo<HD>::CH;
+  for (int i = threadIdx.x; i < 64 * CH; i += kThreads) {
+    const int r = i / CH, c = i - r * CH;
+    const bool ok = r < cnt;
+    const long long tok = ok ? token(r) : 0;
+    cp_async16(tile + swzp<Geo<HD>::PITCH>(r, c), base + tok * row_stride + c * 8, ok);
+  }
+}
+
+// ================================================================================================ forward
+template <int HD>
+__global__ void __launch_bounds__(kThreads) attn_hd_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse,
+                                                               AttnShape a) {
+  using G = Geo<HD>;
+  extern __shared__ __align__(128) uint8_t smem[];   // Q | K0 | V0 | K1 | V1
+  const uint32_t sQ = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const Sets s = decode_sets(a, blockIdx.x);
+  const long long rs = 3LL * a.H * HD;
+  const bf16* qb = qkv + (long long)b * a.N * rs + (long long)h * HD;
+  const bf16* kb = qb + (long long)a.H * HD;
+  const bf16* vb = kb + (long long)a.H * HD;
+  const int total = s.sm_has0 + s.sm_count;
+  int t_end = (total + BN - 1) / BN;
+  if (a.causal) t_end = min(t_end, (s.st_base + (s.st_count - 1) * s.st_stride) / BN + 1);
+
+  g_load_tile<HD>(sQ, qb, rs, s.st_count, [&](int r) { return s.st_base + r * s.st_stride; });
+  auto issue = [&](int t) {
+    const uint32_t sK = sQ + (1 + 2 * (t & 1)) * G::TILE, sV = sK + G::TILE;
+    const int k0 = t * BN, cnt = min(BN, total - k0);
+    g_load_tile<HD>(sK, kb, rs, cnt, [&](int r) { return streamed_token(s, k0 + r); });
+    g_load_tile<HD>(sV, vb, rs, cnt, [&](int r) { return streamed_token(s, k0 + r); });
+  };
+  issue(0);
+  cp_async_commit();
+
+  const bool warp_active = warp * 16 < s.st_count;   // warp-uniform
+  uint32_t qa[G::KS][4];
+  float o[G::ND][4];
+#pragma unroll
+  for (int j = 0; j < G::ND; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const float sl2 = a.scale * LOG2E;
+  const int row0 = warp * 16 + g, row1 = row0 + 8;
+  const int qtok0 = s.st_base + row0 * s.st_stride, qtok1 = s.st_base + row1 * s.st_stride;
+
+  for (int t = 0; t < t_end; ++t) {
+    if (t + 1 < t_end) issue(t + 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    if (t == 0) g_load_a<HD>(sQ, warp * 16, lane, qa);
+    if (warp_active) {
+      const uint32_t sK = sQ + (1 + 2 * (t & 1)) * G::TILE, sV = sK + G::TILE;
+      const int k0 = t * BN, cnt = min(BN, total - k0);
+      float sc[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        if (8 * j < cnt) {     // CTA-uniform: key tiles past the end of a short group are never computed
+#pragma unroll
+          for (int kk = 0; kk < G::KS; ++kk) {
+            uint32_t b0, b1, c0, c1;
+            g_load_b_rows<HD>(sK, j, kk, lane, b0, b1, c0, c1);
+            mma16816(sc[j], qa[kk], b0, b1);
+            mma16816(sc[j + 1], qa[kk], c0, c1);
+          }
+        }
+      }
+      // mask + row max
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (8 * j >= cnt) { sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = -INFINITY; continue; }   // CTA-uniform
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int key = 8 * j + 2 * t4 + e;
+          bool ok = key < cnt;
+          bool ok0 = ok, ok1 = ok;
+          if (a.causal && ok) {
+            const int tok = streamed_token(s, k0 + key);
+            ok0 = tok <= qtok0; ok1 = tok <= qtok1;
+          }
+          if (!ok0) sc[j][e] = -INFINITY;
+          if (!ok1) sc[j][2 + e] = -INFINITY;
+          mx0 = fmaxf(mx0, sc[j][e]);
+          mx1 = fmaxf(mx1, sc[j][2 + e]);
+        }
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+      const float mu0 = mn0 == -INFINITY ? 0.f : mn0, mu1 = mn1 == -INFINITY ? 0.f : mn1;
+      const float corr0 = exp2f((m0 - mu0) * sl2), corr1 = exp2f((m1 - mu1) * sl2);   // m = -inf -> 0
+      m0 = mn0; m1 = mn1;
+      float ps0 = 0.f, ps1 = 0.f;
+      uint32_t pa[4][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (8 * j >= cnt) { pa[j >> 1][(j & 1) * 2] = 0u; pa[j >> 1][(j & 1) * 2 + 1] = 0u; continue; }
+        const float p00 = exp2f((sc[j][0] - mu0) * sl2), p01 = exp2f((sc[j][1] - mu0) * sl2);
+        const float p10 = exp2f((sc[j][2] - mu1) * sl2), p11 = exp2f((sc[j][3] - mu1) * sl2);
+        ps0 += p00 + p01; ps1 += p10 + p11;
+        pa[j >> 1][(j & 1) * 2] = pack_bf16x2(p00, p01);
+        pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p10, p11);
+      }
+      l0 = l0 * corr0 + ps0; l1 = l1 * corr1 + ps1;   // per-thread partial sums; reduced across the quad at the end
+#pragma unroll
+      for (int j = 0; j < G::ND; ++j) { o[j][0] *= corr0; o[j][1] *= corr0; o[j][2] *= corr1; o[j][3] *= corr1; }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        if (16 * kk < cnt) {
+#pragma unroll
+          for (int jd = 0; jd < G::ND; jd += 2) {
+            uint32_t b0, b1, c0, c1;
+            g_load_b_cols<HD>(sV, kk, jd, lane, b0, b1, c0, c1);
+            mma16816(o[jd], pa[kk], b0, b1);
+            mma16816(o[jd + 1], pa[kk], c0, c1);
+          }
+        }
+      }
+    }
+    __syncthreads();   // everyone done with this stage's K/V before it is refilled
+  }
+  cp_async_wait<0>();
+  if (!warp_active) return;
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+  // stage the warp's 16 output rows in its slice of the Q tile (its fragments are in registers), then 16-byte row stores
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < G::ND; ++j) {
+    const uint32_t w0 = pack_bf16x2(o[j][0] * inv0, o[j][1] * inv0), w1 = pack_bf16x2(o[j][2] * inv1, o[j][3] * inv1);
+    *reinterpret_cast<uint32_t*>(smem + swzp<G::PITCH>(row0, j) + 4 * t4) = w0;
+    *reinterpret_cast<uint32_t*>(smem + swzp<G::PITCH>(row1, j) + 4 * t4) = w1;
+  }
+  __syncwarp();
+  const long long ro = (long long)a.H * HD;
+  bf16* ob = out + (long long)b * a.N * ro + (long long)h * HD;
+  for (int i = lane; i < 16 * G::CH; i += 32) {
+    const int rr = i / G::CH, c = i - rr * G::CH;
+    const int r = warp * 16 + rr;
+    if (r < s.st_count) {
+      const uint4 v = *reinterpret_cast<const uint4*>(smem + swzp<G::PITCH>(r, c));
+      *reinterpret_cast<uint4*>(ob + (long long)(s.st_base + r * s.st_stride) * ro + c * 8) = v;
+    }
+  }
+  if (t4 == 0) {
+    float* lb = lse + ((long long)b * a.H + h) * a.N;
+    if (row0 < s.st_count) lb[qtok0] = m0 * a.scale + __logf(l0);
+    if (row1 < s.st_count) lb[qtok1] = m1 * a.scale + __logf(l1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ delta = rowsum(dO * O)
+template <int HD>
+__global__ void __launch_bounds__(256) attn_hd_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout,
+                                                            float* __restrict__ delta, int B, int N, int H) {
+  // 8 lanes per (token, head) row of HD bf16: 16-byte loads of O and dO, chunks strided over the octet, reduce inside the octet
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int sub = threadIdx.x & 7;
+  const bool ok = w < (long long)B * N * H;
+  float s = 0.f;
+  if (ok) {
+    for (int c = sub; c < Geo<HD>::CH; c += 8) {
+      const uint4 o = reinterpret_cast<const uint4*>(out + w * HD)[c];
+      const uint4 d = reinterpret_cast<const uint4*>(dout + w * HD)[c];
+      const uint32_t ov[4] = {o.x, o.y, o.z, o.w}, dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 x = unpack_bf16x2(ov[i]), y = unpack_bf16x2(dv[i]);
+        s = fmaf(x.x, y.x, s);
+        s = fmaf(x.y, y.y, s);
+      }
+    }
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (ok && sub == 0) {
+    const int h = (int)(w % H);
+    const long long bn = w / H;
+    const int i = (int)(bn % N);
+    const int b = (int)(bn / N);
+    delta[((long long)b * H + h) * N + i] = s;
+  }
+}
+
+// ================================================================================================ backward
+// ROLE 0: stationary = query i (tiles Q, dO), streamed X = K, Y = V        -> dq_i = scale * sum_j ds_ij k_j
+// ROLE 1: stationary = key j   (tiles K, V),  streamed X = Q, Y = dO       -> dk_j = scale * sum_i ds_ij q_i ; dv_j = sum_i p_ij do_i
+// with p_ij = exp(scale q_i.k_j - lse_i), ds_ij = p_ij (do_i.v_j - delta_i)   (see attn_bwd_kernel in attention.cu)
+template <int HD, int ROLE>
+__global__ void __launch_bounds__(kThreads) attn_hd_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+                                                               const float* __restrict__ lse, const float* __restrict__ delta,
+                                                               bf16* __restrict__ dqkv, AttnShape a) {
+  using G = Geo<HD>;
+  extern __shared__ __align__(128) uint8_t smem[];   // 4 tiles + lse/delta of the streamed rows for 2 stages
+  // [0] stationary tile 0 (Q or K) -> after the fragment load reused as X stage 1
+  // [1] stationary tile 1 (dO or V) -> reused as Y stage 1
+  // [2] X stage 0, [3] Y stage 0
+  const uint32_t s0 = smem_u32(smem);
+  float* LsDs = reinterpret_cast<float*>(smem + 4 * G::TILE);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const Sets s = decode_sets(a, blockIdx.x, ROLE == 1);
+  const long long rs = 3LL * a.H * HD, ro = (long long)a.H * HD;
+  const bf16* qb = qkv + (long long)b * a.N * rs + (long long)h * HD;
+  const bf16* kb = qb + ro;
+  const bf16* vb = kb + ro;
+  const bf16* dob = dout + (long long)b * a.N * ro + (long long)h * HD;
+  const float* lse_b = lse + ((long long)b * a.H + h) * a.N;
+  const float* delta_b = delta + ((long long)b * a.H + h) * a.N;
+  bf16* dq_b = dqkv + (long long)b * a.N * rs + (long long)h * HD;
+
+  const bf16* xs_base = ROLE == 0 ? kb : qb;
+  const bf16* ys_base = ROLE == 0 ? vb : dob;
+  const long long ys_stride = ROLE == 0 ? rs : ro;
+  const int total = s.sm_has0 + s.sm_count;
+  int t_begin = 0, t_end = (total + BN - 1) / BN;
+  if (a.causal) {
+    if (ROLE == 0) t_end = min(t_end, (s.st_base + (s.st_count - 1) * s.st_stride) / BN + 1);
+    else t_begin = s.st_base / BN;  // queries before the first key of the chunk never see it
+  }
+  auto st_tok = [&](int r) { return s.st_base + r * s.st_stride; };
+  auto issue = [&](int t, int stage) {
+    const uint32_t sX = s0 + (stage == 0 ? 2 : 0) * G::TILE, sY = sX + G::TILE;
+    const int k0 = t * BN, cnt = min(BN, total - k0);
+    g_load_tile<HD>(sX, xs_base, rs, cnt, [&](int r) { return streamed_token(s, k0 + r); });
+    g_load_tile<HD>(sY, ys_base, ys_stride, cnt, [&](int r) { return streamed_token(s, k0 + r); });
+    if (ROLE == 1) {
+      for (int i = threadIdx.x; i < BN; i += kThreads) {
+        float l_ = 0.f, d_ = 0.f;
+        if (i < cnt) { const int tok = streamed_token(s, k0 + i); l_ = lse_b[tok]; d_ = delta_b[tok]; }
+        LsDs[stage * 2 * BN + i] = l_ * LOG2E;
+        LsDs[stage * 2 * BN + BN + i] = d_;
+      }
+    }
+  };
+  if (ROLE == 0) {
+    g_load_tile<HD>(s0, qb, rs, s.st_count, st_tok);
+    g_load_tile<HD>(s0 + G::TILE, dob, ro, s.st_count, st_tok);
+  } else {
+    g_load_tile<HD>(s0, kb, rs, s.st_count, st_tok);
+    g_load_tile<HD>(s0 + G::TILE, vb, rs, s.st_count, st_tok);
+  }
+  issue(t_begin, 0);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  uint32_t fa[G::KS][4], fb[G::KS][4];   // ROLE 0: Q, dO ; ROLE 1: K, V   (A operands, 16 rows of this warp)
+  g_load_a<HD>(s0, warp * 16, lane, fa);
+  g_load_a<HD>(s0 + G::TILE, warp * 16, lane, fb);
+  __syncthreads();                       // tiles 0,1 may now be overwritten (stage 1)
+
+  const bool warp_active = warp * 16 < s.st_count;
+  const int row0 = warp * 16 + g, row1 = row0 + 8;
+  const int stok0 = st_tok(row0), stok1 = st_tok(row1);
+  float lse0 = 0.f, lse1 = 0.f, dl0 = 0.f, dl1 = 0.f;
+  if (ROLE == 0) {
+    if (row0 < s.st_count) { lse0 = lse_b[stok0] * LOG2E; dl0 = delta_b[stok0]; }
+    if (row1 < s.st_count) { lse1 = lse_b[stok1] * LOG2E; dl1 = delta_b[stok1]; }
+  }
+  const float sl2 = a.scale * LOG2E;
+  float acc0[G::ND][4], acc1[ROLE == 1 ? G::ND : 1][4];   // ROLE 0: acc0 = dQ ; ROLE 1: acc0 = dK, acc1 = dV
+#pragma unroll
+  for (int j = 0; j < G::ND; ++j) acc0[j][0] = acc0[j][1] = acc0[j][2] = acc0[j][3] = 0.f;
+#pragma unroll
+  for (int j = 0; j < (ROLE == 1 ? G::ND : 1); ++j) acc1[j][0] = acc1[j][1] = acc1[j][2] = acc1[j][3] = 0.f;
+
+  for (int t = t_begin; t < t_end; ++t) {
+    const int stage = (t - t_begin) & 1;
+    if (t + 1 < t_end) issue(t + 1, stage ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    if (warp_active) {
+      const uint32_t sX = s0 + (stage == 0 ? 2 : 0) * G::TILE, sY = sX + G::TILE;
+      const float* Ls = LsDs + stage * 2 * BN;
+      const float* Ds = Ls + BN;
+      const int k0 = t * BN, cnt = min(BN, total - k0);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {   // 32 streamed rows at a time (register pressure)
+        if (32 * half >= cnt) break;           // CTA-uniform
+        float sc[4][4], dp[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
+#pragma unroll
+        for (int j = 0; j < 4; j += 2) {
+          if (32 * half + 8 * j < cnt) {
+#pragma unroll
+            for (int kk = 0; kk < G::KS; ++kk) {
+              uint32_t b0, b1, c0, c1;
+              g_load_b_rows<HD>(sX, half * 4 + j, kk, lane, b0, b1, c0, c1);
+              mma16816(sc[j], fa[kk], b0, b1);
+              mma16816(sc[j + 1], fa[kk], c0, c1);
+              g_load_b_rows<HD>(sY, half * 4 + j, kk, lane, b0, b1, c0, c1);
+              mma16816(dp[j], fb[kk], b0, b1);
+              mma16816(dp[j + 1], fb[kk], c0, c1);
+            }
+          }
+        }
+        uint32_t pa[2][4], dsa[2][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (32 * half + 8 * j >= cnt) {                        // CTA-uniform: nothing streamed there
+            dsa[j >> 1][(j & 1) * 2] = 0u; dsa[j >> 1][(j & 1) * 2 + 1] = 0u;
+            pa[j >> 1][(j & 1) * 2] = 0u; pa[j >> 1][(j & 1) * 2 + 1] = 0u;
+            continue;
+          }
+          float p[4], ds[4];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = 32 * half + 8 * j + 2 * t4 + e;      // streamed row index inside the tile
+            bool ok = col < cnt, ok0 = ok, ok1 = ok;
+            if (a.causal && ok) {
+              const int tok = streamed_token(s, k0 + col);
+              if (ROLE == 0) { ok0 = tok <= stok0; ok1 = tok <= stok1; }
+              else { ok0 = tok >= stok0; ok1 = tok >= stok1; }
+            }
+            const float la = ROLE == 0 ? lse0 : Ls[col], lb = ROLE == 0 ? lse1 : Ls[col];
+            const float da = ROLE == 0 ? dl0 : Ds[col], db = ROLE == 0 ? dl1 : Ds[col];
+            p[e] = ok0 ? exp2f(sc[j][e] * sl2 - la) : 0.f;
+            p[2 + e] = ok1 ? exp2f(sc[j][2 + e] * sl2 - lb) : 0.f;
+            ds[e] = p[e] * (dp[j][e] - da);
+            ds[2 + e] = p[2 + e] * (dp[j][2 + e] - db);
+          }
+          dsa[j >> 1][(j & 1) * 2] = pack_bf16x2(ds[0], ds[1]);
+          dsa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(ds[2], ds[3]);
+          pa[j >> 1][(j & 1) * 2] = pack_bf16x2(p[0], p[1]);
+          pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p[2], p[3]);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          if (32 * half + 16 * kk >= cnt) break;
+#pragma unroll
+          for (int jd = 0; jd < G::ND; jd += 2) {
+            uint32_t b0, b1, c0, c1;
+            g_load_b_cols<HD>(sX, half * 2 + kk, jd, lane, b0, b1, c0, c1);     // ROLE 0: K (dQ += dS K) ; ROLE 1: Q (dK += dS^T Q)
+            mma16816(acc0[jd], dsa[kk], b0, b1);
+            mma16816(acc0[jd + 1], dsa[kk], c0, c1);
+            if (ROLE == 1) {
+              g_load_b_cols<HD>(sY, half * 2 + kk, jd, lane, b0, b1, c0, c1);   // dO (dV += P^T dO)
+              mma16816(acc1[jd], pa[kk], b0, b1);
+              mma16816(acc1[jd + 1], pa[kk], c0, c1);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+  __syncthreads();   // all warps are past their last tile: tile 2/3 region is free for output staging
+  if (!warp_active) return;
+  // stage through this warp's private 16-row slice of tile 2 (and tile 3 for dV), then 16-byte row stores
+  uint8_t* stg = smem + 2 * G::TILE;
+#pragma unroll
+  for (int j = 0; j < G::ND; ++j) {
+    *reinterpret_cast<uint32_t*>(stg + swzp<G::PITCH>(row0, j) + 4 * t4) = pack_bf16x2(acc0[j][0] * a.scale, acc0[j][1] * a.scale);
+    *reinterpret_cast<uint32_t*>(stg + swzp<G::PITCH>(row1, j) + 4 * t4) = pack_bf16x2(acc0[j][2] * a.scale, acc0[j][3] * a.scale);
+    if (ROLE == 1) {
+      *reinterpret_cast<uint32_t*>(stg + G::TILE + swzp<G::PITCH>(row0, j) + 4 * t4) = pack_bf16x2(acc1[j][0], acc1[j][1]);
+      *reinterpret_cast<uint32_t*>(stg + G::TILE + swzp<G::PITCH>(row1, j) + 4 * t4) = pack_bf16x2(acc1[j][2], acc1[j][3]);
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < 16 * G::CH; i += 32) {
+    const int rr = i / G::CH, c = i - rr * G::CH;
+    const int r = warp * 16 + rr;
+    if (r < s.st_count) {
+      bf16* dst = dq_b + (long long)st_tok(r) * rs + (ROLE == 0 ? 0 : ro) + c * 8;
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(stg + swzp<G::PITCH>(r, c));
+      if (ROLE == 1) *reinterpret_cast<uint4*>(dst + ro) = *reinterpret_cast<const uint4*>(stg + G::TILE + swzp<G::PITCH>(r, c));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+int hd_check_shape(const AttnShape& a, int64_t d) {
+  TVTS_REQUIRE(d == 64 || d == 80, "attention: head dim %lld unsupported (64 and 80 are built)", (long long)d);
+  TVTS_REQUIRE(a.B > 0 && a.N > 0 && a.H > 0, "attention: empty shape");
+  TVTS_REQUIRE(a.mode >= 0 && a.mode <= 2, "attention: bad mode %d", a.mode);
+  if (a.mode != 0) {
+    TVTS_REQUIRE(a.T > 0 && a.n > 0 && a.N == 1 + a.T * a.n, "attention: N=%d != 1 + T*n (T=%d n=%d)", a.N, a.T, a.n);
+    TVTS_REQUIRE(!a.causal, "attention: causal only valid in full mode");
+  }
+  TVTS_REQUIRE(a.H <= 65535 && a.B <= 65535, "attention: grid limits");
+  return TVTS_OK;
+}
+
+template <int HD>
+int hd_launch_fwd(const void* qkv, void* out, float* lse, const AttnShape& a, cudaStream_t st) {
+  constexpr int smem_bytes = 5 * Geo<HD>::TILE;
+  static bool set = false;
+  if (!set) {
+    TVTS_CHECK_CUDA(cudaFuncSetAttribute(attn_hd_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    set = true;
+  }
+  dim3 grid(num_blocks_x(a), (unsigned)a.H, (unsigned)a.B);
+  attn_hd_fwd_kernel<HD><<<grid, kThreads, smem_bytes, st>>>((const bf16*)qkv, (bf16*)out, lse, a);
+  TVTS_LAUNCH_CHECK();
+  return TVTS_OK;
+}
+
+template <int HD>
+int hd_launch_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv, const AttnShape& a,
+                  cudaStream_t st) {
+  constexpr int smem_bytes = 4 * Geo<HD>::TILE + 2 * 2 * BN * 4;
+  static bool set = false;
+  if (!set) {
+    TVTS_CHECK_CUDA(cudaFuncSetAttribute(attn_hd_bwd_kernel<HD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    TVTS_CHECK_CUDA(cudaFuncSetAttribute(attn_hd_bwd_kernel<HD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    set = true;
+  }
+  const long long rows = (long long)a.B * a.N * a.H;
+  attn_hd_delta_kernel<HD><<<(unsigned)((rows + 31) / 32), 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta_ws, a.B, a.N, a.H);
+  TVTS_LAUNCH_CHECK();
+  dim3 g0(num_blocks_x(a, false), (unsigned)a.H, (unsigned)a.B);
+  attn_hd_bwd_kernel<HD, 0><<<g0, kThreads, smem_bytes, st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, a);
+  TVTS_LAUNCH_CHECK();
+  dim3 g1(num_blocks_x(a, true), (unsigned)a.H, (unsigned)a.B);
+  attn_hd_bwd_kernel<HD, 1><<<g1, kThreads, smem_bytes, st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, a);
+  TVTS_LAUNCH_CHECK();
+  return TVTS_OK;
+}
+
+}  // namespace
+
+extern "C" int tvts_attn_generic_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode,
+                                     int64_t T, int64_t n, int64_t causal, float scale, void* stream) {
+  AttnShape a{(int)B, (int)N, (int)H, (int)mode, (int)T, (int)n, (int)causal, scale, 0, 0, 0};
+  if (B == 0) return TVTS_OK;
+  int rc = hd_check_shape(a, d);
+  if (rc) return rc;
+  TVTS_REQUIRE(qkv && out && lse, "attn_generic_fwd: null pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return d == 64 ? hd_launch_fwd<64>(qkv, out, lse, a, st) : hd_launch_fwd<80>(qkv, out, lse, a, st);
+}
+
+extern "C" int tvts_attn_generic_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv,
+                                     int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal,
+                                     float scale, void* stream) {
+  AttnShape a{(int)B, (int)N, (int)H, (int)mode, (int)T, (int)n, (int)causal, scale, 0, 0, 0};
+  if (B == 0) return TVTS_OK;
+  int rc = hd_check_shape(a, d);
+  if (rc) return rc;
+  TVTS_REQUIRE(qkv && out && dout && lse && delta_ws && dqkv, "attn_generic_bwd: null pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return d == 64 ? hd_launch_bwd<64>(qkv, out, dout, lse, delta_ws, dqkv, a, st)
+                 : hd_launch_bwd<80>(qkv, out, dout, lse, delta_ws, dqkv, a, st);
+}

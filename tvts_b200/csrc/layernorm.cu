@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(kWarps * 32) ln_bwd_kernel(const void* __restr
     case 1: MACRO(1); break;      \
     case 2: MACRO(2); break;      \
     case 4: MACRO(4); break;      \
+    case 5: MACRO(5); break;      \
     case 6: MACRO(6); break;      \
     case 8: MACRO(8); break;      \
     case 10: MACRO(10); break;    \

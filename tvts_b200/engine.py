@@ -476,11 +476,22 @@ def video_forward(P, video, keep_ind, cfg):
     K = 3 * p * p
     video = video.contiguous().float()
     keep_ind = keep_ind.to(device=video.device, dtype=torch.int64).contiguous()
-    cols = _empty((B * T * n, K), BF16, video)
-    L.call("patch_gather", video, keep_ind, cols, B, T, R, p, n)
-    w_bf = P.bf("conv1.weight").view(D, K)
     tok = _empty((B * T * n, D), F32, video)
-    L.gemm(cols, w_bf, tok, M=B * T * n, N=D, K=K, lda=K, ldb=K)
+    if p % 4 == 0:
+        cols = _empty((B * T * n, K), BF16, video)
+        L.call("patch_gather", video, keep_ind, cols, B, T, R, p, n)
+        w_bf = P.bf("conv1.weight").view(D, K)
+        L.gemm(cols, w_bf, tok, M=B * T * n, N=D, K=K, lda=K, ldb=K)
+    else:
+        # H/14: 3*14*14 = 588 bf16 per im2col row is not a whole number of 16-byte units -> both GEMM operands are laid out at a
+        # row pitch of Kp (zero tail).  The padded weight copy is re-cast every step (1.5 MB) because the fused optimizer updates
+        # conv1.weight in place without touching its version counter.
+        Kp = (K + 7) // 8 * 8
+        cols = _empty((B * T * n, Kp), BF16, video)
+        L.call("patch_gather_ld", video, keep_ind, cols, B, T, R, p, n, Kp)
+        w_bf = _empty((D, Kp), BF16, video)
+        L.call("cast_bf16_pad", P["conv1.weight"].detach().contiguous(), w_bf, D, K, Kp)
+        L.gemm(cols, w_bf, tok, M=B * T * n, N=D, K=Kp, lda=Kp, ldb=Kp)
     x0 = _empty((B * N, D), F32, video)
     L.call("video_assemble", tok, P["class_embedding"], P["positional_embedding"], P["temporal_embedding"], keep_ind, x0, B, T, n, D)
     x, mu0, rs0 = ln_fwd(x0, P["ln_pre.weight"], P["ln_pre.bias"], cfg.ln_eps, out_dtype=F32)
@@ -488,10 +499,23 @@ def video_forward(P, video, keep_ind, cfg):
     for i in range(cfg.layers):
         x, sv = st_block_fwd(P, f"transformer.resblocks.{i}.", x, B, N, T, n, H, cfg.act, cfg.ln_eps)
         blocks.append(sv)
-    a, mup, rsp = ln_fwd(x, P["ln_post.weight"], P["ln_post.bias"], cfg.ln_eps)
+    if cfg.post_mode == "h14":
+        # video_encoder_ViT_H_14.py:472-484: pooled = ln_post(x[:, 0]) @ proj ; tokens = x[:, 1:] @ proj (no ln_post).  One GEMM over
+        # all B*N rows whose operand holds the normalised CLS rows and the raw patch rows; row 0 of vtok is `pooled`.
+        cls_idx = (torch.arange(B, device=x.device, dtype=torch.int64) * N).contiguous()
+        xc = _empty((B, D), F32, x)
+        L.call("gather_rows", x, cls_idx, xc, B, D)
+        ac, mup, rsp = ln_fwd(xc, P["ln_post.weight"], P["ln_post.bias"], cfg.ln_eps)
+        a = cast_bf16(x)
+        L.call("scatter_rows", ac.view(F32), cls_idx, a.view(F32), B, D // 2, 0)
+        x_last = xc
+    else:
+        cls_idx = None
+        a, mup, rsp = ln_fwd(x, P["ln_post.weight"], P["ln_post.bias"], cfg.ln_eps)
+        x_last = x
     vtok = mat_fwd(a, P.bf("proj"))
-    saved = dict(B=B, T=T, n=n, N=N, keep=keep_ind, cols=cols, x0=x0, mu0=mu0, rs0=rs0, blocks=blocks, x_last=x, a=a, mup=mup,
-                 rsp=rsp)
+    saved = dict(B=B, T=T, n=n, N=N, keep=keep_ind, cols=cols, x0=x0, mu0=mu0, rs0=rs0, blocks=blocks, x_last=x_last, a=a, mup=mup,
+                 rsp=rsp, cls_idx=cls_idx)
     return vtok.view(B, N, -1), saved
 
 
@@ -504,9 +528,21 @@ def video_backward(P, saved, d_vtok, cfg):
         mat_wgrad(saved["a"], d_vtok_bf, P.gbuf("proj"))
     da = mat_dgrad(d_vtok_bf, P.bf("proj"), F32)
     needp = P.need("ln_post.weight") or P.need("ln_post.bias")
-    d_x, d_x_bf = ln_bwd(da, saved["x_last"], saved["mup"], saved["rsp"], P["ln_post.weight"],
-                         dw=P.gbuf("ln_post.weight") if needp else None, db=P.gbuf("ln_post.bias") if needp else None,
-                         dxsum=_bias_buf(P, f"transformer.resblocks.{cfg.layers - 1}.mlp.c_proj.bias") if cfg.layers > 0 else None)
+    last_bias = _bias_buf(P, f"transformer.resblocks.{cfg.layers - 1}.mlp.c_proj.bias") if cfg.layers > 0 else None
+    if cfg.post_mode == "h14":
+        cls_idx = saved["cls_idx"]
+        dac = _empty((B, D), F32, da)
+        L.call("gather_rows", da, cls_idx, dac, B, D)
+        d_xc, _ = ln_bwd(dac, saved["x_last"], saved["mup"], saved["rsp"], P["ln_post.weight"], want_bf16=False,
+                         dw=P.gbuf("ln_post.weight") if needp else None, db=P.gbuf("ln_post.bias") if needp else None)
+        L.call("scatter_rows", d_xc, cls_idx, da, B, D, 0)         # patch rows: d_x = da ; CLS rows: through ln_post
+        d_x, d_x_bf = da, cast_bf16(da)
+        if last_bias is not None:
+            colsum(d_x_bf, last_bias)
+    else:
+        d_x, d_x_bf = ln_bwd(da, saved["x_last"], saved["mup"], saved["rsp"], P["ln_post.weight"],
+                             dw=P.gbuf("ln_post.weight") if needp else None, db=P.gbuf("ln_post.bias") if needp else None,
+                             dxsum=last_bias)
     for i in reversed(range(cfg.layers)):
         prev_bias = f"transformer.resblocks.{i - 1}.mlp.c_proj.bias" if i > 0 else None
         d_x, d_x_bf = st_block_bwd(P, f"transformer.resblocks.{i}.", saved["blocks"][i], d_x, d_x_bf, B, N, T, n, H, cfg.act, prev_bias)
@@ -518,8 +554,13 @@ def video_backward(P, saved, d_vtok, cfg):
     L.call("video_assemble_bwd", d_x0, saved["keep"], P.gbuf("class_embedding"), P.gbuf("positional_embedding"),
            P.gbuf("temporal_embedding"), dtok, B, T, n, D)
     if P.need("conv1.weight"):
-        K = saved["cols"].shape[1]
-        lin_wgrad(dtok, saved["cols"], P.gbuf("conv1.weight").view(D, K))
+        Kp = saved["cols"].shape[1]
+        K = 3 * cfg.patch * cfg.patch
+        if Kp == K:
+            lin_wgrad(dtok, saved["cols"], P.gbuf("conv1.weight").view(D, K))
+        else:                                                     # padded im2col rows (H/14): only the first K columns are real
+            L.gemm(dtok, saved["cols"], P.gbuf("conv1.weight").view(D, K), M=D, N=K, K=dtok.shape[0], lda=D, ldb=Kp, a_mn=True,
+                   b_mn=True, accumulate=True)
 
 
 class _VideoTowerFn(torch.autograd.Function):

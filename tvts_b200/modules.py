@@ -121,27 +121,112 @@ class VisionTransformer(nn.Module):
         return E.video_tower(self.cfg, self._named(), x, keep_ind)
 
 
+class ResidualSpaceTimeAttentionBlockH14(nn.Module):
+    """v2/model/video_encoder_ViT_H_14.py:210-254 (registration order ln_1, attn, timeattn, ln_3, ls_3, ls_1, ln_2, mlp, ls_2; the
+    LayerScales are nn.Identity because ls_init_value is None in ViT-H-14.json)."""
+
+    def __init__(self, d_model, n_head, mlp_ratio=4.0):
+        super().__init__()
+        self.ln_1 = LayerNorm(d_model)
+        self.attn = VarAttention(d_model, num_heads=n_head, qkv_bias=True)
+        self.timeattn = VarAttention(d_model, num_heads=n_head, qkv_bias=True, initialize="zeros")
+        self.ln_3 = LayerNorm(d_model)
+        self.ls_3 = nn.Identity()
+        self.ls_1 = nn.Identity()
+        self.ln_2 = LayerNorm(d_model)
+        mlp_width = int(d_model * mlp_ratio)
+        self.mlp = nn.Sequential(OrderedDict([
+            ("c_fc", nn.Linear(d_model, mlp_width)),
+            ("gelu", nn.GELU()),
+            ("c_proj", nn.Linear(mlp_width, d_model))]))
+        self.ls_2 = nn.Identity()
+
+    forward = _no_direct_call
+
+
+class SpaceTimeTransformerH14(nn.Module):
+    def __init__(self, width, layers, heads, mlp_ratio=4.0):
+        super().__init__()
+        self.width, self.layers = width, layers
+        self.resblocks = nn.ModuleList([ResidualSpaceTimeAttentionBlockH14(width, heads, mlp_ratio) for _ in range(layers)])
+
+    forward = _no_direct_call
+
+
+class VisionTransformerH14(nn.Module):
+    """The modified OpenCLIP video ViT (v2/model/video_encoder_ViT_H_14.py:303-484): exact GELU, ln_post on the CLS token only;
+    forward(x [B,T,3,R,R], keep_ind [B,n]) -> (pooled [B,E], tokens [B,N-1,E]).  Options the H/14 model never enables
+    (LayerScale, patch dropout, patch-norm, attentional / average pooling) are rejected."""
+
+    def __init__(self, image_size, patch_size, width, layers, heads, mlp_ratio=4.0, ls_init_value=None, global_average_pool=False,
+                 attentional_pool=False, n_queries=256, attn_pooler_heads=8, output_dim=512, patch_dropout=0., input_patchnorm=False,
+                 act_layer=nn.GELU, norm_layer=None, output_tokens=False, num_frames=12, mask_ratio=0.):
+        super().__init__()
+        if ls_init_value is not None or global_average_pool or attentional_pool or input_patchnorm or patch_dropout:
+            raise NotImplementedError("VisionTransformerH14: only the configuration of model_dist_TVTSv2_ViT_H_14.py is built")
+        if act_layer is not nn.GELU:
+            raise NotImplementedError("VisionTransformerH14: act_layer must be nn.GELU")
+        self.output_tokens = output_tokens
+        self.image_size, self.patch_size = (image_size, image_size), (patch_size, patch_size)
+        self.grid_size = (image_size // patch_size, image_size // patch_size)
+        self.output_dim = output_dim
+        self.conv1 = nn.Conv2d(3, width, kernel_size=patch_size, stride=patch_size, bias=False)
+        scale = width ** -0.5
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        self.positional_embedding = nn.Parameter(scale * torch.randn(self.grid_size[0] * self.grid_size[1] + 1, width))
+        self.ln_pre = LayerNorm(width)
+        self.transformer = SpaceTimeTransformerH14(width, layers, heads, mlp_ratio)
+        self.ln_post = LayerNorm(width)
+        self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+        self.patches_per_frame = self.grid_size[0] * self.grid_size[1]
+        self.temporal_embedding = nn.Parameter(scale * torch.randn(num_frames, width))
+        self.mask_ratio = mask_ratio
+        self.cfg = C.ArchConfig("video_h14", patch=patch_size, width=width, layers=layers, heads=heads, embed_dim=output_dim,
+                                num_frames=num_frames, mask_ratio=mask_ratio, resolution=image_size, act="gelu", post_mode="h14")
+        self._ordered = None
+
+    def _named(self):
+        if self._ordered is None:
+            have = dict(self.named_parameters())
+            self._ordered = OrderedDict((k, have[k]) for k in E.video_param_names(self.cfg))
+        return self._ordered
+
+    def forward(self, x, keep_ind):
+        out = E.video_tower(self.cfg, self._named(), x, keep_ind)
+        return out[:, 0], out[:, 1:]
+
+
 # ------------------------------------------------------------------------------------------------ CLIP text tower
 class ResidualAttentionBlock(nn.Module):
-    def __init__(self, d_model, n_head, attn_mask=None):
+    def __init__(self, d_model, n_head, attn_mask=None, open_clip=False):
         super().__init__()
-        self.attn = nn.MultiheadAttention(d_model, n_head)
-        self.ln_1 = LayerNorm(d_model)
+        if open_clip:                       # v2/OpenCLIP/transformer.py:189-214: ln_1, attn, ls_1, ln_2, mlp (nn.GELU), ls_2
+            self.ln_1 = LayerNorm(d_model)
+            self.attn = nn.MultiheadAttention(d_model, n_head)
+            self.ls_1 = nn.Identity()
+            self.ln_2 = LayerNorm(d_model)
+        else:                               # v2/CLIP/clip/model.py:171-183: attn, ln_1, mlp (QuickGELU), ln_2
+            self.attn = nn.MultiheadAttention(d_model, n_head)
+            self.ln_1 = LayerNorm(d_model)
         self.mlp = nn.Sequential(OrderedDict([
             ("c_fc", nn.Linear(d_model, d_model * 4)),
-            ("gelu", QuickGELU()),
+            ("gelu", nn.GELU() if open_clip else QuickGELU()),
             ("c_proj", nn.Linear(d_model * 4, d_model))]))
-        self.ln_2 = LayerNorm(d_model)
+        if open_clip:
+            self.ls_2 = nn.Identity()
+        else:
+            self.ln_2 = LayerNorm(d_model)
         self.attn_mask = attn_mask
 
     forward = _no_direct_call
 
 
 class Transformer(nn.Module):
-    def __init__(self, width, layers, heads, attn_mask=None):
+    def __init__(self, width, layers, heads, attn_mask=None, open_clip=False):
         super().__init__()
         self.width, self.layers = width, layers
-        self.resblocks = nn.Sequential(*[ResidualAttentionBlock(width, heads, attn_mask) for _ in range(layers)])
+        blocks = [ResidualAttentionBlock(width, heads, attn_mask, open_clip) for _ in range(layers)]
+        self.resblocks = nn.ModuleList(blocks) if open_clip else nn.Sequential(*blocks)
 
     forward = _no_direct_call
 
@@ -150,10 +235,10 @@ class CLIPTextParts(nn.Module):
     """The pieces of a CLIP model the TVTSv2 constructors pull out (transformer, token/positional embedding, ln_final,
     text_projection), initialised like CLIP.initialize_parameters (v2/CLIP/clip/model.py:301-328)."""
 
-    def __init__(self, embed_dim=512, context_length=77, vocab_size=49408, width=512, heads=8, layers=12):
+    def __init__(self, embed_dim=512, context_length=77, vocab_size=49408, width=512, heads=8, layers=12, open_clip=False):
         super().__init__()
         self.context_length = context_length
-        self.transformer = Transformer(width, layers, heads)
+        self.transformer = Transformer(width, layers, heads, open_clip=open_clip)
         self.token_embedding = nn.Embedding(vocab_size, width)
         self.positional_embedding = nn.Parameter(torch.empty(context_length, width))
         self.ln_final = LayerNorm(width)
@@ -259,6 +344,7 @@ class TVTSv2Base(BaseModel):
     MASK_RATIO = 0.5
     CLIP_FILE = "CLIP/models/ViT-B-16.pt"
     SORT_HEAD = True
+    OPEN_CLIP = False
 
     def __init__(self, args, load_checkpoint=None, arch=None):
         super().__init__()
@@ -267,15 +353,13 @@ class TVTSv2Base(BaseModel):
         from .clip_compat import load as clip_load
         arch = arch or (C.TVTSV2_B_16 if self.PATCH == 16 else C.TVTSV2_B_32)
         self.arch = arch
-        clip_model, clip_visual_sd = clip_load(self.CLIP_FILE, arch)
+        clip_model, clip_visual_sd = clip_load(self.CLIP_FILE, arch, open_clip=self.OPEN_CLIP)
         self.text_model = clip_model.transformer
         self.text_token_embedding = clip_model.token_embedding
         self.text_positional_embedding = clip_model.positional_embedding
         self.text_ln_final = clip_model.ln_final
         self.text_projection = clip_model.text_projection
-        self.video_model = VisionTransformer(input_resolution=arch.resolution, patch_size=arch.patch, width=arch.width,
-                                             layers=arch.layers, heads=arch.heads, output_dim=arch.embed_dim,
-                                             num_frames=arch.num_frames, mask_ratio=arch.mask_ratio)
+        self.video_model = self._build_video_model(arch)
         if load_checkpoint in ["", None] and clip_visual_sd is not None:
             new_sd = {}
             for k, v in clip_visual_sd.items():                     # :36-44 CLIP -> space-time key remap
@@ -293,6 +377,10 @@ class TVTSv2Base(BaseModel):
             self.load_state_dict(state_dict_data_parallel_fix(state_dict, self.state_dict()), strict=True)
             print("loading checkpoint from {}".format(load_checkpoint))
         self._text_named = None
+
+    def _build_video_model(self, arch):
+        return VisionTransformer(input_resolution=arch.resolution, patch_size=arch.patch, width=arch.width, layers=arch.layers,
+                                 heads=arch.heads, output_dim=arch.embed_dim, num_frames=arch.num_frames, mask_ratio=arch.mask_ratio)
 
     def _checkpoint_location(self):
         return "cuda:{}".format(self.args.local_rank)
@@ -347,6 +435,32 @@ class TVTSv2_B_32(TVTSv2Base):
     PATCH, MASK_RATIO, CLIP_FILE = 32, 0.0, "CLIP/models/ViT-B-32.pt"
 
 
+class TVTSv2_H_14(TVTSv2Base):
+    """v2/model/model_dist_TVTSv2_ViT_H_14.py:13-158: OpenCLIP ViT-H/14 towers (video width 1280 / 32 layers / 16 heads of dim 80,
+    text 1024 / 24 layers / 16 heads, embed 1024, exact GELU), mask ratio 0.7, sort head over the PATCH tokens (no CLS), 16 heads.
+    The reference runs forward under fp16 autocast (:96); here the GEMM operands are bf16 with fp32 accumulation like the B models.
+    The OpenCLIP checkpoint (`create_model('ViT-H-14', pretrained='laion2b_s32b_b79k', cache_dir='OpenCLIP/models')`, :22-24) is read
+    from OpenCLIP/models/open_clip_pytorch_model.bin when that file exists."""
+
+    PATCH, MASK_RATIO, CLIP_FILE = 14, 0.7, "OpenCLIP/models/open_clip_pytorch_model.bin"
+    OPEN_CLIP = True
+
+    def __init__(self, args, load_checkpoint=None, arch=None):
+        super().__init__(args, load_checkpoint, arch=arch or C.TVTSV2_H_14)
+        ctx = self.arch.context
+        self.text_attn_mask = torch.full((ctx, ctx), float("-inf")).triu_(1)     # OpenCLIP build_attention_mask; plain attribute (:36)
+
+    def _build_video_model(self, arch):
+        return VisionTransformerH14(image_size=arch.resolution, patch_size=arch.patch, width=arch.width, layers=arch.layers,
+                                    heads=arch.heads, mlp_ratio=4.0, output_dim=arch.embed_dim, act_layer=nn.GELU,
+                                    num_frames=arch.num_frames, mask_ratio=arch.mask_ratio)
+
+    def compute_video(self, video, keep_ind):
+        """-> (video_before_embeddings = patch tokens [B, N-1, E], video_embeddings = pooled CLS [B, E])   (:155-157)"""
+        pooled, tokens = self.video_model(video, keep_ind)
+        return tokens, pooled
+
+
 # ------------------------------------------------------------------------------------------------ downstream (zero-shot / feature extraction)
 class TVTSv2Downstream(TVTSv2Base):
     """v2/downstream/model_TVTSv2_ViT_B_16.py:10-98 (and _B_32): the pre-training towers with mask_ratio 0 and no sort head, used
@@ -357,7 +471,7 @@ class TVTSv2Downstream(TVTSv2Base):
     MEAN_OVER_CLIPS = True        # False in the *_mc variants (model_TVTSv2_ViT_B_16_mc.py:64: the mean over n_trans is commented out)
 
     def __init__(self, load_checkpoint=None, arch=None):
-        base = arch or (C.TVTSV2_B_16 if self.PATCH == 16 else C.TVTSV2_B_32)
+        base = arch or {16: C.TVTSV2_B_16, 32: C.TVTSV2_B_32, 14: C.TVTSV2_H_14}[self.PATCH]
         super().__init__(None, load_checkpoint, arch=base.small(mask_ratio=0.0))
 
     def _checkpoint_location(self):
@@ -391,4 +505,20 @@ class TVTSv2_B_16_downstream_mc(TVTSv2_B_16_downstream):
 
 
 class TVTSv2_B_32_downstream_mc(TVTSv2_B_32_downstream):
+    MEAN_OVER_CLIPS = False
+
+
+class TVTSv2_H_14_downstream(TVTSv2Downstream):
+    """v2/downstream/model_TVTSv2_ViT_H_14.py: the H/14 towers with mask_ratio 0 and no sort head."""
+    PATCH, CLIP_FILE, OPEN_CLIP = 14, "OpenCLIP/models/open_clip_pytorch_model.bin", True
+    _build_video_model = TVTSv2_H_14._build_video_model
+    compute_video = TVTSv2_H_14.compute_video
+
+    def __init__(self, load_checkpoint=None, arch=None):
+        super().__init__(load_checkpoint, arch)
+        ctx = self.arch.context
+        self.text_attn_mask = torch.full((ctx, ctx), float("-inf")).triu_(1)
+
+
+class TVTSv2_H_14_downstream_mc(TVTSv2_H_14_downstream):
     MEAN_OVER_CLIPS = False

@@ -138,13 +138,13 @@ class FlatState:
 
 def reference_param_groups(named_parameters, text_layers=12, tune_from=9):
     """The 4 optimizer groups of the reference entry script; freezes (requires_grad=False) the un-tuned text layers."""
-    no_decay_names = ["bias", "LayerNorm", "ln_", "norm"]
+    no_decay_names = ["bias", "LayerNorm", "ln_", "norm", "ls_", "LayerScale"]   # the last two: H_14 script :17 (no such parameters in B)
     text_tune_layers = ["resblocks.%d." % i for i in range(tune_from, text_layers)]
     decay_clip, no_decay_clip, decay_new, no_decay_new = [], [], [], []
     for name, param in named_parameters:
         nd = any(s in name for s in no_decay_names)
         if "video_model" in name:
-            if "timeattn" in name or "ln_3" in name:
+            if "timeattn" in name or "ln_3" in name or "ls_3" in name:
                 (no_decay_new if nd else decay_new).append(param)
             else:
                 (no_decay_clip if nd else decay_clip).append(param)
@@ -286,7 +286,8 @@ class AdamW:
 
 
 def build_reference_optimizer(model, text_layers=None, tune_from=None):
-    """What v2/train_dist_TVTSv2_ViT_B_16.py:66-125 builds for `model` (H/14: layers 0-17 frozen, :71 of the H_14 script)."""
+    """What v2/train_dist_TVTSv2_ViT_B_16.py:66-125 builds for `model` (train_dist_TVTSv2_ViT_H_14.py:68-127: text layers 0-17 of 24
+    frozen; same 4 groups)."""
     if text_layers is None:
         text_layers = model.arch.text_layers
     if tune_from is None:

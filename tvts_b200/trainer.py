@@ -468,3 +468,4 @@ class Trainer_TVTSv2:
 
 Trainer_TVTSv2_B_16 = Trainer_TVTSv2
 Trainer_TVTSv2_B_32 = Trainer_TVTSv2
+Trainer_TVTSv2_H_14 = Trainer_TVTSv2      # v2/trainer/trainer.py:648-905: the same step (no GradScaler; autocast lives in the model)
