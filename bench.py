@@ -31,7 +31,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", help="c3 = ViT-B/16 T=8 batch 32/GPU (headline); c2 = ViT-B/32 T=8 batch 64")
+    ap.add_argument("--workload", default="c3", help="c3 = ViT-B/16 T=8 batch 32/GPU (headline); c2 = ViT-B/32 T=8 batch 64; c1 = ViT-B/32 T=2 batch 4; "
+                    "c4 = ViT-H/14 T=16 batch 8/GPU (CUDA path not yet GPU-verified)")
     ap.add_argument("--batch", type=int, default=0, help="override per-GPU batch")
     ap.add_argument("--n-trans", type=int, default=4, help="transcripts per clip (4 = both losses, 1 = InfoNCE only)")
     ap.add_argument("--no-optimizer", action="store_true", help="leave the AdamW update out of the step")
@@ -126,7 +127,7 @@ def algorithmic_flops_per_pair(cfg, T, n_trans):
     f_layer = 24 * 77 * W * W + 4 * 77 * 77 * W
     frozen = (cfg.text_layers * 3) // 4
     f_text3 = 3.0 * ((cfg.text_layers - frozen) * f_layer + 2 * W * E) + 2.0 * frozen * f_layer
-    S = N + n_trans
+    S = N + n_trans - (1 if cfg.post_mode == "h14" else 0)     # H/14: the sort head sees the patch tokens only
     f_sort = cfg.sort_depth * (24 * S * E * E + 4 * S * S * E) if n_trans > 1 else 0
     return 3.0 * (f_video + f_sort) + n_trans * f_text3
 
@@ -206,7 +207,8 @@ def run_ours(args):
         _lib.lib().tvts_gemm_set_pair_mode(args.pair_mode)
 
     cfg, batch, frames, n_trans = workload(args)
-    model = M.TVTSv2Base(types.SimpleNamespace(local_rank=local_rank), arch=cfg)
+    model_cls = M.TVTSv2_H_14 if cfg.post_mode == "h14" else M.TVTSv2Base
+    model = model_cls(types.SimpleNamespace(local_rank=local_rank), arch=cfg)
     model.load_state_dict(make_state_dict(cfg, seed=1234), strict=True)
     model = model.to(dev)
     opt = None if args.no_optimizer else optim.build_reference_optimizer(model)

@@ -24,7 +24,9 @@ def test_flop_model_reproduces_survey_table():
     sys.path.insert(0, ROOT)
     import bench
     from tvts_b200 import config as C
-    table = {("c1", C.TVTSV2_B_32, 2): (82.9, 127.1), ("c2", C.TVTSV2_B_32, 8): (289.6, 346.7), ("c3", C.TVTSV2_B_16, 8): (563.7, 641.4)}
+    table = {("c1", C.TVTSV2_B_32, 2): (82.9, 127.1), ("c2", C.TVTSV2_B_32, 8): (289.6, 346.7), ("c3", C.TVTSV2_B_16, 8): (563.7, 641.4),
+             ("c4", C.TVTSV2_H_14.small(num_frames=16), 16): (6317.0, 6855.0)}
     for (name, cfg, T), (a, b) in table.items():
-        assert abs(bench.algorithmic_flops_per_pair(cfg, T, 1) / 1e9 - a) < 0.15, name
-        assert abs(bench.algorithmic_flops_per_pair(cfg, T, 4) / 1e9 - b) < 0.15, name
+        tol = 0.15 if a < 1000 else 1.0
+        assert abs(bench.algorithmic_flops_per_pair(cfg, T, 1) / 1e9 - a) < tol, name
+        assert abs(bench.algorithmic_flops_per_pair(cfg, T, 4) / 1e9 - b) < tol, name

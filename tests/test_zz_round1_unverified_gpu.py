@@ -5,7 +5,11 @@ that `pytest -x` reaches them only after every previously-verified GPU test has 
   * the padded patch-embed path of 14x14 patches (patch_gather_ld, cast_bf16_pad, GEMMs with K = 592 / N = 588)
   * LayerNorm width 640, the TVTSv2_H_14 model (tiny_H640) against the executed-reference fixture and the oracle's gradients
   * the downstream (zero-shot) towers against their executed-reference fixture
-Tolerances as in tests/test_kernels_gpu.py / tests/test_model_gpu.py."""
+Tolerances as in tests/test_kernels_gpu.py / tests/test_model_gpu.py.
+
+Because none of this has met a GPU yet, the module is marked xfail(strict=False): a failure is reported as XFAIL (expected until the
+first GPU run of round 2 debugs it) and a pass as XPASS, without turning the verified suite red.  Round 2: run this file first,
+fix what fails, then delete the xfail mark and fold the cases into test_kernels_gpu.py / test_model_gpu.py."""
 import os
 import types
 
@@ -21,7 +25,8 @@ from tvts_b200 import engine as E
 from tvts_b200 import modules as M
 from tvts_b200.synthetic import make_batch, make_state_dict
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="written after the round-1 GPU budget was spent: never executed on a B200 yet")]
 DEV = "cuda"
 BF16, F32 = torch.bfloat16, torch.float32
 GOLD = os.path.join(os.path.dirname(__file__), "golden")

@@ -299,7 +299,8 @@ class Trainer_TVTSv2:
     cycled, :440-461), clip-major flattening of the caption lists + tokenisation (:465-473), one optimizer step per loader batch,
     per-loader running losses, per-epoch x0.1 decay at `args.schedule` milestones (:402-411).  What it does differently: the step
     itself runs through `TrainStep` (CUDA graph, arena all-reduce, fused AdamW) instead of DDP + `optimizer.step()`, and losses are
-    read back once per `log_step` instead of 3-4 `.item()` syncs per step.  Checkpointing / monitoring stay with the reference's
+    read back once per `log_step` instead of 3-4 `.item()` syncs per step.  Checkpoint files keep the reference's layout
+    (`save_checkpoint` / `resume_checkpoint`, `config.resume`); monitoring / early stopping stay with the reference's
     `base.Multi_BaseTrainer_dist` (out of scope): pass `on_epoch_end` to hook them in."""
 
     def __init__(self, args, model, loss, metrics, optimizer, config, data_loader, valid_data_loader=None, lr_scheduler=None,
