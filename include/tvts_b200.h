@@ -121,6 +121,14 @@ int tvts_attn_generic_fwd(const void* qkv, void* out, float* lse, int64_t B, int
 int tvts_attn_generic_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv, int64_t B,
                           int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal, float scale, void* stream);
 
+/* Key-padded full attention for the TVTS v1 text encoder (DistilBERT, an un-vendored `transformers` dependency; call site
+ * v1/model/model_dist_TVTS.py:124-126): keys at positions >= klen[b] (the right-padded tail of `attention_mask`) are excluded from the
+ * softmax; query rows past klen[b] are still computed, like the reference.  klen [B] int32, 1 <= klen[b] <= N.  d = 64 or 80. */
+int tvts_attn_padded_fwd(const void* qkv, void* out, float* lse, const int32_t* klen, int64_t B, int64_t N, int64_t H, int64_t d,
+                         float scale, void* stream);
+int tvts_attn_padded_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv,
+                         const int32_t* klen, int64_t B, int64_t N, int64_t H, int64_t d, float scale, void* stream);
+
 /* Query-window attention (mode FULL, non-causal): only rows [q0, q0+qn) of every sample are queries, all N tokens are keys/values.
  * Used for the LAST block of the sort head, whose only consumed outputs are its n_trans transcript rows
  * (v2/model/sort_transformer.py:134-142).  fwd writes out / lse for the window rows only.  bwd writes dq for the window rows only
@@ -147,6 +155,19 @@ int tvts_patch_gather(const float* video, const int64_t* keep_ind, void* cols, i
 int tvts_patch_gather_ld(const float* video, const int64_t* keep_ind, void* cols, int64_t B, int64_t T, int64_t R, int64_t p, int64_t n,
                          int64_t ld, void* stream);
 int tvts_cast_bf16_pad(const float* src, void* dst, int64_t rows, int64_t cols, int64_t ld, void* stream);
+/* TVTS v1 front end (v1/model/video_encoder.py:78-99,178-217): Conv3d tubelets of 2 frames with an independent keep mask per tube.
+ *   tubelet_gather: video [B,T,3,R,R] f32 + keep_ind [B,T/2,n] int64 -> cols [(b*T/2+tube)*n+j, ((c*2+dt)*p+u)*p+v] bf16
+ *   video_assemble_tube: x0[b,0] = cls + pos[0]; x0[b,1+t*n+j] = tok[(b*nt+t)*n+j] + pos[1+keep[b,t,j]] + tem[t]  (tok includes the
+ *                        Conv3d bias); _bwd: dcls/dpos/dtem ACCUMULATED, dtok written as bf16
+ *   relu_bf16 / relu_bwd: the ReLU in front of txt_proj's Linear (v1/model/model_dist_TVTS.py:66-69) */
+int tvts_tubelet_gather(const float* video, const int64_t* keep_ind, void* cols, int64_t B, int64_t T, int64_t R, int64_t p, int64_t n,
+                        void* stream);
+int tvts_video_assemble_tube(const float* tok, const float* cls, const float* pos, const float* tem, const int64_t* keep_ind, float* x0,
+                             int64_t B, int64_t nt, int64_t n, int64_t D, void* stream);
+int tvts_video_assemble_tube_bwd(const float* dx0, const int64_t* keep_ind, float* dcls, float* dpos, float* dtem, void* dtok_bf16,
+                                 int64_t B, int64_t nt, int64_t n, int64_t D, void* stream);
+int tvts_relu_bf16(const float* x, void* y, int64_t n, void* stream);
+int tvts_relu_bwd(const float* x, const float* dy, float* dx, int64_t n, void* stream);
 int tvts_video_assemble(const float* tok, const float* cls, const float* pos, const float* tem, const int64_t* keep_ind, float* x0,
                         int64_t B, int64_t T, int64_t n, int64_t D, void* stream);
 int tvts_video_assemble_bwd(const float* dx0, const int64_t* keep_ind, float* dcls, float* dpos, float* dtem, void* dtok_bf16, int64_t B,

@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz by EXECUTING THE UNMODIFIED REFERENCE (build container only).
 
-    python oracle/make_golden.py            # writes tests/golden/{c1_b32,tiny_B,tiny_B_mask,tiny_B_cap,tiny_H,tiny_H640,tiny_ds,tiny_v1}.npz
+    python oracle/make_golden.py            # writes tests/golden/{c1_b32,tiny_B,tiny_B_mask,tiny_B_cap,tiny_H,tiny_H640,tiny_ds,tiny_v1,tiny_v1_full}.npz
 
 For each case: seeded state_dict (tvts_b200.synthetic.make_state_dict) is loaded strict=True into the
 reference modules, the reference forward + the trainer's loss lines (v2/trainer/trainer.py:479-496)
@@ -145,6 +145,7 @@ def main():
     run_case("tiny_H640", C.TINY_H640, batch=2, frames=3, n_trans=4, seed=17)     # ... at the smallest width the CUDA kernels take
     run_case_downstream()                                                         # v2/downstream towers (mask 0, no sort head), forward only
     run_case_v1()                                                                 # TVTS v1 semantics (configs[4]) at toy dims
+    run_case_v1_full()                                                            # ... including the DistilBERT text encoder, head dim 64
 
 
 # ------------------------------------------------------------------------------------------------------------------ TVTS v1
@@ -261,10 +262,81 @@ def run_case_downstream(name="tiny_ds", seed=16):
           f"max|d video_emb| {(ove - torch.from_numpy(out['video_emb'])).abs().max().item():.2e}  text_emb_mc {out['text_emb_mc'].shape} -> {path} ({os.path.getsize(path)} B)")
 
 
+def run_case_v1_full(name="tiny_v1_full", seed=18):
+    """TVTS v1 INCLUDING the text encoder, at toy dims whose head dim is 64 (what the CUDA attention kernels take): video ViT 128 wide /
+    2 heads / 2 blocks on 64x64 frames (16 patches, 8 kept per tube), a randomly initialised 2-layer DistilBERT (dim 128, 2 heads, dropout 0)
+    from the installed `transformers` in place of 'distilbert-base-uncased', right-padded captions.  Every parameter (text encoder
+    included) comes from spec_state_dict(names, shapes, seed), so the fixture only stores names / shapes / results."""
+    from functools import partial
+    from torch import nn
+    import transformers
+    ref_shims.install("v1")
+    import model.model_dist_TVTS as ref_model
+    from model.video_encoder import VisionTransformer
+    from model.sort_transformer import SortTransformer
+    from model.loss import NormSoftmaxLoss
+
+    D, heads, depth, patch, res, frames, nt, B, proj, Lc, vocab = 128, 2, 2, 16, 64, 8, 4, 2, 64, 12, 128
+    torch.manual_seed(seed)
+    m = ref_model.TVTS.__new__(ref_model.TVTS)
+    nn.Module.__init__(m)
+    m.text_params = {"model": "distilbert-base-uncased", "pretrained": True}
+    m.text_model = transformers.DistilBertModel(transformers.DistilBertConfig(vocab_size=vocab, dim=D, n_layers=2, n_heads=heads, hidden_dim=2 * D,
+                                                                              max_position_embeddings=32, dropout=0.0, attention_dropout=0.0))
+    m.video_model = VisionTransformer(img_size=res, patch_size=patch, embed_dim=D, depth=depth, num_heads=heads, mlp_ratio=4, qkv_bias=True,
+                                      norm_layer=partial(nn.LayerNorm, eps=1e-6), num_frames=frames)
+    m.video_model.pre_logits = nn.Identity()
+    m.txt_proj = nn.Sequential(nn.ReLU(), nn.Linear(D, proj))
+    m.vid_proj = nn.Sequential(nn.Linear(D, proj))
+    m.n_trans = nt
+    m.pred_model = SortTransformer(num_classes=nt, embed_dim=D, num_heads=heads)
+    names = [k for k, _ in m.named_parameters()]
+    shapes = [tuple(p.shape) for _, p in m.named_parameters()]
+    sd = spec_state_dict(names, shapes, 4321)
+    m.load_state_dict(sd, strict=True)
+    m.train()
+    g = torch.Generator().manual_seed(seed)
+    P = (res // patch) ** 2
+    n_keep = P // 2
+    video = torch.randn(B, frames, 3, res, res, generator=torch.Generator().manual_seed(seed + 1))
+    keep = torch.stack([torch.stack([torch.randperm(P, generator=g)[:n_keep] for _ in range(frames // 2)]) for _ in range(B)])
+    ids = torch.randint(1, vocab, (nt * B, Lc), generator=g)
+    lens = torch.randint(3, Lc + 1, (nt * B,), generator=g)
+    lens[0] = Lc
+    mask = (torch.arange(Lc)[None, :] < lens[:, None]).long()
+    ids = ids * mask                                                         # [PAD] = 0 on the right, like the tokenizer
+    text = {"input_ids": ids, "attention_mask": mask}
+    labels = torch.arange(nt).repeat(B, 1)
+    te, ve, pred = m({"text": text, "video": video, "keep_ind": keep})
+    loss1 = NormSoftmaxLoss(0.05)(ref_model.sim_matrix(ve, te))
+    loss2 = torch.nn.CrossEntropyLoss()(pred.reshape(-1, nt), labels.reshape(-1)) * 2
+    (loss1 + loss2).backward()
+    gn = {k: p.grad.double().norm().item() for k, p in m.named_parameters() if p.grad is not None}
+    out = dict(names=np.array(names), shapes=np.array([",".join(map(str, s)) for s in shapes]), wseed=4321, video_seed=seed + 1,
+               keep_ind=keep.numpy(), input_ids=ids.numpy(), attention_mask=mask.numpy(), text_emb=te.detach().numpy(),
+               video_emb=ve.detach().numpy(), pred_order=pred.detach().numpy(), loss1=np.float64(loss1.item()), loss2=np.float64(loss2.item()),
+               grad_names=np.array(list(gn)), grad_norms=np.array(list(gn.values())),
+               dims=np.array([D, heads, depth, patch, res, frames, nt, B, proj, Lc, vocab]))
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, **out)
+    import tvts_oracle as O
+    cfg = types.SimpleNamespace(patch=patch, width=D, heads=heads, layers=depth, sort_heads=heads, sort_depth=2, sort_ln_eps=1e-6)
+    l1, l2, (ote, ove, opr), grads = O.v1_step_with_grads(sd, text, video, keep, labels, cfg, heads)
+    # (k_lin.bias has an exactly-zero true gradient -- softmax is invariant to a constant added to every key -- so only noise ~1e-9 there)
+    worst = max(abs(grads[k].double().norm().item() - v) / (v + 1e-12) for k, v in gn.items() if v > 1e-6)
+    print(f"[{name}] loss1 ref {loss1.item():.7f} oracle {l1.item():.7f} | loss2 ref {loss2.item():.7f} oracle {l2.item():.7f}")
+    print(f"   max|d text_emb| {(ote - te).abs().max().item():.2e} max|d video_emb| {(ove - ve).abs().max().item():.2e} "
+          f"max|d pred| {(opr - pred).abs().max().item():.2e}  worst rel grad-norm dev over {len(gn)} params (norm > 1e-6) {worst:.2e} -> {path} ({os.path.getsize(path)} B)")
+
+
 if __name__ == "__main__":
     if "--downstream" in sys.argv:      # regenerate only tests/golden/tiny_ds.npz
         torch.manual_seed(0)
         run_case_downstream()
+    elif "--v1full" in sys.argv:        # regenerate only tests/golden/tiny_v1_full.npz
+        torch.manual_seed(0)
+        torch.set_num_threads(os.cpu_count())
+        run_case_v1_full()
     elif "--h640" in sys.argv:          # regenerate only tests/golden/tiny_H640.npz
         torch.manual_seed(0)
         torch.set_num_threads(os.cpu_count())

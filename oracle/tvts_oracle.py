@@ -333,6 +333,51 @@ def v1_model_forward(sd, text_cls, video, keep_ind, cfg):
     return text_emb, video_emb, pred
 
 
+def distilbert_forward(sd, input_ids, attention_mask, heads, prefix="text_model."):
+    """DistilBertModel.forward -> last_hidden_state [n, L, W]: the v1 text encoder (`AutoModel.from_pretrained('distilbert-base-uncased')`,
+    v1/model/model_dist_TVTS.py:33; called at :124-126 with the tokenizer's input_ids / attention_mask).  UN-VENDORED DEPENDENCY
+    (transformers==4.10.2 in v1's requirements; 5.5.0 installed here): restated from its published algorithm and pinned against the
+    installed implementation by tests/test_oracle_golden.py (same weights, 1e-5).  Algorithm: embeddings = LayerNorm(word[ids] +
+    position[0..L-1]) (eps 1e-12); per layer (POST-LN): q,k,v = three Linears; scores = (q / sqrt(d)) k^T with the padded KEY
+    positions (attention_mask == 0) set to the most negative float; softmax; out_lin; x = sa_layer_norm(attn + x);
+    x = output_layer_norm(lin2(gelu_erf(lin1(x))) + x).  Dropout p = 0.1 in the released config is active in training -- parity runs
+    use p = 0 (as every fixture here does)."""
+    n, L = input_ids.shape
+    W = sd[prefix + "embeddings.word_embeddings.weight"].shape[1]
+    d = W // heads
+    x = sd[prefix + "embeddings.word_embeddings.weight"][input_ids.long()] + sd[prefix + "embeddings.position_embeddings.weight"][:L][None]
+    x = layer_norm(x, sd[prefix + "embeddings.LayerNorm.weight"], sd[prefix + "embeddings.LayerNorm.bias"], 1e-12)
+    key_ok = attention_mask.bool()[:, None, None, :]                                   # [n, 1, 1, L]
+    i = 0
+    while f"{prefix}transformer.layer.{i}.attention.q_lin.weight" in sd:
+        p_ = f"{prefix}transformer.layer.{i}."
+        q = linear(x, sd[p_ + "attention.q_lin.weight"], sd[p_ + "attention.q_lin.bias"]).reshape(n, L, heads, d).transpose(1, 2)
+        k = linear(x, sd[p_ + "attention.k_lin.weight"], sd[p_ + "attention.k_lin.bias"]).reshape(n, L, heads, d).transpose(1, 2)
+        v = linear(x, sd[p_ + "attention.v_lin.weight"], sd[p_ + "attention.v_lin.bias"]).reshape(n, L, heads, d).transpose(1, 2)
+        s_ = (q * (d ** -0.5)) @ k.transpose(-1, -2)
+        s_ = s_.masked_fill(~key_ok, torch.finfo(s_.dtype).min)
+        o = (torch.softmax(s_, -1) @ v).transpose(1, 2).reshape(n, L, W)
+        x = layer_norm(linear(o, sd[p_ + "attention.out_lin.weight"], sd[p_ + "attention.out_lin.bias"]) + x,
+                       sd[p_ + "sa_layer_norm.weight"], sd[p_ + "sa_layer_norm.bias"], 1e-12)
+        f_ = linear(gelu_erf(linear(x, sd[p_ + "ffn.lin1.weight"], sd[p_ + "ffn.lin1.bias"])), sd[p_ + "ffn.lin2.weight"], sd[p_ + "ffn.lin2.bias"])
+        x = layer_norm(f_ + x, sd[p_ + "output_layer_norm.weight"], sd[p_ + "output_layer_norm.bias"], 1e-12)
+        i += 1
+    return x
+
+
+def v1_step_with_grads(sd_tensors, text, video, keep_ind, labels, cfg, text_heads):
+    """One v1 training step (v1/trainer/trainer.py:135-155 at world size 1) INCLUDING the DistilBERT text encoder:
+    text = {'input_ids', 'attention_mask'} [n_trans*B, L] clip-major.  -> loss1, loss2, (text_emb, video_emb, pred), {name: grad}."""
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in sd_tensors.items()}
+    hidden = distilbert_forward(sd, text["input_ids"], text["attention_mask"], text_heads)
+    te, ve, pred = v1_model_forward(sd, hidden[:, 0, :], video, keep_ind, cfg)
+    loss1 = norm_softmax_loss(sim_matrix(ve, te), 0.05)
+    loss2 = sort_ce(pred, labels) if pred is not None else torch.zeros(())
+    (loss1 + loss2).backward()
+    grads = {k: v.grad for k, v in sd.items() if v.requires_grad and v.grad is not None}
+    return loss1.detach(), loss2.detach(), (te.detach(), ve.detach(), None if pred is None else pred.detach()), grads
+
+
 # --------------------------------------------------------------------------------------------------
 # optimiser: transformers==4.10.2 AdamW (un-vendored; parity unpinned by the reference -- restated from its
 # published algorithm: Adam with bias correction, eps added to sqrt(v) BEFORE bias correction is folded

@@ -30,23 +30,27 @@ def _dact(x, a):
     return torch.ones_like(x)
 
 
+def _mat(t, rows, cols, ld):
+    """[rows, cols] matrix at t's data pointer with a row pitch of ld elements (what the C ABI sees: pointer + leading dimension)."""
+    return t.as_strided((rows, cols), (ld, 1), t.storage_offset())
+
+
 def gemm(a, b, out, *, M, N, K, lda, ldb, ldo=None, a_mn=False, b_mn=False, bias=None, residual=None, ldr=None,
          aux=None, ldaux=None, out_pre=None, act=None, dact=None, accumulate=False, splits=0, alpha=1.0):
-    A = a.reshape(-1)[: (K if a_mn else M) * lda].view(-1, lda)
-    A = A[:K, :M].t() if a_mn else A[:M, :K]
-    Bm = b.reshape(-1)[: (K if b_mn else N) * ldb].view(-1, ldb)
-    Bm = Bm[:K, :N].t() if b_mn else Bm[:N, :K]
+    ldo = N if ldo is None else ldo
+    A = _mat(a, K, M, lda).t() if a_mn else _mat(a, M, K, lda)
+    Bm = _mat(b, K, N, ldb).t() if b_mn else _mat(b, N, K, ldb)
     v = alpha * (A.float() @ Bm.float().t())
     if bias is not None:
         v = v + bias.float()
-    o = out.view(M, -1)[:, :N]
+    o = _mat(out, M, N, ldo)
     if out_pre is not None:
-        out_pre.view(M, -1)[:, :N].copy_(v.to(BF16))
+        _mat(out_pre, M, N, ldo).copy_(v.to(BF16))
     v = _act(v, act)
     if dact:
-        v = v * _dact(aux.view(M, -1)[:, :N].float(), dact)
+        v = v * _dact(_mat(aux, M, N, N if ldaux is None else ldaux).float(), dact)
     if residual is not None:
-        v = v + residual.view(M, -1)[:, :N]
+        v = v + _mat(residual, M, N, N if ldr is None else ldr)
     if accumulate:
         o.add_(v.to(o.dtype))
     else:
@@ -116,6 +120,68 @@ def attn_bwd(qkv, out, dout, lse, delta, dqkv, B, N, H, d, mode, T, n, causal, s
     dqkv.view(B, N, 3, H, d).copy_(r.to(BF16))
 
 
+def _padded_scores(qkv, klen, B, N, H, d, scale):
+    t = qkv.view(B, N, 3, H, d).float()
+    q, k, v = (t[:, :, i].transpose(1, 2) for i in range(3))
+    s = (q @ k.transpose(-1, -2)) * scale
+    ok = torch.arange(N, device=qkv.device)[None, :] < klen.view(B, 1).to(torch.int64)          # [B, N] valid KEYS
+    return q, k, v, s.masked_fill(~ok[:, None, None, :], float("-inf"))
+
+
+def attn_padded_fwd(qkv, out, lse, klen, B, N, H, d, scale):
+    q, k, v, s = _padded_scores(qkv, klen, B, N, H, d, scale)
+    l = torch.logsumexp(s, -1)
+    p = torch.exp(s - l[..., None])
+    out.view(B * N, H * d).copy_((p @ v).transpose(1, 2).reshape(B * N, H * d).to(BF16))
+    lse.view(B, H, N).copy_(l)
+
+
+def attn_padded_bwd(qkv, out, dout, lse, delta, dqkv, klen, B, N, H, d, scale):
+    q, k, v, s = _padded_scores(qkv, klen, B, N, H, d, scale)
+    p = torch.exp(s - lse.view(B, H, N)[..., None])
+    do = dout.view(B, N, H, d).float().transpose(1, 2)
+    o = out.view(B, N, H, d).float().transpose(1, 2)
+    dl = (do * o).sum(-1)
+    delta.view(B, H, N).copy_(dl)
+    ds = p * (do @ v.transpose(-1, -2) - dl[..., None])
+    r = torch.stack([(ds @ k) * scale, (ds.transpose(-1, -2) @ q) * scale, p.transpose(-1, -2) @ do], 0).permute(1, 3, 0, 2, 4)
+    dqkv.view(B, N, 3, H, d).copy_(r.to(BF16))
+
+
+def tubelet_gather(video, keep, cols, B, T, R, p, n):
+    g, nt = R // p, T // 2
+    x = video.view(B, nt, 2, 3, g, p, g, p).permute(0, 1, 4, 6, 3, 2, 5, 7).reshape(B, nt, g * g, 3 * 2 * p * p)
+    idx = keep.view(B, nt, n, 1).expand(B, nt, n, x.shape[-1])
+    cols.view(B, nt, n, -1).copy_(torch.gather(x, 2, idx).to(BF16))
+
+
+def video_assemble_tube(tok, cls, pos, tem, keep, x0, B, nt, n, D):
+    pos, tem = pos.view(-1, D), tem.view(-1, D)          # the parameters are [1, P+1, D] / [1, tubes, D]
+    t = tok.view(B, nt, n, D) + pos[1:][keep.view(B, nt, n)] + tem[:nt][None, :, None, :]
+    x = x0.view(B, 1 + nt * n, D)
+    x[:, 0] = cls.reshape(-1) + pos[0]
+    x[:, 1:] = t.reshape(B, nt * n, D)
+
+
+def video_assemble_tube_bwd(dx0, keep, dcls, dpos, dtem, dtok, B, nt, n, D):
+    dpos, dtem = dpos.view(-1, D), dtem.view(-1, D)
+    d = dx0.view(B, 1 + nt * n, D)
+    dcls.view(-1).add_(d[:, 0].sum(0))
+    dpos[0].add_(d[:, 0].sum(0))
+    dp = d[:, 1:].reshape(B, nt, n, D)
+    dtem[:nt].add_(dp.sum((0, 2)))
+    dpos.index_add_(0, (1 + keep.view(-1)), dp.reshape(-1, D))
+    dtok.view(B * nt * n, D).copy_(dp.reshape(-1, D).to(BF16))
+
+
+def relu_bf16(x, y, n):
+    y.view(-1).copy_(torch.relu(x.reshape(-1)).to(BF16))
+
+
+def relu_bwd(x, dy, dx, n):
+    dx.view(-1).copy_(dy.reshape(-1) * (x.reshape(-1) > 0))
+
+
 def attn_window_fwd(qkv, out, lse, B, N, H, d, q0, qn, scale):
     o = torch.empty(B * N, H * d, dtype=BF16, device=qkv.device)
     l = torch.empty(B, H, N, device=qkv.device)
@@ -179,7 +245,7 @@ def cast_bf16(src, dst, n):
 
 
 def colsum_bf16(x, out, M, N, ld):
-    out.add_(x.view(M, ld)[:, :N].float().sum(0))
+    out.add_(_mat(x, M, N, ld).float().sum(0))
 
 
 def patch_gather(video, keep, cols, B, T, R, p, n):
@@ -230,13 +296,13 @@ def video_assemble_bwd(dx0, keep, dcls, dpos, dtem, dtok, B, T, n, D):
 
 
 def text_embed(tok, is64, table, pos, x, rows, L, W):
-    x.view(rows, L, W).copy_(table[tok.view(rows, L).long()] + pos)
+    x.view(rows, L, W).copy_(table[tok.view(rows, L).long()] + pos.view(-1, W)[:L])      # the kernel reads rows 0..L-1 of the position table
 
 
 def text_embed_bwd(dx, tok, is64, dtable, dpos, rows, L, W):
     d = dx.view(rows, L, W)
     if dpos is not None:
-        dpos.add_(d.sum(0))
+        dpos.view(-1, W)[:L].add_(d.sum(0))
     if dtable is not None:
         dtable.index_add_(0, tok.view(-1).long(), d.reshape(rows * L, W))
 

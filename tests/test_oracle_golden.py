@@ -65,3 +65,39 @@ def test_v1_oracle_matches_reference_golden():
     for k, nrm in zip([str(s) for s in g["grad_names"]], g["grad_norms"]):
         gn = sd[k].grad.double().norm().item()
         assert abs(gn - nrm) <= 1e-3 * nrm + 1e-7, (k, gn, nrm)
+
+
+def test_v1_oracle_with_text_encoder_matches_reference_golden():
+    """TVTS v1 end to end INCLUDING the DistilBERT text encoder (right-padded captions): oracle (with its DistilBERT restatement) vs
+    the fixture written by executing v1/model/model_dist_TVTS.py around the installed transformers.DistilBertModel."""
+    import v1_fixture
+    g, dims, cfg, names, sd, data = v1_fixture.load()
+    l1, l2, (te, ve, pr), grads = O.v1_step_with_grads(sd, data["text"], data["video"], data["keep_ind"], data["label"], cfg, dims.heads)
+    assert abs(l1.item() - float(g["loss1"])) < 2e-5 and abs(l2.item() - float(g["loss2"])) < 2e-5
+    np.testing.assert_allclose(te.numpy(), g["text_emb"], atol=2e-5, rtol=1e-4)
+    np.testing.assert_allclose(ve.numpy(), g["video_emb"], atol=2e-5, rtol=1e-4)
+    np.testing.assert_allclose(pr.numpy(), g["pred_order"], atol=5e-5, rtol=1e-4)
+    assert set(grads) == set(str(s) for s in g["grad_names"])
+    for k, nrm in zip([str(s) for s in g["grad_names"]], g["grad_norms"]):
+        gn = grads[k].double().norm().item()
+        assert abs(gn - nrm) <= 1e-3 * nrm + 1e-7, (k, gn, nrm)
+
+
+def test_distilbert_restatement_matches_installed_transformers():
+    """The v1 text encoder is an un-vendored dependency: the oracle's restatement is pinned against the installed implementation
+    (same weights, padded and unpadded sequences)."""
+    transformers = pytest.importorskip("transformers")
+    torch.manual_seed(0)
+    cfg = transformers.DistilBertConfig(vocab_size=128, dim=128, n_layers=2, n_heads=2, hidden_dim=256, max_position_embeddings=32,
+                                        dropout=0.0, attention_dropout=0.0)
+    m = transformers.DistilBertModel(cfg).eval()
+    sd = {"text_model." + k: v for k, v in m.state_dict().items()}
+    ids = torch.randint(1, 128, (6, 12))
+    mask = torch.ones_like(ids)
+    mask[1, 7:] = 0
+    mask[4, 3:] = 0
+    ids = ids * mask
+    with torch.no_grad():
+        ref = m(input_ids=ids, attention_mask=mask).last_hidden_state
+        out = O.distilbert_forward(sd, ids, mask, 2)
+    assert (ref - out).abs().max().item() < 1e-5

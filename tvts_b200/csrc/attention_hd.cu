@@ -62,14 +62,15 @@ __device__ __forceinline__ void g_load_tile(uint32_t tile, const bf16* base, lon
 // ================================================================================================ forward
 template <int HD>
 __global__ void __launch_bounds__(kThreads) attn_hd_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse,
-                                                               AttnShape a) {
+                                                               AttnShape a, const int* __restrict__ klen) {
   using G = Geo<HD>;
   extern __shared__ __align__(128) uint8_t smem[];   // Q | K0 | V0 | K1 | V1
   const uint32_t sQ = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const int h = blockIdx.y, b = blockIdx.z;
-  const Sets s = decode_sets(a, blockIdx.x);
+  Sets s = decode_sets(a, blockIdx.x);
+  if (klen) s.sm_count = min(s.sm_count, klen[b]);   // key padding (mode FULL): keys >= klen[b] are simply never streamed
   const long long rs = 3LL * a.H * HD;
   const bf16* qb = qkv + (long long)b * a.N * rs + (long long)h * HD;
   const bf16* kb = qb + (long long)a.H * HD;
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(256) attn_hd_delta_kernel(const bf16* __restri
 template <int HD, int ROLE>
 __global__ void __launch_bounds__(kThreads) attn_hd_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                                                                const float* __restrict__ lse, const float* __restrict__ delta,
-                                                               bf16* __restrict__ dqkv, AttnShape a) {
+                                                               bf16* __restrict__ dqkv, AttnShape a, const int* __restrict__ klen) {
   using G = Geo<HD>;
   extern __shared__ __align__(128) uint8_t smem[];   // 4 tiles + lse/delta of the streamed rows for 2 stages
   // [0] stationary tile 0 (Q or K) -> after the fragment load reused as X stage 1
@@ -260,7 +261,10 @@ __global__ void __launch_bounds__(kThreads) attn_hd_bwd_kernel(const bf16* __res
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const int h = blockIdx.y, b = blockIdx.z;
-  const Sets s = decode_sets(a, blockIdx.x, ROLE == 1);
+  Sets s = decode_sets(a, blockIdx.x, ROLE == 1);
+  // key padding (mode FULL): ROLE 0 never streams keys >= klen[b]; ROLE 1 masks its stationary keys >= klen[b] (their dk / dv are 0)
+  const int kl = klen ? klen[b] : 0x7fffffff;
+  if (ROLE == 0 && klen) s.sm_count = min(s.sm_count, kl);
   const long long rs = 3LL * a.H * HD, ro = (long long)a.H * HD;
   const bf16* qb = qkv + (long long)b * a.N * rs + (long long)h * HD;
   const bf16* kb = qb + ro;
@@ -375,6 +379,7 @@ __global__ void __launch_bounds__(kThreads) attn_hd_bwd_kernel(const bf16* __res
               if (ROLE == 0) { ok0 = tok <= stok0; ok1 = tok <= stok1; }
               else { ok0 = tok >= stok0; ok1 = tok >= stok1; }
             }
+            if (ROLE == 1) { ok0 = ok0 && stok0 < kl; ok1 = ok1 && stok1 < kl; }
             const float la = ROLE == 0 ? lse0 : Ls[col], lb = ROLE == 0 ? lse1 : Ls[col];
             const float da = ROLE == 0 ? dl0 : Ds[col], db = ROLE == 0 ? dl1 : Ds[col];
             p[e] = ok0 ? exp2f(sc[j][e] * sl2 - la) : 0.f;
@@ -447,7 +452,7 @@ int hd_check_shape(const AttnShape& a, int64_t d) {
 }
 
 template <int HD>
-int hd_launch_fwd(const void* qkv, void* out, float* lse, const AttnShape& a, cudaStream_t st) {
+int hd_launch_fwd(const void* qkv, void* out, float* lse, const AttnShape& a, cudaStream_t st, const int* klen = nullptr) {
   constexpr int smem_bytes = 5 * Geo<HD>::TILE;
   static bool set = false;
   if (!set) {
@@ -455,14 +460,14 @@ int hd_launch_fwd(const void* qkv, void* out, float* lse, const AttnShape& a, cu
     set = true;
   }
   dim3 grid(num_blocks_x(a), (unsigned)a.H, (unsigned)a.B);
-  attn_hd_fwd_kernel<HD><<<grid, kThreads, smem_bytes, st>>>((const bf16*)qkv, (bf16*)out, lse, a);
+  attn_hd_fwd_kernel<HD><<<grid, kThreads, smem_bytes, st>>>((const bf16*)qkv, (bf16*)out, lse, a, klen);
   TVTS_LAUNCH_CHECK();
   return TVTS_OK;
 }
 
 template <int HD>
 int hd_launch_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv, const AttnShape& a,
-                  cudaStream_t st) {
+                  cudaStream_t st, const int* klen = nullptr) {
   constexpr int smem_bytes = 4 * Geo<HD>::TILE + 2 * 2 * BN * 4;
   static bool set = false;
   if (!set) {
@@ -474,10 +479,10 @@ int hd_launch_bwd(const void* qkv, const void* out, const void* dout, const floa
   attn_hd_delta_kernel<HD><<<(unsigned)((rows + 31) / 32), 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta_ws, a.B, a.N, a.H);
   TVTS_LAUNCH_CHECK();
   dim3 g0(num_blocks_x(a, false), (unsigned)a.H, (unsigned)a.B);
-  attn_hd_bwd_kernel<HD, 0><<<g0, kThreads, smem_bytes, st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, a);
+  attn_hd_bwd_kernel<HD, 0><<<g0, kThreads, smem_bytes, st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, a, klen);
   TVTS_LAUNCH_CHECK();
   dim3 g1(num_blocks_x(a, true), (unsigned)a.H, (unsigned)a.B);
-  attn_hd_bwd_kernel<HD, 1><<<g1, kThreads, smem_bytes, st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, a);
+  attn_hd_bwd_kernel<HD, 1><<<g1, kThreads, smem_bytes, st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, a, klen);
   TVTS_LAUNCH_CHECK();
   return TVTS_OK;
 }
@@ -506,4 +511,30 @@ extern "C" int tvts_attn_generic_bwd(const void* qkv, const void* out, const voi
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   return d == 64 ? hd_launch_bwd<64>(qkv, out, dout, lse, delta_ws, dqkv, a, st)
                  : hd_launch_bwd<80>(qkv, out, dout, lse, delta_ws, dqkv, a, st);
+}
+
+// Key-padded full attention (the v1 text encoder, DistilBERT: padded key positions of `attention_mask` are excluded from the softmax;
+// v1/model/model_dist_TVTS.py:124-126).  klen [B] int32 = number of leading valid tokens per sequence (1 <= klen[b] <= N; the tokenizer
+// pads on the right).  Query rows >= klen[b] are still computed (over the valid keys), exactly like the reference.
+extern "C" int tvts_attn_padded_fwd(const void* qkv, void* out, float* lse, const int32_t* klen, int64_t B, int64_t N, int64_t H, int64_t d,
+                                    float scale, void* stream) {
+  AttnShape a{(int)B, (int)N, (int)H, 0, 0, 0, 0, scale, 0, 0, 0};
+  if (B == 0) return TVTS_OK;
+  int rc = hd_check_shape(a, d);
+  if (rc) return rc;
+  TVTS_REQUIRE(qkv && out && lse && klen, "attn_padded_fwd: null pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return d == 64 ? hd_launch_fwd<64>(qkv, out, lse, a, st, klen) : hd_launch_fwd<80>(qkv, out, lse, a, st, klen);
+}
+
+extern "C" int tvts_attn_padded_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv,
+                                    const int32_t* klen, int64_t B, int64_t N, int64_t H, int64_t d, float scale, void* stream) {
+  AttnShape a{(int)B, (int)N, (int)H, 0, 0, 0, 0, scale, 0, 0, 0};
+  if (B == 0) return TVTS_OK;
+  int rc = hd_check_shape(a, d);
+  if (rc) return rc;
+  TVTS_REQUIRE(qkv && out && dout && lse && delta_ws && dqkv && klen, "attn_padded_bwd: null pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return d == 64 ? hd_launch_bwd<64>(qkv, out, dout, lse, delta_ws, dqkv, a, st, klen)
+                 : hd_launch_bwd<80>(qkv, out, dout, lse, delta_ws, dqkv, a, st, klen);
 }

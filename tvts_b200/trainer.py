@@ -106,6 +106,28 @@ def average_gradients(params):
     return flat.numel() * 4
 
 
+def _flatten(data, prefix=""):
+    """{'video': t, 'text': {'input_ids': t, ...}} -> {'video': t, 'text.input_ids': t, ...} (v1 batches nest the tokenizer output)."""
+    out = {}
+    for k, v in data.items():
+        if isinstance(v, dict) or (hasattr(v, "keys") and hasattr(v, "__getitem__") and not torch.is_tensor(v)):
+            out.update(_flatten({kk: v[kk] for kk in v.keys()}, prefix + k + "."))
+        else:
+            out[prefix + k] = v
+    return out
+
+
+def _unflatten(flat):
+    out = {}
+    for k, v in flat.items():
+        d = out
+        parts = k.split(".")
+        for part in parts[:-1]:
+            d = d.setdefault(part, {})
+        d[parts[-1]] = v
+    return out
+
+
 class TrainStep:
     """One optimizer step of Trainer_TVTSv2_*._train_epoch for a tokenised batch.
 
@@ -132,7 +154,10 @@ class TrainStep:
     def to_device(self, data):
         out = {}
         for k, v in data.items():
-            out[k] = v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v
+            if isinstance(v, dict):
+                out[k] = self.to_device(v)
+            else:
+                out[k] = v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v
         return out
 
     def _body(self, data, optimizer_launch_only=False, skip_optimizer=False):
@@ -167,18 +192,19 @@ class TrainStep:
         from . import _lib as L
         if not (self.optimizer is None or hasattr(self.optimizer, "launch")):
             raise RuntimeError("TrainStep(use_graph=True) needs tvts_b200.optim.AdamW (or no optimizer)")
-        static = {k: v.to(self.device, copy=True) for k, v in data.items() if torch.is_tensor(v)}
+        static = {k: v.to(self.device, copy=True) for k, v in data.items() if torch.is_tensor(v)}      # `data` is flat here
+        nested = _unflatten(static)
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
         with torch.cuda.stream(side):               # warm-up outside capture: allocator pools, bf16 weight casts, NCCL, func attributes
-            self._body(static, skip_optimizer=True)
+            self._body(nested, skip_optimizer=True)
         cur.wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         n0 = L.launch_count()
         with torch.cuda.graph(graph):
-            l1, l2 = self._body(static, optimizer_launch_only=True)
+            l1, l2 = self._body(nested, optimizer_launch_only=True)
         self.launches_per_graph = L.launch_count() - n0
         flat = getattr(self.optimizer, "flat", None)
         ent = types.SimpleNamespace(graph=graph, static=static, l1=l1, l2=l2, active=flat.active_mask() if flat is not None else None)
@@ -192,6 +218,7 @@ class TrainStep:
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
             self._stage_bufs = {}
+        data = _flatten(data)
         cs = self._copy_stream
         if self._staged is not None:
             cs.wait_event(self._staged[2])           # the previous consumer has finished reading the staging buffers
@@ -222,10 +249,11 @@ class TrainStep:
                 raise ValueError("TrainStep(None) needs a batch staged with prefetch()")
             data, consumed = self._take_staged()
         if not self.use_graph:
-            out = self._body(self.to_device(data))
+            out = self._body(self.to_device(_unflatten(data) if consumed is not None else data))
             if consumed is not None:
                 consumed.record(torch.cuda.current_stream())
             return out
+        data = _flatten(data)
         key = tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(data.items()) if torch.is_tensor(v))
         ent = self._graphs.get(key)
         if ent is None:
@@ -274,7 +302,8 @@ def validate(model, batches, device=None, metrics=None):
 
     with torch.no_grad():
         for data in batches:
-            data = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in data.items()}
+            data = {k: (v.to(device) if torch.is_tensor(v) else
+                        ({kk: vv.to(device) for kk, vv in v.items()} if isinstance(v, dict) else v)) for k, v in data.items()}
             text_embed, vid_embed, preds = model(data, return_embeds=True)
             vid_arr.append(gather(vid_embed).cpu())
             text_arr.append(gather(text_embed).cpu())
@@ -470,3 +499,35 @@ class Trainer_TVTSv2:
 Trainer_TVTSv2_B_16 = Trainer_TVTSv2
 Trainer_TVTSv2_B_32 = Trainer_TVTSv2
 Trainer_TVTSv2_H_14 = Trainer_TVTSv2      # v2/trainer/trainer.py:648-905: the same step (no GradScaler; autocast lives in the model)
+
+
+class Trainer_TVTS(Trainer_TVTSv2):
+    """v1/trainer/trainer.py:40-260: the same epoch loop and step; the HuggingFace tokenizer is called with
+    `return_tensors='pt', padding=True, truncation=True, max_length=50` (:130-131) and the model receives its
+    {'input_ids', 'attention_mask'} dict.  Learning rate: base_lr x 0.1 per milestone already passed, set absolutely (:80-84)."""
+
+    MAX_LENGTH = 50
+
+    def __init__(self, *a, pad_to_max_length=False, **k):
+        super().__init__(*a, **k)
+        self.pad_to_max_length = pad_to_max_length      # one sequence length -> one CUDA graph (padded keys are masked: same results)
+        self.base_lr = self.optimizer.param_groups[0]["lr"]                        # v1/base/base_trainer.py:30
+
+    def _tokenize(self, data):
+        if self.tokenizer is not None and not isinstance(data["text"], dict):
+            text_all = []
+            for clip in data["text"]:
+                text_all = text_all + list(clip)
+            enc = self.tokenizer(text_all, return_tensors="pt", padding="max_length" if self.pad_to_max_length else True,
+                                 truncation=True, max_length=self.MAX_LENGTH)
+            data = dict(data)
+            data["text"] = {"input_ids": enc["input_ids"], "attention_mask": enc["attention_mask"]}
+        return data
+
+    def _adjust_learning_rate(self, optimizer, epoch, args):
+        lr = self.base_lr
+        for milestone in getattr(args, "schedule", []):
+            lr *= 0.1 if epoch >= milestone else 1.0
+        for group in optimizer.param_groups:
+            group["lr"] = lr
+        return lr
