@@ -1,0 +1,20 @@
+#!/bin/bash
+# First GPU call of round 2: everything that was written after the round-1 GPU budget ran out, in one box session.
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/round2_bringup.sh'
+# Results land in gpurun_out/r2_bringup/.
+set -x
+mkdir -p gpurun_out/r2_bringup
+O=gpurun_out/r2_bringup
+python -c "import __graft_entry__ as g; g.build()" > $O/build.log 2>&1
+# 1. staged tests (H/14 attention d=80, padded patch embed, v1 kernels + models, downstream): run WITHOUT the xfail veil
+timeout 900 python -m pytest tests/test_zz_round1_unverified_gpu.py -q -m gpu --runxfail -x --tb=short > $O/zz_first_failure.log 2>&1
+timeout 900 python -m pytest tests/test_zz_round1_unverified_gpu.py -q -m gpu --runxfail --tb=line > $O/zz_all.log 2>&1
+# 2. the verified suite (must stay green) incl. the tests that were never run on a GPU in round 1
+timeout 1200 python -m pytest tests -q -m gpu -x --deselect tests/test_zz_round1_unverified_gpu.py > $O/gpu_suite.log 2>&1
+# 3. loss trajectories (north star: 100 steps within 1e-3)
+timeout 900 python tools/loss_parity.py 100 c1 > $O/loss_parity_c1_100.log 2>&1
+timeout 300 python tools/loss_parity.py 100 tiny > $O/loss_parity_tiny_100.log 2>&1
+# 4. benches: headline, then H/14
+timeout 600 python bench.py --steps 20 --warmup 5 > $O/bench_c3.json 2> $O/bench_c3.err
+timeout 900 python bench.py --workload c4 --steps 5 --warmup 3 --no-cpu-baseline > $O/bench_c4.json 2> $O/bench_c4.err
+tail -3 $O/*.log $O/*.json
