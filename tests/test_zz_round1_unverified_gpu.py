@@ -9,9 +9,11 @@ that `pytest -x` reaches them only after every previously-verified GPU test has 
     (DistilBERT text encoder included) against the executed-reference fixture tiny_v1_full and the oracle's gradients
 Tolerances as in tests/test_kernels_gpu.py / tests/test_model_gpu.py.
 
-Because none of this has met a GPU yet, the module is marked xfail(strict=False): a failure is reported as XFAIL (expected until the
-first GPU run of round 2 debugs it) and a pass as XPASS, without turning the verified suite red.  Round 2: run this file first,
-fix what fails, then delete the xfail mark and fold the cases into test_kernels_gpu.py / test_model_gpu.py."""
+Because none of this has met a GPU yet, the cases do not run inside the main pytest process: `test_staged_suite_in_subprocess`
+re-runs this file in a CHILD process (TVTS_RUN_STAGED=1) so that a faulting kernel cannot poison the CUDA context of the verified
+suite, prints the child's per-test report, and is itself xfail(strict=False): XPASS when every staged case passes, XFAIL otherwise.
+Round 2: `TVTS_RUN_STAGED=1 python -m pytest tests/test_zz_round1_unverified_gpu.py -m gpu` first, fix what fails, then fold the cases
+into test_kernels_gpu.py / test_model_gpu.py and delete this indirection."""
 import os
 import types
 
@@ -27,11 +29,19 @@ from tvts_b200 import engine as E
 from tvts_b200 import modules as M
 from tvts_b200.synthetic import make_batch, make_state_dict
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="written after the round-1 GPU budget was spent: never executed on a B200 yet")]
+STAGED = os.environ.get("TVTS_RUN_STAGED") == "1"
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not STAGED, reason="staged cases run in a child process (TVTS_RUN_STAGED=1)")]
 DEV = "cuda"
 BF16, F32 = torch.bfloat16, torch.float32
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _run_staged_child():
+    import subprocess
+    import sys
+    env = dict(os.environ, TVTS_RUN_STAGED="1")
+    return subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "--tb=line", "-p", "no:cacheprovider",
+                           "-rA"], env=env, capture_output=True, text=True, timeout=1500, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
 def rnd(*shape, scale=1.0):

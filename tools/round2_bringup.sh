@@ -7,10 +7,10 @@ mkdir -p gpurun_out/r2_bringup
 O=gpurun_out/r2_bringup
 python -c "import __graft_entry__ as g; g.build()" > $O/build.log 2>&1
 # 1. staged tests (H/14 attention d=80, padded patch embed, v1 kernels + models, downstream): run WITHOUT the xfail veil
-timeout 900 python -m pytest tests/test_zz_round1_unverified_gpu.py -q -m gpu --runxfail -x --tb=short > $O/zz_first_failure.log 2>&1
-timeout 900 python -m pytest tests/test_zz_round1_unverified_gpu.py -q -m gpu --runxfail --tb=line > $O/zz_all.log 2>&1
+TVTS_RUN_STAGED=1 timeout 900 python -m pytest tests/test_zz_round1_unverified_gpu.py -q -m gpu -x --tb=short > $O/zz_first_failure.log 2>&1
+TVTS_RUN_STAGED=1 timeout 900 python -m pytest tests/test_zz_round1_unverified_gpu.py -q -m gpu --tb=line -rA > $O/zz_all.log 2>&1
 # 2. the verified suite (must stay green) incl. the tests that were never run on a GPU in round 1
-timeout 1200 python -m pytest tests -q -m gpu -x --deselect tests/test_zz_round1_unverified_gpu.py > $O/gpu_suite.log 2>&1
+timeout 1200 python -m pytest tests -q -m gpu -x --deselect tests/test_zy_staged_wrapper_gpu.py > $O/gpu_suite.log 2>&1
 # 3. loss trajectories (north star: 100 steps within 1e-3)
 timeout 900 python tools/loss_parity.py 100 c1 > $O/loss_parity_c1_100.log 2>&1
 timeout 300 python tools/loss_parity.py 100 tiny > $O/loss_parity_tiny_100.log 2>&1
