@@ -11,7 +11,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_reference_import_paths_resolve():
     code = ("import model.model_dist_TVTSv2_ViT_B_16 as a, model.model_dist_TVTSv2_ViT_B_32 as b, model.loss as l, "
             "trainer.trainer as t, model.sort_transformer as s, model.video_encoder_ViT_B_16 as v;"
-            "assert a.TVTSv2_B_16 and b.TVTSv2_B_32 and a.sim_matrix and l.NormSoftmaxLoss and t.AllGather_multi and s.SortTransformer and v.VisionTransformer")
+            "assert a.TVTSv2_B_16 and b.TVTSv2_B_32 and a.sim_matrix and l.NormSoftmaxLoss and t.AllGather_multi and s.SortTransformer and v.VisionTransformer;"
+            # everything else the entry / downstream scripts import from the shadowed packages (train_dist_TVTSv2_ViT_*.py:8-20, zero_ret_*:9,17)
+            "import model.metric as mm, model.model_dist_TVTSv2_ViT_H_14 as h, model.video_encoder_ViT_H_14 as vh, model.video_encoder_ViT_B_32 as v32;"
+            "from trainer import Trainer_TVTSv2_B_16, Trainer_TVTSv2_B_32, Trainer_TVTSv2_H_14;"
+            "from trainer.trainer import verbose, format_nested_metrics_for_writer;"
+            "assert mm.t2v_metrics and mm.v2t_metrics and h.TVTSv2_H_14 and vh.VisionTransformer and vh.LayerNorm and vh.QuickGELU and v32.VisionTransformer")
     env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "tvts_b200", "dropin") + os.pathsep + ROOT)
     subprocess.run([sys.executable, "-c", code], check=True, env=env, cwd="/tmp")
 

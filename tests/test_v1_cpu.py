@@ -116,7 +116,7 @@ def test_v1_trainer_loop_tokenises_like_the_reference_and_steps(emu_backend):
 
 def test_v1_drop_in_paths_resolve():
     code = ("import model.model_dist_TVTS as a, model.video_encoder as v, model.sort_transformer as s, model.loss as l, trainer.trainer as t;"
-            "from trainer import Trainer_TVTS;"
+            "from trainer import Trainer_TVTS; import model.metric as mm; assert mm.t2v_metrics and mm.v2t_metrics;"
             "assert a.TVTS and a.sim_matrix and v.VisionTransformer and s.SortTransformer and l.NormSoftmaxLoss and t.AllGather_multi")
     env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "tvts_b200", "dropin_v1") + os.pathsep + ROOT)
     subprocess.run([sys.executable, "-c", code], check=True, env=env, cwd="/tmp")

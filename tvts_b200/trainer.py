@@ -501,6 +501,17 @@ Trainer_TVTSv2_B_32 = Trainer_TVTSv2
 Trainer_TVTSv2_H_14 = Trainer_TVTSv2      # v2/trainer/trainer.py:648-905: the same step (no GradScaler; autocast lives in the model)
 
 
+def verbose(epoch, metrics, mode, name="TEST"):
+    """One-line retrieval report (v2/trainer/trainer.py:942-947; imported by the downstream zero_ret_* scripts)."""
+    print(f"[{mode}]{name:s} epoch {epoch}, R@1: {metrics['R1']:.1f}, R@5: {metrics['R5']:.1f}, R@10: {metrics['R10']:.1f}, "
+          f"R@50: {metrics['R50']:.1f}, MedR: {metrics['MedR']:g}, MeanR: {metrics['MeanR']:.1f}")
+
+
+def format_nested_metrics_for_writer(metrics, mode, name="TEST"):
+    """{key: value} -> {'[mode]name_key': value}   (v2/trainer/trainer.py:950-955)"""
+    return {f"[{mode}]{name}_{key}": val for key, val in metrics.items()}
+
+
 class Trainer_TVTS(Trainer_TVTSv2):
     """v1/trainer/trainer.py:40-260: the same epoch loop and step; the HuggingFace tokenizer is called with
     `return_tensors='pt', padding=True, truncation=True, max_length=50` (:130-131) and the model receives its
