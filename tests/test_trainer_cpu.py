@@ -1,5 +1,6 @@
 """Epoch loop of Trainer_TVTSv2_* (tvts_b200/trainer.py) on the torch emulation of the kernels: loader interleaving, clip-major
 caption flattening + tokenisation, one optimizer step per loader batch, milestone decay, validation metrics."""
+import os
 import types
 
 import torch
@@ -156,3 +157,42 @@ def test_parameter_order_matches_the_reference(emu_backend):
     m = M.TVTSv2Base(types.SimpleNamespace(local_rank=0), arch=C.TINY_B)
     ours = [k for k, _ in m.named_parameters() if k in set(ref_order)]
     assert len(ref_order) > 50 and ours == ref_order
+
+
+class SavingCfg(dict):
+    """dict-like config with the two attributes of the reference's ConfigParser the trainer reads (picklable: it goes into the file)."""
+    resume = None
+    save_dir = None
+
+
+def test_save_period_monitor_and_arena_follow(emu_backend, tmp_path):
+    """base_trainer.py:35-53,116-143: checkpoint-epoch{N}.pth every save_period epochs in config.save_dir, model_best.pth when the
+    monitored metric improves; and the optimizer re-creates its arenas when the model's parameters got new storages after the
+    optimizer was built (what `model.to(device)` in the reference's base trainer does to a CPU-built optimizer)."""
+    cfg = C.TINY_B
+    m = M.TVTSv2Base(types.SimpleNamespace(local_rank=0), arch=cfg)
+    m.load_state_dict(make_state_dict(cfg, seed=1234), strict=True)
+    opt = optim.build_reference_optimizer(m)
+    old_flat = opt.flat
+    for p in m.parameters():                      # simulate model.to(device): every parameter gets a fresh storage
+        p.data = p.data.clone()
+    batches = [make_batch(cfg, 2, 2, n_trans=4, seed=80 + i) for i in range(2)]
+    val = [FakeLoader("MSRVTT", [make_batch(cfg, 2, 2, n_trans=4, seed=90)], 2)]
+    args = types.SimpleNamespace(rank=0, local_rank=0, world_size=1, schedule=[])
+    config = SavingCfg({"trainer": {"epochs": 2, "save_period": 2, "monitor": "min val_loss_0", "init_val": False}, "optimizer": {"type": "AdamW"}})
+    config.save_dir = tmp_path / "ckpt"
+    try:
+        tr = Trainer_TVTSv2_B_16(args, m, M.NormSoftmaxLoss(0.05), [MT.t2v_metrics, MT.v2t_metrics], opt, config,
+                                 [FakeLoader("YTTemporal", batches, 2)], valid_data_loader=val, use_graph=False)
+        assert opt.flat is not old_flat                                               # arenas rebuilt next to the parameters
+        w = m.video_model.proj
+        assert w.data_ptr() == opt.flat._view(opt.flat.p, w).data_ptr()
+        w0 = w.detach().clone()
+        tr.train()
+        assert not torch.equal(w0, w.detach())                                         # the rebuilt arena is the one being trained
+        files = sorted(os.listdir(str(config.save_dir)))
+        assert "model_best.pth" in files and "checkpoint-epoch2.pth" in files          # best at epoch 1 (first value), period at epoch 2
+        ck = torch.load(str(config.save_dir / "checkpoint-epoch2.pth"), weights_only=False)
+        assert ck["epoch"] == 2 and ck["monitor_best"] == tr.mnt_best and ck["arch"] == "TVTSv2Base"
+    finally:
+        opt.flat.release()

@@ -191,6 +191,29 @@ class AdamW:
         self._slot = 0
         self.table = torch.zeros(len(flat), 4, dtype=torch.float32, device=self.flat.device)
 
+    def follow_parameters(self):
+        """Re-create the flat arenas on the device the parameters live on NOW.  The reference entry scripts build the optimizer while
+        the model is still on the CPU and let the trainer move the model afterwards (v2/base/base_trainer.py:19-21): `model.to(device)`
+        gives every parameter a fresh storage, so the arenas (and the parameters' arena views) have to be rebuilt there.  Adam moments
+        and step counters are carried over.  No-op when the parameters still are views of the arena."""
+        fs = self.flat
+        p0 = fs.params[0]
+        if p0.device == fs.device and p0.data_ptr() == fs._view(fs.p, p0).data_ptr():
+            return False
+        old_m, old_v = fs.m, fs.v
+        fs.release()
+        self.flat = FlatState(fs.params, fs.chunk)
+        self.flat.m.copy_(old_m)
+        self.flat.v.copy_(old_v)
+        dev = self.flat.device
+        n = len(self.flat.params)
+        self._ring = [torch.zeros(n, 4, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(n, 4, dtype=torch.float32)
+                      for _ in range(4)]
+        self._ring_ev = [None] * 4
+        self._slot = 0
+        self.table = torch.zeros(n, 4, dtype=torch.float32, device=dev)
+        return True
+
     def zero_grad(self, set_to_none=True):
         self.flat.zero_grad()
 

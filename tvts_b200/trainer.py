@@ -356,16 +356,39 @@ class Trainer_TVTSv2:
         self.allgather = AllGather_multi.apply
         self.num_clips = 4
         self.n_trans = 4
-        trainer_cfg = (config["trainer"] if config is not None and "trainer" in config else {})
+        try:                                        # dict or the reference's ConfigParser (only __getitem__ is relied upon)
+            trainer_cfg = config["trainer"]
+        except (KeyError, TypeError, IndexError):
+            trainer_cfg = {}
         self.epochs = trainer_cfg.get("epochs", 1)
         self.start_epoch = 1
-        self.init_val = trainer_cfg.get("init_val", False)
+        self.init_val = trainer_cfg.get("init_val", True)              # base_trainer.py:37
+        # base_trainer.py:19-25: the entry scripts hand over a CPU model whose optimizer already exists; move it to this rank's GPU (no
+        # DDP wrap: TrainStep averages the gradient arena itself) and let the optimizer re-create its arenas next to the parameters
+        try:
+            n_gpu_cfg = config["n_gpu"]
+        except (KeyError, TypeError, IndexError):
+            n_gpu_cfg = 1
+        if torch.cuda.is_available() and n_gpu_cfg > 0 and next(model.parameters()).device.type != "cuda":
+            model.to(torch.device("cuda", getattr(args, "local_rank", 0) or 0))
+        if hasattr(optimizer, "follow_parameters"):
+            optimizer.follow_parameters()
         self.device = next(model.parameters()).device
+        model.device = self.device
+        # checkpoint period / best-model monitor (base_trainer.py:35-53,116-143)
+        self.save_period = trainer_cfg.get("save_period", 0)
+        self.monitor = trainer_cfg.get("monitor", "off")
+        self.checkpoint_dir = getattr(config, "save_dir", None)
+        if self.monitor == "off":
+            self.mnt_mode, self.mnt_metric, self.mnt_best = "off", None, 0
+        else:
+            self.mnt_mode, self.mnt_metric = self.monitor.split()
+            assert self.mnt_mode in ("min", "max")
+            self.mnt_best = float("inf") if self.mnt_mode == "min" else -float("inf")
         temperature = getattr(loss, "temperature", 0.05)
         self.step = TrainStep(model, optimizer, temperature, self.device, use_graph=use_graph and self.device.type == "cuda")
         self.on_epoch_end = on_epoch_end
         self.history = []
-        self.mnt_best = float("inf")
         resume = getattr(config, "resume", None)
         if resume is not None:                                   # base_trainer.py:60-61
             self.resume_checkpoint(resume)
@@ -491,9 +514,33 @@ class Trainer_TVTSv2:
             if getattr(self.args, "rank", 0) == 0:
                 for k, v in log.items():
                     print("    {:15s}: {}".format(str(k), v))
+            best = False
+            if self.mnt_mode != "off" and getattr(self.args, "rank", 0) == 0:
+                if self.mnt_metric in log:
+                    improved = log[self.mnt_metric] <= self.mnt_best if self.mnt_mode == "min" else log[self.mnt_metric] >= self.mnt_best
+                    if improved:
+                        self.mnt_best, best = log[self.mnt_metric], True
+                else:
+                    print("Warning: Metric '{}' is not found. Model performance monitoring is disabled.".format(self.mnt_metric))
+                    self.mnt_mode = "off"
+            if self.checkpoint_dir is not None and getattr(self.args, "rank", 0) == 0 and \
+                    ((self.save_period and epoch % self.save_period == 0) or best):
+                self._save_checkpoint(epoch, save_best=best)
             if self.on_epoch_end is not None:
                 self.on_epoch_end(self, epoch, log)
         return self.history
+
+    def _save_checkpoint(self, epoch, save_best=False):
+        """base_trainer.py:165-194: checkpoint-epoch{N}.pth in config.save_dir (+ model_best.pth when the monitored metric improved)."""
+        import os
+        import shutil
+        os.makedirs(str(self.checkpoint_dir), exist_ok=True)
+        path = self.save_checkpoint(os.path.join(str(self.checkpoint_dir), "checkpoint-epoch{}.pth".format(epoch)), epoch)
+        print("Saving checkpoint: {} ...".format(path))
+        if save_best:
+            shutil.copyfile(path, os.path.join(str(self.checkpoint_dir), "model_best.pth"))
+            print("Saving current best: model_best.pth ...")
+        return path
 
 
 Trainer_TVTSv2_B_16 = Trainer_TVTSv2
