@@ -88,3 +88,60 @@ def test_two_rank_step_matches_single_process_oracle():
     a, b = out["loss1"]
     assert abs(a - b) < 5e-2, (a, b)
     assert out["worst_text_grad_rel"] < 0.08, out["worst_text_grad_rel"]
+
+
+def _worker_v1(rank, world, port, out):
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import emu
+        import tvts_oracle as O
+        import v1_fixture
+        from test_v1_cpu import build
+        from tvts_b200 import engine as E
+        from tvts_b200 import optim
+        from tvts_b200.trainer import TrainStep
+        emu.install()
+        torch.set_num_threads(2)
+        g, dims, cfg, names, sd, data = v1_fixture.load()          # global batch of 2 pairs -> 1 pair per rank
+        assert dims.B == world
+        m = build(dims)
+        m.load_state_dict(sd, strict=True)
+        opt = optim.AdamW([p for p in m.parameters()], lr=1e-4, weight_decay=0.0)
+        E.WEIGHTS.clear()
+        step = TrainStep(m, None, 0.05, torch.device("cpu"))
+        step.optimizer = types.SimpleNamespace(flat=opt.flat, zero_grad=opt.zero_grad, step=lambda: None)   # keep the weights fixed
+        rows = torch.tensor([t * dims.B + rank for t in range(dims.nt)])           # this rank's captions, clip-major
+        local = {"video": data["video"][rank:rank + 1], "keep_ind": data["keep_ind"][rank:rank + 1], "label": data["label"][rank:rank + 1],
+                 "text": {k: v[rows] for k, v in data["text"].items()}}
+        l1, l2 = step(local)
+        grads = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+        if rank == 0:
+            o1, o2, _, og = O.v1_step_with_grads(sd, data["text"], data["video"], data["keep_ind"], data["label"], cfg, dims.heads)
+            out["loss1"] = (l1.item(), o1.item())
+            worst = 0.0
+            for k, gr in og.items():                      # parameters only the contrastive loss reaches: 1/W of the global gradient
+                if not (k.startswith("text_model.") or k.startswith("txt_proj.")) or gr.norm().item() < 1e-6:
+                    continue
+                ref = gr / world
+                worst = max(worst, (grads[k] - ref).norm().item() / (ref.norm().item() + 1e-12))
+            out["worst_text_grad_rel"] = worst
+        opt.flat.release()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_rank_v1_step_matches_single_process_oracle():
+    """TVTS v1 (DistilBERT captions are clip-major across the GLOBAL batch) on 2 gloo ranks vs the oracle on the whole batch."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker_v1, args=(2, port, out), nprocs=2, join=True)
+    a, b = out["loss1"]
+    assert abs(a - b) < 5e-2, (a, b)
+    assert out["worst_text_grad_rel"] < 0.08, out["worst_text_grad_rel"]
