@@ -320,7 +320,7 @@ def run_ours(args):
         flops_pair = algorithmic_flops_per_pair(cfg, frames, n_trans)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": _lib.OPERAND,
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {cfg.name} T={frames} batch {batch}/GPU n_trans={n_trans} (global batch {world * batch})",
                        "step": "fwd+bwd" + ("+grad_allreduce" if world > 1 else "") + ("" if args.no_optimizer else "+adamw"),

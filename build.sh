@@ -1,14 +1,23 @@
 #!/bin/bash
-# Build libtvts_b200.so (sm_100a) in-tree.  Used by __graft_entry__.build().
+# Build the CUDA library (sm_100a) in-tree.  Used by __graft_entry__.build().
+#   ./build.sh                     -> tvts_b200/lib/libtvts_b200.so        (bf16 operands, the default)
+#   TVTS_OPERAND=fp16 ./build.sh   -> tvts_b200/lib/libtvts_b200_fp16.so   (IEEE-half operands: -DTVTS_OPERAND_FP16)
 set -e
 cd "$(dirname "$0")"
-mkdir -p tvts_b200/lib build
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Wno-deprecated-gpu-targets"
+BUILD=build
+LIB=tvts_b200/lib/libtvts_b200.so
+if [ "${TVTS_OPERAND:-bf16}" = "fp16" ]; then
+  FLAGS="$FLAGS -DTVTS_OPERAND_FP16"
+  BUILD=build_fp16
+  LIB=tvts_b200/lib/libtvts_b200_fp16.so
+fi
+mkdir -p tvts_b200/lib $BUILD
 objs=""
 pids=""
 for f in tvts_b200/csrc/*.cu; do
-  o=build/$(basename ${f%.cu}).o
+  o=$BUILD/$(basename ${f%.cu}).o
   objs="$objs $o"
   if [ ! -f $o ] || [ $f -nt $o ] || [ tvts_b200/csrc/common.cuh -nt $o ] || [ tvts_b200/csrc/attention_common.cuh -nt $o ] || [ include/tvts_b200.h -nt $o ]; then
     fm="--use_fast_math"
@@ -18,5 +27,5 @@ for f in tvts_b200/csrc/*.cu; do
   fi
 done
 for p in $pids; do wait $p; done
-$NVCC -shared -o tvts_b200/lib/libtvts_b200.so $objs -Xcompiler -fPIC
-echo "built tvts_b200/lib/libtvts_b200.so"
+$NVCC -shared -o $LIB $objs -Xcompiler -fPIC
+echo "built $LIB"

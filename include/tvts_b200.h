@@ -23,6 +23,10 @@ extern "C" {
 #define TVTS_B200_VERSION 100
 
 int tvts_version(void);
+/* 16-bit operand format this library was built for: 0 = bfloat16 (libtvts_b200.so, the default), 1 = IEEE half (libtvts_b200_fp16.so,
+ * built with -DTVTS_OPERAND_FP16).  Everything this header calls "bf16" (GEMM operands, 16-bit activations and gradients, the weight
+ * shadow arena) is in that format; fp32 tensors are unaffected. */
+int tvts_operand_format(void);
 const char* tvts_last_error(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches claim) */
 long long tvts_launch_count(void);

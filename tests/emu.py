@@ -10,7 +10,9 @@ import math
 
 import torch
 
-BF16, F32 = torch.bfloat16, torch.float32
+from tvts_b200._lib import OPERAND_DTYPE
+
+BF16, F32 = OPERAND_DTYPE, torch.float32      # the 16-bit operand format of the build under test (bfloat16, or float16 with TVTS_OPERAND=fp16)
 
 
 def _act(x, a):
@@ -423,7 +425,7 @@ def adamw_flat(p, g, m, v, pb, chunk_tensor, table, n_chunks, chunk, b1, b2, eps
     Mm.copy_(torch.where(act, m2, Mm)); V.copy_(torch.where(act, v2, V)); P.copy_(torch.where(act, x, P))
     if pb is not None:
         PB = pb.view(n_chunks, chunk)
-        PB.copy_(torch.where(act, P.to(torch.bfloat16), PB))
+        PB.copy_(torch.where(act, P.to(BF16), PB))
 
 
 OPS = {k: v for k, v in list(globals().items()) if callable(v) and not k.startswith("_") and k not in ("install", "uninstall", "gemm")}

@@ -68,3 +68,20 @@ def test_entry_points_validate_arguments_before_touching_the_device():
     # empty problems are no-ops, not errors
     assert lib.tvts_attn_fwd(p, p, p, i64(0), i64(16), i64(2), i64(64), i64(0), i64(0), i64(0), i64(0), f32(0.1), None) == 0
     assert lib.tvts_layernorm_fwd(p, p, p, p, i64(1), p, p, i64(0), i64(128), f32(1e-5), None) == 0
+
+
+def test_fp16_operand_build_is_selected_by_env_and_checked():
+    """TVTS_OPERAND=fp16 loads libtvts_b200_fp16.so (same C ABI, tvts_operand_format() == 1), switches the host-side operand dtype and
+    the loss scale; a library of the other format under that name is refused."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import torch; from tvts_b200 import _lib as L, engine as E; lib = L.lib();"
+            "assert lib.tvts_operand_format() == 1 and L.OPERAND_DTYPE is torch.float16 and E.BF16 is torch.float16;"
+            "assert L.DEFAULT_LOSS_SCALE == 1024.0 and L.LIB_PATH.endswith('libtvts_b200_fp16.so');"
+            "L._lib = None; L.LIB_PATH = L.LIB_PATH.replace('_fp16', '');\\n"
+            "try:\\n    L.lib(); raise SystemExit('format mismatch was not detected')\\n"
+            "except RuntimeError as e:\\n    assert 'operand format' in str(e)")
+    subprocess.run([sys.executable, "-c", code.replace("\\n", "\n")], check=True, cwd=root, env=dict(os.environ, TVTS_OPERAND="fp16", PYTHONPATH=root))
+    from tvts_b200 import _lib
+    assert _lib.lib().tvts_operand_format() == int(_lib.OPERAND == "fp16")

@@ -47,10 +47,10 @@ def _worker(rank, world, port, out):
         opt = optim.build_reference_optimizer(m)
         E.WEIGHTS.clear()
         step = TrainStep(m, None, cfg.temperature, torch.device("cpu"))
-        step.optimizer = types.SimpleNamespace(flat=opt.flat, zero_grad=opt.zero_grad, step=lambda: None)   # keep the weights fixed
+        step.optimizer = types.SimpleNamespace(flat=opt.flat, zero_grad=opt.zero_grad, step=lambda *a: None)   # keep the weights fixed
         local = make_batch(cfg, Bl, T, n_trans=nt, seed=3, rank=rank)
         l1, l2 = step(local)
-        grads = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+        grads = {k: p.grad.clone() / step.loss_scale for k, p in m.named_parameters() if p.grad is not None}   # (fp16 build: loss-scaled)
         if rank == 0:
             parts = [make_batch(cfg, Bl, T, n_trans=nt, seed=3, rank=r) for r in range(world)]
             video = torch.cat([p["video"] for p in parts])
@@ -114,12 +114,12 @@ def _worker_v1(rank, world, port, out):
         opt = optim.AdamW([p for p in m.parameters()], lr=1e-4, weight_decay=0.0)
         E.WEIGHTS.clear()
         step = TrainStep(m, None, 0.05, torch.device("cpu"))
-        step.optimizer = types.SimpleNamespace(flat=opt.flat, zero_grad=opt.zero_grad, step=lambda: None)   # keep the weights fixed
+        step.optimizer = types.SimpleNamespace(flat=opt.flat, zero_grad=opt.zero_grad, step=lambda *a: None)   # keep the weights fixed
         rows = torch.tensor([t * dims.B + rank for t in range(dims.nt)])           # this rank's captions, clip-major
         local = {"video": data["video"][rank:rank + 1], "keep_ind": data["keep_ind"][rank:rank + 1], "label": data["label"][rank:rank + 1],
                  "text": {k: v[rows] for k, v in data["text"].items()}}
         l1, l2 = step(local)
-        grads = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+        grads = {k: p.grad.clone() / step.loss_scale for k, p in m.named_parameters() if p.grad is not None}   # (fp16 build: loss-scaled)
         if rank == 0:
             o1, o2, _, og = O.v1_step_with_grads(sd, data["text"], data["video"], data["keep_ind"], data["label"], cfg, dims.heads)
             out["loss1"] = (l1.item(), o1.item())

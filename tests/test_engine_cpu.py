@@ -6,6 +6,8 @@ import types
 import pytest
 import torch
 
+from tvts_b200._lib import OPERAND_DTYPE
+
 import tvts_oracle as O
 from tvts_b200 import config as C
 from tvts_b200 import engine as E
@@ -78,11 +80,11 @@ def test_weight_cache_rejects_recycled_parameter_ids(emu_backend):
     new = torch.nn.Parameter(torch.randn(8, 8))
     cache._c[id(new)] = (new._version, new.data_ptr(), stale, weakref.ref(old))     # what id reuse leaves behind
     got = cache.get(new)
-    assert got.shape == new.shape and torch.equal(got, new.detach().to(torch.bfloat16))
+    assert got.shape == new.shape and torch.equal(got, new.detach().to(OPERAND_DTYPE))
     assert cache.get(new) is got                                                       # now a genuine hit
     with torch.no_grad():
         new.add_(1.0)                                                                   # version bump -> re-cast
-    assert torch.equal(cache.get(new), new.detach().to(torch.bfloat16))
+    assert torch.equal(cache.get(new), new.detach().to(OPERAND_DTYPE))
 
 
 def test_validate_runs_forward_only(emu_backend):

@@ -8,7 +8,7 @@ from tvts_b200 import _lib as L
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
-BF16, F32 = torch.bfloat16, torch.float32
+BF16, F32 = L.OPERAND_DTYPE, torch.float32
 
 
 def rnd(*shape, dtype=F32, scale=1.0, seed=None):

@@ -17,6 +17,8 @@ from tvts_b200 import engine as E
 from tvts_b200 import modules as M
 from tvts_b200.synthetic import make_batch, make_state_dict
 
+from tvts_b200._lib import DEFAULT_LOSS_SCALE as LOSS_SCALE
+
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -36,7 +38,13 @@ def run_step(m, data, cfg):
     te, ve, pred = m(data)
     loss1 = M.NormSoftmaxLoss(cfg.temperature)(M.sim_matrix(ve, te))
     loss2 = E.sort_ce(pred, data["label"]) if pred is not None else torch.zeros((), device="cuda")
-    (loss1 + loss2).backward()
+    if LOSS_SCALE == 1.0:
+        (loss1 + loss2).backward()
+    else:                                   # fp16-operand build (TVTS_OPERAND=fp16): backward under the static loss scale, like TrainStep
+        ((loss1 + loss2) * LOSS_SCALE).backward()
+        for p in m.parameters():
+            if p.grad is not None:
+                p.grad.div_(LOSS_SCALE)
     torch.cuda.synchronize()
     return loss1.item(), loss2.item(), te.detach().cpu(), ve.detach().cpu(), None if pred is None else pred.detach().cpu()
 

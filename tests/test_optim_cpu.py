@@ -4,6 +4,8 @@ import types
 
 import torch
 
+from tvts_b200._lib import OPERAND_DTYPE
+
 import tvts_oracle as O
 from tvts_b200 import config as C
 from tvts_b200 import engine as E
@@ -47,7 +49,7 @@ def test_flat_adamw_steps_match_oracle(emu_backend):
             data = make_batch(cfg, 2, 2, n_trans=n_trans, seed=it)
             E.WEIGHTS.clear()
             step(data)
-            got = {names[id(p)]: (None if p.grad is None else p.grad.clone()) for p in opt.flat.params}
+            got = {names[id(p)]: (None if p.grad is None else p.grad.clone() / step.loss_scale) for p in opt.flat.params}   # (fp16 build: scaled)
             if n_trans == 1:
                 assert all(g is None for k, g in got.items() if k.startswith("pred_model"))
             for gi, grp in enumerate(opt.param_groups):
@@ -61,7 +63,7 @@ def test_flat_adamw_steps_match_oracle(emu_backend):
                 n = names[id(p)]
                 assert torch.allclose(p.detach(), ref[n], atol=1e-6, rtol=1e-5), (it, n, (p.detach() - ref[n]).abs().max())
                 bf = opt.flat.bf16_view(p)
-                assert torch.equal(bf, p.detach().to(torch.bfloat16)), n
+                assert torch.equal(bf, p.detach().to(OPERAND_DTYPE)), n
         assert any(v == 2 for k, v in nsteps.items() if k.startswith("pred_model")) and nsteps["video_model.proj"] == 3
     finally:
         opt.flat.release()

@@ -5,6 +5,8 @@ import types
 import pytest
 import torch
 
+from tvts_b200._lib import OPERAND_DTYPE
+
 import tvts_oracle as O
 from tvts_b200 import config as C
 from tvts_b200 import engine as E
@@ -75,6 +77,6 @@ def test_fused_adamw_kernel_matches_oracle_restatement():
                 O.adamw_step(ref[i], gs[i].cpu(), mom[i][0], mom[i][1], nsteps, grp["lr"], weight_decay=grp["weight_decay"])
             for i, p in enumerate(ps):
                 assert torch.allclose(p.detach().cpu(), ref[i], atol=2e-6, rtol=2e-6), (t, i)
-                assert torch.equal(opt.flat.bf16_view(p).cpu(), p.detach().cpu().to(torch.bfloat16))
+                assert torch.equal(opt.flat.bf16_view(p).cpu(), p.detach().cpu().to(OPERAND_DTYPE))
     finally:
         opt.flat.release()

@@ -14,16 +14,22 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 pytestmark = pytest.mark.gpu
 
+from tvts_b200._lib import OPERAND  # noqa: E402
+
+# bf16 operands: the conservative bound described above; fp16 operands (TVTS_OPERAND=fp16): the build meant to meet the north star's
+# 1e-3 (emulation: 5e-4 over 20 toy steps, 3e-4 on c1) -- held to 2e-3 until its first GPU run
+BOUND = 5e-2 if OPERAND == "bf16" else 2e-3
+
 
 @pytest.mark.timeout(600)
 def test_toy_model_12_steps():
     import loss_parity
     d1, d2, dt = loss_parity.run(12, "tiny", verbose=False)
-    assert d1 < 5e-2 and d2 < 5e-2, (d1, d2)
+    assert d1 < BOUND and d2 < BOUND, (d1, d2)
 
 
 @pytest.mark.timeout(900)
 def test_c1_6_steps():
     import loss_parity
     d1, d2, dt = loss_parity.run(6, "c1", verbose=False)
-    assert d1 < 5e-2 and d2 < 5e-2, (d1, d2)
+    assert d1 < BOUND and d2 < BOUND, (d1, d2)

@@ -32,7 +32,7 @@ from tvts_b200.synthetic import make_batch, make_state_dict
 STAGED = os.environ.get("TVTS_RUN_STAGED") == "1"
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not STAGED, reason="staged cases run in a child process (TVTS_RUN_STAGED=1)")]
 DEV = "cuda"
-BF16, F32 = torch.bfloat16, torch.float32
+BF16, F32 = L.OPERAND_DTYPE, torch.float32
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 

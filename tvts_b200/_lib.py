@@ -9,7 +9,16 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtvts_b200.so")
+
+# 16-bit operand format (include/tvts_b200.h: tvts_operand_format).  TVTS_OPERAND=bf16 (default) -> libtvts_b200.so;
+# TVTS_OPERAND=fp16 -> libtvts_b200_fp16.so (IEEE half: 11-bit mantissa, what the loss-parity target needs -- DESIGN.md section 2) with
+# the backward run under a static loss scale (TVTS_LOSS_SCALE, default 1024; un-scaled inside the fused AdamW kernel).
+OPERAND = os.environ.get("TVTS_OPERAND", "bf16").lower()
+if OPERAND not in ("bf16", "fp16"):
+    raise ValueError(f"TVTS_OPERAND={OPERAND!r}: expected 'bf16' or 'fp16'")
+OPERAND_DTYPE = torch.float16 if OPERAND == "fp16" else torch.bfloat16
+DEFAULT_LOSS_SCALE = float(os.environ.get("TVTS_LOSS_SCALE", "1024" if OPERAND == "fp16" else "1"))
+LIB_PATH = os.path.join(_HERE, "lib", "libtvts_b200_fp16.so" if OPERAND == "fp16" else "libtvts_b200.so")
 
 _lib = None
 
@@ -39,6 +48,9 @@ def lib():
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.tvts_last_error.restype = ctypes.c_char_p
         _lib.tvts_launch_count.restype = ctypes.c_longlong
+        if int(_lib.tvts_operand_format()) != int(OPERAND == "fp16"):
+            fmt, _lib = int(_lib.tvts_operand_format()), None
+            raise RuntimeError(f"tvts_b200: {LIB_PATH} was built for operand format {fmt}, TVTS_OPERAND={OPERAND} -- rebuild")
     return _lib
 
 
@@ -103,11 +115,11 @@ def gemm(a, b, out, *, M, N, K, lda, ldb, ldo=None, a_mn=False, b_mn=False, bias
     g.a_mn, g.b_mn = int(a_mn), int(b_mn)
     if out.dtype == torch.float32:
         g.out_dtype = 0
-    elif out.dtype == torch.bfloat16:
+    elif out.dtype == OPERAND_DTYPE:
         g.out_dtype = 1
     else:
-        raise TypeError("gemm output must be float32 or bfloat16")
-    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+        raise TypeError(f"gemm output must be float32 or {OPERAND_DTYPE}")
+    assert a.dtype == OPERAND_DTYPE and b.dtype == OPERAND_DTYPE
     g.act, g.dact = ACT[act], ACT[dact]
     g.accumulate, g.splits, g.alpha = int(accumulate), splits, alpha
     check(lib().tvts_gemm(ctypes.byref(g), stream_ptr()), "gemm")

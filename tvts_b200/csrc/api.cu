@@ -31,6 +31,7 @@ int tvts_num_sms() {
 }
 
 extern "C" int tvts_version(void) { return TVTS_B200_VERSION; }
+extern "C" int tvts_operand_format(void) { return TVTS_OPERAND_IS_FP16; }
 extern "C" const char* tvts_last_error(void) { return g_err; }
 extern "C" long long tvts_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

@@ -1192,7 +1192,7 @@ __global__ void __launch_bounds__(CLS_THREADS) attn_cls_fwd_kernel(const bf16* _
     float o = 0.f;
 #pragma unroll
     for (int w = 0; w < CLS_THREADS / 32; ++w) o += accs[w * 64 + threadIdx.x];
-    out[(long long)b * a.N * ro + (long long)h * HD + threadIdx.x] = __float2bfloat16(o / sum);
+    out[(long long)b * a.N * ro + (long long)h * HD + threadIdx.x] = opnd_from_float(o / sum);
   }
   if (threadIdx.x == 0) lse[((long long)b * a.H + h) * a.N] = mx + __logf(sum);
 }
@@ -1317,7 +1317,7 @@ __global__ void __launch_bounds__(CLS_THREADS) attn_cls_bwd_kernel(const bf16* _
     for (int w = 0; w < CLS_THREADS / 32; ++w) o += accs[w * 192 + threadIdx.x];
     const int which = threadIdx.x >> 6, dim = threadIdx.x & 63;       // 0 dq, 1 dk, 2 dv
     if (which < 2) o *= a.scale;
-    dqkv[(long long)b * a.N * rs + (long long)which * ro + (long long)h * HD + dim] = __float2bfloat16(o);
+    dqkv[(long long)b * a.N * rs + (long long)which * ro + (long long)h * HD + dim] = opnd_from_float(o);
   }
 }
 

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -44,7 +45,19 @@ bool tvts_prof_begin(cudaStream_t stream, double flops, double bytes, int* slot)
 void tvts_prof_end(cudaStream_t stream, int slot);
 void tvts_prof_tag(int slot, long long a, long long b, long long c, long long d);
 
+// 16-bit OPERAND format of every GEMM / attention operand and 16-bit activation.  Default: bfloat16.  Building with
+// -DTVTS_OPERAND_FP16 (build.sh: TVTS_OPERAND=fp16 -> libtvts_b200_fp16.so) switches the whole library to IEEE half: same tensor-core
+// throughput, 11-bit instead of 8-bit mantissa (what the loss-parity target of the north star needs: DESIGN.md section 2); the host then
+// runs the backward under a static loss scale.  The identifiers keep their `bf16` names in both builds.
+#ifdef TVTS_OPERAND_FP16
+typedef __half bf16;
+#define TVTS_OPERAND_IS_FP16 1
+#define TVTS_MMA_TYPE "f16"
+#else
 typedef __nv_bfloat16 bf16;
+#define TVTS_OPERAND_IS_FP16 0
+#define TVTS_MMA_TYPE "bf16"
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // small device utilities
@@ -65,6 +78,17 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+#ifdef TVTS_OPERAND_FP16
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  __half2 v = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(v);
+}
+__device__ __forceinline__ bf16 opnd_from_float(float x) { return __float2half_rn(x); }
+#else
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -73,6 +97,8 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
+__device__ __forceinline__ bf16 opnd_from_float(float x) { return __float2bfloat16(x); }
+#endif
 
 // activations (forward + derivative).  1 = QuickGELU (x*sigmoid(1.702x)), 2 = exact erf GELU.
 #define TVTS_ACT_NONE 0

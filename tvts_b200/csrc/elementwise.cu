@@ -21,7 +21,7 @@ __global__ void cast_kernel(const float* __restrict__ src, bf16* __restrict__ ds
     reinterpret_cast<uint2*>(dst)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
   }
   if (i == 0)
-    for (long long j = n4 * 4; j < n; ++j) dst[j] = __float2bfloat16(src[j]);
+    for (long long j = n4 * 4; j < n; ++j) dst[j] = opnd_from_float(src[j]);
 }
 
 // ---------------------------------------------------------------- column sums of a bf16 matrix (bias gradients)

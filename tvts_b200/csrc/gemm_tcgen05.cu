@@ -168,8 +168,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   } else if (warp == 1 && lane == 0 && cta_rank == 0) {
     // ===================== MMA issuer (single thread; the leader CTA of a pair) =====================
-    // instruction descriptor: D=f32 (bit4), A=B=bf16 (bits 7,10), major bits 15/16, N>>3 at 17, M>>4 at 24
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+    // instruction descriptor: D=f32 (bit4), A / B format at bits 7 / 10 (kind::f16: 0 = f16, 1 = bf16), major bits 15/16, N>>3 at 17, M>>4 at 24
+    constexpr uint32_t kOperandFormat = TVTS_OPERAND_IS_FP16 ? 0u : ((1u << 7) | (1u << 10));
+    const uint32_t idesc = (1u << 4) | kOperandFormat | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BLOCK_M * CTAS) >> 4) << 24);
     // K-major SW128: 8-row groups are 1024 B apart (SBO); LBO unused.  Advance 32 B per UMMA_K inside the row.
     // MN-major SW128: 64-element MN groups are one TMA box (8192 B) apart (LBO); 8-k-row groups 1024 B apart (SBO);
@@ -459,7 +460,8 @@ int make_tmap(CUtensorMap* m, const void* ptr, long long d0, long long d1, long 
   cuuint64_t strides[1] = {(cuuint64_t)ld * (cuuint64_t)esize};
   cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides,
+  const CUtensorMapDataType t16 = TVTS_OPERAND_IS_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = fn(m, esize == 2 ? t16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)

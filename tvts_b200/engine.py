@@ -21,7 +21,7 @@ import torch
 
 from . import _lib as L
 
-BF16 = torch.bfloat16
+BF16 = L.OPERAND_DTYPE          # the 16-bit operand format of the loaded library: bfloat16 (default) or float16 (TVTS_OPERAND=fp16)
 F32 = torch.float32
 
 MODE_FULL, MODE_SPACE, MODE_TIME = 0, 1, 2

@@ -53,7 +53,7 @@ class FlatState:
         self.g = torch.zeros(off, dtype=torch.float32, device=dev)
         self.m = torch.zeros(off, dtype=torch.float32, device=dev)
         self.v = torch.zeros(off, dtype=torch.float32, device=dev)
-        self.bf = torch.zeros(off, dtype=torch.bfloat16, device=dev)
+        self.bf = torch.zeros(off, dtype=L.OPERAND_DTYPE, device=dev)
         self.chunk_tensor = torch.tensor(chunk_tensor, dtype=torch.int32, device=dev)
         self.synced = [-1] * len(self.params)       # parameter ._version for which self.bf holds the bf16 copy
         self.touched = set()

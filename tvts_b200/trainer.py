@@ -146,6 +146,8 @@ class TrainStep:
         self.device = device if device is not None else next(model.parameters()).device
         self.params = [p for p in model.parameters() if p.requires_grad]   # after the optimizer applied the freeze policy
         self.use_graph = use_graph
+        from . import _lib as L
+        self.loss_scale = L.DEFAULT_LOSS_SCALE     # 1 for bf16 operands; fp16 operands: static scale, undone inside the AdamW kernel
         self._graphs = {}
         self.launches_per_graph = 0
         self._copy_stream = None
@@ -173,16 +175,24 @@ class TrainStep:
         loss1 = self.loss(output)
         if pred_order is not None:
             loss2 = E.sort_ce(pred_order, data["label"], 2.0)           # trainer.py:487-492
-            (loss1 + loss2).backward()
+            total = loss1 + loss2
         else:
             loss2 = torch.zeros((), device=loss1.device)
-            loss1.backward()
+            total = loss1
+        if self.loss_scale != 1.0:
+            total = total * self.loss_scale                             # fp16 operands only: keeps 16-bit gradient operands in range
+        total.backward()
         if flat is not None:
             average_flat(flat)
         else:
             average_gradients(self.params)
         if self.optimizer is not None and not skip_optimizer:
-            if optimizer_launch_only:
+            if self.loss_scale != 1.0:
+                if optimizer_launch_only:
+                    self.optimizer.launch(1.0 / self.loss_scale)
+                else:
+                    self.optimizer.step(1.0 / self.loss_scale)
+            elif optimizer_launch_only:
                 self.optimizer.launch()
             else:
                 self.optimizer.step()
