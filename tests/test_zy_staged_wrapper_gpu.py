@@ -18,15 +18,16 @@ def test_staged_suite_in_subprocess():
 @pytest.mark.gpu
 @pytest.mark.xfail(strict=False, reason="fp16-operand build: written after the round-1 GPU budget was spent, never executed on a B200")
 def test_fp16_operand_build_in_subprocess():
-    """The verified GPU suites (per-kernel parity, model parity, train step, loss trajectories) re-run against libtvts_b200_fp16.so
-    (TVTS_OPERAND=fp16: IEEE-half operands + static loss scale; the torch restatements follow the operand dtype)."""
+    """The verified GPU suites (per-kernel parity, model parity, train step) re-run against libtvts_b200_fp16.so (TVTS_OPERAND=fp16:
+    IEEE-half operands + static loss scale; the torch restatements follow the operand dtype).  The loss-trajectory runs of that build
+    are part of tools/round2_bringup.sh (kept out of here to bound the suite's run time)."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    files = ["tests/test_kernels_gpu.py", "tests/test_model_gpu.py", "tests/test_trainstep_gpu.py", "tests/test_trajectory_gpu.py"]
+    files = ["tests/test_kernels_gpu.py", "tests/test_model_gpu.py", "tests/test_trainstep_gpu.py"]
     r = subprocess.run([sys.executable, "-m", "pytest", *files, "-q", "-m", "gpu", "--tb=line", "-p", "no:cacheprovider", "-rA"],
-                       env=dict(os.environ, TVTS_OPERAND="fp16"), capture_output=True, text=True, timeout=2400, cwd=root)
+                       env=dict(os.environ, TVTS_OPERAND="fp16"), capture_output=True, text=True, timeout=1200, cwd=root)
     print(r.stdout[-12000:])
     print(r.stderr[-3000:])
     assert r.returncode == 0, "GPU suites failed against the fp16-operand build (see captured output)"
