@@ -196,3 +196,32 @@ def test_save_period_monitor_and_arena_follow(emu_backend, tmp_path):
         assert ck["epoch"] == 2 and ck["monitor_best"] == tr.mnt_best and ck["arch"] == "TVTSv2Base"
     finally:
         opt.flat.release()
+
+
+def test_gpu_epoch_loop_runs_one_batch_ahead(emu_backend):
+    """On a CUDA device the loop enqueues step i, then fetches / tokenises batch i+1 and starts its host->device copy (prefetch) under
+    the kernels of step i.  Checked on the control flow with a recording stand-in for TrainStep."""
+    cfg = C.TINY_B
+    m = M.TVTSv2Base(types.SimpleNamespace(local_rank=0), arch=cfg)
+    opt = optim.build_reference_optimizer(m)
+    batches = [make_batch(cfg, 2, 2, n_trans=4, seed=60 + i) for i in range(3)]
+    args = types.SimpleNamespace(rank=0, local_rank=0, world_size=1, schedule=[])
+    try:
+        tr = Trainer_TVTSv2_B_16(args, m, M.NormSoftmaxLoss(0.05), [], opt, {"trainer": {"epochs": 1}}, [FakeLoader("YTTemporal", batches, 2)],
+                                 use_graph=False)
+        events = []
+
+        class FakeStep:
+            def prefetch(self, data):
+                events.append(("prefetch", float(data["video"].sum())))
+
+            def __call__(self, data=None):
+                events.append(("step", data))
+                return torch.zeros(()), torch.zeros(())
+
+        tr.step, tr.device = FakeStep(), torch.device("cuda")
+        tr._train_epoch(1)
+        sums = [float(b["video"].sum()) for b in batches]
+        assert events == [("prefetch", sums[0]), ("step", None), ("prefetch", sums[1]), ("step", None), ("prefetch", sums[2]), ("step", None)]
+    finally:
+        opt.flat.release()

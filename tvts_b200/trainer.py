@@ -476,25 +476,40 @@ class Trainer_TVTSv2:
         if loop_dl is None:
             loop_dl, loop_dl_idx = self.data_loader[0], 0
             iter_dl[0] = None
-        for batch_idx, loop_dl_data in enumerate(loop_dl):
-            data_li = [None] * len(self.data_loader)
-            for dl_idx in range(len(iter_dl)):
-                if dl_idx != loop_dl_idx:
-                    try:
-                        data_li[dl_idx] = next(iter_dl[dl_idx])
-                    except StopIteration:
-                        iter_dl[dl_idx] = iter(self.data_loader[dl_idx])
-                        data_li[dl_idx] = next(iter_dl[dl_idx])
-            data_li[loop_dl_idx] = loop_dl_data
-            for dl_idx, data in enumerate(data_li):
-                data = self._tokenize(data)
-                batch = {k: data[k] for k in ("text", "video", "keep_ind", "label") if k in data}
-                loss1, loss2 = self.step(batch)
-                step_loss = (loss1 + loss2).reshape(())
-                total_loss[dl_idx] = step_loss.clone() if total_loss[dl_idx] is None else total_loss[dl_idx] + step_loss
-                if batch_idx % self.log_step == 0 and getattr(self.args, "local_rank", 0) == 0:
-                    print("Train Epoch: {} dl{} [{}/{}] Loss_ct: {:.6f} Loss_ce: {:.6f} Loss: {:.6f}".format(
-                        epoch, dl_idx, batch_idx, self.len_epoch, loss1.item(), loss2.item(), step_loss.item()))
+        def batches():
+            """(batch_idx, loader index, tokenised batch) in the reference's order: per iteration one batch of every loader (:440-475)."""
+            for batch_idx, loop_dl_data in enumerate(loop_dl):
+                data_li = [None] * len(self.data_loader)
+                for dl_idx in range(len(iter_dl)):
+                    if dl_idx != loop_dl_idx:
+                        try:
+                            data_li[dl_idx] = next(iter_dl[dl_idx])
+                        except StopIteration:
+                            iter_dl[dl_idx] = iter(self.data_loader[dl_idx])
+                            data_li[dl_idx] = next(iter_dl[dl_idx])
+                data_li[loop_dl_idx] = loop_dl_data
+                for dl_idx, data in enumerate(data_li):
+                    data = self._tokenize(data)
+                    yield batch_idx, dl_idx, {k: data[k] for k in ("text", "video", "keep_ind", "label") if k in data}
+
+        # On a GPU the loop runs one batch ahead: step i is enqueued (asynchronously: one CUDA-graph launch), THEN batch i+1 is fetched
+        # from its loader, tokenised and its host->device copy started on the copy stream -- all of it under the kernels of step i.
+        stream = batches()
+        pipelined = self.device.type == "cuda"
+        cur = next(stream, None)
+        if pipelined and cur is not None:
+            self.step.prefetch(cur[2])
+        while cur is not None:
+            batch_idx, dl_idx, batch = cur
+            loss1, loss2 = self.step(None) if pipelined else self.step(batch)
+            cur = next(stream, None)
+            if pipelined and cur is not None:
+                self.step.prefetch(cur[2])
+            step_loss = (loss1 + loss2).reshape(())
+            total_loss[dl_idx] = step_loss.clone() if total_loss[dl_idx] is None else total_loss[dl_idx] + step_loss
+            if batch_idx % self.log_step == 0 and getattr(self.args, "local_rank", 0) == 0:
+                print("Train Epoch: {} dl{} [{}/{}] Loss_ct: {:.6f} Loss_ce: {:.6f} Loss: {:.6f}".format(
+                    epoch, dl_idx, batch_idx, self.len_epoch, loss1.item(), loss2.item(), step_loss.item()))
         log = {f"loss_{i}": (float(t.item()) / self.len_epoch if t is not None else 0.0) for i, t in enumerate(total_loss)}
         if self.do_validation:
             val_log = self._valid_epoch(epoch)
