@@ -172,6 +172,11 @@ int tvts_video_assemble_tube_bwd(const float* dx0, const int64_t* keep_ind, floa
                                  int64_t B, int64_t nt, int64_t n, int64_t D, void* stream);
 int tvts_relu_bf16(const float* x, void* y, int64_t n, void* stream);
 int tvts_relu_bwd(const float* x, const float* dy, float* dx, int64_t n, void* stream);
+/* Input stage fused into the gather: video [B,T,3,R,R] UINT8 crops; the reference's x/255 then (x-mean[c])/std[c]
+ * (v2/video_transforms/video_transform.py:24-76,627-650; mean3 / std3 are HOST pointers to 3 floats, videoaug.py:16) are applied on the
+ * fly with IEEE fp32 operations in the reference's order, so cols is bit-identical to patch_gather on the normalised fp32 clip. */
+int tvts_patch_gather_u8(const void* video_u8, const int64_t* keep_ind, void* cols, int64_t B, int64_t T, int64_t R, int64_t p, int64_t n,
+                         const float* mean3, const float* std3, void* stream);
 int tvts_video_assemble(const float* tok, const float* cls, const float* pos, const float* tem, const int64_t* keep_ind, float* x0,
                         int64_t B, int64_t T, int64_t n, int64_t D, void* stream);
 int tvts_video_assemble_bwd(const float* dx0, const int64_t* keep_ind, float* dcls, float* dpos, float* dtem, void* dtok_bf16, int64_t B,

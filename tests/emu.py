@@ -257,6 +257,13 @@ def patch_gather(video, keep, cols, B, T, R, p, n):
     cols.view(B, T, n, -1).copy_(torch.gather(v, 2, idx).to(BF16))
 
 
+def patch_gather_u8(video, keep, cols, B, T, R, p, n, mean, std):
+    m = torch.tensor(list(mean), dtype=torch.float32, device=video.device)[None, None, :, None, None]
+    s = torch.tensor(list(std), dtype=torch.float32, device=video.device)[None, None, :, None, None]
+    x = video.view(B, T, 3, R, R).float().div(255).sub_(m).div_(s)        # ClipToTensor + Normalize of the reference, in its order
+    patch_gather(x, keep, cols, B, T, R, p, n)
+
+
 def patch_gather_ld(video, keep, cols, B, T, R, p, n, ld):
     K = 3 * p * p
     tmp = torch.empty(B * T * n, K, dtype=BF16, device=video.device)

@@ -126,3 +126,23 @@ def test_h14_engine_matches_reference_golden_and_oracle(emu_backend, cfg, name):
         assert rel < 0.08, (k, rel)
     ref_order = [str(s) for s in g["grad_names"]]
     assert [k for k, _ in m.named_parameters() if k in set(ref_order)] == ref_order
+
+
+def test_uint8_clips_take_the_fused_input_stage(emu_backend):
+    """uint8 crops fed to the model give EXACTLY what the reference's CPU transform (x/255, then (x-mean)/std in fp32:
+    video_transforms/video_transform.py:24-76,627-650) followed by the float path gives -- forward and gradients."""
+    cfg = C.TINY_B_MASK
+    data = make_batch(cfg, 2, 3, n_trans=4, seed=7)
+    u8 = torch.randint(0, 256, data["video"].shape, dtype=torch.uint8, generator=torch.Generator().manual_seed(3))
+    mean = torch.tensor(cfg.input_mean)[None, None, :, None, None]
+    std = torch.tensor(cfg.input_std)[None, None, :, None, None]
+    ref_video = u8.float().div(255).sub(mean).div(std)
+    outs = []
+    for video in (u8, ref_video):
+        torch.manual_seed(0)
+        m, _ = build(cfg)
+        E.WEIGHTS.clear()
+        l1, l2, te, ve, pred = run_step(m, dict(data, video=video), cfg)
+        outs.append((l1, l2, ve, pred, m.video_model.conv1.weight.grad.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)

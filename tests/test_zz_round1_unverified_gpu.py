@@ -5,6 +5,7 @@ that `pytest -x` reaches them only after every previously-verified GPU test has 
   * the padded patch-embed path of 14x14 patches (patch_gather_ld, cast_bf16_pad, GEMMs with K = 592 / N = 588)
   * LayerNorm width 640, the TVTSv2_H_14 model (tiny_H640) against the executed-reference fixture and the oracle's gradients
   * the downstream (zero-shot) towers against their executed-reference fixture
+  * the fused uint8 input stage (tvts_b200/csrc/input_stage.cu): bit-exact against the float path
   * TVTS v1: tubelet gather / per-tube assembly / ReLU kernels (tvts_b200/csrc/v1_glue.cu), key-padded attention, and the whole v1 model
     (DistilBERT text encoder included) against the executed-reference fixture tiny_v1_full and the oracle's gradients
 Tolerances as in tests/test_kernels_gpu.py / tests/test_model_gpu.py.
@@ -127,6 +128,27 @@ def test_padded_patch_gather_and_weight_cast(B, T, R, p, n):
     L.call("cast_bf16_pad", w, got, 640, K, Kp)
     emu.cast_bf16_pad(w, ref, 640, K, Kp)
     assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("B,T,R,p,n", [(2, 3, 224, 16, 98), (2, 2, 224, 32, 49), (1, 1, 64, 16, 7)])
+def test_fused_uint8_input_stage(B, T, R, p, n):
+    """uint8 crops -> x/255 -> (x-mean)/std -> bf16 im2col of the kept patches, in one kernel: bit-identical to the float path."""
+    import ctypes
+    P = (R // p) ** 2
+    torch.manual_seed(R + p)
+    keep = torch.stack([torch.randperm(P, device=DEV)[:n] for _ in range(B)]).contiguous()
+    u8 = torch.randint(0, 256, (B, T, 3, R, R), device=DEV, dtype=torch.uint8)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    got = torch.empty(B * T * n, 3 * p * p, device=DEV, dtype=BF16)
+    ref = torch.empty_like(got)
+    L.call("patch_gather_u8", u8, keep, got, B, T, R, p, n, (ctypes.c_float * 3)(*mean), (ctypes.c_float * 3)(*std))
+    emu.patch_gather_u8(u8, keep, ref, B, T, R, p, n, mean, std)
+    assert torch.equal(got, ref), (got.float() - ref.float()).abs().max()
+    via_float = torch.empty_like(got)
+    m = torch.tensor(mean, device=DEV)[None, None, :, None, None]
+    s_ = torch.tensor(std, device=DEV)[None, None, :, None, None]
+    L.call("patch_gather", u8.float().div(255).sub(m).div(s_).contiguous(), keep, via_float, B, T, R, p, n)
+    assert torch.equal(got, via_float)
 
 
 def test_patch_embed_gemms_with_padded_rows():

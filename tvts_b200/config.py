@@ -36,6 +36,9 @@ class ArchConfig:
     n_trans: int = 4
     sort_ln_eps: float = 1e-6
     temperature: float = 0.05
+    # input normalisation applied by the data pipeline (v2/video_transforms/videoaug.py:16); used only when uint8 clips are fed
+    input_mean: tuple = (0.485, 0.456, 0.406)
+    input_std: tuple = (0.229, 0.224, 0.225)
 
     @property
     def patches_per_frame(self):

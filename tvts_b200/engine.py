@@ -474,12 +474,21 @@ def video_forward(P, video, keep_ind, cfg):
         raise ValueError(f"{T} frames exceed num_frames={P['temporal_embedding'].shape[0]}")
     N = 1 + T * n
     K = 3 * p * p
-    video = video.contiguous().float()
+    as_u8 = video.dtype == torch.uint8      # uint8 crops: x/255 and (x-mean)/std of the CPU transform run inside the gather kernel
+    video = video.contiguous() if as_u8 else video.contiguous().float()
     keep_ind = keep_ind.to(device=video.device, dtype=torch.int64).contiguous()
     tok = _empty((B * T * n, D), F32, video)
+    if as_u8 and p % 4 != 0:
+        raise NotImplementedError("uint8 clips are supported for patch sizes that are a multiple of 4 (B/16, B/32)")
     if p % 4 == 0:
         cols = _empty((B * T * n, K), BF16, video)
-        L.call("patch_gather", video, keep_ind, cols, B, T, R, p, n)
+        if as_u8:
+            import ctypes
+            mean = (ctypes.c_float * 3)(*getattr(cfg, "input_mean", (0.485, 0.456, 0.406)))
+            std = (ctypes.c_float * 3)(*getattr(cfg, "input_std", (0.229, 0.224, 0.225)))
+            L.call("patch_gather_u8", video, keep_ind, cols, B, T, R, p, n, mean, std)
+        else:
+            L.call("patch_gather", video, keep_ind, cols, B, T, R, p, n)
         w_bf = P.bf("conv1.weight").view(D, K)
         L.gemm(cols, w_bf, tok, M=B * T * n, N=D, K=K, lda=K, ldb=K)
     else:
