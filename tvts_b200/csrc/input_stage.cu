@@ -4,8 +4,12 @@
 // (4x fewer host->device bytes, no fp32 video tensor in HBM at all).  The three fp32 operations are the reference's, in its order, with
 // IEEE round-to-nearest intrinsics (this file must not contract or approximate them), so the bf16 im2col rows are bit-identical to
 // patch_gather applied to the normalised fp32 clip.
+#ifdef TVTS_HOST_SHIM          // tests/host_kernels: the kernel bodies below are also compiled for the CPU to execute their index math
+#include "host_shim.h"
+#else
 #include "common.cuh"
 #include "../../include/tvts_b200.h"
+#endif
 
 namespace {
 
@@ -40,6 +44,7 @@ __global__ void patch_gather_u8_kernel(const uint8_t* __restrict__ video, const 
 
 }  // namespace
 
+#ifndef TVTS_HOST_SHIM
 extern "C" int tvts_patch_gather_u8(const void* video_u8, const int64_t* keep_ind, void* cols, int64_t B, int64_t T, int64_t R, int64_t p,
                                     int64_t n, const float* mean3, const float* std3, void* stream) {
   TVTS_REQUIRE(video_u8 && keep_ind && cols && mean3 && std3, "patch_gather_u8: null pointer (mean3 / std3 are HOST arrays of 3 floats)");
@@ -54,6 +59,8 @@ extern "C" int tvts_patch_gather_u8(const void* video_u8, const int64_t* keep_in
   TVTS_LAUNCH_CHECK();
   return TVTS_OK;
 }
+
+#endif  // !TVTS_HOST_SHIM
 
 namespace {
 inline unsigned grid_for(long long work_items, int threads) {
@@ -114,6 +121,7 @@ __global__ void cast_pad_kernel(const float* __restrict__ src, bf16* __restrict_
 
 }  // namespace
 
+#ifndef TVTS_HOST_SHIM
 extern "C" int tvts_patch_gather_ld(const float* video, const int64_t* keep_ind, void* cols, int64_t B, int64_t T, int64_t R, int64_t p,
                                     int64_t n, int64_t ld, void* stream) {
   TVTS_REQUIRE(video && keep_ind && cols, "patch_gather_ld: null pointer");
@@ -138,3 +146,4 @@ extern "C" int tvts_cast_bf16_pad(const float* src, void* dst, int64_t rows, int
   TVTS_LAUNCH_CHECK();
   return TVTS_OK;
 }
+#endif  // !TVTS_HOST_SHIM

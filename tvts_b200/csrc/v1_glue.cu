@@ -1,8 +1,12 @@
 // Glue kernels of the TVTS v1 video front end and projection heads (v1/model/video_encoder.py:78-99,178-217,
 // v1/model/model_dist_TVTS.py:64-74): tubelet im2col with a PER-TUBE keep mask, token assembly (+ backward), ReLU.
 // HBM-bound streaming kernels like elementwise.cu: vectorised coalesced accesses, fp32 arithmetic, exact integer indexing.
+#ifdef TVTS_HOST_SHIM          // tests/host_kernels: the kernel bodies below are also compiled for the CPU to execute their index math
+#include "host_shim.h"
+#else
 #include "common.cuh"
 #include "../../include/tvts_b200.h"
+#endif
 
 namespace {
 
@@ -118,6 +122,7 @@ __global__ void relu_bwd_kernel(const float* __restrict__ x, const float* __rest
 
 }  // namespace
 
+#ifndef TVTS_HOST_SHIM
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
 extern "C" int tvts_tubelet_gather(const float* video, const int64_t* keep_ind, void* cols, int64_t B, int64_t T, int64_t R, int64_t p,
@@ -171,3 +176,4 @@ extern "C" int tvts_relu_bwd(const float* x, const float* dy, float* dx, int64_t
   TVTS_LAUNCH_CHECK();
   return TVTS_OK;
 }
+#endif  // !TVTS_HOST_SHIM
