@@ -117,3 +117,68 @@ def test_padded_patch_gather_and_weight_cast(hk, B, T, R, p, n):
     hk.h_cast_pad(P(w), P(got), I(10), I(K), I(Kp))
     emu.cast_bf16_pad(w, ref, 10, K, Kp)
     assert torch.equal(got, ref)
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core attention kernels
+@pytest.fixture(scope="module")
+def hattn(tmp_path_factory):
+    """attention_hd.cu compiled for the CPU SIMT stand-in (tests/host_kernels/host_simt.h): CUDA threads = OS threads, ldmatrix / mma.sync /
+    cp.async / shfl restated with their architectural layouts."""
+    out = str(tmp_path_factory.mktemp("hostattn") / "libhostattn.so")
+    subprocess.run(["g++", "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC", "-DTVTS_HOST_SHIM", "-I", HERE,
+                    os.path.join(HERE, "harness_attn.cpp"), "-o", out], check=True)
+    return ctypes.CDLL(out)
+
+
+ATTN_HOST_CASES = [
+    # B, H, mode, T, n, N, causal, d, padded
+    (2, 2, 0, 0, 0, 77, True, 80, False),      # causal, two streamed tiles
+    (1, 2, 0, 0, 0, 150, False, 80, False),    # full, three tiles, ragged last tile
+    (2, 2, 1, 2, 49, 99, False, 80, False),    # space
+    (1, 2, 2, 3, 20, 61, False, 80, False),    # time (strided groups)
+    (1, 2, 1, 3, 76, 229, False, 80, False),   # space at the H/14 kept-patch count: two stationary chunks per frame
+    (1, 2, 2, 16, 6, 97, False, 80, False),    # time, 16 frames (c4)
+    (2, 2, 1, 2, 49, 99, False, 64, False),    # the same code at head dim 64 (layouts shared with the GPU-verified kernels)
+    (2, 1, 0, 0, 0, 130, True, 64, False),
+    (5, 3, 0, 0, 0, 50, False, 64, True),      # key-padded (DistilBERT, v1)
+    (2, 2, 0, 0, 0, 70, False, 80, True),
+]
+
+
+@pytest.mark.parametrize("B,H,mode,T,n,N,causal,d,padded", ATTN_HOST_CASES)
+def test_generic_attention_kernels_on_the_cpu_simt_stand_in(hattn, B, H, mode, T, n, N, causal, d, padded):
+    torch.manual_seed(N + mode + d)
+    qkv = torch.randn(B, N, 3 * H * d).to(BF16)
+    dout = torch.randn(B * N, H * d).to(BF16)
+    scale = d ** -0.5
+    klen = None
+    if padded:
+        klen = torch.randint(1, N + 1, (B,), dtype=torch.int32)
+        klen[0] = N
+    kp = ctypes.c_void_p(klen.data_ptr()) if padded else ctypes.c_void_p(None)
+    out = torch.full((B * N, H * d), float("nan"), dtype=BF16)
+    lse = torch.full((B, H, N), float("nan"))
+    assert hattn.h_attn_fwd(P(qkv), P(out), P(lse), kp, I(B), I(N), I(H), I(d), I(mode), I(T), I(n), I(int(causal)), ctypes.c_float(scale)) == 0
+    ro, rl = torch.empty_like(out), torch.empty_like(lse)
+    if padded:
+        emu.attn_padded_fwd(qkv, ro, rl, klen, B, N, H, d, scale)
+    else:
+        emu.attn_fwd(qkv, ro, rl, B, N, H, d, mode, T, n, int(causal), scale)
+    assert torch.allclose(out.float(), ro.float(), atol=2e-2), (out.float() - ro.float()).abs().max()
+    assert torch.allclose(lse, rl, atol=1e-4)
+    dqkv = torch.full_like(qkv, float("nan"))
+    delta = torch.empty_like(lse)
+    assert hattn.h_attn_bwd(P(qkv), P(ro), P(dout), P(rl), P(delta), P(dqkv), kp, I(B), I(N), I(H), I(d), I(mode), I(T), I(n), I(int(causal)),
+                            ctypes.c_float(scale)) == 0
+    rd, rdel = torch.empty_like(qkv), torch.empty_like(lse)
+    if padded:
+        emu.attn_padded_bwd(qkv, ro, dout, rl, rdel, rd, klen, B, N, H, d, scale)
+    else:
+        emu.attn_bwd(qkv, ro, dout, rl, rdel, rd, B, N, H, d, mode, T, n, int(causal), scale)
+    assert torch.isfinite(dqkv.float()).all(), "backward left elements unwritten"
+    assert torch.allclose(dqkv.float(), rd.float(), atol=3e-2, rtol=3e-2), (dqkv.float() - rd.float()).abs().max()
+    assert torch.allclose(delta, rdel, atol=1e-3)
+    if padded:                                   # masked keys receive exactly zero dk / dv
+        g5 = dqkv.view(B, N, 3, H, d)
+        for b in range(B):
+            assert (g5[b, int(klen[b]):, 1:] == 0).all()

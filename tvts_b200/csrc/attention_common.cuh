@@ -1,7 +1,11 @@
 // Head-dim independent pieces of the attention kernels (attention.cu: head dim 64 fast paths; attention_hd.cu: generic head dim):
 // launch geometry, the index sets of the three attention modes, and the cp.async / ldmatrix / mma.sync primitives.
 #pragma once
+#ifdef TVTS_HOST_SHIM          // tests/host_kernels: the kernels are also compiled for a CPU SIMT stand-in that supplies the primitives below
+#include "host_simt.h"
+#else
 #include "common.cuh"
+#endif
 
 namespace {
 
@@ -77,6 +81,7 @@ __device__ __forceinline__ int streamed_token(const Sets& s, int k) {
 }
 
 // ------------------------------------------------------------------------------------------------ primitives
+#ifndef TVTS_HOST_SHIM
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
   const int sz = valid ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled
@@ -100,5 +105,6 @@ __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+#endif  // !TVTS_HOST_SHIM
 
 }  // namespace

@@ -9,7 +9,9 @@
 // tvts_attn_fwd / tvts_attn_bwd (attention.cu) forward here whenever d != 64; the HD = 64 instantiation exists only so that the
 // generic code can be checked against the specialised kernels (tests call tvts_attn_generic_* with d = 64 directly).
 #include "attention_common.cuh"
+#ifndef TVTS_HOST_SHIM
 #include "../../include/tvts_b200.h"
+#endif
 
 namespace {
 
@@ -439,6 +441,7 @@ __global__ void __launch_bounds__(kThreads) attn_hd_bwd_kernel(const bf16* __res
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+#ifndef TVTS_HOST_SHIM
 int hd_check_shape(const AttnShape& a, int64_t d) {
   TVTS_REQUIRE(d == 64 || d == 80, "attention: head dim %lld unsupported (64 and 80 are built)", (long long)d);
   TVTS_REQUIRE(a.B > 0 && a.N > 0 && a.H > 0, "attention: empty shape");
@@ -487,8 +490,11 @@ int hd_launch_bwd(const void* qkv, const void* out, const void* dout, const floa
   return TVTS_OK;
 }
 
+#endif  // !TVTS_HOST_SHIM
+
 }  // namespace
 
+#ifndef TVTS_HOST_SHIM
 extern "C" int tvts_attn_generic_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode,
                                      int64_t T, int64_t n, int64_t causal, float scale, void* stream) {
   AttnShape a{(int)B, (int)N, (int)H, (int)mode, (int)T, (int)n, (int)causal, scale, 0, 0, 0};
@@ -538,3 +544,4 @@ extern "C" int tvts_attn_padded_bwd(const void* qkv, const void* out, const void
   return d == 64 ? hd_launch_bwd<64>(qkv, out, dout, lse, delta_ws, dqkv, a, st, klen)
                  : hd_launch_bwd<80>(qkv, out, dout, lse, delta_ws, dqkv, a, st, klen);
 }
+#endif  // !TVTS_HOST_SHIM
