@@ -225,3 +225,21 @@ def test_gpu_epoch_loop_runs_one_batch_ahead(emu_backend):
         assert events == [("prefetch", sums[0]), ("step", None), ("prefetch", sums[1]), ("step", None), ("prefetch", sums[2]), ("step", None)]
     finally:
         opt.flat.release()
+
+
+def test_trainer_accepts_a_stock_torch_optimizer(emu_backend):
+    """The unmodified entry script hands over whatever `transformers.AdamW` / torch optimizer it built: gradients then arrive through
+    ordinary .grad tensors and the optimizer's own step() (no flat arena, no CUDA graph)."""
+    cfg = C.TINY_B
+    m = M.TVTSv2Base(types.SimpleNamespace(local_rank=0), arch=cfg)
+    m.load_state_dict(make_state_dict(cfg, seed=1234), strict=True)
+    groups = optim.reference_param_groups(list(m.named_parameters()), cfg.text_layers, (cfg.text_layers * 3) // 4)
+    opt = torch.optim.AdamW([{**g, "lr": g["lr"] * 100} for g in groups], eps=1e-6)
+    batches = [make_batch(cfg, 2, 2, n_trans=4, seed=40 + i) for i in range(2)]
+    args = types.SimpleNamespace(rank=0, local_rank=0, world_size=1, schedule=[])
+    tr = Trainer_TVTSv2_B_16(args, m, M.NormSoftmaxLoss(0.05), [], opt, {"trainer": {"epochs": 1}}, [FakeLoader("YTTemporal", batches, 2)])
+    assert tr.step.use_graph is False
+    w0 = m.video_model.proj.detach().clone()
+    hist = tr.train()
+    assert hist[0]["loss_0"] > 0 and not torch.equal(w0, m.video_model.proj.detach())
+    assert all(p.grad is not None for n, p in m.named_parameters() if p.requires_grad)

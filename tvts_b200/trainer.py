@@ -396,7 +396,10 @@ class Trainer_TVTSv2:
             assert self.mnt_mode in ("min", "max")
             self.mnt_best = float("inf") if self.mnt_mode == "min" else -float("inf")
         temperature = getattr(loss, "temperature", 0.05)
-        self.step = TrainStep(model, optimizer, temperature, self.device, use_graph=use_graph and self.device.type == "cuda")
+        # whole-step CUDA graphs need the fused flat optimizer (its update is one capturable launch); with a stock torch / transformers
+        # optimizer (the unmodified entry script on transformers==4.10.2) the step runs launch by launch
+        graphable = self.device.type == "cuda" and (optimizer is None or hasattr(optimizer, "launch"))
+        self.step = TrainStep(model, optimizer, temperature, self.device, use_graph=use_graph and graphable)
         self.on_epoch_end = on_epoch_end
         self.history = []
         resume = getattr(config, "resume", None)
