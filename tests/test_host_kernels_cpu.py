@@ -142,6 +142,9 @@ ATTN_HOST_CASES = [
     (2, 1, 0, 0, 0, 130, True, 64, False),
     (5, 3, 0, 0, 0, 50, False, 64, True),      # key-padded (DistilBERT, v1)
     (2, 2, 0, 0, 0, 70, False, 80, True),
+    (1, 1, 1, 16, 76, 1217, False, 80, False),  # the full c4 (H/14, 16 frames) token count, one head
+    (2, 1, 0, 0, 0, 1, False, 80, False),       # a single token
+    (1, 2, 0, 0, 0, 128, True, 80, False),      # sequence = exactly two tiles, causal
 ]
 
 
@@ -155,6 +158,7 @@ def test_generic_attention_kernels_on_the_cpu_simt_stand_in(hattn, B, H, mode, T
     if padded:
         klen = torch.randint(1, N + 1, (B,), dtype=torch.int32)
         klen[0] = N
+        klen[-1] = 1                               # a sequence with a single valid key
     kp = ctypes.c_void_p(klen.data_ptr()) if padded else ctypes.c_void_p(None)
     out = torch.full((B * N, H * d), float("nan"), dtype=BF16)
     lse = torch.full((B, H, N), float("nan"))
