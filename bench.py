@@ -31,6 +31,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--trim-text", action="store_true",
+                    help="trim the token matrix to the longest caption of the batch (exact for the causal text tower; fewer padded rows)")
     ap.add_argument("--u8-input", action="store_true", help="feed uint8 clips (GPU-side normalisation fused into the patch gather)")
     ap.add_argument("--workload", default="c3", help="c3 = ViT-B/16 T=8 batch 32/GPU (headline); c2 = ViT-B/32 T=8 batch 64; c1 = ViT-B/32 T=2 batch 4; "
                     "c4 = ViT-H/14 T=16 batch 8/GPU (CUDA path not yet GPU-verified)")
@@ -217,6 +219,9 @@ def run_ours(args):
     step = TrainStep(model, opt, cfg.temperature, dev, use_graph=use_graph)
 
     host = make_batch(cfg, batch, frames, n_trans=n_trans, seed=0, rank=rank)
+    if args.trim_text:
+        from tvts_b200.trainer import trim_text_context
+        host["text"] = trim_text_context(host["text"])
     if args.u8_input:        # uint8 crops: normalisation runs inside the gather kernel (input_stage.cu), 4x fewer host->device bytes
         host["video"] = torch.randint(0, 256, host["video"].shape, dtype=torch.uint8, generator=torch.Generator().manual_seed(rank))
     pinned = {k: v.pin_memory() for k, v in host.items()}

@@ -4,24 +4,21 @@
 #include "host_simt.h"
 
 namespace hd {
-namespace {
-alignas(128) uint8_t smem[128 * 1024];   // what `extern __shared__ uint8_t smem[]` inside the kernels refers to
-}
 #include "../../tvts_b200/csrc/attention_hd.cu"
 
 template <int HD>
 void fwd(const void* qkv, void* out, float* lse, const int* klen, AttnShape a) {
-  simt::launch((unsigned)num_blocks_x(a), (unsigned)a.H, (unsigned)a.B, kThreads, smem,
+  simt::launch((unsigned)num_blocks_x(a), (unsigned)a.H, (unsigned)a.B, kThreads,
                [&] { attn_hd_fwd_kernel<HD>((const bf16*)qkv, (bf16*)out, lse, a, klen); });
 }
 template <int HD>
 void bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, const int* klen, AttnShape a) {
   const long long rows = (long long)a.B * a.N * a.H;
-  simt::launch((unsigned)((rows + 31) / 32), 1, 1, 256, smem,
+  simt::launch((unsigned)((rows + 31) / 32), 1, 1, 256,
                [&] { attn_hd_delta_kernel<HD>((const bf16*)out, (const bf16*)dout, delta, a.B, a.N, a.H); });
-  simt::launch((unsigned)num_blocks_x(a, false), (unsigned)a.H, (unsigned)a.B, kThreads, smem,
+  simt::launch((unsigned)num_blocks_x(a, false), (unsigned)a.H, (unsigned)a.B, kThreads,
                [&] { attn_hd_bwd_kernel<HD, 0>((const bf16*)qkv, (const bf16*)dout, lse, delta, (bf16*)dqkv, a, klen); });
-  simt::launch((unsigned)num_blocks_x(a, true), (unsigned)a.H, (unsigned)a.B, kThreads, smem,
+  simt::launch((unsigned)num_blocks_x(a, true), (unsigned)a.H, (unsigned)a.B, kThreads,
                [&] { attn_hd_bwd_kernel<HD, 1>((const bf16*)qkv, (const bf16*)dout, lse, delta, (bf16*)dqkv, a, klen); });
 }
 }  // namespace hd

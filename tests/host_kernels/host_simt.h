@@ -11,13 +11,17 @@
 
 #include "host_shim.h"
 
-#define __shared__
-#define __align__(x)
+#define __shared__ static                 // a function-local static array is shared by all (OS-thread) CUDA threads: one CTA runs at a time
+#define __align__(x) __attribute__((aligned(x)))
+#define TVTS_DYN_SMEM(type, name, align) type* const name = reinterpret_cast<type*>(simt::dyn_smem)
+#define __expf(x) expf(x)
 #ifndef INFINITY
 #define INFINITY (__builtin_inff())
 #endif
 
 struct uint4 { uint32_t x, y, z, w; };
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return {x, y, z, w}; }
+static inline bf16 opnd_from_float(float x) { return bf16{f32_to_bf16_rn(x)}; }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 #define __logf(x) logf(x)      // (glibc declares a __logf of its own)
@@ -29,15 +33,17 @@ struct Warp {
   uint32_t addr[32];
   float f32[32];
 };
-inline uint8_t* smem_base = nullptr;
+alignas(128) inline uint8_t dyn_smem[232 * 1024];      // the dynamic shared memory of the running CTA
+// anchor of the 32-bit "shared window" addresses: every static array of this module (the kernels' `__shared__` arrays included) lies
+// within +-2 GB of it.  Kept as an integer so that no object bounds are attached to the derived pointers.
+inline uintptr_t smem_anchor = reinterpret_cast<uintptr_t>(dyn_smem);
 inline std::vector<Warp>* warps = nullptr;
 inline std::barrier<>* cta_bar = nullptr;
 inline thread_local int lane = 0, warp = 0;
 inline Warp& W() { return (*warps)[warp]; }
 
 // run `body` once per CUDA thread of every CTA of the grid; CTAs run one after the other, the threads of a CTA concurrently
-inline void launch(unsigned gx, unsigned gy, unsigned gz, unsigned block, uint8_t* smem, const std::function<void()>& body) {
-  smem_base = smem;
+inline void launch(unsigned gx, unsigned gy, unsigned gz, unsigned block, const std::function<void()>& body) {
   for (unsigned bz = 0; bz < gz; ++bz)
     for (unsigned by = 0; by < gy; ++by)
       for (unsigned bx = 0; bx < gx; ++bx) {
@@ -68,12 +74,21 @@ static inline float __shfl_xor_sync(unsigned, float v, int lanemask) {
   w.bar.arrive_and_wait();
   return r;
 }
-static inline uint32_t smem_u32(const void* p) { return (uint32_t)((const uint8_t*)p - simt::smem_base); }
+static inline float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+static inline float warp_max(float v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+static inline uint32_t smem_u32(const void* p) { return (uint32_t)(int32_t)(int64_t)(reinterpret_cast<uintptr_t>(p) - simt::smem_anchor); }
+static inline uint8_t* smem_ptr(uint32_t a) { return reinterpret_cast<uint8_t*>(simt::smem_anchor + (uintptr_t)(int64_t)(int32_t)a); }
 
 // cp.async.cg.shared.global 16 bytes (src-size 0 -> zero fill); executed synchronously, so commit / wait are no-ops
 static inline void cp_async16(uint32_t dst, const void* src, bool valid) {
-  if (valid) std::memcpy(simt::smem_base + dst, src, 16);
-  else std::memset(simt::smem_base + dst, 0, 16);
+  if (valid) std::memcpy(smem_ptr(dst), src, 16);
+  else std::memset(smem_ptr(dst), 0, 16);
 }
 static inline void cp_async_commit() {}
 template <int N>
@@ -88,11 +103,11 @@ static inline void ldsm_impl(uint32_t addr, uint32_t* r, bool trans) {
   w.bar.arrive_and_wait();
   for (int i = 0; i < 4; ++i) {
     if (!trans) {
-      std::memcpy(&r[i], simt::smem_base + w.addr[8 * i + T / 4] + 4 * (T % 4), 4);
+      std::memcpy(&r[i], smem_ptr(w.addr[8 * i + T / 4]) + 4 * (T % 4), 4);
     } else {
       uint16_t lo, hi;
-      std::memcpy(&lo, simt::smem_base + w.addr[8 * i + 2 * (T % 4)] + 2 * (T / 4), 2);
-      std::memcpy(&hi, simt::smem_base + w.addr[8 * i + 2 * (T % 4) + 1] + 2 * (T / 4), 2);
+      std::memcpy(&lo, smem_ptr(w.addr[8 * i + 2 * (T % 4)]) + 2 * (T / 4), 2);
+      std::memcpy(&hi, smem_ptr(w.addr[8 * i + 2 * (T % 4) + 1]) + 2 * (T / 4), 2);
       r[i] = (uint32_t)lo | ((uint32_t)hi << 16);
     }
   }

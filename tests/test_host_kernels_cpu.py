@@ -125,7 +125,7 @@ def hattn(tmp_path_factory):
     """attention_hd.cu compiled for the CPU SIMT stand-in (tests/host_kernels/host_simt.h): CUDA threads = OS threads, ldmatrix / mma.sync /
     cp.async / shfl restated with their architectural layouts."""
     out = str(tmp_path_factory.mktemp("hostattn") / "libhostattn.so")
-    subprocess.run(["g++", "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC", "-DTVTS_HOST_SHIM", "-I", HERE,
+    subprocess.run(["g++", "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC", "-U_FORTIFY_SOURCE", "-D_FORTIFY_SOURCE=0", "-DTVTS_HOST_SHIM", "-I", HERE,
                     os.path.join(HERE, "harness_attn.cpp"), "-o", out], check=True)
     return ctypes.CDLL(out)
 
@@ -186,3 +186,54 @@ def test_generic_attention_kernels_on_the_cpu_simt_stand_in(hattn, B, H, mode, T
         g5 = dqkv.view(B, N, 3, H, d)
         for b in range(B):
             assert (g5[b, int(klen[b]):, 1:] == 0).all()
+
+
+# ------------------------------------------------------------------------------------------------ the specialised head-dim-64 kernels
+@pytest.fixture(scope="module")
+def hattn64(tmp_path_factory):
+    """attention.cu (the GPU-verified streamed / group-resident / time / CLS kernels) on the same stand-in, with the real kernel selection."""
+    out = str(tmp_path_factory.mktemp("hostattn64") / "libhostattn64.so")
+    subprocess.run(["g++", "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC", "-U_FORTIFY_SOURCE", "-D_FORTIFY_SOURCE=0", "-DTVTS_HOST_SHIM",
+                    "-I", HERE, os.path.join(HERE, "harness_attn64.cpp"), "-o", out], check=True)
+    return ctypes.CDLL(out)
+
+
+STREAMED, GROUP, TIME, CLS = 1, 2, 4, 8
+ATTN64_CASES = [
+    # B, H, mode, T, n, N, causal, kernels the dispatch must pick
+    (1, 2, 0, 0, 0, 77, True, GROUP),            # GPU-verified list: the stand-in must agree with what is known to be right on a B200
+    (1, 1, 0, 0, 0, 200, False, STREAMED),
+    (1, 2, 1, 2, 49, 99, False, GROUP | CLS),
+    (1, 2, 2, 8, 5, 41, False, TIME | CLS),
+    (1, 1, 2, 16, 6, 97, False, STREAMED),
+    (2, 2, 0, 0, 0, 16, True, STREAMED),         # causal text sequences trimmed to the longest caption of a batch (trainer.trim_text_context):
+    (2, 2, 0, 0, 0, 24, True, GROUP),            # group-resident kernels with 2..6 warps in causal mode, not part of the GPU test list
+    (2, 2, 0, 0, 0, 40, True, GROUP),
+    (2, 2, 0, 0, 0, 48, True, GROUP),
+    (2, 2, 0, 0, 0, 64, True, GROUP),
+    (2, 2, 0, 0, 0, 96, True, GROUP),
+]
+
+
+@pytest.mark.parametrize("B,H,mode,T,n,N,causal,expect", ATTN64_CASES)
+def test_specialised_attention_kernels_on_the_cpu_simt_stand_in(hattn64, B, H, mode, T, n, N, causal, expect):
+    d = 64
+    torch.manual_seed(N + mode)
+    qkv = torch.randn(B, N, 3 * H * d).to(BF16)
+    dout = torch.randn(B * N, H * d).to(BF16)
+    scale = d ** -0.5
+    out = torch.full((B * N, H * d), float("nan"), dtype=BF16)
+    lse = torch.full((B, H, N), float("nan"))
+    kinds = ctypes.c_int(0)
+    hattn64.h64_attn_fwd(P(qkv), P(out), P(lse), I(B), I(N), I(H), I(mode), I(T), I(n), I(int(causal)), ctypes.c_float(scale), ctypes.byref(kinds))
+    assert kinds.value == expect
+    ro, rl = torch.empty_like(out), torch.empty_like(lse)
+    emu.attn_fwd(qkv, ro, rl, B, N, H, d, mode, T, n, int(causal), scale)
+    assert torch.allclose(out.float(), ro.float(), atol=2e-2) and torch.allclose(lse, rl, atol=1e-4)
+    dqkv = torch.full_like(qkv, float("nan"))
+    delta = torch.empty_like(lse)
+    hattn64.h64_attn_bwd(P(qkv), P(ro), P(dout), P(rl), P(delta), P(dqkv), I(B), I(N), I(H), I(mode), I(T), I(n), I(int(causal)), ctypes.c_float(scale))
+    rd, rdel = torch.empty_like(qkv), torch.empty_like(lse)
+    emu.attn_bwd(qkv, ro, dout, rl, rdel, rd, B, N, H, d, mode, T, n, int(causal), scale)
+    assert torch.isfinite(dqkv.float()).all()
+    assert torch.allclose(dqkv.float(), rd.float(), atol=3e-2, rtol=3e-2), (dqkv.float() - rd.float()).abs().max()

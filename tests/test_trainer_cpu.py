@@ -243,3 +243,29 @@ def test_trainer_accepts_a_stock_torch_optimizer(emu_backend):
     hist = tr.train()
     assert hist[0]["loss_0"] > 0 and not torch.equal(w0, m.video_model.proj.detach())
     assert all(p.grad is not None for n, p in m.named_parameters() if p.requires_grad)
+
+
+def test_text_context_trimming_is_exact(emu_backend):
+    """Dropping the token columns that are padding in every caption of the batch (causal text tower: positions after EOT never reach
+    the pooled EOT row) leaves embeddings, losses and every gradient unchanged."""
+    from tvts_b200.trainer import trim_text_context
+    from tvts_b200 import engine as E
+    cfg = C.TINY_B
+    data = make_batch(cfg, 3, 2, n_trans=4, seed=21)
+    trimmed = trim_text_context(data["text"])
+    longest = int(data["text"].argmax(-1).max()) + 1
+    assert trimmed.shape[1] == min(cfg.context, -(-longest // 8) * 8) < cfg.context
+    assert torch.equal(trimmed, data["text"][:, :trimmed.shape[1]]) and (data["text"][:, trimmed.shape[1]:] == 0).all()
+    outs = []
+    for text in (data["text"], trimmed):
+        m = M.TVTSv2Base(types.SimpleNamespace(local_rank=0), arch=cfg)
+        m.load_state_dict(make_state_dict(cfg, seed=1234), strict=True)
+        E.WEIGHTS.clear()
+        te, ve, pred = m(dict(data, text=text))
+        loss = M.NormSoftmaxLoss(0.05)(M.sim_matrix(ve, te)) + E.sort_ce(pred, data["label"], 2.0)
+        loss.backward()
+        outs.append((te.detach(), loss.detach(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}))
+    assert torch.allclose(outs[0][0], outs[1][0], atol=1e-6) and torch.allclose(outs[0][1], outs[1][1], atol=1e-6)
+    assert set(outs[0][2]) == set(outs[1][2])
+    for k, g in outs[0][2].items():
+        assert torch.allclose(g, outs[1][2][k], atol=1e-6 + 1e-5 * g.abs().max().item()), k

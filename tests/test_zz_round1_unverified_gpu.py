@@ -6,6 +6,7 @@ that `pytest -x` reaches them only after every previously-verified GPU test has 
   * LayerNorm width 640, the TVTSv2_H_14 model (tiny_H640) against the executed-reference fixture and the oracle's gradients
   * the downstream (zero-shot) towers against their executed-reference fixture
   * the fused uint8 input stage (tvts_b200/csrc/input_stage.cu): bit-exact against the float path
+  * text-context trimming (trainer.trim_text_context): same results from a token matrix cut to the batch's longest caption
   * TVTS v1: tubelet gather / per-tube assembly / ReLU kernels (tvts_b200/csrc/v1_glue.cu), key-padded attention, and the whole v1 model
     (DistilBERT text encoder included) against the executed-reference fixture tiny_v1_full and the oracle's gradients
 Tolerances as in tests/test_kernels_gpu.py / tests/test_model_gpu.py.
@@ -240,6 +241,32 @@ def test_downstream_model_against_reference_golden():
             np.testing.assert_allclose(ve.cpu().numpy(), g["video_emb" + tag], atol=3e-2, rtol=3e-2)
             if tag == "":
                 np.testing.assert_allclose(m(to_cuda(data), return_embeds=False).cpu().numpy(), g["sims"], atol=3e-2)
+
+
+def test_text_context_trimming_on_the_gpu():
+    """trainer.trim_text_context: the text tower on a token matrix cut to the longest caption of the batch (causal group-resident
+    kernels at sequence lengths < 77) gives the same embeddings / losses / gradients as the full 77-column matrix."""
+    from tvts_b200.trainer import trim_text_context
+    cfg = C.TINY_B
+    data = make_batch(cfg, 3, 2, n_trans=4, seed=21)
+    trimmed = trim_text_context(data["text"])
+    assert trimmed.shape[1] < cfg.context
+    outs = []
+    for text in (data["text"], trimmed):
+        m = M.TVTSv2Base(types.SimpleNamespace(local_rank=0), arch=cfg)
+        m.load_state_dict(make_state_dict(cfg, seed=1234), strict=True)
+        m = m.cuda()
+        dd = to_cuda(dict(data, text=text))
+        te, ve, pred = m(dd)
+        loss = M.NormSoftmaxLoss(cfg.temperature)(M.sim_matrix(ve, te)) + E.sort_ce(pred, dd["label"])
+        loss.backward()
+        torch.cuda.synchronize()
+        outs.append((te.detach(), loss.detach(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}))
+    close(outs[0][0], outs[1][0], atol=2e-3, what="text embeddings")          # same math per row; different kernel tiling only
+    assert abs(outs[0][1].item() - outs[1][1].item()) < 2e-3
+    for k, g in outs[0][2].items():
+        rel = (g.double() - outs[1][2][k].double()).norm().item() / (g.double().norm().item() + 1e-8)
+        assert rel < 2e-2, (k, rel)
 
 
 # ------------------------------------------------------------------------------------------------ TVTS v1 (configs[4])

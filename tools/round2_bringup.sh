@@ -22,6 +22,7 @@ TVTS_OPERAND=fp16 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-bas
 # 4. benches: headline, then H/14
 timeout 600 python bench.py --steps 20 --warmup 5 > $O/bench_c3.json 2> $O/bench_c3.err
 timeout 600 python bench.py --steps 20 --warmup 5 --u8-input --no-cpu-baseline > $O/bench_c3_u8.json 2> $O/bench_c3_u8.err
+timeout 600 python bench.py --steps 20 --warmup 5 --trim-text --no-cpu-baseline > $O/bench_c3_trim.json 2> $O/bench_c3_trim.err
 timeout 900 python bench.py --workload c4 --steps 5 --warmup 3 --no-cpu-baseline > $O/bench_c4.json 2> $O/bench_c4.err
 tail -3 $O/*.log $O/*.json
 timeout 600 python tools/bench_v1.py --steps 5 --warmup 3 > $O/bench_v1_c5.json 2> $O/bench_v1_c5.err

@@ -19,7 +19,9 @@
 //     whole backward (dq, dk, dv of the slot) each run in a single pass (more frames fall back to the streamed kernels).
 // fp32 softmax statistics (online max/sum in forward; saved log-sum-exp in backward), bf16 I/O.
 #include "attention_common.cuh"
+#ifndef TVTS_HOST_SHIM
 #include "../../include/tvts_b200.h"
+#endif
 
 namespace {
 
@@ -845,7 +847,7 @@ __global__ void __launch_bounds__(NW * 32, 2) attn_group_bwd_kernel(const bf16* 
                                                                      const float* __restrict__ lse, const float* __restrict__ delta,
                                                                      bf16* __restrict__ dqkv, AttnShape a) {
   constexpr int R = NW * 16;
-  extern __shared__ __align__(128) uint8_t gsm[];      // Q | K | V | dO | dQ-staging tiles, then lse*log2e [R], delta [R]
+  TVTS_DYN_SMEM(uint8_t, gsm, 128);                    // Q | K | V | dO | dQ-staging tiles, then lse*log2e [R], delta [R]
   const uint32_t sQ = smem_u32(gsm), sK = sQ + R * 128, sV = sK + R * 128, sD = sV + R * 128;
   uint8_t* gO = gsm + 4 * R * 128;
   float* Ls = reinterpret_cast<float*>(gsm + 5 * R * 128);
@@ -1056,6 +1058,7 @@ inline int group_warps(const AttnShape& a) {
   return (nw >= 2 && nw <= 7) ? nw : 0;
 }
 
+#ifndef TVTS_HOST_SHIM
 int check_shape(const AttnShape& a, int64_t d) {
   TVTS_REQUIRE(d == HD, "attention: head dim %lld unsupported (only 64)", (long long)d);
   TVTS_REQUIRE(a.B > 0 && a.N > 0 && a.H > 0, "attention: empty shape");
@@ -1067,6 +1070,7 @@ int check_shape(const AttnShape& a, int64_t d) {
   TVTS_REQUIRE(a.H <= 65535 && a.B <= 65535, "attention: grid limits");
   return TVTS_OK;
 }
+#endif  // !TVTS_HOST_SHIM
 
 // ================================================================================================ CLS row / column kernels
 // In the divided modes the CLS token attends to (and is attended by) ALL N tokens: one query row and one key column per (batch,
@@ -1104,7 +1108,7 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
 // out[b, 0, h, :] = softmax(scale * q0 . K^T) V  over all N tokens; lse[b, h, 0]
 __global__ void __launch_bounds__(CLS_THREADS) attn_cls_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse,
                                                                    AttnShape a) {
-  extern __shared__ __align__(16) float csm[];           // q0 [64] | red [16] | acc [8][64] | p [N]
+  TVTS_DYN_SMEM(float, csm, 16);                         // q0 [64] | red [16] | acc [8][64] | p [N]
   float* q0 = csm;
   float* red = csm + 64;
   float* accs = csm + 80;
@@ -1201,7 +1205,7 @@ __global__ void __launch_bounds__(CLS_THREADS) attn_cls_fwd_kernel(const bf16* _
 __global__ void __launch_bounds__(CLS_THREADS) attn_cls_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                                                                    const float* __restrict__ lse, const float* __restrict__ delta,
                                                                    bf16* __restrict__ dqkv, AttnShape a) {
-  extern __shared__ __align__(16) float csm[];           // q0 | do0 | k0 | v0 [64 each] | acc [8][192] | dsA [N] | pB [N] | dsB [N]
+  TVTS_DYN_SMEM(float, csm, 16);                         // q0 | do0 | k0 | v0 [64 each] | acc [8][192] | dsA [N] | pB [N] | dsB [N]
   float* q0 = csm;
   float* do0 = csm + 64;
   float* k0 = csm + 128;
@@ -1325,6 +1329,7 @@ __global__ void __launch_bounds__(CLS_THREADS) attn_cls_bwd_kernel(const bf16* _
 // 13 tiles each) is latency-bound and independent of the group kernels (disjoint outputs), so it runs on a side stream forked
 // from / joined back into the caller's stream with events -- also legal inside a CUDA-graph capture, where it becomes a parallel
 // branch of the graph.
+#ifndef TVTS_HOST_SHIM
 struct SideStream {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
@@ -1342,11 +1347,13 @@ SideStream* side_stream() {
   return &s;
 }
 int g_attn_side = 1;
+#endif  // !TVTS_HOST_SHIM
 
 inline bool use_time_kernels(const AttnShape& a) { return a.mode == 2 && a.T <= T_MAX; }
 
 }  // namespace
 
+#ifndef TVTS_HOST_SHIM
 extern "C" int tvts_attn_set_side_stream(int on) {
   g_attn_side = on;
   return TVTS_OK;
@@ -1520,3 +1527,4 @@ extern "C" int tvts_attn_window_bwd(const void* qkv, const void* out, const void
   TVTS_LAUNCH_CHECK();
   return TVTS_OK;
 }
+#endif  // !TVTS_HOST_SHIM

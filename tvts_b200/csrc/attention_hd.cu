@@ -66,7 +66,7 @@ template <int HD>
 __global__ void __launch_bounds__(kThreads) attn_hd_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse,
                                                                AttnShape a, const int* __restrict__ klen) {
   using G = Geo<HD>;
-  extern __shared__ __align__(128) uint8_t smem[];   // Q | K0 | V0 | K1 | V1
+  TVTS_DYN_SMEM(uint8_t, smem, 128);   // Q | K0 | V0 | K1 | V1
   const uint32_t sQ = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(kThreads) attn_hd_bwd_kernel(const bf16* __res
                                                                const float* __restrict__ lse, const float* __restrict__ delta,
                                                                bf16* __restrict__ dqkv, AttnShape a, const int* __restrict__ klen) {
   using G = Geo<HD>;
-  extern __shared__ __align__(128) uint8_t smem[];   // 4 tiles + lse/delta of the streamed rows for 2 stages
+  TVTS_DYN_SMEM(uint8_t, smem, 128);   // 4 tiles + lse/delta of the streamed rows for 2 stages
   // [0] stationary tile 0 (Q or K) -> after the fragment load reused as X stage 1
   // [1] stationary tile 1 (dO or V) -> reused as Y stage 1
   // [2] X stage 0, [3] Y stage 0

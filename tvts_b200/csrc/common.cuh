@@ -59,6 +59,9 @@ typedef __nv_bfloat16 bf16;
 #define TVTS_MMA_TYPE "bf16"
 #endif
 
+// dynamic shared memory of a kernel (one macro so that the off-GPU test stand-in, tests/host_kernels, can supply its own definition)
+#define TVTS_DYN_SMEM(type, name, align) extern __shared__ __align__(align) type name[]
+
 // ------------------------------------------------------------------------------------------------
 // small device utilities
 // ------------------------------------------------------------------------------------------------

@@ -106,6 +106,18 @@ def average_gradients(params):
     return flat.numel() * 4
 
 
+def trim_text_context(tokens, multiple=8):
+    """Cut a CLIP token matrix [n_txt, ctx] (EOT = the row maximum, zeros after it) down to the longest caption of the batch, rounded up
+    to `multiple`.  EXACT for the causal text towers: positions after a sequence's EOT never influence its EOT row (the only row that is
+    pooled, model_dist_TVTSv2_ViT_B_16.py:104-108) and receive zero gradient, so dropping trailing columns that are padding in EVERY
+    sequence changes nothing but the amount of padding work (77 -> typically 24..48 columns: GEMM rows, LayerNorm rows and attention
+    of the text tower shrink proportionally).  Intended for HOST tensors (the tokenizer's output); on a device tensor it costs a sync."""
+    ctx = tokens.shape[1]
+    longest = int(tokens.argmax(dim=-1).max().item()) + 1
+    keep = min(ctx, max(multiple, -(-longest // multiple) * multiple))
+    return tokens if keep == ctx else tokens[:, :keep].contiguous()
+
+
 def _flatten(data, prefix=""):
     """{'video': t, 'text': {'input_ids': t, ...}} -> {'video': t, 'text.input_ids': t, ...} (v1 batches nest the tokenizer output)."""
     out = {}
@@ -213,7 +225,11 @@ class TrainStep:
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         n0 = L.launch_count()
-        with torch.cuda.graph(graph):
+        # further input signatures (caption vs transcript batches, trimmed text lengths) capture into the FIRST graph's memory pool: the
+        # graphs replay one at a time, so their multi-GB activation workspaces can overlap instead of adding up
+        first = next(iter(self._graphs.values()), None)
+        ctx = torch.cuda.graph(graph) if first is None else torch.cuda.graph(graph, pool=first.graph.pool())
+        with ctx:
             l1, l2 = self._body(nested, optimizer_launch_only=True)
         self.launches_per_graph = L.launch_count() - n0
         flat = getattr(self.optimizer, "flat", None)
@@ -344,13 +360,14 @@ class Trainer_TVTSv2:
 
     def __init__(self, args, model, loss, metrics, optimizer, config, data_loader, valid_data_loader=None, lr_scheduler=None,
                  len_epoch=None, writer=None, visualizer=None, tokenizer=None, max_samples_per_epoch=50000, use_graph=True,
-                 on_epoch_end=None):
+                 on_epoch_end=None, trim_text=True):
         self.args, self.model, self.loss, self.metrics, self.optimizer, self.config = args, model, loss, metrics, optimizer, config
         self.data_loader = list(data_loader)
         self.valid_data_loader = valid_data_loader
         self.do_validation = valid_data_loader is not None
         self.lr_scheduler, self.writer, self.visualizer, self.tokenizer = lr_scheduler, writer, visualizer, tokenizer
         self.max_samples_per_epoch = max_samples_per_epoch
+        self.trim_text = trim_text                   # drop token columns that are padding in every caption of the batch (exact: causal text tower)
         if len_epoch is None:
             self.len_epoch = None
             for x in self.data_loader:
@@ -415,6 +432,9 @@ class Trainer_TVTSv2:
                 text_all = text_all + list(clip)
             data = dict(data)
             data["text"] = self.tokenizer(text_all, truncate=True)
+        if self.trim_text and torch.is_tensor(data["text"]) and data["text"].dim() == 2:
+            data = dict(data)
+            data["text"] = trim_text_context(data["text"])
         return data
 
     def _adjust_learning_rate(self, optimizer, epoch, args):
