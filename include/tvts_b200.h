@@ -120,6 +120,9 @@ int tvts_attn_bwd(const void* qkv, const void* out, const void* dout, const floa
 
 /* The head-dim generic streamed kernels behind tvts_attn_fwd / tvts_attn_bwd for d != 64, callable directly (d = 64 or 80; same
  * arguments and results): with d = 64 they cross-check the generic code against the specialised kernels. */
+/* 1 (default): groups that fit one CTA (space attention of H/14: 77 rows; short full-attention sequences) use the group-resident generic
+ * kernels + a CLS launch; 0: streamed generic kernels only */
+int tvts_attn_hd_set_group(int on);
 int tvts_attn_generic_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T,
                           int64_t n, int64_t causal, float scale, void* stream);
 int tvts_attn_generic_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv, int64_t B,

@@ -131,7 +131,7 @@ def hattn(tmp_path_factory):
 
 
 ATTN_HOST_CASES = [
-    # B, H, mode, T, n, N, causal, d, padded
+    # B, H, mode, T, n, N, causal, d, padded   (each case runs with the group-resident kernels allowed and with streamed kernels only)
     (2, 2, 0, 0, 0, 77, True, 80, False),      # causal, two streamed tiles
     (1, 2, 0, 0, 0, 150, False, 80, False),    # full, three tiles, ragged last tile
     (2, 2, 1, 2, 49, 99, False, 80, False),    # space
@@ -145,11 +145,19 @@ ATTN_HOST_CASES = [
     (1, 1, 1, 16, 76, 1217, False, 80, False),  # the full c4 (H/14, 16 frames) token count, one head
     (2, 1, 0, 0, 0, 1, False, 80, False),       # a single token
     (1, 2, 0, 0, 0, 128, True, 80, False),      # sequence = exactly two tiles, causal
+    (1, 2, 1, 2, 100, 201, False, 80, False),   # space, 101 rows per group: 7 warps
+    (1, 2, 1, 2, 20, 41, False, 80, False),     # space, 21 rows: 2 warps
+    (2, 2, 0, 0, 0, 40, False, 80, False),      # short full-attention sequence: group-resident in mode 0
+    (1, 2, 0, 0, 0, 112, True, 64, False),      # largest group (7 warps), causal
 ]
 
 
+@pytest.mark.parametrize("group", [1, 0])
 @pytest.mark.parametrize("B,H,mode,T,n,N,causal,d,padded", ATTN_HOST_CASES)
-def test_generic_attention_kernels_on_the_cpu_simt_stand_in(hattn, B, H, mode, T, n, N, causal, d, padded):
+def test_generic_attention_kernels_on_the_cpu_simt_stand_in(hattn, B, H, mode, T, n, N, causal, d, padded, group):
+    fits = (not padded) and mode != 2 and 2 <= ((N if mode == 0 else n + 1) + 15) // 16 <= 7
+    if not group and not fits:
+        pytest.skip("the streamed kernels are what runs in both settings")
     torch.manual_seed(N + mode + d)
     qkv = torch.randn(B, N, 3 * H * d).to(BF16)
     dout = torch.randn(B * N, H * d).to(BF16)
@@ -162,7 +170,9 @@ def test_generic_attention_kernels_on_the_cpu_simt_stand_in(hattn, B, H, mode, T
     kp = ctypes.c_void_p(klen.data_ptr()) if padded else ctypes.c_void_p(None)
     out = torch.full((B * N, H * d), float("nan"), dtype=BF16)
     lse = torch.full((B, H, N), float("nan"))
-    assert hattn.h_attn_fwd(P(qkv), P(out), P(lse), kp, I(B), I(N), I(H), I(d), I(mode), I(T), I(n), I(int(causal)), ctypes.c_float(scale)) == 0
+    used = hattn.h_attn_fwd(P(qkv), P(out), P(lse), kp, I(B), I(N), I(H), I(d), I(mode), I(T), I(n), I(int(causal)), ctypes.c_float(scale),
+                            ctypes.c_int(group))
+    assert used == int(bool(group) and fits)      # 1: the group-resident kernels ran (same selection rule as hd_launch_fwd)
     ro, rl = torch.empty_like(out), torch.empty_like(lse)
     if padded:
         emu.attn_padded_fwd(qkv, ro, rl, klen, B, N, H, d, scale)
@@ -173,7 +183,7 @@ def test_generic_attention_kernels_on_the_cpu_simt_stand_in(hattn, B, H, mode, T
     dqkv = torch.full_like(qkv, float("nan"))
     delta = torch.empty_like(lse)
     assert hattn.h_attn_bwd(P(qkv), P(ro), P(dout), P(rl), P(delta), P(dqkv), kp, I(B), I(N), I(H), I(d), I(mode), I(T), I(n), I(int(causal)),
-                            ctypes.c_float(scale)) == 0
+                            ctypes.c_float(scale), ctypes.c_int(group)) == used
     rd, rdel = torch.empty_like(qkv), torch.empty_like(lse)
     if padded:
         emu.attn_padded_bwd(qkv, ro, dout, rl, rdel, rd, klen, B, N, H, d, scale)

@@ -72,12 +72,23 @@ GENERIC_ATTN_CASES = [
     (1, 2, 2, 16, 6, 97, False),    # time, c4's 16 frames
     (1, 2, 1, 16, 76, 1217, False),  # space at c4's token count
     (3, 2, 0, 0, 0, 130, True),     # causal across tiles
+    (1, 2, 1, 2, 100, 201, False),  # space, 101 rows per group (7 warps)
+    (2, 2, 0, 0, 0, 40, False),     # short full-attention sequence (group-resident in mode 0)
 ]
 
 
+@pytest.fixture
+def hd_group(request):
+    """tvts_attn_hd_set_group: group-resident generic kernels allowed (default) or streamed kernels only"""
+    L.lib().tvts_attn_hd_set_group(int(request.param))
+    yield request.param
+    L.lib().tvts_attn_hd_set_group(1)
+
+
+@pytest.mark.parametrize("hd_group", [1, 0], indirect=True)
 @pytest.mark.parametrize("d", [80, 64])
 @pytest.mark.parametrize("B,H,mode,T,n,N,causal", GENERIC_ATTN_CASES)
-def test_generic_attention(B, H, mode, T, n, N, causal, d):
+def test_generic_attention(B, H, mode, T, n, N, causal, d, hd_group):
     torch.manual_seed(N + mode + d)
     qkv = rnd(B, N, 3 * H * d).to(BF16)
     dout = rnd(B * N, H * d).to(BF16)

@@ -440,6 +440,355 @@ __global__ void __launch_bounds__(kThreads) attn_hd_bwd_kernel(const bf16* __res
   }
 }
 
+
+// ================================================================================================ group-resident kernels
+// One CTA holds a whole (batch, head, group) in shared memory -- the divided SPACE attention of the H/14 tower (n = 76 kept patches + the
+// CLS key = 77 rows -> 5 warps) or a short full-attention sequence -- and finishes it in ONE pass: warp w owns query rows 16w..16w+15
+// (and, in the transposed pass of the backward, key rows 16w..16w+15).  Same algorithm as attn_group_fwd/bwd_kernel in attention.cu
+// (head dim 64), on tiles of pitch Geo<HD>::PITCH.  In space mode the CLS query row / CLS key column are produced by a `cls_only` launch
+// of the streamed kernels above.
+struct GroupSetsHD {
+  int q_base, q_stride, nq;                  // queries owned by the group
+  int k_has0, k_base, k_stride, nk_patch;    // keys: [token 0 if k_has0] ; nk_patch tokens
+};
+__device__ __forceinline__ GroupSetsHD hd_group_sets(const AttnShape& a, int g) {
+  GroupSetsHD s;
+  if (a.mode == 0) { s.q_base = 0; s.q_stride = 1; s.nq = a.N; s.k_has0 = 0; s.k_base = 0; s.k_stride = 1; s.nk_patch = a.N; }
+  else { s.q_base = 1 + g * a.n; s.q_stride = 1; s.nq = a.n; s.k_has0 = 1; s.k_base = 1 + g * a.n; s.k_stride = 1; s.nk_patch = a.n; }
+  return s;
+}
+
+template <int HD, int NW>
+__global__ void __launch_bounds__(NW * 32) attn_hd_group_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
+                                                                    float* __restrict__ lse, AttnShape a) {
+  using G = Geo<HD>;
+  constexpr int R = NW * 16, P = G::PITCH, CH = G::CH;
+  TVTS_DYN_SMEM(uint8_t, smem, 128);                   // Q | K | V tiles of R rows
+  const uint32_t sQ = smem_u32(smem), sK = sQ + R * P, sV = sK + R * P;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const GroupSetsHD s = hd_group_sets(a, blockIdx.x);
+  const int nk = s.k_has0 + s.nk_patch;
+  const long long rs = 3LL * a.H * HD, ro = (long long)a.H * HD;
+  const bf16* qb = qkv + (long long)b * a.N * rs + (long long)h * HD;
+  for (int i = threadIdx.x; i < R * CH; i += NW * 32) {
+    const int r = i / CH, c = i - r * CH;
+    const bool okq = r < s.nq, okk = r < nk;
+    const long long qt = okq ? s.q_base + (long long)r * s.q_stride : 0;
+    const long long kt = (!okk || (s.k_has0 && r == 0)) ? 0 : s.k_base + (long long)(r - s.k_has0) * s.k_stride;
+    cp_async16(sQ + swzp<P>(r, c), qb + qt * rs + c * 8, okq);
+    cp_async16(sK + swzp<P>(r, c), qb + kt * rs + ro + c * 8, okk);
+    cp_async16(sV + swzp<P>(r, c), qb + kt * rs + 2 * ro + c * 8, okk);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  if (warp * 16 >= s.nq) return;
+  uint32_t qa[G::KS][4];
+  g_load_a<HD>(sQ, warp * 16, lane, qa);
+  float sc[2 * NW][4];
+#pragma unroll
+  for (int j = 0; j < 2 * NW; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+  const int row0 = warp * 16 + g, row1 = row0 + 8;
+  const int qtok0 = s.q_base + row0 * s.q_stride, qtok1 = s.q_base + row1 * s.q_stride;
+  const int k_lim = a.causal ? min(nk, warp * 16 + 16) : nk;     // causal: keys beyond this warp's last query are never needed
+#pragma unroll
+  for (int j = 0; j < 2 * NW; j += 2) {
+    if (8 * j < k_lim) {
+#pragma unroll
+      for (int kk = 0; kk < G::KS; ++kk) {
+        uint32_t b0, b1, c0, c1;
+        g_load_b_rows<HD>(sK, j, kk, lane, b0, b1, c0, c1);
+        mma16816(sc[j], qa[kk], b0, b1);
+        mma16816(sc[j + 1], qa[kk], c0, c1);
+      }
+    }
+  }
+  const float sl2 = a.scale * LOG2E;
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 2 * NW; ++j) {
+    if (8 * j >= k_lim) { sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = -INFINITY; continue; }
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int key = 8 * j + 2 * t4 + e;
+      bool ok0 = key < nk, ok1 = ok0;
+      if (a.causal) { ok0 = ok0 && key <= qtok0; ok1 = ok1 && key <= qtok1; }     // mode 0: token index == row index
+      if (!ok0) sc[j][e] = -INFINITY;
+      if (!ok1) sc[j][2 + e] = -INFINITY;
+      mx0 = fmaxf(mx0, sc[j][e]); mx1 = fmaxf(mx1, sc[j][2 + e]);
+    }
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  if (mx0 == -INFINITY) mx0 = 0.f;     // padded query rows
+  if (mx1 == -INFINITY) mx1 = 0.f;
+  float l0 = 0.f, l1 = 0.f;
+  uint32_t pa[NW][4];
+#pragma unroll
+  for (int j = 0; j < 2 * NW; ++j) {
+    if (8 * j >= k_lim) { pa[j >> 1][(j & 1) * 2] = 0u; pa[j >> 1][(j & 1) * 2 + 1] = 0u; continue; }
+    const float p00 = exp2f((sc[j][0] - mx0) * sl2), p01 = exp2f((sc[j][1] - mx0) * sl2);
+    const float p10 = exp2f((sc[j][2] - mx1) * sl2), p11 = exp2f((sc[j][3] - mx1) * sl2);
+    l0 += p00 + p01; l1 += p10 + p11;
+    pa[j >> 1][(j & 1) * 2] = pack_bf16x2(p00, p01);
+    pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p10, p11);
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  float o[G::ND][4];
+#pragma unroll
+  for (int j = 0; j < G::ND; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < NW; ++kk) {
+    if (16 * kk < k_lim) {
+#pragma unroll
+      for (int jd = 0; jd < G::ND; jd += 2) {
+        uint32_t b0, b1, c0, c1;
+        g_load_b_cols<HD>(sV, kk, jd, lane, b0, b1, c0, c1);
+        mma16816(o[jd], pa[kk], b0, b1);
+        mma16816(o[jd + 1], pa[kk], c0, c1);
+      }
+    }
+  }
+  const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+  __syncwarp();     // this warp's Q rows are only read by this warp (fragments already in registers): reuse them for staging
+#pragma unroll
+  for (int j = 0; j < G::ND; ++j) {
+    *reinterpret_cast<uint32_t*>(smem + swzp<P>(row0, j) + 4 * t4) = pack_bf16x2(o[j][0] * inv0, o[j][1] * inv0);
+    *reinterpret_cast<uint32_t*>(smem + swzp<P>(row1, j) + 4 * t4) = pack_bf16x2(o[j][2] * inv1, o[j][3] * inv1);
+  }
+  __syncwarp();
+  bf16* ob = out + (long long)b * a.N * ro + (long long)h * HD;
+  for (int i = lane; i < 16 * CH; i += 32) {
+    const int rr = i / CH, c = i - rr * CH;
+    const int r = warp * 16 + rr;
+    if (r < s.nq)
+      *reinterpret_cast<uint4*>(ob + (long long)(s.q_base + r * s.q_stride) * ro + c * 8) = *reinterpret_cast<const uint4*>(smem + swzp<P>(r, c));
+  }
+  if (t4 == 0) {
+    float* lb = lse + ((long long)b * a.H + h) * a.N;
+    if (row0 < s.nq) lb[qtok0] = mx0 * a.scale + __logf(l0);
+    if (row1 < s.nq) lb[qtok1] = mx1 * a.scale + __logf(l1);
+  }
+}
+
+template <int HD, int NW>
+__global__ void __launch_bounds__(NW * 32) attn_hd_group_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+                                                                    const float* __restrict__ lse, const float* __restrict__ delta,
+                                                                    bf16* __restrict__ dqkv, AttnShape a) {
+  using G = Geo<HD>;
+  constexpr int R = NW * 16, P = G::PITCH, CH = G::CH;
+  TVTS_DYN_SMEM(uint8_t, gsm, 128);                    // Q | K | V | dO | dQ-staging tiles, then lse*log2e [R], delta [R]
+  const uint32_t sQ = smem_u32(gsm), sK = sQ + R * P, sV = sK + R * P, sD = sV + R * P;
+  uint8_t* gO = gsm + 4 * R * P;
+  float* Ls = reinterpret_cast<float*>(gsm + 5 * R * P);
+  float* Ds = Ls + R;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const GroupSetsHD s = hd_group_sets(a, blockIdx.x);
+  const int nk = s.k_has0 + s.nk_patch;
+  const int nq_all = s.nq + s.k_has0;                 // space mode: the CLS query is row nq of the Q / dO tiles
+  const long long rs = 3LL * a.H * HD, ro = (long long)a.H * HD;
+  const bf16* qb = qkv + (long long)b * a.N * rs + (long long)h * HD;
+  const bf16* dob = dout + (long long)b * a.N * ro + (long long)h * HD;
+  const float* lse_b = lse + ((long long)b * a.H + h) * a.N;
+  const float* delta_b = delta + ((long long)b * a.H + h) * a.N;
+  bf16* dq_b = dqkv + (long long)b * a.N * rs + (long long)h * HD;
+  auto q_token = [&](int r) -> long long { return r < s.nq ? s.q_base + (long long)r * s.q_stride : 0; };   // r == nq: CLS query
+  for (int i = threadIdx.x; i < R * CH; i += NW * 32) {
+    const int r = i / CH, c = i - r * CH;
+    const bool okq = r < nq_all, okk = r < nk;
+    const long long qt = okq ? q_token(r) : 0;
+    const long long kt = (!okk || (s.k_has0 && r == 0)) ? 0 : s.k_base + (long long)(r - s.k_has0) * s.k_stride;
+    cp_async16(sQ + swzp<P>(r, c), qb + qt * rs + c * 8, okq);
+    cp_async16(sD + swzp<P>(r, c), dob + qt * ro + c * 8, okq);
+    cp_async16(sK + swzp<P>(r, c), qb + kt * rs + ro + c * 8, okk);
+    cp_async16(sV + swzp<P>(r, c), qb + kt * rs + 2 * ro + c * 8, okk);
+  }
+  cp_async_commit();
+  for (int r = threadIdx.x; r < R; r += NW * 32) {
+    const bool ok = r < nq_all;
+    const long long tok = ok ? q_token(r) : 0;
+    Ls[r] = ok ? lse_b[tok] * LOG2E : 0.f;
+    Ds[r] = ok ? delta_b[tok] : 0.f;
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  const float sl2 = a.scale * LOG2E;
+  const int row0 = warp * 16 + g, row1 = row0 + 8;
+  const int arow = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;     // this lane's ldmatrix row for A fragments
+  const bool own_q = warp * 16 < s.nq;       // this warp owns query rows
+  const bool own_k = warp * 16 < nk;         // ... and key rows
+
+  // ---------------- pass A: rows = this warp's queries, columns = keys in chunks of 32: dQ = scale * dS K
+  if (own_q) {
+    float dq[G::ND][4];
+#pragma unroll
+    for (int j = 0; j < G::ND; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
+    const float l0 = Ls[row0], l1 = Ls[row1], d0 = Ds[row0], d1 = Ds[row1];
+    const int k_lim = a.causal ? min(nk, warp * 16 + 16) : nk;
+#pragma unroll 1
+    for (int kc = 0; kc < k_lim; kc += 32) {
+      float sc[4][4], dp[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
+#pragma unroll
+      for (int kk = 0; kk < G::KS; ++kk) {
+        uint32_t qa[4], da[4];       // A fragments are re-read per chunk (2 ldmatrix) instead of living in registers
+        ldsm_x4(sQ + swzp<P>(arow, 2 * kk + (lane >> 4)), qa[0], qa[1], qa[2], qa[3]);
+        ldsm_x4(sD + swzp<P>(arow, 2 * kk + (lane >> 4)), da[0], da[1], da[2], da[3]);
+#pragma unroll
+        for (int j = 0; j < 4; j += 2) {
+          if (kc + 8 * j < k_lim) {
+            uint32_t b0, b1, c0, c1;
+            g_load_b_rows<HD>(sK, (kc >> 3) + j, kk, lane, b0, b1, c0, c1);
+            mma16816(sc[j], qa, b0, b1);
+            mma16816(sc[j + 1], qa, c0, c1);
+            g_load_b_rows<HD>(sV, (kc >> 3) + j, kk, lane, b0, b1, c0, c1);
+            mma16816(dp[j], da, b0, b1);
+            mma16816(dp[j + 1], da, c0, c1);
+          }
+        }
+      }
+      uint32_t dsa[2][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float ds[4];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int key = kc + 8 * j + 2 * t4 + e;
+          bool ok0 = key < nk && row0 < s.nq, ok1 = key < nk && row1 < s.nq;
+          if (a.causal) { ok0 = ok0 && key <= row0; ok1 = ok1 && key <= row1; }
+          const float p0 = ok0 ? exp2f(sc[j][e] * sl2 - l0) : 0.f;
+          const float p1 = ok1 ? exp2f(sc[j][2 + e] * sl2 - l1) : 0.f;
+          ds[e] = p0 * (dp[j][e] - d0);
+          ds[2 + e] = p1 * (dp[j][2 + e] - d1);
+        }
+        dsa[j >> 1][(j & 1) * 2] = pack_bf16x2(ds[0], ds[1]);
+        dsa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(ds[2], ds[3]);
+      }
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        if (kc + 16 * kk < k_lim) {
+#pragma unroll
+          for (int jd = 0; jd < G::ND; jd += 2) {
+            uint32_t b0, b1, c0, c1;
+            g_load_b_cols<HD>(sK, (kc >> 4) + kk, jd, lane, b0, b1, c0, c1);
+            mma16816(dq[jd], dsa[kk], b0, b1);
+            mma16816(dq[jd + 1], dsa[kk], c0, c1);
+          }
+        }
+      }
+    }
+    // dq of this warp's rows -> its private rows of the staging tile (frees the registers before pass B)
+#pragma unroll
+    for (int j = 0; j < G::ND; ++j) {
+      *reinterpret_cast<uint32_t*>(gO + swzp<P>(row0, j) + 4 * t4) = pack_bf16x2(dq[j][0] * a.scale, dq[j][1] * a.scale);
+      *reinterpret_cast<uint32_t*>(gO + swzp<P>(row1, j) + 4 * t4) = pack_bf16x2(dq[j][2] * a.scale, dq[j][3] * a.scale);
+    }
+  }
+  // ---------------- pass B: rows = this warp's keys, columns = queries (+ CLS query) in chunks of 32: dK = scale * dS^T Q ; dV = P^T dO
+  float dk[G::ND][4], dv[G::ND][4];
+#pragma unroll
+  for (int j = 0; j < G::ND; ++j) {
+    dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f;
+    dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f;
+  }
+  if (own_k) {
+    const int q_begin = a.causal ? (warp * 16) & ~31 : 0;      // queries before this warp's first key never see it
+#pragma unroll 1
+    for (int qc = q_begin; qc < nq_all; qc += 32) {
+      float sc[4][4], dp[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
+#pragma unroll
+      for (int kk = 0; kk < G::KS; ++kk) {
+        uint32_t ka[4], va[4];
+        ldsm_x4(sK + swzp<P>(arow, 2 * kk + (lane >> 4)), ka[0], ka[1], ka[2], ka[3]);
+        ldsm_x4(sV + swzp<P>(arow, 2 * kk + (lane >> 4)), va[0], va[1], va[2], va[3]);
+#pragma unroll
+        for (int j = 0; j < 4; j += 2) {
+          if (qc + 8 * j < nq_all) {
+            uint32_t b0, b1, c0, c1;
+            g_load_b_rows<HD>(sQ, (qc >> 3) + j, kk, lane, b0, b1, c0, c1);
+            mma16816(sc[j], ka, b0, b1);
+            mma16816(sc[j + 1], ka, c0, c1);
+            g_load_b_rows<HD>(sD, (qc >> 3) + j, kk, lane, b0, b1, c0, c1);
+            mma16816(dp[j], va, b0, b1);
+            mma16816(dp[j + 1], va, c0, c1);
+          }
+        }
+      }
+      uint32_t pa[2][4], dsa[2][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float p[4], ds[4];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int q = qc + 8 * j + 2 * t4 + e;
+          const bool okq = q < nq_all;
+          bool ok0 = okq && row0 < nk, ok1 = okq && row1 < nk;
+          if (a.causal) { ok0 = ok0 && q >= row0; ok1 = ok1 && q >= row1; }
+          const float lq = okq ? Ls[q] : 0.f, dq_ = okq ? Ds[q] : 0.f;
+          p[e] = ok0 ? exp2f(sc[j][e] * sl2 - lq) : 0.f;
+          p[2 + e] = ok1 ? exp2f(sc[j][2 + e] * sl2 - lq) : 0.f;
+          ds[e] = p[e] * (dp[j][e] - dq_);
+          ds[2 + e] = p[2 + e] * (dp[j][2 + e] - dq_);
+        }
+        pa[j >> 1][(j & 1) * 2] = pack_bf16x2(p[0], p[1]); pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p[2], p[3]);
+        dsa[j >> 1][(j & 1) * 2] = pack_bf16x2(ds[0], ds[1]); dsa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(ds[2], ds[3]);
+      }
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        if (qc + 16 * kk < nq_all) {
+#pragma unroll
+          for (int jd = 0; jd < G::ND; jd += 2) {
+            uint32_t b0, b1, c0, c1;
+            g_load_b_cols<HD>(sQ, (qc >> 4) + kk, jd, lane, b0, b1, c0, c1);
+            mma16816(dk[jd], dsa[kk], b0, b1);
+            mma16816(dk[jd + 1], dsa[kk], c0, c1);
+            g_load_b_cols<HD>(sD, (qc >> 4) + kk, jd, lane, b0, b1, c0, c1);
+            mma16816(dv[jd], pa[kk], b0, b1);
+            mma16816(dv[jd + 1], pa[kk], c0, c1);
+          }
+        }
+      }
+    }
+  }
+  // ---------------- outputs: every warp is done reading the tiles -> stage dk / dv in place of this warp's K / V rows
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < G::ND; ++j) {
+    *reinterpret_cast<uint32_t*>(gsm + R * P + swzp<P>(row0, j) + 4 * t4) = pack_bf16x2(dk[j][0] * a.scale, dk[j][1] * a.scale);
+    *reinterpret_cast<uint32_t*>(gsm + R * P + swzp<P>(row1, j) + 4 * t4) = pack_bf16x2(dk[j][2] * a.scale, dk[j][3] * a.scale);
+    *reinterpret_cast<uint32_t*>(gsm + 2 * R * P + swzp<P>(row0, j) + 4 * t4) = pack_bf16x2(dv[j][0], dv[j][1]);
+    *reinterpret_cast<uint32_t*>(gsm + 2 * R * P + swzp<P>(row1, j) + 4 * t4) = pack_bf16x2(dv[j][2], dv[j][3]);
+  }
+  __syncwarp();
+  for (int i = lane; i < 16 * CH; i += 32) {
+    const int rr = i / CH, c = i - rr * CH;
+    const int r = warp * 16 + rr;
+    if (r < s.nq)
+      *reinterpret_cast<uint4*>(dq_b + (s.q_base + (long long)r * s.q_stride) * rs + c * 8) = *reinterpret_cast<const uint4*>(gO + swzp<P>(r, c));
+    if (r < nk && !(s.k_has0 && r == 0)) {            // key 0 = CLS in space mode: written by the cls_only launch
+      const long long kt = s.k_base + (long long)(r - s.k_has0) * s.k_stride;
+      *reinterpret_cast<uint4*>(dq_b + kt * rs + ro + c * 8) = *reinterpret_cast<const uint4*>(gsm + R * P + swzp<P>(r, c));
+      *reinterpret_cast<uint4*>(dq_b + kt * rs + 2 * ro + c * 8) = *reinterpret_cast<const uint4*>(gsm + 2 * R * P + swzp<P>(r, c));
+    }
+  }
+}
+
+// number of warps a group-resident launch needs (0: not applicable -> streamed kernels); same rule as group_warps() in attention.cu
+__host__ __device__ inline int hd_group_warps(const AttnShape& a) {
+  if (a.mode == 2) return 0;
+  const int m = a.mode == 0 ? a.N : a.n + 1;           // space mode: the CLS key / (in backward) the CLS query is one extra row
+  const int nw = (m + 15) / 16;
+  return (nw >= 2 && nw <= 7) ? nw : 0;
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 #ifndef TVTS_HOST_SHIM
 int hd_check_shape(const AttnShape& a, int64_t d) {
@@ -454,8 +803,10 @@ int hd_check_shape(const AttnShape& a, int64_t d) {
   return TVTS_OK;
 }
 
+int g_hd_group = 1;      // 1: group-resident kernels where a group fits one CTA; 0: streamed kernels only (tvts_attn_hd_set_group)
+
 template <int HD>
-int hd_launch_fwd(const void* qkv, void* out, float* lse, const AttnShape& a, cudaStream_t st, const int* klen = nullptr) {
+int hd_streamed_fwd(const void* qkv, void* out, float* lse, const AttnShape& a, cudaStream_t st, const int* klen) {
   constexpr int smem_bytes = 5 * Geo<HD>::TILE;
   static bool set = false;
   if (!set) {
@@ -468,9 +819,43 @@ int hd_launch_fwd(const void* qkv, void* out, float* lse, const AttnShape& a, cu
   return TVTS_OK;
 }
 
+template <int HD, int NW>
+int hd_group_fwd(const void* qkv, void* out, float* lse, const AttnShape& a, cudaStream_t st) {
+  constexpr int smem_bytes = 3 * NW * 16 * Geo<HD>::PITCH;
+  static bool set = false;
+  if (!set) {
+    TVTS_CHECK_CUDA(cudaFuncSetAttribute(attn_hd_group_fwd_kernel<HD, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    set = true;
+  }
+  dim3 gg((unsigned)(a.mode == 0 ? 1 : a.T), (unsigned)a.H, (unsigned)a.B);
+  attn_hd_group_fwd_kernel<HD, NW><<<gg, NW * 32, smem_bytes, st>>>((const bf16*)qkv, (bf16*)out, lse, a);
+  TVTS_LAUNCH_CHECK();
+  return TVTS_OK;
+}
+
 template <int HD>
-int hd_launch_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv, const AttnShape& a,
-                  cudaStream_t st, const int* klen = nullptr) {
+int hd_launch_fwd(const void* qkv, void* out, float* lse, const AttnShape& a, cudaStream_t st, const int* klen = nullptr) {
+  const int gw = (klen == nullptr && g_hd_group) ? hd_group_warps(a) : 0;
+  if (!gw) return hd_streamed_fwd<HD>(qkv, out, lse, a, st, klen);
+  if (a.mode != 0) {                     // the CLS query over all tokens
+    AttnShape c = a;
+    c.cls_only = 1;
+    int rc = hd_streamed_fwd<HD>(qkv, out, lse, c, st, nullptr);
+    if (rc) return rc;
+  }
+  switch (gw) {
+    case 2: return hd_group_fwd<HD, 2>(qkv, out, lse, a, st);
+    case 3: return hd_group_fwd<HD, 3>(qkv, out, lse, a, st);
+    case 4: return hd_group_fwd<HD, 4>(qkv, out, lse, a, st);
+    case 5: return hd_group_fwd<HD, 5>(qkv, out, lse, a, st);
+    case 6: return hd_group_fwd<HD, 6>(qkv, out, lse, a, st);
+    default: return hd_group_fwd<HD, 7>(qkv, out, lse, a, st);
+  }
+}
+
+template <int HD>
+int hd_streamed_bwd(const void* qkv, const void* dout, const float* lse, const float* delta_ws, void* dqkv, const AttnShape& a,
+                    cudaStream_t st, const int* klen) {
   constexpr int smem_bytes = 4 * Geo<HD>::TILE + 2 * 2 * BN * 4;
   static bool set = false;
   if (!set) {
@@ -478,9 +863,6 @@ int hd_launch_bwd(const void* qkv, const void* out, const void* dout, const floa
     TVTS_CHECK_CUDA(cudaFuncSetAttribute(attn_hd_bwd_kernel<HD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     set = true;
   }
-  const long long rows = (long long)a.B * a.N * a.H;
-  attn_hd_delta_kernel<HD><<<(unsigned)((rows + 31) / 32), 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta_ws, a.B, a.N, a.H);
-  TVTS_LAUNCH_CHECK();
   dim3 g0(num_blocks_x(a, false), (unsigned)a.H, (unsigned)a.B);
   attn_hd_bwd_kernel<HD, 0><<<g0, kThreads, smem_bytes, st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, a, klen);
   TVTS_LAUNCH_CHECK();
@@ -490,11 +872,54 @@ int hd_launch_bwd(const void* qkv, const void* out, const void* dout, const floa
   return TVTS_OK;
 }
 
+template <int HD, int NW>
+int hd_group_bwd(const void* qkv, const void* dout, const float* lse, const float* delta_ws, void* dqkv, const AttnShape& a, cudaStream_t st) {
+  constexpr int smem_bytes = 5 * NW * 16 * Geo<HD>::PITCH + 2 * NW * 16 * 4;
+  static bool set = false;
+  if (!set) {
+    TVTS_CHECK_CUDA(cudaFuncSetAttribute(attn_hd_group_bwd_kernel<HD, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    set = true;
+  }
+  dim3 gg((unsigned)(a.mode == 0 ? 1 : a.T), (unsigned)a.H, (unsigned)a.B);
+  attn_hd_group_bwd_kernel<HD, NW><<<gg, NW * 32, smem_bytes, st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, a);
+  TVTS_LAUNCH_CHECK();
+  return TVTS_OK;
+}
+
+template <int HD>
+int hd_launch_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv, const AttnShape& a,
+                  cudaStream_t st, const int* klen = nullptr) {
+  const long long rows = (long long)a.B * a.N * a.H;
+  attn_hd_delta_kernel<HD><<<(unsigned)((rows + 31) / 32), 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta_ws, a.B, a.N, a.H);
+  TVTS_LAUNCH_CHECK();
+  const int gw = (klen == nullptr && g_hd_group) ? hd_group_warps(a) : 0;
+  if (!gw) return hd_streamed_bwd<HD>(qkv, dout, lse, delta_ws, dqkv, a, st, klen);
+  if (a.mode != 0) {                     // dq of the CLS query, dk / dv of the CLS key
+    AttnShape c = a;
+    c.cls_only = 1;
+    int rc = hd_streamed_bwd<HD>(qkv, dout, lse, delta_ws, dqkv, c, st, nullptr);
+    if (rc) return rc;
+  }
+  switch (gw) {
+    case 2: return hd_group_bwd<HD, 2>(qkv, dout, lse, delta_ws, dqkv, a, st);
+    case 3: return hd_group_bwd<HD, 3>(qkv, dout, lse, delta_ws, dqkv, a, st);
+    case 4: return hd_group_bwd<HD, 4>(qkv, dout, lse, delta_ws, dqkv, a, st);
+    case 5: return hd_group_bwd<HD, 5>(qkv, dout, lse, delta_ws, dqkv, a, st);
+    case 6: return hd_group_bwd<HD, 6>(qkv, dout, lse, delta_ws, dqkv, a, st);
+    default: return hd_group_bwd<HD, 7>(qkv, dout, lse, delta_ws, dqkv, a, st);
+  }
+}
+
 #endif  // !TVTS_HOST_SHIM
 
 }  // namespace
 
 #ifndef TVTS_HOST_SHIM
+extern "C" int tvts_attn_hd_set_group(int on) {
+  g_hd_group = on;
+  return TVTS_OK;
+}
+
 extern "C" int tvts_attn_generic_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode,
                                      int64_t T, int64_t n, int64_t causal, float scale, void* stream) {
   AttnShape a{(int)B, (int)N, (int)H, (int)mode, (int)T, (int)n, (int)causal, scale, 0, 0, 0};
