@@ -149,13 +149,22 @@ ATTN_HOST_CASES = [
     (1, 2, 1, 2, 20, 41, False, 80, False),     # space, 21 rows: 2 warps
     (2, 2, 0, 0, 0, 40, False, 80, False),      # short full-attention sequence: group-resident in mode 0
     (1, 2, 0, 0, 0, 112, True, 64, False),      # largest group (7 warps), causal
+    (1, 2, 2, 12, 76, 913, False, 80, False),   # time attention at the shipped H/14 clip length (3 frames x 4 clips): warp-per-slot kernels
+    (1, 2, 2, 15, 6, 91, False, 80, False),     # the largest T the warp-per-slot kernels take
+    (2, 1, 2, 8, 5, 41, False, 64, False),
 ]
 
 
 @pytest.mark.parametrize("group", [1, 0])
 @pytest.mark.parametrize("B,H,mode,T,n,N,causal,d,padded", ATTN_HOST_CASES)
 def test_generic_attention_kernels_on_the_cpu_simt_stand_in(hattn, B, H, mode, T, n, N, causal, d, padded, group):
-    fits = (not padded) and mode != 2 and 2 <= ((N if mode == 0 else n + 1) + 15) // 16 <= 7
+    # kernel selection of hd_launch_fwd / hd_launch_bwd: 0 streamed, 1 group-resident (+ CLS launch), 2 time kernels (+ CLS launch)
+    fits = 0
+    if not padded:
+        if mode == 2:
+            fits = 2 if T <= 15 else 0
+        elif 2 <= ((N if mode == 0 else n + 1) + 15) // 16 <= 7:
+            fits = 1
     if not group and not fits:
         pytest.skip("the streamed kernels are what runs in both settings")
     torch.manual_seed(N + mode + d)
@@ -172,7 +181,7 @@ def test_generic_attention_kernels_on_the_cpu_simt_stand_in(hattn, B, H, mode, T
     lse = torch.full((B, H, N), float("nan"))
     used = hattn.h_attn_fwd(P(qkv), P(out), P(lse), kp, I(B), I(N), I(H), I(d), I(mode), I(T), I(n), I(int(causal)), ctypes.c_float(scale),
                             ctypes.c_int(group))
-    assert used == int(bool(group) and fits)      # 1: the group-resident kernels ran (same selection rule as hd_launch_fwd)
+    assert used == (fits if group else 0)
     ro, rl = torch.empty_like(out), torch.empty_like(lse)
     if padded:
         emu.attn_padded_fwd(qkv, ro, rl, klen, B, N, H, d, scale)

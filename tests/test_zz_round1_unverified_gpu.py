@@ -74,6 +74,8 @@ GENERIC_ATTN_CASES = [
     (3, 2, 0, 0, 0, 130, True),     # causal across tiles
     (1, 2, 1, 2, 100, 201, False),  # space, 101 rows per group (7 warps)
     (2, 2, 0, 0, 0, 40, False),     # short full-attention sequence (group-resident in mode 0)
+    (1, 2, 2, 12, 76, 913, False),  # time attention at the shipped H/14 clip length: warp-per-slot kernels
+    (1, 2, 2, 15, 6, 91, False),    # the largest T the warp-per-slot kernels take
 ]
 
 
