@@ -27,3 +27,8 @@ timeout 900 python bench.py --workload c4 --steps 5 --warmup 3 --no-cpu-baseline
 tail -3 $O/*.log $O/*.json
 timeout 600 python tools/bench_v1.py --steps 5 --warmup 3 > $O/bench_v1_c5.json 2> $O/bench_v1_c5.err
 tail -2 $O/bench_v1_c5.json $O/bench_v1_c5.err
+# 5. launch lists (cold-cache, serialised: shares only) of the H/14 step and of the trimmed-text c3 step
+timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file $O/c4_launches.csv python bench.py --workload c4 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-graph > $O/c4_ncu.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $O/c3_trim_launches.csv python bench.py --trim-text --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-graph > $O/c3_trim_ncu.log 2>&1
+python tools/launch_summary.py $O/c4_launches.csv > $O/c4_launch_summary.txt 2>&1
+python tools/launch_summary.py $O/c3_trim_launches.csv > $O/c3_trim_launch_summary.txt 2>&1
