@@ -334,7 +334,11 @@ def run_ours(args):
                        "step": "fwd+bwd" + ("+grad_allreduce" if world > 1 else "") + ("" if args.no_optimizer else "+adamw"),
                        "launch": "one CUDA graph per step" if use_graph else "kernel-by-kernel from Python",
                        "parallelism": f"dp{world}", "l2": "per-step inputs (154 MB video) and activations (>10 GB) exceed the 126 MB L2",
-                       "numerics": "bf16 GEMM operands, fp32 accumulate/residual/LN/softmax/loss, fp32 master weights"},
+                       "numerics": f"{_lib.OPERAND} GEMM operands, fp32 accumulate/residual/LN/softmax/loss, fp32 master weights"
+                                   + (f", backward under loss scale {_lib.DEFAULT_LOSS_SCALE:g}" if _lib.DEFAULT_LOSS_SCALE != 1.0 else ""),
+                       "input": ("uint8 clips, normalised inside the patch-gather kernel" if args.u8_input else "fp32 normalised clips")
+                                + (f"; token matrix trimmed to the batch's longest caption ({host['text'].shape[1]} of {cfg.context} columns; exact for the causal text tower)"
+                                   if args.trim_text else "")},
             "clocks": clocks, "gpu_launches": launches, "loss": loss,
             "step_model_tflops": flops_pair * batch / (ms_step / 1e3) / 1e12,
             "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05)", "achieved": achieved, "peak": pk["bf16_sustained"],
