@@ -30,3 +30,17 @@ def test_flop_model_reproduces_survey_table():
         tol = 0.15 if a < 1000 else 1.0
         assert abs(bench.algorithmic_flops_per_pair(cfg, T, 1) / 1e9 - a) < tol, name
         assert abs(bench.algorithmic_flops_per_pair(cfg, T, 4) / 1e9 - b) < tol, name
+
+
+def test_bench_control_flow_dry_run():
+    """bench.run_ours end to end on the CPU (torch restatements for the kernels, stand-ins for torch.cuda's device / stream / event / graph
+    objects; tests/bench_dryrun.py, own process because it patches torch globally): every key of the contract is on the JSON line, the
+    CUDA-graph path is the default, and the uint8 / trimmed-text input options shrink the per-step host->device bytes."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "bench_dryrun.py")], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [json.loads(l[len("DRYRUN "):]) for l in r.stdout.splitlines() if l.startswith("DRYRUN ")]
+    assert len(lines) == 2 and all(not l["missing"] for l in lines)
+    assert lines[0]["launch"].startswith("one CUDA graph") and lines[0]["dtype"] in ("bf16", "fp16") and lines[0]["value"] > 0
+    assert lines[1]["h2d"] < lines[0]["h2d"] / 3 and "uint8" in lines[1]["input"] and "trimmed" in lines[1]["input"]

@@ -95,4 +95,6 @@ WORKLOADS = {
     "c3": Workload("c3", TVTSV2_B_16, batch=32, frames=8),
     # BASELINE.json configs[3]: H/14, 16 frames (the temporal table is built with num_frames=16); per-GPU batch 8
     "c4": Workload("c4", TVTSV2_H_14.small(num_frames=16), batch=8, frames=16),
+    # not a BASELINE config: the toy model, for dry runs of the bench script (tests/bench_dryrun.py)
+    "tiny": Workload("tiny", TINY_B_MASK, batch=2, frames=3),
 }
