@@ -50,7 +50,16 @@ torch.cuda.graph = graph_ctx
 torch.device = lambda *a, **k: real_device("cpu")
 torch.Tensor.pin_memory = lambda self, *a, **k: self
 lib = _lib.lib()
+import torch.distributed as dist
+_real_init = dist.init_process_group
+dist.init_process_group = lambda backend=None, **k: _real_init("gloo")      # multi-rank dry run (torchrun): gloo in place of nccl
 import bench
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    # multi-rank dry run (launched by torchrun): one configuration, printed straight to stdout -- run_ours leaves through the barrier +
+    # os._exit(0) path that replaced destroy_process_group after round 1's teardown hangs, so nothing after this call executes
+    sys.argv = ["bench.py", "--gpus", os.environ["WORLD_SIZE"], "--workload", "tiny", "--steps", "2", "--warmup", "1", "--no-cpu-baseline"]
+    bench.run_ours(bench.parse())
+    raise SystemExit("run_ours returned in a multi-rank run (expected os._exit(0))")
 for extra in ([], ["--u8-input", "--trim-text"]) + ((["--no-graph"],) if "--all" in sys.argv[1:] else ()):
     sys.argv = ["bench.py", "--workload", "tiny", "--steps", "2", "--warmup", "1", "--no-cpu-baseline"] + extra
     buf = io.StringIO()

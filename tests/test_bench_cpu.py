@@ -44,3 +44,17 @@ def test_bench_control_flow_dry_run():
     assert len(lines) == 2 and all(not l["missing"] for l in lines)
     assert lines[0]["launch"].startswith("one CUDA graph") and lines[0]["dtype"] in ("bf16", "fp16") and lines[0]["value"] > 0
     assert lines[1]["h2d"] < lines[0]["h2d"] / 3 and "uint8" in lines[1]["input"] and "trimmed" in lines[1]["input"]
+
+
+def test_bench_two_rank_dry_run_prints_one_line_and_exits_cleanly():
+    """The multi-rank path of bench.py under torchrun (2 gloo ranks, same stand-ins): rank 0 prints ONE JSON line with the aggregate
+    value, and every rank leaves through the barrier + os._exit(0) path (no destroy_process_group: round 1's NCCL teardown hang)."""
+    import json
+    import subprocess
+    port = 29700 + (os.getpid() % 200)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(ROOT, "tests", "bench_dryrun.py")], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1 and lines[0]["n_gpus"] == 2 and lines[0]["config"]["parallelism"] == "dp2" and lines[0]["value"] > 0
+    assert "grad_allreduce" in lines[0]["config"]["step"]
