@@ -2,7 +2,8 @@
 CPU oracle (reference algorithm in fp32 + the restated transformers.AdamW) from the same initial weights on the same synthetic
 batches.  Prints the per-step losses of both and the maximum deviation.   usage: python tools/loss_parity.py [steps] [workload]
 
-workloads: c1 = BASELINE.json configs[0] (TVTSv2 ViT-B/32, 2 frames, 4 pairs, n_trans 4);  tiny = the test-suite toy model."""
+workloads: c1 = BASELINE.json configs[0] (TVTSv2 ViT-B/32, 2 frames, 4 pairs, n_trans 4);  tiny = the test-suite toy model;
+tiny_h = the H/14-shaped toy model (width 640, head dim 80, 14x14 patches).   TVTS_OPERAND=fp16 selects the IEEE-half build."""
 import os
 import sys
 import time
@@ -38,12 +39,14 @@ def oracle_run(cfg, sd0, groups_by_name, batches, frozen):
 def run(steps=100, workload="c1", lr_scale=1.0, use_graph=True, verbose=True):
     if workload == "c1":
         cfg, batch, frames = C.TVTSV2_B_32, 4, 2
+    elif workload == "tiny_h":
+        cfg, batch, frames = C.TINY_H640, 2, 3
     else:
         cfg, batch, frames = C.TINY_B_MASK, 2, 3
     torch.set_num_threads(os.cpu_count() or 1)
     sd0 = make_state_dict(cfg, seed=1234)
     batches = [make_batch(cfg, batch, frames, n_trans=4, seed=100 + i) for i in range(steps)]
-    m = M.TVTSv2Base(types.SimpleNamespace(local_rank=0), arch=cfg)
+    m = (M.TVTSv2_H_14 if cfg.post_mode == "h14" else M.TVTSv2Base)(types.SimpleNamespace(local_rank=0), arch=cfg)
     m.load_state_dict(sd0, strict=True)
     m = m.cuda()
     opt = optim.build_reference_optimizer(m)
