@@ -331,7 +331,8 @@ def run_ours(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": _lib.OPERAND,
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {cfg.name} T={frames} batch {batch}/GPU n_trans={n_trans} (global batch {world * batch})",
-                       "step": "fwd+bwd" + ("+grad_allreduce" if world > 1 else "") + ("" if args.no_optimizer else "+adamw"),
+                       "step": "fwd+bwd" + (("+grad_allreduce" + ("(overlapped with the text-tower backward)" if step.overlap else "")) if world > 1 else "")
+                               + ("" if args.no_optimizer else "+adamw"),
                        "launch": "one CUDA graph per step" if use_graph else "kernel-by-kernel from Python",
                        "parallelism": f"dp{world}", "l2": "per-step inputs (154 MB video) and activations (>10 GB) exceed the 126 MB L2",
                        "numerics": f"{_lib.OPERAND} GEMM operands, fp32 accumulate/residual/LN/softmax/loss, fp32 master weights"

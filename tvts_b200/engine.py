@@ -572,6 +572,10 @@ def video_backward(P, saved, d_vtok, cfg):
                    b_mn=True, accumulate=True)
 
 
+# set by trainer.TrainStep (opt-in all-reduce overlap): called once when the video tower's backward has written its last gradient
+AFTER_VIDEO_BACKWARD = None
+
+
 class _VideoTowerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg, names, video, keep_ind, *params):
@@ -585,7 +589,10 @@ class _VideoTowerFn(torch.autograd.Function):
         P = ParamView(ctx.names, ctx.params, ctx.needs_input_grad[4:])
         video_backward(P, ctx.saved, d_vtok, ctx.cfg)
         ctx.saved = None
-        return (None, None, None, None) + P.grad_tuple()
+        grads = (None, None, None, None) + P.grad_tuple()
+        if AFTER_VIDEO_BACKWARD is not None:
+            AFTER_VIDEO_BACKWARD()
+        return grads
 
 
 def video_tower(cfg, named_params, video, keep_ind):

@@ -85,6 +85,36 @@ def average_flat(fs):
     return fs.g.numel() * 4
 
 
+def _average_tensor(t):
+    if dist.get_backend() == "nccl":
+        dist.all_reduce(t, op=dist.ReduceOp.AVG)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t.mul_(1.0 / _world())
+
+
+def arena_ranges(fs, late):
+    """Split the gradient arena into maximal contiguous runs of tensors: -> (early, late) lists of (start, end) element offsets, `late[i]`
+    telling whether parameter i's gradient becomes final late in the backward (the text tower, whose backward runs last)."""
+    early_r, late_r = [], []
+    for i, p in enumerate(fs.params):
+        start = fs.offsets[i]
+        end = fs.offsets[i + 1] if i + 1 < len(fs.params) else fs.total
+        dst = late_r if late[i] else early_r
+        if dst and dst[-1][1] == start:
+            dst[-1] = (dst[-1][0], end)
+        else:
+            dst.append((start, end))
+    return early_r, late_r
+
+
+def average_ranges(fs, ranges):
+    if _world() == 1:
+        return
+    for a, b in ranges:
+        _average_tensor(fs.g[a:b])
+
+
 def average_gradients(params):
     """DDP semantics on explicit buffers: all-reduce(sum)/W of every parameter that has a gradient on this rank.
     All ranks run the same graph on the hot path (same n_trans per step), so the set of parameters with gradients is
@@ -160,6 +190,13 @@ class TrainStep:
         self.use_graph = use_graph
         from . import _lib as L
         self.loss_scale = L.DEFAULT_LOSS_SCALE     # 1 for bf16 operands; fp16 operands: static scale, undone inside the AdamW kernel
+        # opt-in (TVTS_OVERLAP_ALLREDUCE=1): the gradient ranges of everything but the text tower are all-reduced on a side stream as soon
+        # as the video tower's backward has finished (the sort head's finishes before it), i.e. under the text tower's backward, which
+        # autograd runs last; the text ranges follow at the end.  Same sums, same result; default off until measured on NVLink.
+        import os
+        self.overlap = os.environ.get("TVTS_OVERLAP_ALLREDUCE", "0") == "1"
+        self._ranges = None
+        self._comm_stream = None
         self._graphs = {}
         self.launches_per_graph = 0
         self._copy_stream = None
@@ -181,6 +218,9 @@ class TrainStep:
         else:
             for p in self.params:                   # optimizer.zero_grad() (torch 2.x: set_to_none)
                 p.grad = None
+        overlapped = self.overlap and flat is not None and _world() > 1
+        if overlapped:
+            self._arm_early_allreduce(flat)
         text_embeds, video_embeds, pred_order = self.model(data)
         video_all, text_all = gather_embeddings(video_embeds, text_embeds)
         output = M.sim_matrix(video_all, text_all)                      # rows videos, cols texts (trainer.py:484)
@@ -194,7 +234,16 @@ class TrainStep:
         if self.loss_scale != 1.0:
             total = total * self.loss_scale                             # fp16 operands only: keeps 16-bit gradient operands in range
         total.backward()
-        if flat is not None:
+        if overlapped:
+            fired = E.AFTER_VIDEO_BACKWARD is None       # the hook disarms itself when it runs
+            E.AFTER_VIDEO_BACKWARD = None
+            if not fired:                                # no video backward this step (cannot happen on the hot path): do it all here
+                average_flat(flat)
+            else:
+                average_ranges(flat, self._ranges[1])    # the text tower's ranges
+                if self._comm_stream is not None:
+                    torch.cuda.current_stream().wait_stream(self._comm_stream)
+        elif flat is not None:
             average_flat(flat)
         else:
             average_gradients(self.params)
@@ -209,6 +258,26 @@ class TrainStep:
             else:
                 self.optimizer.step()
         return loss1.detach(), loss2.detach()
+
+    def _arm_early_allreduce(self, flat):
+        if self._ranges is None:
+            names = {id(p): n for n, p in self.model.named_parameters()}
+            late = [names.get(id(p), "").startswith("text_") for p in flat.params]
+            self._ranges = arena_ranges(flat, late)
+            if self.device.type == "cuda":
+                self._comm_stream = torch.cuda.Stream(device=self.device)
+        early = self._ranges[0]
+        side = self._comm_stream
+
+        def hook():
+            E.AFTER_VIDEO_BACKWARD = None
+            if side is None:
+                average_ranges(flat, early)
+                return
+            side.wait_stream(torch.cuda.current_stream())       # the video / sort-head gradients are complete on the main stream
+            with torch.cuda.stream(side):
+                average_ranges(flat, early)
+        E.AFTER_VIDEO_BACKWARD = hook
 
     def _capture(self, key, data):
         from . import _lib as L
