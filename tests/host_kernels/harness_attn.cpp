@@ -29,17 +29,19 @@ void group_bwd(const void* qkv, const void* dout, const float* lse, const float*
                [&] { attn_hd_group_bwd_kernel<HD, NW>((const bf16*)qkv, (const bf16*)dout, lse, delta, (bf16*)dqkv, a); });
 }
 
-// same kernel selection as hd_launch_fwd / hd_launch_bwd; returns 0 streamed, 1 group-resident (+ CLS launch), 2 time kernels (+ CLS launch)
+// same kernel selection as hd_launch_fwd / hd_launch_bwd; returns 0 streamed, 1 group-resident (+ CLS launch), 2 / 3 time kernels with 1 / 2 row tiles per slot (+ CLS launch)
 template <int HD>
 int fwd(const void* qkv, void* out, float* lse, const int* klen, AttnShape a, int group) {
   const int gw = (klen == nullptr && group) ? hd_group_warps(a) : 0;
-  const bool time_k = klen == nullptr && group && hd_use_time_kernels(a);
+  const int time_k = (klen == nullptr && group) ? hd_time_tiles(a) : 0;
   if (!gw && !time_k) { streamed_fwd<HD>(qkv, out, lse, klen, a); return 0; }
   if (a.mode != 0) { AttnShape c = a; c.cls_only = 1; streamed_fwd<HD>(qkv, out, lse, nullptr, c); }
   if (time_k) {
-    simt::launch((unsigned)((a.n + HD_TW - 1) / HD_TW), (unsigned)a.H, (unsigned)a.B, HD_TW * 32,
-                 [&] { attn_hd_time_fwd_kernel<HD>((const bf16*)qkv, (bf16*)out, lse, a); });
-    return 2;
+    simt::launch((unsigned)((a.n + HD_TW - 1) / HD_TW), (unsigned)a.H, (unsigned)a.B, HD_TW * 32, [&] {
+      if (time_k == 1) attn_hd_time_fwd_kernel<HD, 1>((const bf16*)qkv, (bf16*)out, lse, a);
+      else attn_hd_time_fwd_kernel<HD, 2>((const bf16*)qkv, (bf16*)out, lse, a);
+    });
+    return 1 + time_k;
   }
   switch (gw) {
     case 2: group_fwd<HD, 2>(qkv, out, lse, a); break;
@@ -57,13 +59,15 @@ int bwd(const void* qkv, const void* out, const void* dout, const float* lse, fl
   simt::launch((unsigned)((rows + 31) / 32), 1, 1, 256,
                [&] { attn_hd_delta_kernel<HD>((const bf16*)out, (const bf16*)dout, delta, a.B, a.N, a.H); });
   const int gw = (klen == nullptr && group) ? hd_group_warps(a) : 0;
-  const bool time_k = klen == nullptr && group && hd_use_time_kernels(a);
+  const int time_k = (klen == nullptr && group) ? hd_time_tiles(a) : 0;
   if (!gw && !time_k) { streamed_bwd<HD>(qkv, dout, lse, delta, dqkv, klen, a); return 0; }
   if (a.mode != 0) { AttnShape c = a; c.cls_only = 1; streamed_bwd<HD>(qkv, dout, lse, delta, dqkv, nullptr, c); }
   if (time_k) {
-    simt::launch((unsigned)((a.n + HD_TW - 1) / HD_TW), (unsigned)a.H, (unsigned)a.B, HD_TW * 32,
-                 [&] { attn_hd_time_bwd_kernel<HD>((const bf16*)qkv, (const bf16*)dout, lse, delta, (bf16*)dqkv, a); });
-    return 2;
+    simt::launch((unsigned)((a.n + HD_TW - 1) / HD_TW), (unsigned)a.H, (unsigned)a.B, HD_TW * 32, [&] {
+      if (time_k == 1) attn_hd_time_bwd_kernel<HD, 1>((const bf16*)qkv, (const bf16*)dout, lse, delta, (bf16*)dqkv, a);
+      else attn_hd_time_bwd_kernel<HD, 2>((const bf16*)qkv, (const bf16*)dout, lse, delta, (bf16*)dqkv, a);
+    });
+    return 1 + time_k;
   }
   switch (gw) {
     case 2: group_bwd<HD, 2>(qkv, dout, lse, delta, dqkv, a); break;

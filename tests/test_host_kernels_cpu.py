@@ -152,17 +152,22 @@ ATTN_HOST_CASES = [
     (1, 2, 2, 12, 76, 913, False, 80, False),   # time attention at the shipped H/14 clip length (3 frames x 4 clips): warp-per-slot kernels
     (1, 2, 2, 15, 6, 91, False, 80, False),     # the largest T the warp-per-slot kernels take
     (2, 1, 2, 8, 5, 41, False, 64, False),
+    (1, 1, 2, 16, 76, 1217, False, 80, False),  # time attention of c4 (16 frames): two row tiles per slot
+    (1, 2, 2, 31, 2, 63, False, 80, False),     # the largest T of the two-tile kernels
+    (1, 2, 2, 32, 2, 65, False, 80, False),     # beyond it: streamed
+    (2, 1, 2, 17, 5, 86, False, 64, False),
 ]
 
 
 @pytest.mark.parametrize("group", [1, 0])
 @pytest.mark.parametrize("B,H,mode,T,n,N,causal,d,padded", ATTN_HOST_CASES)
 def test_generic_attention_kernels_on_the_cpu_simt_stand_in(hattn, B, H, mode, T, n, N, causal, d, padded, group):
-    # kernel selection of hd_launch_fwd / hd_launch_bwd: 0 streamed, 1 group-resident (+ CLS launch), 2 time kernels (+ CLS launch)
+    # kernel selection of hd_launch_fwd / hd_launch_bwd: 0 streamed, 1 group-resident (+ CLS launch), 2 / 3 warp-per-slot time kernels
+    # with 1 / 2 row tiles per slot (+ CLS launch)
     fits = 0
     if not padded:
         if mode == 2:
-            fits = 2 if T <= 15 else 0
+            fits = 2 if T <= 15 else (3 if T <= 31 else 0)
         elif 2 <= ((N if mode == 0 else n + 1) + 15) // 16 <= 7:
             fits = 1
     if not group and not fits:

@@ -75,7 +75,10 @@ GENERIC_ATTN_CASES = [
     (1, 2, 1, 2, 100, 201, False),  # space, 101 rows per group (7 warps)
     (2, 2, 0, 0, 0, 40, False),     # short full-attention sequence (group-resident in mode 0)
     (1, 2, 2, 12, 76, 913, False),  # time attention at the shipped H/14 clip length: warp-per-slot kernels
-    (1, 2, 2, 15, 6, 91, False),    # the largest T the warp-per-slot kernels take
+    (1, 2, 2, 15, 6, 91, False),    # the largest T of the one-tile warp-per-slot kernels
+    (1, 2, 2, 16, 76, 1217, False),  # time attention of c4 (16 frames): two row tiles per slot
+    (1, 2, 2, 31, 2, 63, False),    # the largest T of the two-tile kernels
+    (1, 2, 2, 32, 2, 65, False),    # beyond it: streamed (strided groups)
 ]
 
 

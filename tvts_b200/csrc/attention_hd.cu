@@ -783,20 +783,20 @@ __global__ void __launch_bounds__(NW * 32) attn_hd_group_bwd_kernel(const bf16* 
 
 
 // ================================================================================================ time mode: warp per slot
-// One warp owns (batch b, head h, slot j): queries = tokens 1 + f*n + j (f < T <= 15), keys = [CLS ; the same T tokens] (T + 1 <= 16: one
-// 16x16 score tile).  Same algorithm as attn_time_fwd/bwd_kernel in attention.cu on rows of pitch Geo<HD>::PITCH; per-warp shared memory
-//   forward : Q [16] | K [16] | V [16]            backward: Q [16] | K [16] | V [16] | dO [16]
+// One warp owns (batch b, head h, slot j): queries = tokens 1 + f*n + j (f < T), keys = [CLS ; the same T tokens].  The slot's rows fill
+// MT 16-row MMA tiles (MT = 1: T <= 15, the shipped 12-frame clips -- same algorithm as attn_time_fwd/bwd_kernel in attention.cu;
+// MT = 2: T <= 31, the 16-frame clips of BASELINE.json configs[3]).  Per-warp shared memory, rows of pitch Geo<HD>::PITCH, R = 16*MT:
+//   forward : Q [R] | K [R] | V [R]            backward: Q [R] | K [R] | V [R] | dO [R]
 // In backward, row T of the Q / dO tiles holds the CLS query (one more column of the transposed pass that produces dK / dV); its own dq
 // and the CLS key's dk / dv come from the cls_only streamed launch.
 constexpr int HD_TW = 4;            // warps (slots) per CTA
-constexpr int HD_T_MAX = 15;
 
-template <int HD, bool BWD>
+template <int HD, int MT, bool BWD>
 __device__ __forceinline__ void hd_time_load(uint32_t base, const bf16* qb, const bf16* dob, long long rs, long long ro, int T, int n, int slot,
                                              int lane) {
-  constexpr int P = Geo<HD>::PITCH, CH = Geo<HD>::CH;
+  constexpr int P = Geo<HD>::PITCH, CH = Geo<HD>::CH, R = 16 * MT;
   const bf16* cls = qb;                                        // token 0
-  for (int i = lane; i < 16 * CH; i += 32) {
+  for (int i = lane; i < R * CH; i += 32) {
     const int rr = i / CH, c = i - rr * CH;
     const uint32_t so = swzp<P>(rr, c);                        // block bases are multiples of 8 rows: same swizzle in every block
     const bool okq = rr < T, okc = BWD && rr == T, okk = rr <= T;
@@ -804,17 +804,17 @@ __device__ __forceinline__ void hd_time_load(uint32_t base, const bf16* qb, cons
     const bf16* pk = qb + (1LL + slot + (long long)(rr - 1) * n) * rs + ro + c * 8;  // key-side row rr >= 1: token 1 + (rr-1)*n + slot
     // (rows that are not loaded are zero-filled; they are still given a valid address)
     cp_async16(base + so, okq ? pq : cls + c * 8, okq || okc);                                               // Q  (row T: the CLS query, backward)
-    cp_async16(base + 16 * P + so, (rr == 0 || !okk) ? cls + ro + c * 8 : pk, okk);                          // K  (row 0: the CLS key)
-    cp_async16(base + 32 * P + so, (rr == 0 || !okk) ? cls + 2 * ro + c * 8 : pk + ro, okk);                 // V
-    if (BWD) cp_async16(base + 48 * P + so, okq ? dob + (1LL + slot + (long long)rr * n) * ro + c * 8 : dob + c * 8, okq || okc);   // dO
+    cp_async16(base + R * P + so, (rr == 0 || !okk) ? cls + ro + c * 8 : pk, okk);                           // K  (row 0: the CLS key)
+    cp_async16(base + 2 * R * P + so, (rr == 0 || !okk) ? cls + 2 * ro + c * 8 : pk + ro, okk);              // V
+    if (BWD) cp_async16(base + 3 * R * P + so, okq ? dob + (1LL + slot + (long long)rr * n) * ro + c * 8 : dob + c * 8, okq || okc);   // dO
   }
 }
 
-template <int HD>
+template <int HD, int MT>
 __global__ void __launch_bounds__(HD_TW * 32) attn_hd_time_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
                                                                       float* __restrict__ lse, AttnShape a) {
   using G = Geo<HD>;
-  constexpr int P = G::PITCH, CH = G::CH, ROWS = 48;
+  constexpr int P = G::PITCH, CH = G::CH, R = 16 * MT, ROWS = 3 * R;
   TVTS_DYN_SMEM(uint8_t, smem, 128);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
@@ -824,93 +824,105 @@ __global__ void __launch_bounds__(HD_TW * 32) attn_hd_time_fwd_kernel(const bf16
   const long long rs = 3LL * a.H * HD, ro = (long long)a.H * HD;
   const bf16* qb = qkv + (long long)b * a.N * rs + (long long)h * HD;
   const uint32_t base = smem_u32(smem) + warp * ROWS * P;
-  hd_time_load<HD, false>(base, qb, nullptr, rs, ro, a.T, a.n, slot, lane);
+  hd_time_load<HD, MT, false>(base, qb, nullptr, rs, ro, a.T, a.n, slot, lane);
   cp_async_commit();
   cp_async_wait<0>();
   __syncwarp();
-  const uint32_t sQ = base, sK = base + 16 * P, sV = base + 32 * P;
+  const uint32_t sQ = base, sK = base + R * P, sV = base + 2 * R * P;
   const int nk = a.T + 1;
-  uint32_t qa[G::KS][4];
-  g_load_a<HD>(sQ, 0, lane, qa);
-  float sc[2][4];
-#pragma unroll
-  for (int j = 0; j < 2; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
-#pragma unroll
-  for (int kk = 0; kk < G::KS; ++kk) {
-    uint32_t b0, b1, c0, c1;
-    g_load_b_rows<HD>(sK, 0, kk, lane, b0, b1, c0, c1);
-    mma16816(sc[0], qa[kk], b0, b1);
-    mma16816(sc[1], qa[kk], c0, c1);
-  }
   const float sl2 = a.scale * LOG2E;
-  float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < 2; ++j)
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      if (8 * j + 2 * t4 + e >= nk) { sc[j][e] = -INFINITY; sc[j][2 + e] = -INFINITY; }
-      mx0 = fmaxf(mx0, sc[j][e]); mx1 = fmaxf(mx1, sc[j][2 + e]);
-    }
-  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-  float l0 = 0.f, l1 = 0.f;
-  uint32_t pa[4];
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const float p00 = exp2f((sc[j][0] - mx0) * sl2), p01 = exp2f((sc[j][1] - mx0) * sl2);
-    const float p10 = exp2f((sc[j][2] - mx1) * sl2), p11 = exp2f((sc[j][3] - mx1) * sl2);
-    l0 += p00 + p01; l1 += p10 + p11;
-    pa[j * 2] = pack_bf16x2(p00, p01);
-    pa[j * 2 + 1] = pack_bf16x2(p10, p11);
-  }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  float o[G::ND][4];
-#pragma unroll
-  for (int j = 0; j < G::ND; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
-#pragma unroll
-  for (int jd = 0; jd < G::ND; jd += 2) {
-    uint32_t b0, b1, c0, c1;
-    g_load_b_cols<HD>(sV, 0, jd, lane, b0, b1, c0, c1);
-    mma16816(o[jd], pa, b0, b1);
-    mma16816(o[jd + 1], pa, c0, c1);
-  }
-  const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
-  __syncwarp();
-  uint8_t* stg = smem + warp * ROWS * P;   // reuse the Q rows
-#pragma unroll
-  for (int j = 0; j < G::ND; ++j) {
-    *reinterpret_cast<uint32_t*>(stg + swzp<P>(g, j) + 4 * t4) = pack_bf16x2(o[j][0] * inv0, o[j][1] * inv0);
-    *reinterpret_cast<uint32_t*>(stg + swzp<P>(g + 8, j) + 4 * t4) = pack_bf16x2(o[j][2] * inv1, o[j][3] * inv1);
-  }
-  __syncwarp();
+  uint8_t* stg = smem + warp * ROWS * P;   // the Q rows are reused for output staging (each m-tile's rows after its fragments are loaded)
   bf16* ob = out + (long long)b * a.N * ro + (long long)h * HD;
-  for (int i = lane; i < 16 * CH; i += 32) {
-    const int r = i / CH, c = i - r * CH;
-    if (r < a.T) *reinterpret_cast<uint4*>(ob + (long long)(1 + r * a.n + slot) * ro + c * 8) = *reinterpret_cast<const uint4*>(stg + swzp<P>(r, c));
-  }
-  if (t4 == 0) {
-    float* lb = lse + ((long long)b * a.H + h) * a.N;
-    if (g < a.T) lb[1 + g * a.n + slot] = mx0 * a.scale + __logf(l0);
-    if (g + 8 < a.T) lb[1 + (g + 8) * a.n + slot] = mx1 * a.scale + __logf(l1);
+  float* lb = lse + ((long long)b * a.H + h) * a.N;
+#pragma unroll
+  for (int mi = 0; mi < MT; ++mi) {
+    if (16 * mi >= a.T) break;                                   // warp-uniform
+    uint32_t qa[G::KS][4];
+    g_load_a<HD>(sQ, 16 * mi, lane, qa);
+    float sc[2 * MT][4];
+#pragma unroll
+    for (int j = 0; j < 2 * MT; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2 * MT; j += 2) {
+#pragma unroll
+      for (int kk = 0; kk < G::KS; ++kk) {
+        uint32_t b0, b1, c0, c1;
+        g_load_b_rows<HD>(sK, j, kk, lane, b0, b1, c0, c1);
+        mma16816(sc[j], qa[kk], b0, b1);
+        mma16816(sc[j + 1], qa[kk], c0, c1);
+      }
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 2 * MT; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (8 * j + 2 * t4 + e >= nk) { sc[j][e] = -INFINITY; sc[j][2 + e] = -INFINITY; }
+        mx0 = fmaxf(mx0, sc[j][e]); mx1 = fmaxf(mx1, sc[j][2 + e]);
+      }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float l0 = 0.f, l1 = 0.f;
+    uint32_t pa[MT][4];
+#pragma unroll
+    for (int j = 0; j < 2 * MT; ++j) {
+      const float p00 = exp2f((sc[j][0] - mx0) * sl2), p01 = exp2f((sc[j][1] - mx0) * sl2);
+      const float p10 = exp2f((sc[j][2] - mx1) * sl2), p11 = exp2f((sc[j][3] - mx1) * sl2);
+      l0 += p00 + p01; l1 += p10 + p11;
+      pa[j >> 1][(j & 1) * 2] = pack_bf16x2(p00, p01);
+      pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p10, p11);
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    float o[G::ND][4];
+#pragma unroll
+    for (int j = 0; j < G::ND; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < MT; ++kk) {
+#pragma unroll
+      for (int jd = 0; jd < G::ND; jd += 2) {
+        uint32_t b0, b1, c0, c1;
+        g_load_b_cols<HD>(sV, kk, jd, lane, b0, b1, c0, c1);
+        mma16816(o[jd], pa[kk], b0, b1);
+        mma16816(o[jd + 1], pa[kk], c0, c1);
+      }
+    }
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+    __syncwarp();
+    const int r0 = 16 * mi + g, r1 = r0 + 8;
+#pragma unroll
+    for (int j = 0; j < G::ND; ++j) {
+      *reinterpret_cast<uint32_t*>(stg + swzp<P>(r0, j) + 4 * t4) = pack_bf16x2(o[j][0] * inv0, o[j][1] * inv0);
+      *reinterpret_cast<uint32_t*>(stg + swzp<P>(r1, j) + 4 * t4) = pack_bf16x2(o[j][2] * inv1, o[j][3] * inv1);
+    }
+    __syncwarp();
+    for (int i = lane; i < 16 * CH; i += 32) {
+      const int rr = i / CH, c = i - rr * CH;
+      const int r = 16 * mi + rr;
+      if (r < a.T) *reinterpret_cast<uint4*>(ob + (long long)(1 + r * a.n + slot) * ro + c * 8) = *reinterpret_cast<const uint4*>(stg + swzp<P>(r, c));
+    }
+    if (t4 == 0) {
+      if (r0 < a.T) lb[1 + r0 * a.n + slot] = mx0 * a.scale + __logf(l0);
+      if (r1 < a.T) lb[1 + r1 * a.n + slot] = mx1 * a.scale + __logf(l1);
+    }
   }
 }
 
 // backward of one slot: dq (T rows) and dk / dv of the slot's T patch keys (including the CLS query's contribution)
-template <int HD>
+template <int HD, int MT>
 __global__ void __launch_bounds__(HD_TW * 32) attn_hd_time_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                                                                       const float* __restrict__ lse, const float* __restrict__ delta,
                                                                       bf16* __restrict__ dqkv, AttnShape a) {
   using G = Geo<HD>;
-  constexpr int P = G::PITCH, CH = G::CH, ROWS = 64;
-  TVTS_DYN_SMEM(uint8_t, smem, 128);                   // per warp: Q | K | V | dO (16 rows each); then stat[HD_TW][2][16]
+  constexpr int P = G::PITCH, CH = G::CH, R = 16 * MT, ROWS = 4 * R;
+  TVTS_DYN_SMEM(uint8_t, smem, 128);                   // per warp: Q | K | V | dO (R rows each); then per warp lse*log2e [R], delta [R]
   float* stat_all = reinterpret_cast<float*>(smem + HD_TW * ROWS * P);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const int slot = blockIdx.x * HD_TW + warp;
   if (slot >= a.n) return;
-  float* st_l = stat_all + warp * 32;                  // lse * log2e of query rows 0..T-1 (slot) and T (CLS)
-  float* st_d = st_l + 16;                             // delta of the same rows
+  float* st_l = stat_all + warp * 2 * R;               // lse * log2e of query rows 0..T-1 (slot) and T (CLS)
+  float* st_d = st_l + R;                              // delta of the same rows
   const int h = blockIdx.y, b = blockIdx.z;
   const long long rs = 3LL * a.H * HD, ro = (long long)a.H * HD;
   const bf16* qb = qkv + (long long)b * a.N * rs + (long long)h * HD;
@@ -918,9 +930,9 @@ __global__ void __launch_bounds__(HD_TW * 32) attn_hd_time_bwd_kernel(const bf16
   const float* lse_b = lse + ((long long)b * a.H + h) * a.N;
   const float* delta_b = delta + ((long long)b * a.H + h) * a.N;
   const uint32_t base = smem_u32(smem) + warp * ROWS * P;
-  hd_time_load<HD, true>(base, qb, dob, rs, ro, a.T, a.n, slot, lane);
+  hd_time_load<HD, MT, true>(base, qb, dob, rs, ro, a.T, a.n, slot, lane);
   cp_async_commit();
-  if (lane < 16) {
+  if (lane < R) {
     const bool ok = lane <= a.T;
     const int tok = lane < a.T ? 1 + lane * a.n + slot : 0;
     st_l[lane] = ok ? lse_b[tok] * LOG2E : 0.f;
@@ -928,133 +940,157 @@ __global__ void __launch_bounds__(HD_TW * 32) attn_hd_time_bwd_kernel(const bf16
   }
   cp_async_wait<0>();
   __syncwarp();
-  const uint32_t sQ = base, sK = base + 16 * P, sV = base + 32 * P, sD = base + 48 * P;
-  const int nk = a.T + 1;
+  const uint32_t sQ = base, sK = base + R * P, sV = base + 2 * R * P, sD = base + 3 * R * P;
+  const int nk = a.T + 1, nq_all = a.T + 1;            // keys: CLS + T ; query columns of the transposed pass: T + the CLS query
   const float sl2 = a.scale * LOG2E;
   uint8_t* wsm = smem + warp * ROWS * P;
   bf16* dq_b = dqkv + (long long)b * a.N * rs + (long long)h * HD;
 
-  // ---------------- pass A: rows = queries, cols = keys: dQ = scale * dS K
-  float dq[G::ND][4];
-  {
+  // Both passes only READ the Q / K / V / dO tiles; their results are staged into the tiles AFTER the last read (dq over Q, dk over K,
+  // dv over V), which needs all of dq / dk / dv in registers at once only for MT = 1.  For MT = 2 the m-tiles are processed one at a
+  // time and each tile's dq is parked in ITS OWN rows of the dO tile... which pass B still reads -- so dq goes to global memory directly.
+  // ---------------- pass A: rows = queries (m-tile mi), cols = keys: dQ = scale * dS K
+#pragma unroll
+  for (int mi = 0; mi < MT; ++mi) {
+    if (16 * mi >= a.T) break;                         // warp-uniform: no slot query in this m-tile (row T = CLS is not this kernel's)
     uint32_t qa[G::KS][4], da[G::KS][4];
-    g_load_a<HD>(sQ, 0, lane, qa);
-    g_load_a<HD>(sD, 0, lane, da);
-    float sc[2][4], dp[2][4];
+    g_load_a<HD>(sQ, 16 * mi, lane, qa);
+    g_load_a<HD>(sD, 16 * mi, lane, da);
+    float sc[2 * MT][4], dp[2 * MT][4];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) { sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
+    for (int j = 0; j < 2 * MT; ++j) { sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
 #pragma unroll
-    for (int kk = 0; kk < G::KS; ++kk) {
-      uint32_t b0, b1, c0, c1;
-      g_load_b_rows<HD>(sK, 0, kk, lane, b0, b1, c0, c1);
-      mma16816(sc[0], qa[kk], b0, b1);
-      mma16816(sc[1], qa[kk], c0, c1);
-      g_load_b_rows<HD>(sV, 0, kk, lane, b0, b1, c0, c1);
-      mma16816(dp[0], da[kk], b0, b1);
-      mma16816(dp[1], da[kk], c0, c1);
+    for (int j = 0; j < 2 * MT; j += 2) {
+#pragma unroll
+      for (int kk = 0; kk < G::KS; ++kk) {
+        uint32_t b0, b1, c0, c1;
+        g_load_b_rows<HD>(sK, j, kk, lane, b0, b1, c0, c1);
+        mma16816(sc[j], qa[kk], b0, b1);
+        mma16816(sc[j + 1], qa[kk], c0, c1);
+        g_load_b_rows<HD>(sV, j, kk, lane, b0, b1, c0, c1);
+        mma16816(dp[j], da[kk], b0, b1);
+        mma16816(dp[j + 1], da[kk], c0, c1);
+      }
     }
-    const float l0 = st_l[g], l1 = st_l[g + 8], d0 = st_d[g], d1 = st_d[g + 8];
-    uint32_t dsa[4];
+    const int r0 = 16 * mi + g, r1 = r0 + 8;
+    const float l0 = st_l[r0], l1 = st_l[r1], d0 = st_d[r0], d1 = st_d[r1];
+    uint32_t dsa[MT][4];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < 2 * MT; ++j) {
       float ds[4];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const bool ok = 8 * j + 2 * t4 + e < nk;
-        const float p0 = (ok && g < a.T) ? exp2f(sc[j][e] * sl2 - l0) : 0.f;          // row T (CLS) is not this kernel's
-        const float p1 = (ok && g + 8 < a.T) ? exp2f(sc[j][2 + e] * sl2 - l1) : 0.f;
+        const float p0 = (ok && r0 < a.T) ? exp2f(sc[j][e] * sl2 - l0) : 0.f;          // row T (CLS) is not this kernel's
+        const float p1 = (ok && r1 < a.T) ? exp2f(sc[j][2 + e] * sl2 - l1) : 0.f;
         ds[e] = p0 * (dp[j][e] - d0);
         ds[2 + e] = p1 * (dp[j][2 + e] - d1);
       }
-      dsa[j * 2] = pack_bf16x2(ds[0], ds[1]);
-      dsa[j * 2 + 1] = pack_bf16x2(ds[2], ds[3]);
+      dsa[j >> 1][(j & 1) * 2] = pack_bf16x2(ds[0], ds[1]);
+      dsa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(ds[2], ds[3]);
     }
+    float dq[G::ND][4];
 #pragma unroll
     for (int j = 0; j < G::ND; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
 #pragma unroll
-    for (int jd = 0; jd < G::ND; jd += 2) {
-      uint32_t b0, b1, c0, c1;
-      g_load_b_cols<HD>(sK, 0, jd, lane, b0, b1, c0, c1);
-      mma16816(dq[jd], dsa, b0, b1);
-      mma16816(dq[jd + 1], dsa, c0, c1);
+    for (int kk = 0; kk < MT; ++kk) {
+#pragma unroll
+      for (int jd = 0; jd < G::ND; jd += 2) {
+        uint32_t b0, b1, c0, c1;
+        g_load_b_cols<HD>(sK, kk, jd, lane, b0, b1, c0, c1);
+        mma16816(dq[jd], dsa[kk], b0, b1);
+        mma16816(dq[jd + 1], dsa[kk], c0, c1);
+      }
+    }
+    // dq rows of this m-tile straight to global memory (4-byte stores; 2 rows x HD/8 chunks per lane)
+#pragma unroll
+    for (int j = 0; j < G::ND; ++j) {
+      if (r0 < a.T)
+        *reinterpret_cast<uint32_t*>(dq_b + (1LL + (long long)r0 * a.n + slot) * rs + 8 * j + 2 * t4) = pack_bf16x2(dq[j][0] * a.scale, dq[j][1] * a.scale);
+      if (r1 < a.T)
+        *reinterpret_cast<uint32_t*>(dq_b + (1LL + (long long)r1 * a.n + slot) * rs + 8 * j + 2 * t4) = pack_bf16x2(dq[j][2] * a.scale, dq[j][3] * a.scale);
     }
   }
-  // ---------------- pass B: rows = keys, cols = queries (slot queries + CLS query): dK = scale * dS^T Q ; dV = P^T dO
-  float dk[G::ND][4], dv[G::ND][4];
-  {
+  // ---------------- pass B: rows = keys (m-tile mi), cols = queries (slot queries + CLS query): dK = scale * dS^T Q ; dV = P^T dO
+#pragma unroll
+  for (int mi = 0; mi < MT; ++mi) {
+    if (16 * mi >= nk) break;
+    float dk[G::ND][4], dv[G::ND][4];
 #pragma unroll
     for (int j = 0; j < G::ND; ++j) {
       dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f;
       dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f;
     }
     uint32_t ka[G::KS][4], va[G::KS][4];
-    g_load_a<HD>(sK, 0, lane, ka);
-    g_load_a<HD>(sV, 0, lane, va);
-    float sc[2][4], dp[2][4];
+    g_load_a<HD>(sK, 16 * mi, lane, ka);
+    g_load_a<HD>(sV, 16 * mi, lane, va);
+    float sc[2 * MT][4], dp[2 * MT][4];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) { sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
+    for (int j = 0; j < 2 * MT; ++j) { sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
 #pragma unroll
-    for (int kk = 0; kk < G::KS; ++kk) {
-      uint32_t b0, b1, c0, c1;
-      g_load_b_rows<HD>(sQ, 0, kk, lane, b0, b1, c0, c1);
-      mma16816(sc[0], ka[kk], b0, b1);
-      mma16816(sc[1], ka[kk], c0, c1);
-      g_load_b_rows<HD>(sD, 0, kk, lane, b0, b1, c0, c1);
-      mma16816(dp[0], va[kk], b0, b1);
-      mma16816(dp[1], va[kk], c0, c1);
+    for (int j = 0; j < 2 * MT; j += 2) {
+#pragma unroll
+      for (int kk = 0; kk < G::KS; ++kk) {
+        uint32_t b0, b1, c0, c1;
+        g_load_b_rows<HD>(sQ, j, kk, lane, b0, b1, c0, c1);
+        mma16816(sc[j], ka[kk], b0, b1);
+        mma16816(sc[j + 1], ka[kk], c0, c1);
+        g_load_b_rows<HD>(sD, j, kk, lane, b0, b1, c0, c1);
+        mma16816(dp[j], va[kk], b0, b1);
+        mma16816(dp[j + 1], va[kk], c0, c1);
+      }
     }
-    uint32_t pa[4], dsa[4];
-    const int key0 = g, key1 = g + 8;
+    uint32_t pa[MT][4], dsa[MT][4];
+    const int key0 = 16 * mi + g, key1 = key0 + 8;
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < 2 * MT; ++j) {
       float p[4], ds[4];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int q = 8 * j + 2 * t4 + e;
-        const bool okq = q <= a.T;           // q == T: the CLS query
+        const bool okq = q < nq_all;         // q == T: the CLS query
         const float lq = st_l[q], dq_ = st_d[q];
         p[e] = (okq && key0 < nk) ? exp2f(sc[j][e] * sl2 - lq) : 0.f;
         p[2 + e] = (okq && key1 < nk) ? exp2f(sc[j][2 + e] * sl2 - lq) : 0.f;
         ds[e] = p[e] * (dp[j][e] - dq_);
         ds[2 + e] = p[2 + e] * (dp[j][2 + e] - dq_);
       }
-      pa[j * 2] = pack_bf16x2(p[0], p[1]); pa[j * 2 + 1] = pack_bf16x2(p[2], p[3]);
-      dsa[j * 2] = pack_bf16x2(ds[0], ds[1]); dsa[j * 2 + 1] = pack_bf16x2(ds[2], ds[3]);
+      pa[j >> 1][(j & 1) * 2] = pack_bf16x2(p[0], p[1]); pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p[2], p[3]);
+      dsa[j >> 1][(j & 1) * 2] = pack_bf16x2(ds[0], ds[1]); dsa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(ds[2], ds[3]);
     }
 #pragma unroll
-    for (int jd = 0; jd < G::ND; jd += 2) {
-      uint32_t b0, b1, c0, c1;
-      g_load_b_cols<HD>(sQ, 0, jd, lane, b0, b1, c0, c1);
-      mma16816(dk[jd], dsa, b0, b1);
-      mma16816(dk[jd + 1], dsa, c0, c1);
-      g_load_b_cols<HD>(sD, 0, jd, lane, b0, b1, c0, c1);
-      mma16816(dv[jd], pa, b0, b1);
-      mma16816(dv[jd + 1], pa, c0, c1);
+    for (int kk = 0; kk < MT; ++kk) {
+#pragma unroll
+      for (int jd = 0; jd < G::ND; jd += 2) {
+        uint32_t b0, b1, c0, c1;
+        g_load_b_cols<HD>(sQ, kk, jd, lane, b0, b1, c0, c1);
+        mma16816(dk[jd], dsa[kk], b0, b1);
+        mma16816(dk[jd + 1], dsa[kk], c0, c1);
+        g_load_b_cols<HD>(sD, kk, jd, lane, b0, b1, c0, c1);
+        mma16816(dv[jd], pa[kk], b0, b1);
+        mma16816(dv[jd + 1], pa[kk], c0, c1);
+      }
+    }
+    // dk / dv rows of this key m-tile straight to global memory (key row 0 = CLS: written by the cls_only launch)
+#pragma unroll
+    for (int j = 0; j < G::ND; ++j) {
+      if (key0 >= 1 && key0 < nk) {
+        bf16* dst = dq_b + (1LL + (long long)(key0 - 1) * a.n + slot) * rs + 8 * j + 2 * t4;
+        *reinterpret_cast<uint32_t*>(dst + ro) = pack_bf16x2(dk[j][0] * a.scale, dk[j][1] * a.scale);
+        *reinterpret_cast<uint32_t*>(dst + 2 * ro) = pack_bf16x2(dv[j][0], dv[j][1]);
+      }
+      if (key1 < nk) {
+        bf16* dst = dq_b + (1LL + (long long)(key1 - 1) * a.n + slot) * rs + 8 * j + 2 * t4;
+        *reinterpret_cast<uint32_t*>(dst + ro) = pack_bf16x2(dk[j][2] * a.scale, dk[j][3] * a.scale);
+        *reinterpret_cast<uint32_t*>(dst + 2 * ro) = pack_bf16x2(dv[j][2], dv[j][3]);
+      }
     }
   }
-  // ---------------- outputs: stage in this warp's smem (all operand reads are done), 16-byte row stores
-  __syncwarp();
-#pragma unroll
-  for (int j = 0; j < G::ND; ++j) {
-    *reinterpret_cast<uint32_t*>(wsm + swzp<P>(g, j) + 4 * t4) = pack_bf16x2(dq[j][0] * a.scale, dq[j][1] * a.scale);
-    *reinterpret_cast<uint32_t*>(wsm + swzp<P>(g + 8, j) + 4 * t4) = pack_bf16x2(dq[j][2] * a.scale, dq[j][3] * a.scale);
-    *reinterpret_cast<uint32_t*>(wsm + swzp<P>(16 + g, j) + 4 * t4) = pack_bf16x2(dk[j][0] * a.scale, dk[j][1] * a.scale);
-    *reinterpret_cast<uint32_t*>(wsm + swzp<P>(24 + g, j) + 4 * t4) = pack_bf16x2(dk[j][2] * a.scale, dk[j][3] * a.scale);
-    *reinterpret_cast<uint32_t*>(wsm + swzp<P>(32 + g, j) + 4 * t4) = pack_bf16x2(dv[j][0], dv[j][1]);
-    *reinterpret_cast<uint32_t*>(wsm + swzp<P>(40 + g, j) + 4 * t4) = pack_bf16x2(dv[j][2], dv[j][3]);
-  }
-  __syncwarp();
-  for (int i = lane; i < 48 * CH; i += 32) {
-    const int r = i / CH, c = i - r * CH;
-    const int blk = r >> 4, rr = r & 15;     // 0 = dq, 1 = dk, 2 = dv
-    long long tok;
-    if (blk == 0) { if (rr >= a.T) continue; tok = 1 + (long long)rr * a.n + slot; }
-    else { if (rr == 0 || rr > a.T) continue; tok = 1 + (long long)(rr - 1) * a.n + slot; }   // key 0 = CLS: cls_only launch
-    *reinterpret_cast<uint4*>(dq_b + tok * rs + blk * ro + c * 8) = *reinterpret_cast<const uint4*>(wsm + swzp<P>(r, c));
-  }
+  (void)wsm; (void)CH;
 }
 
-__host__ __device__ inline bool hd_use_time_kernels(const AttnShape& a) { return a.mode == 2 && a.T <= HD_T_MAX; }
+// tiles per slot for the warp-per-slot time kernels (0: T too large -> streamed kernels)
+__host__ __device__ inline int hd_time_tiles(const AttnShape& a) { return a.mode != 2 ? 0 : (a.T <= 15 ? 1 : (a.T <= 31 ? 2 : 0)); }
 
 // number of warps a group-resident launch needs (0: not applicable -> streamed kernels); same rule as group_warps() in attention.cu
 __host__ __device__ inline int hd_group_warps(const AttnShape& a) {
@@ -1108,10 +1144,38 @@ int hd_group_fwd(const void* qkv, void* out, float* lse, const AttnShape& a, cud
   return TVTS_OK;
 }
 
+template <int HD, int MT>
+int hd_time_fwd(const void* qkv, void* out, float* lse, const AttnShape& a, cudaStream_t st) {
+  constexpr int smem_bytes = HD_TW * 3 * 16 * MT * Geo<HD>::PITCH;
+  static bool set = false;
+  if (!set) {
+    TVTS_CHECK_CUDA(cudaFuncSetAttribute(attn_hd_time_fwd_kernel<HD, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    set = true;
+  }
+  dim3 tg((unsigned)((a.n + HD_TW - 1) / HD_TW), (unsigned)a.H, (unsigned)a.B);
+  attn_hd_time_fwd_kernel<HD, MT><<<tg, HD_TW * 32, smem_bytes, st>>>((const bf16*)qkv, (bf16*)out, lse, a);
+  TVTS_LAUNCH_CHECK();
+  return TVTS_OK;
+}
+
+template <int HD, int MT>
+int hd_time_bwd(const void* qkv, const void* dout, const float* lse, const float* delta_ws, void* dqkv, const AttnShape& a, cudaStream_t st) {
+  constexpr int smem_bytes = HD_TW * 4 * 16 * MT * Geo<HD>::PITCH + HD_TW * 2 * 16 * MT * 4;
+  static bool set = false;
+  if (!set) {
+    TVTS_CHECK_CUDA(cudaFuncSetAttribute(attn_hd_time_bwd_kernel<HD, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    set = true;
+  }
+  dim3 tg((unsigned)((a.n + HD_TW - 1) / HD_TW), (unsigned)a.H, (unsigned)a.B);
+  attn_hd_time_bwd_kernel<HD, MT><<<tg, HD_TW * 32, smem_bytes, st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, a);
+  TVTS_LAUNCH_CHECK();
+  return TVTS_OK;
+}
+
 template <int HD>
 int hd_launch_fwd(const void* qkv, void* out, float* lse, const AttnShape& a, cudaStream_t st, const int* klen = nullptr) {
   const int gw = (klen == nullptr && g_hd_group) ? hd_group_warps(a) : 0;
-  const bool time_k = klen == nullptr && g_hd_group && hd_use_time_kernels(a);
+  const int time_k = (klen == nullptr && g_hd_group) ? hd_time_tiles(a) : 0;
   if (!gw && !time_k) return hd_streamed_fwd<HD>(qkv, out, lse, a, st, klen);
   if (a.mode != 0) {                     // the CLS query over all tokens
     AttnShape c = a;
@@ -1119,18 +1183,7 @@ int hd_launch_fwd(const void* qkv, void* out, float* lse, const AttnShape& a, cu
     int rc = hd_streamed_fwd<HD>(qkv, out, lse, c, st, nullptr);
     if (rc) return rc;
   }
-  if (time_k) {
-    constexpr int smem_bytes = HD_TW * 48 * Geo<HD>::PITCH;
-    static bool set = false;
-    if (!set) {
-      TVTS_CHECK_CUDA(cudaFuncSetAttribute(attn_hd_time_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-      set = true;
-    }
-    dim3 tg((unsigned)((a.n + HD_TW - 1) / HD_TW), (unsigned)a.H, (unsigned)a.B);
-    attn_hd_time_fwd_kernel<HD><<<tg, HD_TW * 32, smem_bytes, st>>>((const bf16*)qkv, (bf16*)out, lse, a);
-    TVTS_LAUNCH_CHECK();
-    return TVTS_OK;
-  }
+  if (time_k) return time_k == 1 ? hd_time_fwd<HD, 1>(qkv, out, lse, a, st) : hd_time_fwd<HD, 2>(qkv, out, lse, a, st);
   switch (gw) {
     case 2: return hd_group_fwd<HD, 2>(qkv, out, lse, a, st);
     case 3: return hd_group_fwd<HD, 3>(qkv, out, lse, a, st);
@@ -1181,7 +1234,7 @@ int hd_launch_bwd(const void* qkv, const void* out, const void* dout, const floa
   attn_hd_delta_kernel<HD><<<(unsigned)((rows + 31) / 32), 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta_ws, a.B, a.N, a.H);
   TVTS_LAUNCH_CHECK();
   const int gw = (klen == nullptr && g_hd_group) ? hd_group_warps(a) : 0;
-  const bool time_k = klen == nullptr && g_hd_group && hd_use_time_kernels(a);
+  const int time_k = (klen == nullptr && g_hd_group) ? hd_time_tiles(a) : 0;
   if (!gw && !time_k) return hd_streamed_bwd<HD>(qkv, dout, lse, delta_ws, dqkv, a, st, klen);
   if (a.mode != 0) {                     // dq of the CLS query, dk / dv of the CLS key
     AttnShape c = a;
@@ -1189,18 +1242,8 @@ int hd_launch_bwd(const void* qkv, const void* out, const void* dout, const floa
     int rc = hd_streamed_bwd<HD>(qkv, dout, lse, delta_ws, dqkv, c, st, nullptr);
     if (rc) return rc;
   }
-  if (time_k) {
-    constexpr int smem_bytes = HD_TW * 64 * Geo<HD>::PITCH + HD_TW * 32 * 4;
-    static bool set = false;
-    if (!set) {
-      TVTS_CHECK_CUDA(cudaFuncSetAttribute(attn_hd_time_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-      set = true;
-    }
-    dim3 tg((unsigned)((a.n + HD_TW - 1) / HD_TW), (unsigned)a.H, (unsigned)a.B);
-    attn_hd_time_bwd_kernel<HD><<<tg, HD_TW * 32, smem_bytes, st>>>((const bf16*)qkv, (const bf16*)dout, lse, delta_ws, (bf16*)dqkv, a);
-    TVTS_LAUNCH_CHECK();
-    return TVTS_OK;
-  }
+  if (time_k)
+    return time_k == 1 ? hd_time_bwd<HD, 1>(qkv, dout, lse, delta_ws, dqkv, a, st) : hd_time_bwd<HD, 2>(qkv, dout, lse, delta_ws, dqkv, a, st);
   switch (gw) {
     case 2: return hd_group_bwd<HD, 2>(qkv, dout, lse, delta_ws, dqkv, a, st);
     case 3: return hd_group_bwd<HD, 3>(qkv, dout, lse, delta_ws, dqkv, a, st);
