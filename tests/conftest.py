@@ -1,5 +1,6 @@
 import os
 import sys
+import time
 
 import pytest
 
@@ -7,6 +8,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
+
+
+SESSION_START = time.time()
 
 
 def pytest_configure(config):

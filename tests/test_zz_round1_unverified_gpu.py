@@ -43,7 +43,7 @@ def _run_staged_child():
     import sys
     env = dict(os.environ, TVTS_RUN_STAGED="1")
     return subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "--tb=line", "-p", "no:cacheprovider",
-                           "-rA"], env=env, capture_output=True, text=True, timeout=1500, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+                           "-rA"], env=env, capture_output=True, text=True, timeout=900, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
 def rnd(*shape, scale=1.0):
