@@ -10,11 +10,13 @@ Mirrors (paths relative to /root/reference):
 The two embedding gathers of the reference are fused into ONE NCCL all-gather of the concatenated [B_local, 2E] buffer;
 the gradient all-reduce runs over a flat fp32 arena (one NCCL call per arena chunk), averaged by 1/W like DDP.
 """
+import os
 import types
 
 import torch
 import torch.distributed as dist
 
+from . import _lib as L
 from . import engine as E
 from . import modules as M
 
@@ -188,12 +190,10 @@ class TrainStep:
         self.device = device if device is not None else next(model.parameters()).device
         self.params = [p for p in model.parameters() if p.requires_grad]   # after the optimizer applied the freeze policy
         self.use_graph = use_graph
-        from . import _lib as L
         self.loss_scale = L.DEFAULT_LOSS_SCALE     # 1 for bf16 operands; fp16 operands: static scale, undone inside the AdamW kernel
         # opt-in (TVTS_OVERLAP_ALLREDUCE=1): the gradient ranges of everything but the text tower are all-reduced on a side stream as soon
         # as the video tower's backward has finished (the sort head's finishes before it), i.e. under the text tower's backward, which
         # autograd runs last; the text ranges follow at the end.  Same sums, same result; default off until measured on NVLink.
-        import os
         self.overlap = os.environ.get("TVTS_OVERLAP_ALLREDUCE", "0") == "1"
         self._ranges = None
         self._comm_stream = None
@@ -280,7 +280,6 @@ class TrainStep:
         E.AFTER_VIDEO_BACKWARD = hook
 
     def _capture(self, key, data):
-        from . import _lib as L
         if not (self.optimizer is None or hasattr(self.optimizer, "launch")):
             raise RuntimeError("TrainStep(use_graph=True) needs tvts_b200.optim.AdamW (or no optimizer)")
         static = {k: v.to(self.device, copy=True) for k, v in data.items() if torch.is_tensor(v)}      # `data` is flat here
@@ -649,7 +648,6 @@ class Trainer_TVTSv2:
 
     def _save_checkpoint(self, epoch, save_best=False):
         """base_trainer.py:165-194: checkpoint-epoch{N}.pth in config.save_dir (+ model_best.pth when the monitored metric improved)."""
-        import os
         import shutil
         os.makedirs(str(self.checkpoint_dir), exist_ok=True)
         path = self.save_checkpoint(os.path.join(str(self.checkpoint_dir), "checkpoint-epoch{}.pth".format(epoch)), epoch)
