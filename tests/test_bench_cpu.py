@@ -58,3 +58,14 @@ def test_bench_two_rank_dry_run_prints_one_line_and_exits_cleanly():
     lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1 and lines[0]["n_gpus"] == 2 and lines[0]["config"]["parallelism"] == "dp2" and lines[0]["value"] > 0
     assert "grad_allreduce" in lines[0]["config"]["step"]
+
+
+def test_v1_flop_model_reproduces_survey_row_c5():
+    """tools/bench_v1.py: SURVEY section 8d row c5 -- 76.2 GF video + 4 x ~4.3 GF text + 12.2 GF sort head per pair forward, x3 for fwd+bwd."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_v1
+    fwd = bench_v1.flops_per_pair() / 3e9
+    assert abs(fwd - (76.2 + 4 * 4.3 + 12.2)) < 0.5, fwd
+    b = bench_v1.make_batch(2)
+    assert b["video"].shape == (2, 16, 3, 224, 224) and b["keep_ind"].shape == (2, 8, 49) and b["text"]["input_ids"].shape == (8, 50)
+    assert (b["text"]["input_ids"] * (1 - b["text"]["attention_mask"])).abs().sum() == 0          # right padding with id 0
