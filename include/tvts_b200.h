@@ -2,7 +2,8 @@
  *
  * The reference (TencentARC/TVTS) has no native/FFI layer: its hot path is stock PyTorch modules
  * (SURVEY.md section 8b).  This header is therefore the boundary our own Python mirror of the reference
- * modules (tvts_b200/v2/model/..., tvts_b200/v2/trainer/...) binds through ctypes; each entry point names
+ * modules (tvts_b200/modules.py, modules_v1.py, trainer.py; drop-in trees tvts_b200/dropin, dropin_v1) binds through ctypes
+ * (tvts_b200/_lib.py); each entry point names
  * the reference computation (file:line under /root/reference) it replaces.
  *
  * Conventions
@@ -123,6 +124,9 @@ int tvts_attn_bwd(const void* qkv, const void* out, const void* dout, const floa
 /* 1 (default): groups that fit one CTA (space attention of H/14: 77 rows; short full-attention sequences) use the group-resident generic
  * kernels + a CLS launch; 0: streamed generic kernels only */
 int tvts_attn_hd_set_group(int on);
+/* 1 (default): with the fast paths, the CLS row / column launch of the divided modes runs on an internal side stream (fork / join with
+ * events, capture-safe), like tvts_attn_set_side_stream for the head-dim-64 kernels; 0: everything on `stream` */
+int tvts_attn_hd_set_side_stream(int on);
 int tvts_attn_generic_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T,
                           int64_t n, int64_t causal, float scale, void* stream);
 int tvts_attn_generic_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv, int64_t B,

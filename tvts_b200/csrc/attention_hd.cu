@@ -1116,6 +1116,27 @@ int hd_check_shape(const AttnShape& a, int64_t d) {
 
 int g_hd_group = 1;      // 1: group-resident kernels where a group fits one CTA; 0: streamed kernels only (tvts_attn_hd_set_group)
 
+// The CLS row / column launch of the divided modes is latency-bound and writes outputs disjoint from the group / time kernels', so it
+// runs on a side stream forked from / joined back into the caller's stream with events (legal inside a CUDA-graph capture: a parallel
+// branch) -- the same arrangement as in attention.cu.
+struct HdSideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+HdSideStream* hd_side_stream() {
+  static HdSideStream per_dev[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  HdSideStream& s = per_dev[dev];
+  if (s.stream == nullptr) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return &s;
+}
+int g_hd_side = 1;       // tvts_attn_hd_set_side_stream
+
 template <int HD>
 int hd_streamed_fwd(const void* qkv, void* out, float* lse, const AttnShape& a, cudaStream_t st, const int* klen) {
   constexpr int smem_bytes = 5 * Geo<HD>::TILE;
@@ -1177,21 +1198,35 @@ int hd_launch_fwd(const void* qkv, void* out, float* lse, const AttnShape& a, cu
   const int gw = (klen == nullptr && g_hd_group) ? hd_group_warps(a) : 0;
   const int time_k = (klen == nullptr && g_hd_group) ? hd_time_tiles(a) : 0;
   if (!gw && !time_k) return hd_streamed_fwd<HD>(qkv, out, lse, a, st, klen);
+  HdSideStream* sd = (a.mode != 0 && g_hd_side) ? hd_side_stream() : nullptr;
   if (a.mode != 0) {                     // the CLS query over all tokens
+    cudaStream_t cls_st = st;
+    if (sd) {
+      TVTS_CHECK_CUDA(cudaEventRecord(sd->fork, st));
+      TVTS_CHECK_CUDA(cudaStreamWaitEvent(sd->stream, sd->fork, 0));
+      cls_st = sd->stream;
+    }
     AttnShape c = a;
     c.cls_only = 1;
-    int rc = hd_streamed_fwd<HD>(qkv, out, lse, c, st, nullptr);
+    int rc = hd_streamed_fwd<HD>(qkv, out, lse, c, cls_st, nullptr);
     if (rc) return rc;
   }
-  if (time_k) return time_k == 1 ? hd_time_fwd<HD, 1>(qkv, out, lse, a, st) : hd_time_fwd<HD, 2>(qkv, out, lse, a, st);
-  switch (gw) {
-    case 2: return hd_group_fwd<HD, 2>(qkv, out, lse, a, st);
-    case 3: return hd_group_fwd<HD, 3>(qkv, out, lse, a, st);
-    case 4: return hd_group_fwd<HD, 4>(qkv, out, lse, a, st);
-    case 5: return hd_group_fwd<HD, 5>(qkv, out, lse, a, st);
-    case 6: return hd_group_fwd<HD, 6>(qkv, out, lse, a, st);
-    default: return hd_group_fwd<HD, 7>(qkv, out, lse, a, st);
+  int rc;
+  if (time_k) rc = time_k == 1 ? hd_time_fwd<HD, 1>(qkv, out, lse, a, st) : hd_time_fwd<HD, 2>(qkv, out, lse, a, st);
+  else
+    switch (gw) {
+      case 2: rc = hd_group_fwd<HD, 2>(qkv, out, lse, a, st); break;
+      case 3: rc = hd_group_fwd<HD, 3>(qkv, out, lse, a, st); break;
+      case 4: rc = hd_group_fwd<HD, 4>(qkv, out, lse, a, st); break;
+      case 5: rc = hd_group_fwd<HD, 5>(qkv, out, lse, a, st); break;
+      case 6: rc = hd_group_fwd<HD, 6>(qkv, out, lse, a, st); break;
+      default: rc = hd_group_fwd<HD, 7>(qkv, out, lse, a, st); break;
+    }
+  if (sd) {                              // join (also on the error path, so that the side branch never dangles in a capture)
+    TVTS_CHECK_CUDA(cudaEventRecord(sd->join, sd->stream));
+    TVTS_CHECK_CUDA(cudaStreamWaitEvent(st, sd->join, 0));
   }
+  return rc;
 }
 
 template <int HD>
@@ -1236,22 +1271,35 @@ int hd_launch_bwd(const void* qkv, const void* out, const void* dout, const floa
   const int gw = (klen == nullptr && g_hd_group) ? hd_group_warps(a) : 0;
   const int time_k = (klen == nullptr && g_hd_group) ? hd_time_tiles(a) : 0;
   if (!gw && !time_k) return hd_streamed_bwd<HD>(qkv, dout, lse, delta_ws, dqkv, a, st, klen);
+  HdSideStream* sd = (a.mode != 0 && g_hd_side) ? hd_side_stream() : nullptr;
   if (a.mode != 0) {                     // dq of the CLS query, dk / dv of the CLS key
+    cudaStream_t cls_st = st;
+    if (sd) {
+      TVTS_CHECK_CUDA(cudaEventRecord(sd->fork, st));      // after delta
+      TVTS_CHECK_CUDA(cudaStreamWaitEvent(sd->stream, sd->fork, 0));
+      cls_st = sd->stream;
+    }
     AttnShape c = a;
     c.cls_only = 1;
-    int rc = hd_streamed_bwd<HD>(qkv, dout, lse, delta_ws, dqkv, c, st, nullptr);
+    int rc = hd_streamed_bwd<HD>(qkv, dout, lse, delta_ws, dqkv, c, cls_st, nullptr);
     if (rc) return rc;
   }
-  if (time_k)
-    return time_k == 1 ? hd_time_bwd<HD, 1>(qkv, dout, lse, delta_ws, dqkv, a, st) : hd_time_bwd<HD, 2>(qkv, dout, lse, delta_ws, dqkv, a, st);
-  switch (gw) {
-    case 2: return hd_group_bwd<HD, 2>(qkv, dout, lse, delta_ws, dqkv, a, st);
-    case 3: return hd_group_bwd<HD, 3>(qkv, dout, lse, delta_ws, dqkv, a, st);
-    case 4: return hd_group_bwd<HD, 4>(qkv, dout, lse, delta_ws, dqkv, a, st);
-    case 5: return hd_group_bwd<HD, 5>(qkv, dout, lse, delta_ws, dqkv, a, st);
-    case 6: return hd_group_bwd<HD, 6>(qkv, dout, lse, delta_ws, dqkv, a, st);
-    default: return hd_group_bwd<HD, 7>(qkv, dout, lse, delta_ws, dqkv, a, st);
+  int rc;
+  if (time_k) rc = time_k == 1 ? hd_time_bwd<HD, 1>(qkv, dout, lse, delta_ws, dqkv, a, st) : hd_time_bwd<HD, 2>(qkv, dout, lse, delta_ws, dqkv, a, st);
+  else
+    switch (gw) {
+      case 2: rc = hd_group_bwd<HD, 2>(qkv, dout, lse, delta_ws, dqkv, a, st); break;
+      case 3: rc = hd_group_bwd<HD, 3>(qkv, dout, lse, delta_ws, dqkv, a, st); break;
+      case 4: rc = hd_group_bwd<HD, 4>(qkv, dout, lse, delta_ws, dqkv, a, st); break;
+      case 5: rc = hd_group_bwd<HD, 5>(qkv, dout, lse, delta_ws, dqkv, a, st); break;
+      case 6: rc = hd_group_bwd<HD, 6>(qkv, dout, lse, delta_ws, dqkv, a, st); break;
+      default: rc = hd_group_bwd<HD, 7>(qkv, dout, lse, delta_ws, dqkv, a, st); break;
+    }
+  if (sd) {
+    TVTS_CHECK_CUDA(cudaEventRecord(sd->join, sd->stream));
+    TVTS_CHECK_CUDA(cudaStreamWaitEvent(st, sd->join, 0));
   }
+  return rc;
 }
 
 #endif  // !TVTS_HOST_SHIM
@@ -1261,6 +1309,11 @@ int hd_launch_bwd(const void* qkv, const void* out, const void* dout, const floa
 #ifndef TVTS_HOST_SHIM
 extern "C" int tvts_attn_hd_set_group(int on) {
   g_hd_group = on;
+  return TVTS_OK;
+}
+
+extern "C" int tvts_attn_hd_set_side_stream(int on) {
+  g_hd_side = on;
   return TVTS_OK;
 }
 
