@@ -251,8 +251,13 @@ class TrainStep:
             if self.loss_scale != 1.0:
                 if optimizer_launch_only:
                     self.optimizer.launch(1.0 / self.loss_scale)
-                else:
-                    self.optimizer.step(1.0 / self.loss_scale)
+                elif hasattr(self.optimizer, "launch"):
+                    self.optimizer.step(1.0 / self.loss_scale)          # the fused kernel un-scales the gradients itself
+                else:                                                   # stock torch / transformers optimizer: un-scale in place first
+                    for p in self.params:
+                        if p.grad is not None:
+                            p.grad.mul_(1.0 / self.loss_scale)
+                    self.optimizer.step()
             elif optimizer_launch_only:
                 self.optimizer.launch()
             else:
