@@ -47,7 +47,7 @@ def _worker(rank, world, port, out):
         opt = optim.build_reference_optimizer(m)
         E.WEIGHTS.clear()
         step = TrainStep(m, None, cfg.temperature, torch.device("cpu"))
-        step.optimizer = types.SimpleNamespace(flat=opt.flat, zero_grad=opt.zero_grad, step=lambda *a: None)   # keep the weights fixed
+        step.optimizer = types.SimpleNamespace(flat=opt.flat, zero_grad=opt.zero_grad, step=lambda *a: None, launch=lambda *a: None)   # keep the weights fixed
         local = make_batch(cfg, Bl, T, n_trans=nt, seed=3, rank=rank)
         l1, l2 = step(local)
         grads = {k: p.grad.clone() / step.loss_scale for k, p in m.named_parameters() if p.grad is not None}   # (fp16 build: loss-scaled)
@@ -129,7 +129,7 @@ def _worker_v1(rank, world, port, out):
         opt = optim.AdamW([p for p in m.parameters()], lr=1e-4, weight_decay=0.0)
         E.WEIGHTS.clear()
         step = TrainStep(m, None, 0.05, torch.device("cpu"))
-        step.optimizer = types.SimpleNamespace(flat=opt.flat, zero_grad=opt.zero_grad, step=lambda *a: None)   # keep the weights fixed
+        step.optimizer = types.SimpleNamespace(flat=opt.flat, zero_grad=opt.zero_grad, step=lambda *a: None, launch=lambda *a: None)   # keep the weights fixed
         rows = torch.tensor([t * dims.B + rank for t in range(dims.nt)])           # this rank's captions, clip-major
         local = {"video": data["video"][rank:rank + 1], "keep_ind": data["keep_ind"][rank:rank + 1], "label": data["label"][rank:rank + 1],
                  "text": {k: v[rows] for k, v in data["text"].items()}}
