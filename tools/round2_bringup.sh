@@ -1,6 +1,7 @@
 #!/bin/bash
 # First GPU call of round 2: everything that was written after the round-1 GPU budget ran out, in one box session.
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/round2_bringup.sh'
+#   /usr/local/graft/bin/gpurun --timeout 3300 -- 'bash tools/round2_bringup.sh'          (~40-50 min of box time; every step has
+#   its own `timeout`; run sections 1-2 alone first -- `bash tools/round2_bringup.sh quick` -- if the budget is tight)
 # Results land in gpurun_out/r2_bringup/.
 set -x
 mkdir -p gpurun_out/r2_bringup
@@ -11,6 +12,7 @@ TVTS_RUN_STAGED=1 timeout 900 python -m pytest tests/test_zz_round1_unverified_g
 TVTS_RUN_STAGED=1 timeout 900 python -m pytest tests/test_zz_round1_unverified_gpu.py -q -m gpu --tb=line -rA > $O/zz_all.log 2>&1
 # 2. the verified suite (must stay green) incl. the tests that were never run on a GPU in round 1
 timeout 1200 python -m pytest tests -q -m gpu -x --deselect tests/test_zy_staged_wrapper_gpu.py > $O/gpu_suite.log 2>&1
+if [ "$1" = "quick" ]; then tail -5 $O/zz_all.log $O/gpu_suite.log; exit 0; fi
 # 3. loss trajectories (north star: 100 steps within 1e-3)
 timeout 900 python tools/loss_parity.py 100 c1 > $O/loss_parity_c1_100.log 2>&1
 timeout 300 python tools/loss_parity.py 100 tiny > $O/loss_parity_tiny_100.log 2>&1
