@@ -85,3 +85,45 @@ def test_fp16_operand_build_is_selected_by_env_and_checked():
     subprocess.run([sys.executable, "-c", code.replace("\\n", "\n")], check=True, cwd=root, env=dict(os.environ, TVTS_OPERAND="fp16", PYTHONPATH=root))
     from tvts_b200 import _lib
     assert _lib.lib().tvts_operand_format() == int(_lib.OPERAND == "fp16")
+
+
+def test_torch_restatements_take_the_arguments_of_the_c_entry_points():
+    """tests/emu.py stands in for the library in every CPU host-logic test, so each restatement must take exactly the arguments of the
+    C entry point it mirrors (minus the trailing stream): same count, checked against the prototypes in include/tvts_b200.h."""
+    import inspect
+    import emu
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "include", "tvts_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = dict(re.findall(r"\bint\s+tvts_(\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S))
+    checked = 0
+    for name, fn in emu.OPS.items():
+        if name not in protos:
+            continue
+        params = [p.strip() for p in protos[name].split(",") if p.strip() and p.strip() != "void"]
+        assert params and params[-1].replace(" ", "").startswith("void*stream"), (name, params[-1])
+        arity = len([p for p in inspect.signature(fn).parameters.values() if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)])
+        var = any(p.kind == p.VAR_POSITIONAL for p in inspect.signature(fn).parameters.values())
+        assert var or arity == len(params) - 1, (name, arity, len(params) - 1)
+        checked += 1
+    assert checked >= 35, checked
+
+
+def test_gemm_args_struct_layout_matches_the_header(tmp_path):
+    """tvts_b200/_lib.GemmArgs (ctypes) must mirror `struct tvts_gemm_args` byte for byte: size and every field offset, as compiled by gcc."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        import pytest
+        pytest.skip("needs gcc")
+    from tvts_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fields = [f[0] for f in _lib.GemmArgs._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "tvts_b200.h"\nint main(void) {\n  printf("%zu\\n", sizeof(tvts_gemm_args));\n'
+                   + "".join(f'  printf("%zu\\n", offsetof(tvts_gemm_args, {f}));\n' for f in fields) + "  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert out[0] == ctypes.sizeof(_lib.GemmArgs)
+    assert out[1:] == [getattr(_lib.GemmArgs, f).offset for f in fields]
