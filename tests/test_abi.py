@@ -127,3 +127,14 @@ def test_gemm_args_struct_layout_matches_the_header(tmp_path):
     out = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     assert out[0] == ctypes.sizeof(_lib.GemmArgs)
     assert out[1:] == [getattr(_lib.GemmArgs, f).offset for f in fields]
+
+
+def test_product_package_never_imports_the_oracle_or_the_test_restatements():
+    """The oracle and tests/emu.py are test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import them."""
+    import glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r"^\s*(from|import)\s+(emu|tvts_oracle|oracle|tests)\b", re.M)
+    for path in glob.glob(os.path.join(root, "tvts_b200", "**", "*.py"), recursive=True):
+        assert not pat.search(open(path).read()), path
+    bench_src = open(os.path.join(root, "bench.py")).read()
+    assert len(re.findall(r"import tvts_oracle", bench_src)) == 1 and "def cpu_oracle_steps" in bench_src     # the CPU legs only
