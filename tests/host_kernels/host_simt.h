@@ -15,6 +15,7 @@
 #define __align__(x) __attribute__((aligned(x)))
 #define TVTS_DYN_SMEM(type, name, align) type* const name = reinterpret_cast<type*>(simt::dyn_smem)
 #define __expf(x) expf(x)
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #ifndef INFINITY
 #define INFINITY (__builtin_inff())
 #endif

@@ -261,3 +261,48 @@ def test_specialised_attention_kernels_on_the_cpu_simt_stand_in(hattn64, B, H, m
     emu.attn_bwd(qkv, ro, dout, rl, rdel, rd, B, N, H, d, mode, T, n, int(causal), scale)
     assert torch.isfinite(dqkv.float()).all()
     assert torch.allclose(dqkv.float(), rd.float(), atol=3e-2, rtol=3e-2), (dqkv.float() - rd.float()).abs().max()
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+@pytest.fixture(scope="module")
+def hln(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("hostln") / "libhostln.so")
+    subprocess.run(["g++", "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC", "-U_FORTIFY_SOURCE", "-D_FORTIFY_SOURCE=0", "-DTVTS_HOST_SHIM", "-I", HERE,
+                    os.path.join(HERE, "harness_ln.cpp"), "-o", out], check=True)
+    return ctypes.CDLL(out)
+
+
+@pytest.mark.parametrize("M,D,grid", [(37, 640, 2), (21, 768, 3), (9, 128, 1), (12, 1280, 5)])
+def test_layernorm_kernels_on_the_cpu_simt_stand_in(hln, M, D, grid):
+    """layernorm.cu on the stand-in: width 640 (NV = 5, added for the H/14 test model) and the backward with the fused bias-gradient
+    column sums (`dxsum`), neither of which has been through a GPU test yet; 768 / 128 / 1280 are the GPU-verified widths."""
+    g_ = torch.Generator().manual_seed(M + D)
+    x = torch.randn(M, D, generator=g_) * 2 + 0.5
+    gam, bet = 1 + 0.1 * torch.randn(D, generator=g_), 0.1 * torch.randn(D, generator=g_)
+    for y_bf16 in (1, 0):
+        y = torch.empty(M, D, dtype=BF16 if y_bf16 else torch.float32)
+        mean, rstd = torch.empty(M), torch.empty(M)
+        assert hln.h_ln_fwd(P(x), P(gam), P(bet), P(y), ctypes.c_int(y_bf16), P(mean), P(rstd), I(M), I(D), ctypes.c_float(1e-5)) == 0
+        ry = torch.empty_like(y)
+        rm, rr = torch.empty(M), torch.empty(M)
+        emu.layernorm_fwd(x, gam, bet, ry, y_bf16, rm, rr, M, D, 1e-5)
+        assert torch.allclose(y.float(), ry.float(), atol=2e-2 if y_bf16 else 2e-5)
+        assert torch.allclose(mean, rm, atol=1e-5) and torch.allclose(rstd, rr, atol=1e-5, rtol=1e-4)
+    for dy_bf16 in (1, 0):
+        dy = torch.randn(M, D, generator=g_).to(BF16 if dy_bf16 else torch.float32)
+        r1, r2 = torch.randn(M, D, generator=g_), torch.randn(M, D, generator=g_)
+        res = []
+        for host in (True, False):
+            dx, dxb = torch.empty(M, D), torch.empty(M, D, dtype=BF16)
+            dg, db, dxs = torch.zeros(D), torch.zeros(D), torch.ones(D)
+            if host:
+                assert hln.h_ln_bwd(P(dy), ctypes.c_int(dy_bf16), P(x), P(rm), P(rr), P(gam), P(r1), P(r2), P(dx), P(dxb), P(dg), P(db), P(dxs),
+                                    I(M), I(D), ctypes.c_int(grid)) == 0
+            else:
+                emu.layernorm_bwd_colsum(dy, dy_bf16, x, rm, rr, gam, r1, r2, dx, dxb, dg, db, dxs, M, D)
+            res.append((dx, dxb, dg, db, dxs))
+        assert torch.allclose(res[0][0], res[1][0], atol=2e-4)
+        assert torch.allclose(res[0][1].float(), res[1][1].float(), atol=5e-2)
+        for i in (2, 3, 4):
+            assert torch.allclose(res[0][i], res[1][i], atol=1e-3 * M ** 0.5), i
+        assert torch.allclose(res[0][4], 1.0 + res[0][0].sum(0), atol=1e-3)        # dxsum accumulates the column sums of dx

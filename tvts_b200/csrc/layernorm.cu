@@ -7,8 +7,12 @@
 // (bf16) directly, or fp32 for the residual stream (ln_pre).  The backward fuses: up to two incoming residual
 // gradients, the fp32 result, a bf16 copy of the result (operand of the next dgrad/wgrad GEMMs) and the
 // dgamma/dbeta column reductions (register partials per warp -> smem -> one atomicAdd per column per CTA).
+#ifdef TVTS_HOST_SHIM          // tests/host_kernels: the kernels are also compiled for the CPU SIMT stand-in
+#include "host_simt.h"
+#else
 #include "common.cuh"
 #include "../../include/tvts_b200.h"
+#endif
 
 namespace {
 
@@ -146,6 +150,7 @@ __global__ void __launch_bounds__(kWarps * 32) ln_bwd_kernel(const void* __restr
 
 }  // namespace
 
+#ifndef TVTS_HOST_SHIM
 #define LN_DISPATCH_NV(D, MACRO)  \
   switch ((D) / 128) {            \
     case 1: MACRO(1); break;      \
@@ -203,3 +208,4 @@ extern "C" int tvts_layernorm_bwd(const void* dy, int64_t dy_is_bf16, const floa
                                   float* dbeta, int64_t M, int64_t D, void* stream_) {
   return tvts_layernorm_bwd_colsum(dy, dy_is_bf16, x, mean, rstd, gamma, res1, res2, dx, dx_bf16, dgamma, dbeta, nullptr, M, D, stream_);
 }
+#endif  // !TVTS_HOST_SHIM
