@@ -100,26 +100,3 @@ def test_missing_library_is_loud(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libtvts_b200.so")
     with pytest.raises(RuntimeError, match="no CPU / PyTorch fallback"):
         _lib.lib()
-
-
-def test_validation_path_runs_and_similarities_match_oracle():
-    """Validation path (forward only, v2/trainer/trainer.py:527-635): metrics are produced, no gradients appear, and the
-    text x video similarity matrix the metrics are computed from matches the CPU oracle's (bf16 tolerance).  (Rank-based R@k of a
-    RANDOM-INIT toy model is decided by similarity gaps far below bf16 noise, so ranks themselves are compared only on CPU with
-    exact inputs: tests/test_metrics_cpu.py.)"""
-    from tvts_b200.trainer import validate
-    cfg = C.TINY_B
-    m, sd = build(cfg)
-    batch = make_batch(cfg, 12, 2, n_trans=4, seed=40)
-    res = validate(m, [to_cuda(batch)])
-    assert set(res) == {"t2v_metrics", "v2t_metrics", "order_acc"}
-    for k in ("t2v_metrics", "v2t_metrics"):
-        assert 0.0 <= res[k]["R1"] <= 100.0 and res[k]["MedR"] >= 1.0
-    assert res["order_acc"] is not None and all(p.grad is None for p in m.parameters())
-    with torch.no_grad():
-        te, ve, _ = m(to_cuda(batch))
-        sims = M.sim_matrix(te, ve).cpu()
-        ote, ove, _ = O.model_forward(sd, batch["text"], batch["video"], batch["keep_ind"], cfg)
-    osims = O.sim_matrix(ote, ove)
-    assert (sims - osims).abs().max().item() < 8e-2, (sims - osims).abs().max()
-

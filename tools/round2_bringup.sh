@@ -18,7 +18,7 @@ timeout 900 python tools/loss_parity.py 100 c1 > $O/loss_parity_c1_100.log 2>&1
 timeout 300 python tools/loss_parity.py 100 tiny > $O/loss_parity_tiny_100.log 2>&1
 timeout 600 python tools/loss_parity.py 30 tiny_h > $O/loss_parity_tiny_h_30.log 2>&1
 # 3b. the fp16-operand build (libtvts_b200_fp16.so): kernel / model / train-step suites, then the same trajectories and the headline bench
-TVTS_OPERAND=fp16 timeout 1500 python -m pytest tests/test_kernels_gpu.py tests/test_model_gpu.py tests/test_trainstep_gpu.py -q -m gpu --tb=line -rA > $O/fp16_suites.log 2>&1
+TVTS_OPERAND=fp16 timeout 1500 python -m pytest tests/test_kernels_gpu.py tests/test_model_gpu.py tests/test_trainstep_gpu.py tests/test_y_late_additions_gpu.py -q -m gpu --tb=line -rA > $O/fp16_suites.log 2>&1
 TVTS_OPERAND=fp16 timeout 900 python tools/loss_parity.py 100 c1 > $O/fp16_loss_parity_c1_100.log 2>&1
 TVTS_OPERAND=fp16 timeout 300 python tools/loss_parity.py 100 tiny > $O/fp16_loss_parity_tiny_100.log 2>&1
 TVTS_OPERAND=fp16 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $O/fp16_bench_c3.json 2> $O/fp16_bench_c3.err
