@@ -358,21 +358,12 @@ def run_ours(args):
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
+    step.close()            # destroy the captured graphs (they hold the step's NCCL kernels) BEFORE the process group goes away
     if world > 1:
-        # Leave WITHOUT tearing the process group down: destroying it while CUDA graphs that captured its NCCL kernels are still
-        # alive hung every multi-rank run of round 1 after the line had been printed (profiles/r1_final_scaling.md).  All ranks
-        # meet at a last barrier (everything, including rank 0's print, is done), then exit without running finalizers.
         sys.stdout.flush()
         sys.stderr.flush()
-        watchdog = threading.Timer(30.0, lambda: os._exit(0))     # the measurement is complete: never let teardown hold the job
-        watchdog.daemon = True
-        watchdog.start()
-        try:
-            dist.barrier()
-            torch.cuda.synchronize()
-        except Exception:
-            pass
-        os._exit(0)
+        barrier()
+        dist.destroy_process_group()
 
 
 def main():

@@ -255,6 +255,15 @@ int tvts_sort_ce(const float* logits, const int64_t* labels, const float* gout, 
 int tvts_adamw_flat(float* p, const float* g, float* m, float* v, void* p_bf16, const int32_t* chunk_tensor, const float* table,
                     int64_t n_chunks, int64_t chunk_elems, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
+/* The same update under DYNAMIC loss scaling (IEEE-half operand build), decided entirely on the device so that the step stays one
+ * CUDA graph: a finite check over the gradient arena, the update (skipped as a whole when a non-finite gradient was seen; gradients
+ * are divided by the current scale; bias correction evaluated from the device-side per-tensor step counters `steps`), and the scale
+ * policy of torch.cuda.amp.GradScaler (x0.5 + skip on overflow, x2 after `growth_interval` finite steps, capped at max_scale).
+ * table[t] = {lr, lr*weight_decay, active, correct_bias};  state = {scale, finite_steps, found_inf, skipped_steps} (fp32[4]). */
+int tvts_adamw_flat_dyn(float* p, const float* g, float* m, float* v, void* p_bf16, const int32_t* chunk_tensor, const float* table,
+                        int32_t* steps, float* state, int64_t n_tensors, int64_t n_chunks, int64_t chunk_elems, float beta1, float beta2,
+                        float eps, float growth_interval, float max_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

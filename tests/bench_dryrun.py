@@ -23,6 +23,7 @@ class FakeEvent:
 class FakeGraph:
     def __init__(self): self.fn = None; self.outs = None
     def pool(self): return "pool"
+    def reset(self): self.fn = None
     def replay(self):
         for d, s in zip(self.outs, self.fn()): d.copy_(s)
 state = types.SimpleNamespace(capturing=None)
@@ -55,11 +56,12 @@ _real_init = dist.init_process_group
 dist.init_process_group = lambda backend=None, **k: _real_init("gloo")      # multi-rank dry run (torchrun): gloo in place of nccl
 import bench
 if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-    # multi-rank dry run (launched by torchrun): one configuration, printed straight to stdout -- run_ours leaves through the barrier +
-    # os._exit(0) path that replaced destroy_process_group after round 1's teardown hangs, so nothing after this call executes
+    # multi-rank dry run (launched by torchrun): one configuration, printed straight to stdout -- run_ours destroys its captured graphs,
+    # then the process group, and RETURNS (round 1 left through os._exit because the teardown hung under live graphs)
     sys.argv = ["bench.py", "--gpus", os.environ["WORLD_SIZE"], "--workload", "tiny", "--steps", "2", "--warmup", "1", "--no-cpu-baseline"]
     bench.run_ours(bench.parse())
-    raise SystemExit("run_ours returned in a multi-rank run (expected os._exit(0))")
+    assert not dist.is_initialized(), "run_ours must leave the process group destroyed"
+    raise SystemExit(0)
 for extra in ([], ["--u8-input", "--trim-text"]) + ((["--no-graph"],) if "--all" in sys.argv[1:] else ()):
     sys.argv = ["bench.py", "--workload", "tiny", "--steps", "2", "--warmup", "1", "--no-cpu-baseline"] + extra
     buf = io.StringIO()

@@ -435,6 +435,26 @@ def adamw_flat(p, g, m, v, pb, chunk_tensor, table, n_chunks, chunk, b1, b2, eps
         PB.copy_(torch.where(act, P.to(BF16), PB))
 
 
+def adamw_flat_dyn(p, g, m, v, pb, chunk_tensor, table, steps, state, n_tensors, n_chunks, chunk, b1, b2, eps, growth_interval, max_scale):
+    bad = not bool(torch.isfinite(g).all())
+    if not bad:
+        t = (steps.float() + 1.0)
+        tab = table.clone()
+        corr = torch.sqrt(1.0 - torch.pow(torch.tensor(b2), t)) / (1.0 - torch.pow(torch.tensor(b1), t))
+        tab[:, 0] = torch.where(table[:, 3] != 0, table[:, 0] * corr, table[:, 0])
+        adamw_flat(p, g, m, v, pb, chunk_tensor, tab, n_chunks, chunk, b1, b2, eps, 1.0 / float(state[0]))
+        steps += (table[:, 2] != 0).to(steps.dtype)
+        state[1] += 1
+        if float(state[1]) >= growth_interval:
+            state[0] = min(float(state[0]) * 2.0, max_scale)
+            state[1] = 0
+    else:
+        state[0] = max(float(state[0]) * 0.5, 1.0)
+        state[1] = 0
+        state[3] += 1
+    state[2] = 0
+
+
 OPS = {k: v for k, v in list(globals().items()) if callable(v) and not k.startswith("_") and k not in ("install", "uninstall", "gemm")}
 
 _saved = {}

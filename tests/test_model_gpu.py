@@ -94,6 +94,29 @@ def test_c1_against_reference_golden():
     assert not bad, bad[:8]
 
 
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("wl,batch", [("c3", 2), ("c2", 2)])
+def test_production_shape_matches_oracle(wl, batch):
+    """The shapes bench.py times (BASELINE.json configs[2] / [1]): real ViT-B/16 (mask 0.5, N = 785) / ViT-B/32 towers, T = 8, n_trans = 4,
+    a 2-pair sample: the only cases that run the 99-token space groups, the T = 8 time kernels and the deep-K split-K weight gradients.
+    Losses, embeddings, order logits and EVERY parameter gradient against the CPU oracle (a few seconds of host time)."""
+    w = C.WORKLOADS[wl]
+    cfg = w.arch
+    m, sd = build(cfg)
+    data = make_batch(cfg, batch, w.frames, n_trans=w.n_trans, seed=11)
+    l1, l2, te, ve, pred = run_step(m, to_cuda(data), cfg)
+    o1, o2, (ote, ove, opred), ograds = O.step_with_grads(sd, data["text"], data["video"], data["keep_ind"], data["label"], cfg)
+    assert torch.allclose(te, ote, atol=3e-2, rtol=3e-2), (te - ote).abs().max()
+    assert torch.allclose(ve, ove, atol=3e-2, rtol=3e-2), (ve - ove).abs().max()
+    assert torch.allclose(pred, opred, atol=5e-2, rtol=5e-2), (pred - opred).abs().max()
+    assert abs(l1 - o1.item()) < 2e-2 and abs(l2 - o2.item()) < 2e-2, (l1, o1.item(), l2, o2.item())
+    got = {k: p.grad.cpu() for k, p in m.named_parameters() if p.grad is not None}
+    assert set(got.keys()) == set(ograds.keys()), set(got.keys()) ^ set(ograds.keys())
+    worst = max(((got[k].double() - g.double()).norm().item() / (g.double().norm().item() + 1e-8), k) for k, g in ograds.items())
+    print(f"{wl}: |dloss1|={abs(l1 - o1.item()):.2e} |dloss2|={abs(l2 - o2.item()):.2e} worst grad rel-L2 {worst[0]:.3f} ({worst[1]})")
+    assert worst[0] < 0.08, worst
+
+
 def test_missing_library_is_loud(monkeypatch):
     from tvts_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)

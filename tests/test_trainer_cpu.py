@@ -74,7 +74,7 @@ def test_epoch_loop_interleaves_loaders_and_decays_lr(emu_backend):
         assert all(k in hist[0] for k in ("loss_0", "loss_1", "val_0_t2v_metrics_R1", "val_loss_0"))
         assert hist[0]["loss_0"] > 0 and hist[0]["loss_1"] > 0
         assert not torch.equal(w0, m.video_model.proj.detach())
-        steps = {id(p): s for s, p in zip(opt.steps, opt.flat.params)}
+        steps = {id(p): s for s, p in zip(opt.sync_steps(), opt.flat.params)}
         assert steps[id(m.video_model.proj)] == 12                         # every loader batch of both epochs
         assert steps[id(m.pred_model.head.weight)] == 6                    # transcript (YT) batches only: WebVid steps skip the sort head
     finally:
@@ -133,7 +133,7 @@ def test_checkpoint_file_has_the_reference_layout_and_resumes_exactly(emu_backen
     tr2, m2, opt2, _ = _mini_trainer(cfg, seed_sd=99, config=Cfg({"trainer": {"epochs": 1}, "optimizer": {"type": "AdamW"}}))
     try:
         assert tr2.start_epoch == 2
-        assert opt2.steps[0] == 2 and opt2.param_groups[0]["lr"] == opt.param_groups[0]["lr"]
+        assert opt2.sync_steps()[0] == 2 and opt2.param_groups[0]["lr"] == opt.param_groups[0]["lr"]
         assert m2.video_model.proj.data_ptr() == opt2.flat._view(opt2.flat.p, m2.video_model.proj).data_ptr()   # still arena views
         got = [tuple(x.item() for x in tr2.step(b)) for b in batches[2:]]
         assert got == ref_losses, (got, ref_losses)

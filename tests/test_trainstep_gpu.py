@@ -18,13 +18,16 @@ from tvts_b200.trainer import TrainStep
 pytestmark = pytest.mark.gpu
 
 
-def run(cfg, use_graph, n_steps=4):
+def run(cfg, use_graph, n_steps=6, lr_scale=1.0):
     m = M.TVTSv2Base(types.SimpleNamespace(local_rank=0), arch=cfg)
     m.load_state_dict(make_state_dict(cfg, seed=1234), strict=True)
     m = m.cuda()
     opt = optim.build_reference_optimizer(m)
     for g in opt.param_groups:
-        g["lr"] *= 30.0                      # visible updates within a few steps
+        g["lr"] *= lr_scale
+    names = {id(p): n for n, p in m.named_parameters()}
+    groups_by_name = {names[id(p)]: (g["lr"], g["weight_decay"]) for g in opt.param_groups for p in g["params"]}
+    frozen = {n for n, p in m.named_parameters() if not p.requires_grad}
     step = TrainStep(m, opt, cfg.temperature, torch.device("cuda"), use_graph=use_graph)
     losses = []
     try:
@@ -33,22 +36,87 @@ def run(cfg, use_graph, n_steps=4):
             l1, l2 = step(data)
             losses.append((l1.item(), l2.item()))
         params = {k: p.detach().float().cpu().clone() for k, p in m.named_parameters()}
+        skipped = opt.skipped_steps
     finally:
         opt.flat.release()
-    return losses, params, step
+        step.close()
+    return losses, params, step, (groups_by_name, frozen), skipped
 
 
-def test_graph_replay_matches_eager_steps():
+def oracle_losses(cfg, n_steps, groups_by_name, frozen):
+    """The reference algorithm in fp32 on the CPU + the restated transformers.AdamW, same init, same batches."""
+    sd = {k: v.clone() for k, v in make_state_dict(cfg, seed=1234).items()}
+    mom = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in sd.items()}
+    trainable = {k for k in sd if k not in frozen}
+    out = []
+    for t in range(1, n_steps + 1):
+        data = make_batch(cfg, 2, 3, n_trans=4, seed=t - 1)
+        l1, l2, _, grads = O.step_with_grads(sd, data["text"], data["video"], data["keep_ind"], data["label"], cfg, trainable=trainable)
+        out.append((l1.item(), l2.item()))
+        for k, g in grads.items():
+            lr, wd = groups_by_name[k]
+            O.adamw_step(sd[k], g, mom[k][0], mom[k][1], t, lr, weight_decay=wd)
+    return out
+
+
+# Bounds on |loss(ours) - loss(oracle)| per step at the toy widths, from the B200 runs recorded in profiles/r2_loss_trajectory.md
+# (fp16 operands: 1.1e-3 / 6.5e-4 over 100 toy steps; bf16 operands: 8.7e-3 / 4.1e-3)
+ORACLE_BOUND = 2e-3 if OPERAND_DTYPE == torch.float16 else 1e-2
+
+
+def test_graph_replay_and_eager_steps_match_each_other_and_the_oracle():
+    """The CUDA-graph replay (what bench.py times) and kernel-by-kernel launching are the same program: at the reference learning rates
+    their losses agree to fp32 summation-order noise (split-K / LayerNorm-gradient atomics: 1e-7 relative on a gradient, measured with
+    tools/diag_graph.py) and BOTH track the oracle + restated AdamW.  (Round 1 compared the two paths at 30x the learning rate: Adam's
+    m/(sqrt(v)+eps) has a gain of lr/eps = 3000 there for parameters whose gradient is below eps = 1e-6, which turns that 1e-7 noise
+    into a bimodal 3e-3 loss split between ANY two runs -- eager vs eager included; profiles/r2_graph_vs_eager_diag.md.)"""
     cfg = C.TINY_B_MASK
-    le, pe, _ = run(cfg, False)
-    lg, pg, step = run(cfg, True)
+    le, pe, _, (groups, frozen), sk_e = run(cfg, False)
+    lg, pg, step, _, sk_g = run(cfg, True)
     assert step.launches_per_graph > 100
+    assert sk_e == 0 and sk_g == 0                                       # no step was skipped by the dynamic loss scale
     for (a1, a2), (b1, b2) in zip(le, lg):
-        assert abs(a1 - b1) < 2e-3 and abs(a2 - b2) < 2e-3, (le, lg)      # split-K / LN-gradient atomics reorder fp32 sums
+        assert abs(a1 - b1) < 2e-5 and abs(a2 - b2) < 2e-5, (le, lg)
     for k in pe:
         d = (pe[k] - pg[k]).abs().max().item()
-        assert d < 5e-3 * max(1.0, pe[k].abs().max().item()), (k, d)
-    assert le[-1][0] != le[0][0]                                          # the weights did move
+        assert d < 2e-5 * max(1.0, pe[k].abs().max().item()), (k, d)
+    lo = oracle_losses(cfg, len(le), groups, frozen)
+    for path in (le, lg):
+        for (a1, a2), (o1, o2) in zip(path, lo):
+            assert abs(a1 - o1) < ORACLE_BOUND and abs(a2 - o2) < ORACLE_BOUND, (path, lo)
+    assert le[-1][0] != le[0][0]
+
+
+def test_dynamic_loss_scale_skips_overflowing_step_and_recovers():
+    """IEEE-half operand build: a step whose gradients overflow is skipped ON THE DEVICE (weights, moments and step counters untouched,
+    scale halved), inside the same captured graph; the next steps run normally."""
+    if OPERAND_DTYPE != torch.float16:
+        pytest.skip("bf16 operand build runs without a loss scale")
+    cfg = C.TINY_B_MASK
+    m = M.TVTSv2Base(types.SimpleNamespace(local_rank=0), arch=cfg)
+    m.load_state_dict(make_state_dict(cfg, seed=1234), strict=True)
+    m = m.cuda()
+    opt = optim.build_reference_optimizer(m)
+    step = TrainStep(m, opt, cfg.temperature, torch.device("cuda"), use_graph=True)
+    try:
+        data = make_batch(cfg, 2, 3, n_trans=4, seed=0)
+        step(data)
+        torch.cuda.synchronize()
+        assert opt.skipped_steps == 0 and float(opt.scale_tensor) == 1024.0 and max(opt.sync_steps()) == 1
+        before = opt.flat.p.clone()
+        opt.scale_state[0] = 2.0 ** 40                                   # force an overflow of the 16-bit gradient operands
+        step(data)
+        torch.cuda.synchronize()
+        assert opt.skipped_steps == 1 and float(opt.scale_tensor) == 2.0 ** 39
+        assert torch.equal(before, opt.flat.p) and max(opt.sync_steps()) == 1
+        opt.scale_state[0] = 1024.0
+        l1, l2 = step(data)
+        torch.cuda.synchronize()
+        assert opt.skipped_steps == 1 and max(opt.sync_steps()) == 2 and not torch.equal(before, opt.flat.p)
+        assert torch.isfinite(opt.flat.p).all() and torch.isfinite(l1) and torch.isfinite(l2)
+    finally:
+        opt.flat.release()
+        step.close()
 
 
 def test_fused_adamw_kernel_matches_oracle_restatement():
@@ -56,7 +124,7 @@ def test_fused_adamw_kernel_matches_oracle_restatement():
     ps = [torch.nn.Parameter(torch.randn(5000, device="cuda")), torch.nn.Parameter(torch.randn(33, 7, device="cuda")),
           torch.nn.Parameter(torch.randn(4096, device="cuda"))]
     groups = [{"params": [ps[0], ps[2]], "lr": 1e-2, "weight_decay": 0.05}, {"params": [ps[1]], "lr": 3e-3, "weight_decay": 0.0}]
-    opt = optim.AdamW(groups)
+    opt = optim.AdamW(groups, dynamic_scale=False)       # raw (unscaled) gradients are written below
     try:
         ref = [p.detach().cpu().clone() for p in ps]
         mom = [(torch.zeros_like(r), torch.zeros_like(r)) for r in ref]

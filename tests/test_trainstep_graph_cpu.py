@@ -45,6 +45,9 @@ class FakeGraph:
     def pool(self):
         return ("pool-of", id(self))
 
+    def reset(self):
+        self.fn = None
+
     def replay(self):
         new = self.fn()
         for dst, src in zip(self.outs, new):
@@ -59,14 +62,16 @@ def fake_cuda(monkeypatch, emu_backend):
     def graph_ctx(g, pool=None):
         FakeGraph.captured_pools.append(pool)
         fs = state.step.optimizer.flat
-        snap = (fs.p.clone(), fs.m.clone(), fs.v.clone(), fs.bf.clone(), list(state.step.optimizer.steps))
+        opt = state.step.optimizer
+        snap = (fs.p.clone(), fs.m.clone(), fs.v.clone(), fs.bf.clone(), list(opt.steps), opt.steps_dev.clone(), opt.scale_state.clone())
         state.capturing = g
         try:
             yield
         finally:
             state.capturing = None
             fs.p.copy_(snap[0]); fs.m.copy_(snap[1]); fs.v.copy_(snap[2]); fs.bf.copy_(snap[3])      # a capture executes nothing
-            state.step.optimizer.steps[:] = snap[4]
+            opt.steps[:] = snap[4]
+            opt.steps_dev.copy_(snap[5]); opt.scale_state.copy_(snap[6])       # (dynamic loss scaling keeps its counters on the device)
 
     orig_body = TR.TrainStep._body
 

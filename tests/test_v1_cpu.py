@@ -109,7 +109,7 @@ def test_v1_trainer_loop_tokenises_like_the_reference_and_steps(emu_backend):
         assert tok.calls[0][1] is True and tok.calls[0][2] == 50                                                     # trainer.py:130-131
         assert not torch.equal(w0, m.text_model.transformer.layer[0].ffn.lin1.weight.detach())                        # DistilBERT is trained
         assert opt.param_groups[0]["lr"] == 1e-3 * 0.1                        # absolute schedule: base_lr x 0.1 once epoch >= 2
-        assert all(s == 4 for s in opt.steps)
+        assert all(s == 4 for s in opt.sync_steps())
     finally:
         opt.flat.release()
 

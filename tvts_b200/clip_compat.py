@@ -19,11 +19,11 @@ def _read_state_dict(path):
         jit = torch.jit.load(path, map_location="cpu")
         return jit.state_dict()
     except Exception:
-        sd = torch.load(path, map_location="cpu")
+        sd = torch.load(path, map_location="cpu", weights_only=False)
         return sd.get("state_dict", sd) if isinstance(sd, dict) else sd.state_dict()
 
 
-def load(name, arch, device="cpu", open_clip=False):
+def load(name, arch, device="cpu", open_clip=False, allow_missing=False):
     """-> (CLIPTextParts, visual_state_dict | None).  open_clip=True: the text blocks register their parameters in OpenCLIP's order
     (v2/OpenCLIP/transformer.py:189-214); an OpenCLIP `open_clip_pytorch_model.bin` has the same key layout as an OpenAI state_dict."""
     parts = M.CLIPTextParts(embed_dim=arch.embed_dim, context_length=arch.context, vocab_size=arch.vocab,
@@ -37,6 +37,9 @@ def load(name, arch, device="cpu", open_clip=False):
         if missing.missing_keys:
             warnings.warn(f"CLIP checkpoint {name} lacks text keys: {missing.missing_keys[:4]}...")
         visual_sd = {k[len("visual."):]: v for k, v in sd.items() if k.startswith("visual.")}
+    elif not allow_missing:
+        raise RuntimeError(f"Model {name} not found (the reference's clip.load raises here too); pass arch= / load_checkpoint= or set "
+                           "TVTS_ALLOW_RANDOM_CLIP=1 to build the towers from a random initialisation")
     else:
         warnings.warn(f"CLIP checkpoint '{name}' not found: text tower random-initialised (CLIP.initialize_parameters), "
                       "video tower keeps its fresh init")

@@ -14,6 +14,7 @@ Reference classes mirrored (paths relative to /root/reference):
   sim_matrix                                          v2/model/model_dist_TVTSv2_ViT_B_16.py:119-127
 """
 import math
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -351,9 +352,12 @@ class TVTSv2Base(BaseModel):
         self.args = args
         self.num_clips = 4
         from .clip_compat import load as clip_load
+        # an explicit `arch=` (tests, bench: synthetic weights) or a checkpoint that overwrites every weight anyway may run without the
+        # released CLIP file; the plain reference-style construction raises like clip.load does (v2/CLIP/clip/clip.py:120-127)
+        allow_missing = arch is not None or load_checkpoint not in ["", None] or os.environ.get("TVTS_ALLOW_RANDOM_CLIP") == "1"
         arch = arch or (C.TVTSV2_B_16 if self.PATCH == 16 else C.TVTSV2_B_32)
         self.arch = arch
-        clip_model, clip_visual_sd = clip_load(self.CLIP_FILE, arch, open_clip=self.OPEN_CLIP)
+        clip_model, clip_visual_sd = clip_load(self.CLIP_FILE, arch, open_clip=self.OPEN_CLIP, allow_missing=allow_missing)
         self.text_model = clip_model.transformer
         self.text_token_embedding = clip_model.token_embedding
         self.text_positional_embedding = clip_model.positional_embedding
@@ -371,7 +375,8 @@ class TVTSv2Base(BaseModel):
             self.n_trans = arch.n_trans
             self.pred_model = SortTransformer(num_classes=self.n_trans, embed_dim=arch.embed_dim, num_heads=arch.sort_heads)
         if load_checkpoint not in ["", None]:
-            checkpoint = torch.load(load_checkpoint, map_location=self._checkpoint_location())
+            # reference checkpoints pickle their ConfigParser next to the weights (base_trainer.py:173-181): weights_only must be off
+            checkpoint = torch.load(load_checkpoint, map_location=self._checkpoint_location(), weights_only=False)
             state_dict = checkpoint["state_dict"]
             from .compat import state_dict_data_parallel_fix
             self.load_state_dict(state_dict_data_parallel_fix(state_dict, self.state_dict()), strict=True)

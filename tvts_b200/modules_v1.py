@@ -227,7 +227,7 @@ class TVTS(BaseModel):
             if load_checkpoint in ["", None]:
                 import os
                 if os.path.isfile("./mae_pretrain_vit_base.pth"):                    # :49-61 MAE IN-1K init, 2-D kernel repeated over dt
-                    sd = torch.load("./mae_pretrain_vit_base.pth", map_location="cpu")["model"]
+                    sd = torch.load("./mae_pretrain_vit_base.pth", map_location="cpu", weights_only=False)["model"]
                     if "patch_embed.proj.weight" in sd and sd["patch_embed.proj.weight"].dim() == 4:
                         sd["patch_embed.proj.weight"] = sd["patch_embed.proj.weight"].unsqueeze(2).repeat(1, 1, 2, 1, 1)
                     video_model.load_state_dict(sd, strict=False)
@@ -244,7 +244,7 @@ class TVTS(BaseModel):
         self.n_trans = 4
         self.pred_model = SortTransformer(num_classes=self.n_trans, embed_dim=ftr_dim, num_heads=sort_heads)
         if load_checkpoint not in ["", None]:
-            checkpoint = torch.load(load_checkpoint, map_location="cuda:{}".format(self.args.local_rank))
+            checkpoint = torch.load(load_checkpoint, map_location="cuda:{}".format(self.args.local_rank), weights_only=False)
             from .compat import state_dict_data_parallel_fix
             self.load_state_dict(state_dict_data_parallel_fix(checkpoint["state_dict"], self.state_dict()), strict=True)
             print("loading checkpoint from {}".format(load_checkpoint))

@@ -169,7 +169,14 @@ def reference_param_groups(named_parameters, text_layers=12, tune_from=9):
 class AdamW:
     """transformers.AdamW semantics (see module docstring) over a FlatState; `param_groups` is mutable like torch's."""
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, correct_bias=True):
+    GROWTH_INTERVAL = 2000          # torch.cuda.amp.GradScaler defaults (x2 after 2000 finite steps, x0.5 + skipped step on overflow)
+    MAX_SCALE = 2.0 ** 24
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, correct_bias=True, dynamic_scale=None,
+                 init_scale=None):
+        """dynamic_scale (default: on for the IEEE-half operand build, off for bf16): the backward runs under a loss scale that lives
+        on the device (`scale_tensor`); launch() checks the gradient arena for non-finite values, skips the whole update when it finds
+        one and adapts the scale -- all inside the captured step, no host synchronisation."""
         groups = list(params)
         if groups and not isinstance(groups[0], dict):
             groups = [{"params": groups}]
@@ -190,6 +197,25 @@ class AdamW:
         self._ring_ev = [None] * 4
         self._slot = 0
         self.table = torch.zeros(len(flat), 4, dtype=torch.float32, device=self.flat.device)
+        self.dynamic_scale = (L.OPERAND == "fp16") if dynamic_scale is None else bool(dynamic_scale)
+        self._init_scale = float(init_scale if init_scale is not None else (L.DEFAULT_LOSS_SCALE if L.DEFAULT_LOSS_SCALE != 1.0 else 1024.0))
+        self._make_scale_state()
+
+    def _make_scale_state(self, scale=None, steps=None):
+        dev = self.flat.device
+        self.scale_state = torch.tensor([self._init_scale if scale is None else scale, 0.0, 0.0, 0.0], dtype=torch.float32, device=dev)
+        self.steps_dev = torch.tensor(self.steps if steps is None else steps, dtype=torch.int32, device=dev)
+        self.scale_tensor = self.scale_state[0]          # 0-d view: `loss * optimizer.scale_tensor` is what the backward starts from
+
+    def sync_steps(self):
+        """Device-side step counters -> self.steps (dynamic scaling only: skipped steps do not count, and only the device knows)."""
+        if self.dynamic_scale:
+            self.steps = [int(x) for x in self.steps_dev.tolist()]
+        return self.steps
+
+    @property
+    def skipped_steps(self):
+        return int(self.scale_state[3].item()) if self.dynamic_scale else 0
 
     def follow_parameters(self):
         """Re-create the flat arenas on the device the parameters live on NOW.  The reference entry scripts build the optimizer while
@@ -212,6 +238,7 @@ class AdamW:
         self._ring_ev = [None] * 4
         self._slot = 0
         self.table = torch.zeros(n, 4, dtype=torch.float32, device=dev)
+        self._make_scale_state(scale=float(self.scale_state[0].item()), steps=[int(x) for x in self.steps_dev.tolist()])
         return True
 
     def zero_grad(self, set_to_none=True):
@@ -232,6 +259,12 @@ class AdamW:
                 rows[i, 2] = 0.0
                 continue
             g = self.param_groups[self.group_of[i]]
+            rows[i, 1] = g["lr"] * g["weight_decay"] if g["weight_decay"] > 0.0 else 0.0
+            rows[i, 2] = 1.0
+            if self.dynamic_scale:              # the kernel evaluates the bias correction from its own step counters
+                rows[i, 0] = g["lr"]
+                rows[i, 3] = 1.0 if g["correct_bias"] else 0.0
+                continue
             self.steps[i] += 1
             t = self.steps[i]
             b1, b2 = g["betas"]
@@ -239,8 +272,6 @@ class AdamW:
             if g["correct_bias"]:
                 step_size = step_size * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
             rows[i, 0] = step_size
-            rows[i, 1] = g["lr"] * g["weight_decay"] if g["weight_decay"] > 0.0 else 0.0
-            rows[i, 2] = 1.0
         self.table.copy_(host, non_blocking=True)
         if fs.device.type == "cuda":
             ev = torch.cuda.Event()
@@ -251,8 +282,13 @@ class AdamW:
         """Device half of step(): ONE kernel over the arena (capturable in a CUDA graph: it only reads device-resident state)."""
         fs = self.flat
         b1, b2 = self.param_groups[0]["betas"]
-        L.call("adamw_flat", fs.p, fs.g, fs.m, fs.v, fs.bf, self.chunk_tensor_arg(), self.table, fs.n_chunks, fs.chunk, float(b1), float(b2),
-               float(self.param_groups[0]["eps"]), float(grad_scale))
+        if self.dynamic_scale:
+            L.call("adamw_flat_dyn", fs.p, fs.g, fs.m, fs.v, fs.bf, self.chunk_tensor_arg(), self.table, self.steps_dev, self.scale_state,
+                   len(fs.params), fs.n_chunks, fs.chunk, float(b1), float(b2), float(self.param_groups[0]["eps"]),
+                   float(self.GROWTH_INTERVAL), float(self.MAX_SCALE))
+        else:
+            L.call("adamw_flat", fs.p, fs.g, fs.m, fs.v, fs.bf, self.chunk_tensor_arg(), self.table, fs.n_chunks, fs.chunk, float(b1),
+                   float(b2), float(self.param_groups[0]["eps"]), float(grad_scale))
         for i, p in enumerate(fs.params):
             if p.grad is not None:
                 fs.synced[i] = p._version      # the kernel refreshed the bf16 copy of every active tensor
@@ -269,6 +305,7 @@ class AdamW:
         (v2/base/base_trainer.py:173-181): param ids = positions in group order; per stepped parameter {'step' (int), 'exp_avg',
         'exp_avg_sq'} shaped like the parameter; groups carry lr / betas / eps / weight_decay / correct_bias."""
         fs = self.flat
+        self.sync_steps()
         groups, idx = [], 0
         for g in self.param_groups:
             d = {k: v for k, v in g.items() if k != "params"}
@@ -306,6 +343,7 @@ class AdamW:
                 fs._view(fs.v, p).copy_(st["exp_avg_sq"])
         for g, s_ in zip(self.param_groups, sd["param_groups"]):
             g.update({k: (tuple(v) if k == "betas" else v) for k, v in s_.items() if k != "params"})
+        self.steps_dev.copy_(torch.tensor(self.steps, dtype=torch.int32))
 
 
 def build_reference_optimizer(model, text_layers=None, tune_from=None):

@@ -21,7 +21,12 @@ from . import engine as E
 from . import modules as M
 
 
+_COLLECTIVES_OFF = False      # set around the pre-capture warm-up of TrainStep._capture: that run must not issue collectives
+
+
 def _world():
+    if _COLLECTIVES_OFF:
+        return 1
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
@@ -40,6 +45,7 @@ class AllGather_multi(torch.autograd.Function):
         ctx.rank = getattr(args, "rank", _rank()) if args is not None else _rank()
         ctx.batch_size = tensor.shape[0]
         if W == 1:
+            ctx.rank = 0
             return tensor.clone()
         out = torch.empty((W * tensor.shape[0],) + tuple(tensor.shape[1:]), dtype=tensor.dtype, device=tensor.device)
         dist.all_gather_into_tensor(out, tensor)
@@ -57,7 +63,7 @@ class _GatherPair(torch.autograd.Function):
     def forward(ctx, video, text):
         W, r = _world(), _rank()
         B, Edim = video.shape
-        ctx.B, ctx.r = B, r
+        ctx.B, ctx.r = B, (r if W > 1 else 0)
         if W == 1:
             return video.clone(), text.clone()
         local = torch.cat([video, text], 1).contiguous()
@@ -201,6 +207,39 @@ class TrainStep:
         self.launches_per_graph = 0
         self._copy_stream = None
         self._staged = None
+        if use_graph and _world() > 1:
+            self._warm_collectives()
+
+    def _warm_collectives(self):
+        """Every rank constructs its TrainStep at the same point of the program, so this is where the communicator, its channels and
+        its scratch buffers come to life (an all-gather and an arena-sized all-reduce, the two collectives of the step) -- NOT in the
+        pre-capture warm-up of _capture(): ranks meet new input signatures (trimmed caption lengths, v1 `padding=True`) at different
+        steps, and a warm-up that really ran the step's collectives would pair them with another rank's NEXT step."""
+        flat = getattr(self.optimizer, "flat", None)
+        t = torch.zeros(8, dtype=torch.float32, device=self.device)
+        out = torch.empty(8 * _world(), dtype=torch.float32, device=self.device)
+        dist.all_gather_into_tensor(out, t)
+        if flat is not None:
+            average_flat(flat)                 # gradients are zeroed at the start of every step: averaging them here is harmless
+        else:
+            _average_tensor(t)
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+
+    def close(self):
+        """Destroy the captured graphs (their executables hold the NCCL kernels of the step; the process group must not be torn down
+        underneath them -- round 1's multi-rank exit hang) and the staging state.  Call before dist.destroy_process_group()."""
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+        for ent in self._graphs.values():
+            ent.graph.reset()
+            ent.static.clear()
+            ent.l1 = ent.l2 = None
+        self._graphs.clear()
+        self._last_key = None
+        self._staged = None
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
 
     def to_device(self, data):
         out = {}
@@ -231,8 +270,11 @@ class TrainStep:
         else:
             loss2 = torch.zeros((), device=loss1.device)
             total = loss1
-        if self.loss_scale != 1.0:
-            total = total * self.loss_scale                             # fp16 operands only: keeps 16-bit gradient operands in range
+        dynamic = getattr(self.optimizer, "dynamic_scale", False)
+        if dynamic:
+            total = total * self.optimizer.scale_tensor                 # device-resident dynamic loss scale (IEEE-half operand build)
+        elif self.loss_scale != 1.0:
+            total = total * self.loss_scale                             # static scale: optimizer-less / stock-optimizer runs of that build
         total.backward()
         if overlapped:
             fired = E.AFTER_VIDEO_BACKWARD is None       # the hook disarms itself when it runs
@@ -248,7 +290,12 @@ class TrainStep:
         else:
             average_gradients(self.params)
         if self.optimizer is not None and not skip_optimizer:
-            if self.loss_scale != 1.0:
+            if dynamic:                              # finite check + un-scale + update + scale policy: all on the device
+                if optimizer_launch_only:
+                    self.optimizer.launch()
+                else:
+                    self.optimizer.step()
+            elif self.loss_scale != 1.0:
                 if optimizer_launch_only:
                     self.optimizer.launch(1.0 / self.loss_scale)
                 elif hasattr(self.optimizer, "launch"):
@@ -292,8 +339,13 @@ class TrainStep:
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
-        with torch.cuda.stream(side):               # warm-up outside capture: allocator pools, bf16 weight casts, NCCL, func attributes
-            self._body(nested, skip_optimizer=True)
+        global _COLLECTIVES_OFF
+        with torch.cuda.stream(side):               # warm-up outside capture: allocator pools, bf16 weight casts, func attributes.
+            _COLLECTIVES_OFF = True                 # Collective-free (see _warm_collectives): the captured collectives have the same
+            try:                                    # sizes for every input signature, so ranks may capture at different steps
+                self._body(nested, skip_optimizer=True)
+            finally:
+                _COLLECTIVES_OFF = False
         cur.wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
@@ -626,6 +678,12 @@ class Trainer_TVTSv2:
         return out
 
     def train(self):
+        try:
+            return self._train()
+        finally:
+            self.step.close()         # captured graphs hold NCCL kernels: release them before the script destroys the process group
+
+    def _train(self):
         if self.init_val and self.do_validation:
             self._valid_epoch(-1)
         for epoch in range(self.start_epoch, self.epochs + 1):
@@ -687,6 +745,10 @@ class Trainer_TVTS(Trainer_TVTSv2):
     MAX_LENGTH = 50
 
     def __init__(self, *a, pad_to_max_length=False, **k):
+        if k.get("len_epoch") is None and len(a) < 10:
+            # v1/trainer/trainer.py:50-54: the LONGEST loader sets the epoch length (and therefore drives; the others are cycled)
+            loaders = list(k["data_loader"] if "data_loader" in k else a[6])
+            k["len_epoch"] = max(len(x) for x in loaders)
         super().__init__(*a, **k)
         self.pad_to_max_length = pad_to_max_length      # one sequence length -> one CUDA graph (padded keys are masked: same results)
         self.base_lr = self.optimizer.param_groups[0]["lr"]                        # v1/base/base_trainer.py:30
