@@ -22,6 +22,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "video-text pairs/sec (ViT-B/16, 8x224^2 frames) fwd+bwd"
+METRIC_V1 = "video-text pairs/sec (TVTS v1 ViT-B/16 tubelets, 16x224^2 frames) fwd+bwd"
 UNIT = "pairs/s"
 
 
@@ -35,12 +36,13 @@ def parse():
                     help="trim the token matrix to the longest caption of the batch (exact for the causal text tower; fewer padded rows)")
     ap.add_argument("--u8-input", action="store_true", help="feed uint8 clips (GPU-side normalisation fused into the patch gather)")
     ap.add_argument("--workload", default="c3", help="c3 = ViT-B/16 T=8 batch 32/GPU (headline); c2 = ViT-B/32 T=8 batch 64; c1 = ViT-B/32 T=2 batch 4; "
-                    "c4 = ViT-H/14 T=16 batch 8/GPU (CUDA path not yet GPU-verified)")
+                    "c4 = ViT-H/14 T=16 batch 8/GPU; c5 = TVTS v1 (ViT-B/16 tubelets, 16 frames, DistilBERT) batch 24/GPU")
     ap.add_argument("--batch", type=int, default=0, help="override per-GPU batch")
     ap.add_argument("--n-trans", type=int, default=4, help="transcripts per clip (4 = both losses, 1 = InfoNCE only)")
     ap.add_argument("--no-optimizer", action="store_true", help="leave the AdamW update out of the step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the stock-PyTorch-eager-on-the-same-GPU leg (N=1 only)")
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
     ap.add_argument("--gemm-breakdown", action="store_true", help="print a per-shape table of the GEMM launches (stderr)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
@@ -111,6 +113,64 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------- workload
+def v1_setup(args, dev, rank):
+    """BASELINE.json configs[4]: TVTS v1 (v1/model/model_dist_TVTS.py:95-141, v1/configs/dist-yt-pt.json): ViT-B/16 with 2-frame tubelets over
+    16 frames, 49 of 196 patches kept per tube (N = 393 tokens), DistilBERT-base on 4 captions of 50 padded tokens per clip, projection
+    heads, sort head, both losses, AdamW (one group, lr 1e-4, wd 0).  -> (model, optimizer, host batch, flops per pair, oracle cfg)"""
+    import types
+
+    import torch
+    from tvts_b200 import modules_v1 as V1, optim
+    batch = args.batch or 24                       # v1/configs/dist-yt-pt.json:28 (per GPU)
+    T, P, n, n_trans, ctx, vocab, D, L_, p, Lt = 16, 196, 49, 4, 50, 30522, 768, 12, 16, 6
+    torch.manual_seed(0)
+    model = V1.TVTS(types.SimpleNamespace(local_rank=dev.index or 0), {"num_frames": T}, {"model": "distilbert-base-uncased", "pretrained": True},
+                    text_model=V1.DistilBertShell()).to(dev)
+    opt = None if args.no_optimizer else optim.AdamW([q for q in model.parameters() if q.requires_grad], lr=1e-4, betas=(0.9, 0.999),
+                                                     weight_decay=0.0)
+    g = torch.Generator().manual_seed(rank)
+    video = torch.randn(batch, T, 3, 224, 224, generator=g)
+    keep = torch.stack([torch.stack([torch.randperm(P, generator=g)[:n] for _ in range(T // 2)]) for _ in range(batch)])
+    ids = torch.randint(1000, vocab, (n_trans * batch, ctx), generator=g)
+    lens = torch.randint(6, ctx + 1, (n_trans * batch,), generator=g)
+    mask = (torch.arange(ctx)[None, :] < lens[:, None]).long()
+    host = {"video": video, "keep_ind": keep, "label": torch.arange(n_trans).repeat(batch, 1),
+            "text": {"input_ids": ids * mask, "attention_mask": mask}}
+    nt = T // 2
+    N = 1 + nt * n
+    f_video = 2 * nt * P * (3 * 2 * p * p) * D + L_ * (24 * N * D * D + 4 * N * N * D)
+    f_text = Lt * (24 * ctx * D * D + 4 * ctx * ctx * D)
+    S = N + n_trans
+    f_sort = 2 * (24 * S * D * D + 4 * S * S * D)
+    flops = 3.0 * (f_video + n_trans * f_text + f_sort)      # SURVEY.md section 8d row c5 (2*MAC, fwd+bwd = 3x fwd)
+    ocfg = types.SimpleNamespace(patch=p, width=D, heads=12, layers=L_, sort_heads=12, sort_depth=2, sort_ln_eps=1e-6)
+    return model, opt, host, batch, flops, ocfg
+
+
+def v1_cpu_oracle_steps(model, host, ocfg, sample, steps, warmup, max_seconds):
+    """fwd+bwd of the v1 oracle (torch CPU fp32, all host threads) on the first `sample` pairs of the bench batch."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import tvts_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = {k: v.detach().float().cpu().clone() for k, v in model.state_dict().items()}
+    nt = host["label"].shape[1]
+    B = host["video"].shape[0]
+    rows = torch.cat([torch.arange(sample) + t * B for t in range(nt)])          # clip-major caption rows of the first `sample` clips
+    text = {k: v[rows] for k, v in host["text"].items()}
+    times, t_begin = [], time.perf_counter()
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.v1_step_with_grads(sd, text, host["video"][:sample], host["keep_ind"][:sample], host["label"][:sample], ocfg, 12)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        if times and time.perf_counter() - t_begin > max_seconds:
+            break
+    return times, cores
+
+
 def workload(args):
     from tvts_b200 import config as C
     wl = C.WORKLOADS[args.workload]
@@ -161,17 +221,71 @@ def cpu_oracle_steps(cfg, batch, frames, n_trans, steps, warmup, max_seconds=1e9
     return times, cores
 
 
+def eager_gpu_steps(cfg, batch, frames, n_trans, steps, dev):
+    """SURVEY.md section 8d's "real bar on the same box": the reference's algorithm as stock PyTorch eager ops + autograd ON THE GPU (the
+    oracle's functional restatement is device-agnostic torch code: same ops as the reference modules, cuBLAS / cuDNN kernels underneath),
+    fwd+bwd of the full per-GPU batch, no optimizer.  Three numeric modes: fp32 (TF32 off), TF32, autocast(bf16).  CUDA-event timed."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import tvts_oracle as O
+    from tvts_b200.synthetic import make_batch, make_state_dict
+    sd = {k: v.to(dev) for k, v in make_state_dict(cfg, seed=1234).items()}
+    frozen = (cfg.text_layers * 3) // 4
+    trainable = {k for k in sd if not (k.startswith("text_model.resblocks.") and int(k.split(".")[2]) < frozen)}
+    data = {k: v.to(dev) for k, v in make_batch(cfg, batch, frames, n_trans=n_trans, seed=0).items()}
+    out = {}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        for mode in ("fp32", "tf32", "autocast_bf16"):
+            torch.backends.cuda.matmul.allow_tf32 = mode != "fp32"
+            torch.backends.cudnn.allow_tf32 = mode != "fp32"
+
+            def one():
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode == "autocast_bf16"):
+                    O.step_with_grads(sd, data["text"], data["video"], data["keep_ind"], data["label"], cfg, trainable=trainable)
+            try:
+                for _ in range(2):
+                    one()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    one()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / steps
+                out[mode] = {"pairs_per_s": batch / (ms / 1e3), "ms_per_step": ms}
+            except Exception as ex:     # e.g. out of memory: report, never take the bench line down
+                out[mode] = {"error": f"{type(ex).__name__}: {str(ex)[:160]}"}
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    out["what"] = (f"stock PyTorch eager + autograd on the same GPU, fwd+bwd of {batch} pairs (no optimizer step), {steps} timed steps after 2 "
+                   "warm-ups; the oracle's functional restatement of the reference modules, run on cuda")
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg, batch, frames, n_trans = workload(args)
     sample = args.cpu_sample_batch
-    times, cores = cpu_oracle_steps(cfg, sample, frames, n_trans, args.steps, min(args.warmup, 1), max_seconds=240)
+    if args.workload == "c5":
+        import types
+
+        import torch
+        from tvts_b200 import _lib
+        _lib.lib = lambda: (_ for _ in ()).throw(RuntimeError("the reference arm must not touch the CUDA library"))
+        model, _, host, batch, _, ocfg = v1_setup(argparse.Namespace(batch=args.batch, no_optimizer=True), torch.device("cpu"), 0)
+        cfg, frames, n_trans = types.SimpleNamespace(name="TVTS_v1_base_patch16_224"), 16, 4
+        times, cores = v1_cpu_oracle_steps(model, host, ocfg, sample, args.steps, min(args.warmup, 1), 240)
+    else:
+        cfg, batch, frames, n_trans = workload(args)
+        times, cores = cpu_oracle_steps(cfg, sample, frames, n_trans, args.steps, min(args.warmup, 1), max_seconds=240)
     ms = 1e3 * sum(times) / len(times)
     val = sample / (ms / 1e3)
     sample_desc = f"{sample} pairs of the {args.workload} shape ({cfg.name}, T={frames}, n_trans={n_trans}) per step, oracle fwd+bwd fp32, {len(times)} timed steps"
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+    line = {"impl": "reference", "metric": METRIC_V1 if args.workload == "c5" else METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
             "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {cfg.name} T={frames} n_trans={n_trans}, CPU sample batch {sample}"},
@@ -209,24 +323,34 @@ def run_ours(args):
     if args.pair_mode >= 0:
         _lib.lib().tvts_gemm_set_pair_mode(args.pair_mode)
 
-    cfg, batch, frames, n_trans = workload(args)
-    model_cls = M.TVTSv2_H_14 if cfg.post_mode == "h14" else M.TVTSv2Base
-    model = model_cls(types.SimpleNamespace(local_rank=local_rank), arch=cfg)
-    model.load_state_dict(make_state_dict(cfg, seed=1234), strict=True)
-    model = model.to(dev)
-    opt = None if args.no_optimizer else optim.build_reference_optimizer(model)
+    v1 = args.workload == "c5"
     use_graph = not args.no_graph
+    if v1:
+        model, opt, host, batch, v1_flops, v1_ocfg = v1_setup(args, dev, rank)
+        cfg, frames, n_trans = types.SimpleNamespace(name="TVTS_v1_base_patch16_224", temperature=0.05), 16, 4
+    else:
+        cfg, batch, frames, n_trans = workload(args)
+        model_cls = M.TVTSv2_H_14 if cfg.post_mode == "h14" else M.TVTSv2Base
+        model = model_cls(types.SimpleNamespace(local_rank=local_rank), arch=cfg)
+        model.load_state_dict(make_state_dict(cfg, seed=1234), strict=True)
+        model = model.to(dev)
+        opt = None if args.no_optimizer else optim.build_reference_optimizer(model)
+        host = make_batch(cfg, batch, frames, n_trans=n_trans, seed=0, rank=rank)
+        if args.trim_text:
+            from tvts_b200.trainer import trim_text_context
+            host["text"] = trim_text_context(host["text"])
+        if args.u8_input:        # uint8 crops: normalisation runs inside the gather kernel (input_stage.cu), 4x fewer host->device bytes
+            host["video"] = torch.randint(0, 256, host["video"].shape, dtype=torch.uint8, generator=torch.Generator().manual_seed(rank))
     step = TrainStep(model, opt, cfg.temperature, dev, use_graph=use_graph)
 
-    host = make_batch(cfg, batch, frames, n_trans=n_trans, seed=0, rank=rank)
-    if args.trim_text:
-        from tvts_b200.trainer import trim_text_context
-        host["text"] = trim_text_context(host["text"])
-    if args.u8_input:        # uint8 crops: normalisation runs inside the gather kernel (input_stage.cu), 4x fewer host->device bytes
-        host["video"] = torch.randint(0, 256, host["video"].shape, dtype=torch.uint8, generator=torch.Generator().manual_seed(rank))
-    pinned = {k: v.pin_memory() for k, v in host.items()}
-    resident = {k: v.to(dev) for k, v in host.items()}
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    def tmap(fn, d):
+        return {k: (tmap(fn, v) if isinstance(v, dict) else fn(v)) for k, v in d.items()}
+
+    def nbytes(d):
+        return sum(nbytes(v) if isinstance(v, dict) else v.numel() * v.element_size() for v in d.values())
+    pinned = tmap(lambda v: v.pin_memory(), host)
+    resident = tmap(lambda v: v.to(dev), host)
+    h2d = nbytes(host)
 
     def barrier():
         if world > 1:
@@ -315,31 +439,40 @@ def run_ours(args):
     cpu = None
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         sample = args.cpu_sample_batch
-        times, cores = cpu_oracle_steps(cfg, sample, frames, n_trans, 2, 1, max_seconds=40)
+        if v1:
+            times, cores = v1_cpu_oracle_steps(model, host, v1_ocfg, sample, 2, 1, 40)
+        else:
+            times, cores = cpu_oracle_steps(cfg, sample, frames, n_trans, 2, 1, max_seconds=40)
         cms = sum(times) / len(times)
         cpu = {"value": sample / cms, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{sample} pairs of the {args.workload} shape per step, oracle fwd+bwd fp32 (no optimizer), {len(times)} timed steps after 1 warm-up"}
+
+    eager = None
+    if rank == 0 and world == 1 and not args.no_eager_baseline and not args.no_cpu_baseline and not v1:
+        step.close()                                  # free the graph's activation pool before the eager leg allocates its own
+        torch.cuda.empty_cache()
+        eager = eager_gpu_steps(cfg, batch, frames, n_trans, 5, dev)
 
     if rank == 0:
         pk = peaks()
         ms_step = ms_total / args.steps
         value = world * batch * args.steps / (ms_total / 1e3)
         achieved = (t_fl.value / 1e12) / (t_ms.value / 1e3) if t_ms.value > 0 else None
-        flops_pair = algorithmic_flops_per_pair(cfg, frames, n_trans)
+        flops_pair = v1_flops if v1 else algorithmic_flops_per_pair(cfg, frames, n_trans)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC_V1 if v1 else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": _lib.OPERAND,
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {cfg.name} T={frames} batch {batch}/GPU n_trans={n_trans} (global batch {world * batch})",
                        "step": "fwd+bwd" + (("+grad_allreduce" + ("(overlapped with the text-tower backward)" if step.overlap else "")) if world > 1 else "")
                                + ("" if args.no_optimizer else "+adamw"),
                        "launch": "one CUDA graph per step" if use_graph else "kernel-by-kernel from Python",
-                       "parallelism": f"dp{world}", "l2": "per-step inputs (154 MB video) and activations (>10 GB) exceed the 126 MB L2",
+                       "parallelism": f"dp{world}", "l2": f"per-step inputs ({h2d / 1e6:.0f} MB) and activations (GBs) exceed the 126 MB L2",
                        "numerics": f"{_lib.OPERAND} GEMM operands, fp32 accumulate/residual/LN/softmax/loss, fp32 master weights"
                                    + (f", backward under loss scale {_lib.DEFAULT_LOSS_SCALE:g}" if _lib.DEFAULT_LOSS_SCALE != 1.0 else ""),
                        "input": ("uint8 clips, normalised inside the patch-gather kernel" if args.u8_input else "fp32 normalised clips")
                                 + (f"; token matrix trimmed to the batch's longest caption ({host['text'].shape[1]} of {cfg.context} columns; exact for the causal text tower)"
-                                   if args.trim_text else "")},
+                                   if (args.trim_text and not v1) else "")},
             "clocks": clocks, "gpu_launches": launches, "loss": loss,
             "step_model_tflops": flops_pair * batch / (ms_step / 1e3) / 1e12,
             "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05)", "achieved": achieved, "peak": pk["bf16_sustained"],
@@ -357,6 +490,8 @@ def run_ours(args):
             line["e2e"] = e2e
         if cpu:
             line["cpu_baseline"] = cpu
+        if eager:
+            line["eager_gpu_baseline"] = eager
         print(json.dumps(line), flush=True)
     step.close()            # destroy the captured graphs (they hold the step's NCCL kernels) BEFORE the process group goes away
     if world > 1:

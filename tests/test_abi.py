@@ -137,4 +137,9 @@ def test_product_package_never_imports_the_oracle_or_the_test_restatements():
     for path in glob.glob(os.path.join(root, "tvts_b200", "**", "*.py"), recursive=True):
         assert not pat.search(open(path).read()), path
     bench_src = open(os.path.join(root, "bench.py")).read()
-    assert len(re.findall(r"import tvts_oracle", bench_src)) == 1 and "def cpu_oracle_steps" in bench_src     # the CPU legs only
+    # the baseline legs only: the two CPU-oracle legs (v2, v1) and the stock-PyTorch-eager-on-the-GPU baseline; never the timed product path
+    assert len(re.findall(r"import tvts_oracle", bench_src)) == 3
+    for fn in ("def cpu_oracle_steps", "def v1_cpu_oracle_steps", "def eager_gpu_steps"):
+        body = bench_src.split(fn)[1].split("\ndef ")[0]
+        assert "import tvts_oracle" in body, fn
+    assert "tvts_oracle" not in bench_src.split("def run_ours")[1].split("\ndef ")[0]

@@ -1,5 +1,5 @@
-"""GPU parity tests for code written AFTER the round-1 GPU budget was spent (never executed on a B200 yet; the file name sorts last so
-that `pytest -x` reaches them only after every previously-verified GPU test has run):
+"""GPU parity tests of the H/14 (c4), TVTS v1 (c5), uint8-input, text-trimming and downstream paths (first executed on a B200 in round 2,
+GPU call 1: 87 of 87 cases green -- profiles/r2/call1_staged_suite_87_passed.txt):
   * the head-dim-generic streamed attention kernels (tvts_b200/csrc/attention_hd.cu): d = 80 (ViT-H/14) against the torch
     restatement, d = 64 against the restatement AND against the specialised kernels of attention.cu
   * the padded patch-embed path of 14x14 patches (patch_gather_ld, cast_bf16_pad, GEMMs with K = 592 / N = 588)
@@ -9,13 +9,7 @@ that `pytest -x` reaches them only after every previously-verified GPU test has 
   * text-context trimming (trainer.trim_text_context): same results from a token matrix cut to the batch's longest caption
   * TVTS v1: tubelet gather / per-tube assembly / ReLU kernels (tvts_b200/csrc/v1_glue.cu), key-padded attention, and the whole v1 model
     (DistilBERT text encoder included) against the executed-reference fixture tiny_v1_full and the oracle's gradients
-Tolerances as in tests/test_kernels_gpu.py / tests/test_model_gpu.py.
-
-Because none of this has met a GPU yet, the cases do not run inside the main pytest process: `test_staged_suite_in_subprocess`
-re-runs this file in a CHILD process (TVTS_RUN_STAGED=1) so that a faulting kernel cannot poison the CUDA context of the verified
-suite, prints the child's per-test report, and is itself xfail(strict=False): XPASS when every staged case passes, XFAIL otherwise.
-Round 2: `TVTS_RUN_STAGED=1 python -m pytest tests/test_zz_round1_unverified_gpu.py -m gpu` first, fix what fails, then fold the cases
-into test_kernels_gpu.py / test_model_gpu.py and delete this indirection."""
+Tolerances as in tests/test_kernels_gpu.py / tests/test_model_gpu.py."""
 import os
 import types
 
@@ -31,19 +25,10 @@ from tvts_b200 import engine as E
 from tvts_b200 import modules as M
 from tvts_b200.synthetic import make_batch, make_state_dict
 
-STAGED = os.environ.get("TVTS_RUN_STAGED") == "1"
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not STAGED, reason="staged cases run in a child process (TVTS_RUN_STAGED=1)")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
 BF16, F32 = L.OPERAND_DTYPE, torch.float32
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-
-
-def _run_staged_child():
-    import subprocess
-    import sys
-    env = dict(os.environ, TVTS_RUN_STAGED="1")
-    return subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "--tb=line", "-p", "no:cacheprovider",
-                           "-rA"], env=env, capture_output=True, text=True, timeout=900, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
 def rnd(*shape, scale=1.0):

@@ -131,8 +131,27 @@ ATTN_CASES = [
 ]
 
 
-@pytest.mark.parametrize("B,H,mode,T,n,N,causal", ATTN_CASES)
-def test_attention(B, H, mode, T, n, N, causal):
+@pytest.fixture
+def attn_tc(request):
+    """tvts_attn_set_tc: tcgen05 one-tile kernels (csrc/attention_tc.cu; default) or the mma.sync kernels for every shape"""
+    L.lib().tvts_attn_set_tc(int(request.param))
+    yield request.param
+    L.lib().tvts_attn_set_tc(1)
+
+
+ATTN_CASES_TC = ATTN_CASES + [
+    (3, 12, 1, 8, 98, 785, False),  # space at the c3 head count: 288 tcgen05 tiles + the CLS merge over 8 frames
+    (2, 8, 0, 0, 0, 77, True),      # text tower heads
+    (2, 2, 0, 0, 0, 128, True),     # a full 128-row tile (no padding rows), causal
+    (2, 2, 0, 0, 0, 17, False),     # a nearly empty tile
+    (1, 2, 1, 1, 127, 128, False),  # the largest space group (127 patches + CLS)
+    (2, 2, 1, 3, 5, 16, False),     # tiny space groups
+]
+
+
+@pytest.mark.parametrize("attn_tc", [1, 0], indirect=True)
+@pytest.mark.parametrize("B,H,mode,T,n,N,causal", ATTN_CASES_TC)
+def test_attention(B, H, mode, T, n, N, causal, attn_tc):
     torch.manual_seed(N + mode)
     d = 64
     qkv = rnd(B, N, 3 * H * d, scale=1.0).to(BF16)

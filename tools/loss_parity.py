@@ -2,7 +2,8 @@
 CPU oracle (reference algorithm in fp32 + the restated transformers.AdamW) from the same initial weights on the same synthetic
 batches.  Prints the per-step losses of both and the maximum deviation.   usage: python tools/loss_parity.py [steps] [workload]
 
-workloads: c1 = BASELINE.json configs[0] (TVTSv2 ViT-B/32, 2 frames, 4 pairs, n_trans 4);  tiny = the test-suite toy model;
+workloads: c1 = BASELINE.json configs[0] (TVTSv2 ViT-B/32, 2 frames, 4 pairs, n_trans 4);  c3s = 2 pairs of the headline shape
+(ViT-B/16, mask 0.5, 8 frames);  tiny = the test-suite toy model;
 tiny_h = the H/14-shaped toy model (width 640, head dim 80, 14x14 patches).   TVTS_OPERAND=fp16 selects the IEEE-half build."""
 import os
 import sys
@@ -39,6 +40,8 @@ def oracle_run(cfg, sd0, groups_by_name, batches, frozen):
 def run(steps=100, workload="c1", lr_scale=1.0, use_graph=True, verbose=True):
     if workload == "c1":
         cfg, batch, frames = C.TVTSV2_B_32, 4, 2
+    elif workload == "c3s":            # a 2-pair sample of the headline shape (ViT-B/16, mask 0.5, T = 8): what bench.py times
+        cfg, batch, frames = C.TVTSV2_B_16, 2, 8
     elif workload == "tiny_h":
         cfg, batch, frames = C.TINY_H640, 2, 3
     else:

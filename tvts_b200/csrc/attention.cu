@@ -1362,6 +1362,8 @@ extern "C" int tvts_attn_set_side_stream(int on) {
 extern "C" int tvts_attn_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T,
                              int64_t n, int64_t causal, float scale, void* stream) {
   if (d != HD) return tvts_attn_generic_fwd(qkv, out, lse, B, N, H, d, mode, T, n, causal, scale, stream);   // attention_hd.cu
+  if (tvts_attn_tc_supported(B, N, H, d, mode, T, n, causal))                                                 // attention_tc.cu (tcgen05)
+    return tvts_attn_tc_fwd(qkv, out, lse, B, N, H, d, mode, T, n, causal, scale, stream);
   AttnShape a{(int)B, (int)N, (int)H, (int)mode, (int)T, (int)n, (int)causal, scale, 0, 0, 0};
   if (B == 0) return TVTS_OK;
   int rc = check_shape(a, d);
@@ -1419,6 +1421,8 @@ extern "C" int tvts_attn_bwd(const void* qkv, const void* out, const void* dout,
                              void* stream) {
   if (d != HD)                                                                                               // attention_hd.cu
     return tvts_attn_generic_bwd(qkv, out, dout, lse, delta_ws, dqkv, B, N, H, d, mode, T, n, causal, scale, stream);
+  if (tvts_attn_tc_supported(B, N, H, d, mode, T, n, causal))                                                 // attention_tc.cu (tcgen05)
+    return tvts_attn_tc_bwd(qkv, out, dout, lse, dqkv, B, N, H, d, mode, T, n, causal, scale, stream);
   AttnShape a{(int)B, (int)N, (int)H, (int)mode, (int)T, (int)n, (int)causal, scale, 0, 0, 0};
   if (B == 0) return TVTS_OK;
   int rc = check_shape(a, d);

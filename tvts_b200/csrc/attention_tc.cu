@@ -1,0 +1,601 @@
+// tcgen05 attention for the SHORT groups of the hot path (head dim 64): the divided-space attention of the video tower
+// (v2/model/video_encoder_ViT_B_16.py:38-76, `'b (f n) d -> (b f) n d'`: n kept patches of one frame + the CLS key, 99 rows for ViT-B/16
+// at mask 0.5) and one-tile full / causal sequences (the 77-token CLIP text tower, v2/CLIP/clip/model.py:171-203).
+//
+// One CTA owns one (batch, head, group).  The whole group fits ONE 128-row UMMA tile, so there is no streaming loop and no online
+// rescaling:
+//   forward : TMA(Q,K,V) -> S = Q K^T (tcgen05.mma, fp32 in TMEM) -> row softmax straight out of TMEM (tcgen05.ld: one thread = one
+//             query row, no shuffles) -> P (16-bit, 128B-swizzled shared memory) -> O = P V (tcgen05.mma) -> TMA store
+//   backward: TMA(Q,K,V,dO) -> S, dP = dO V^T -> P = exp(S - lse), delta = rowsum(P o dP) (in the tile: no separate delta pass) ->
+//             dV = P^T dO -> dS = P o (dP - delta) * scale -> dK = dS^T Q, dQ = dS K -> three TMA stores
+// Every tile is read from HBM exactly once and every output written once: the kernels are HBM-bound by construction
+// (forward 4 x n x 128 B per tile, backward 7 x n x 128 B).
+//
+// CLS token (space mode).  The CLS QUERY attends to every token of the clip and the CLS KEY is seen by every query.  It rides along as
+// row / column n of every frame tile: the tile computes the CLS query's softmax over ITS keys (the CLS key itself is counted by frame
+// 0 only) and writes a normalised partial (o, lse) to a small workspace; a tiny second kernel merges the T partials
+// (log-sum-exp combine).  The backward does the same with partial dq(CLS query), dk / dv(CLS key) sums.  This replaces the separate
+// latency-bound attn_cls_* launches (and their side stream) of the mma.sync path.
+#include <cuda.h>
+#include <stdlib.h>
+#include "common.cuh"
+#include "../../include/tvts_b200.h"
+
+namespace {
+
+constexpr int HD = 64;
+constexpr uint32_t ATOM = 16384;   // one [128 rows x 128 B] 128B-swizzled tile
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr uint32_t kOperandFormat = TVTS_OPERAND_IS_FP16 ? 0u : ((1u << 7) | (1u << 10));
+
+struct TcShape {
+  int B, N, H;
+  int mode;     // 0: one group per (b, h) = the whole sequence (N <= 128); 1: space groups
+  int T, n;
+  int causal;   // mode 0 only
+  float scale;
+  int nrow;     // rows the TMA boxes move per tile (mode 0: N, mode 1: n)
+  int L;        // rows = keys of the tile (mode 0: N, mode 1: n + 1; the last one is the CLS token)
+  int LP;       // L rounded up to a multiple of 16 (UMMA N / K granularity)
+};
+
+__device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4); }
+
+// tcgen05.ld is .sync.aligned: reconverge the warp first (per-row predicates / the single CLS-row thread may have diverged it)
+__device__ __forceinline__ void tmem_ld_row32(uint32_t taddr, uint32_t* v) {
+  __syncwarp();
+  tmem_ld_32x32(taddr, v);
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// instruction descriptor (kind::f16): D = f32, A/B = the library's 16-bit operand format, majors at bits 15 / 16 (1 = MN-major), N >> 3 at 17,
+// M >> 4 at 24 (same encoding as gemm_tcgen05.cu)
+__device__ __forceinline__ uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | kOperandFormat | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+// K-major operand tile(s) [rows x 64 k] per 16 KB atom: k-step ks (16 elements) lives in atom ks / 4 at byte offset (ks % 4) * 32
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int ks) {
+  return umma_smem_desc(tile + (uint32_t)(ks >> 2) * ATOM + (uint32_t)(ks & 3) * 32u, 16, 1024);
+}
+// MN-major operand: tile(s) [k rows x 64 mn] -- 16 k-rows per step = 2048 B; 64-wide MN groups are one atom apart
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int ks) { return umma_smem_desc(tile + (uint32_t)ks * 2048u, ATOM, 1024); }
+
+// ================================================================================================ forward
+// shared memory: Q | K | V tiles (P overlays Q|K once S is complete; the output staging tile overlays P), 3 mbarriers, TMEM holder
+constexpr int FWD_SMEM = 3 * ATOM + 64 + 1024;
+
+__global__ void __launch_bounds__(128, 4)
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out, const bf16* __restrict__ qkv,
+                   float* __restrict__ lse, float* __restrict__ cls_ws, TcShape a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sQ = base, sK = base + ATOM, sV = base + 2 * ATOM, sP = base;
+  const uint32_t bar_ld = base + 3 * ATOM, bar_s = bar_ld + 8, bar_o = bar_ld + 16, holder = bar_ld + 24;
+  volatile uint32_t* holder_gen = reinterpret_cast<volatile uint32_t*>(gen + 3 * ATOM + 24);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int tok0 = a.mode == 1 ? 1 + g * a.n : 0;
+  const int row0 = b * a.N + tok0;
+  const long long ld = 3LL * a.H * HD;
+
+  if (warp == 0) {
+    tmem_alloc(holder, 128);
+  } else if (warp == 1 && lane == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_out);
+    mbar_init(bar_ld, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(bar_ld, 3u * (uint32_t)a.nrow * 128u);
+    tma_load_2d(sQ, &tm_qkv, bar_ld, h * HD, row0);
+    tma_load_2d(sK, &tm_qkv, bar_ld, a.H * HD + h * HD, row0);
+    tma_load_2d(sV, &tm_qkv, bar_ld, 2 * a.H * HD + h * HD, row0);
+  } else if (warp == 2) {
+    if (a.mode == 1 && lane < 24) {      // the CLS token's q / k / v rows -> row n of the three tiles (generic-proxy stores, swizzled by hand)
+      const int m = lane >> 3, c = lane & 7;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(qkv + (long long)b * a.N * ld + (long long)m * a.H * HD + h * HD + c * 8));
+      st_shared_v4(base + (uint32_t)m * ATOM + swz(a.n, c), v.x, v.y, v.z, v.w);
+    }
+  } else {
+    for (int i = lane; i < (a.LP - a.L) * 8; i += 32)      // V rows [L, LP) take part in P V with P = 0: they must be finite
+      st_shared_v4(sV + swz(a.L + (i >> 3), i & 7), 0u, 0u, 0u, 0u);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *holder_gen;
+
+  if (warp == 1 && lane == 0) {
+    mbar_wait(bar_ld, 0);
+    tc_fence_after();
+    const uint32_t idesc = make_idesc(a.LP, false, false);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem, desc_kmajor(sQ, k), desc_kmajor(sK, k), idesc, k > 0 ? 1u : 0u);
+    umma_commit(bar_s);
+  }
+  __syncwarp();
+  mbar_wait(bar_s, 0);
+  tc_fence_after();
+
+  // ---- softmax: thread = query row; the row's S values come straight out of TMEM
+  const int r = tid;
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  int kend = a.L;
+  if (a.causal) kend = min(kend, r + 1);
+  if (a.mode == 1 && r == a.n && g != 0) kend = a.n;     // CLS query: the CLS key (last column) is counted by frame 0's tile only
+  const float sl2 = a.scale * LOG2E;
+  const int nch = (a.LP + 31) >> 5;
+  uint32_t v[32];
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < nch; ++c) {
+    tmem_ld_row32(trow + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (c * 32 + j < kend) mx = fmaxf(mx, __uint_as_float(v[j]));
+  }
+  if (!(fabsf(mx) < INFINITY)) mx = 0.f;                  // padding rows (r >= L) hold whatever the tile's unused rows contained
+  float l = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < nch; ++c) {
+    tmem_ld_row32(trow + c * 32, v);
+    tmem_ld_wait();
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int col = c * 32 + 2 * j;
+      const float p0 = col < kend ? exp2f((__uint_as_float(v[2 * j]) - mx) * sl2) : 0.f;
+      const float p1 = col + 1 < kend ? exp2f((__uint_as_float(v[2 * j + 1]) - mx) * sl2) : 0.f;
+      l += p0 + p1;
+      pk[j] = pack_bf16x2(p0, p1);
+    }
+    const uint32_t atom = sP + (uint32_t)(c >> 1) * ATOM;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) st_shared_v4(atom + swz(r, (c & 1) * 4 + q), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();          // every row of P is in shared memory and every thread is done reading S (O overwrites its columns)
+
+  if (warp == 1 && lane == 0) {
+    tc_fence_after();
+    const uint32_t idesc = make_idesc(HD, false, true);
+    const int ksteps = a.LP >> 4;
+    for (int ks = 0; ks < ksteps; ++ks) umma_bf16(tmem, desc_kmajor(sP, ks), desc_mnmajor(sV, ks), idesc, ks > 0 ? 1u : 0u);
+    umma_commit(bar_o);
+  }
+  __syncwarp();
+  mbar_wait(bar_o, 0);
+  tc_fence_after();
+
+  // ---- epilogue: O / l -> 16-bit rows in the staging tile (overlays P: the P V MMAs have completed) -> one TMA store
+  const float inv = 1.0f / l;
+  const bool cls_row = a.mode == 1 && r == a.n;
+  float* ws = cls_row ? cls_ws + (((long long)b * a.H + h) * a.T + g) * 65 : nullptr;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    tmem_ld_row32(trow + c * 32, v);
+    tmem_ld_wait();
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]) * inv, __uint_as_float(v[2 * j + 1]) * inv);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) st_shared_v4(sP + swz(r, c * 4 + q), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    if (cls_row) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) ws[c * 32 + j] = __uint_as_float(v[j]) * inv;
+    }
+  }
+  const float row_lse = mx * a.scale + __logf(l);
+  if (cls_row) ws[64] = row_lse;
+  if (r < a.nrow) lse[((long long)b * a.H + h) * a.N + tok0 + r] = row_lse;
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tma_store_2d(&tm_out, sP, h * HD, row0);
+    bulk_commit();
+    bulk_wait_all();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
+// merge the T per-frame partials of the CLS query: out[b, 0, h, :] and lse[b, h, 0]
+__global__ void __launch_bounds__(64) attn_tc_cls_merge_fwd_kernel(const float* __restrict__ ws, bf16* __restrict__ out, float* __restrict__ lse,
+                                                                   TcShape a) {
+  const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
+  const float* w = ws + (((long long)b * a.H + h) * a.T) * 65;
+  float m = -INFINITY;
+  for (int g = 0; g < a.T; ++g) m = fmaxf(m, w[g * 65 + 64]);
+  float acc = 0.f, sw = 0.f;
+  for (int g = 0; g < a.T; ++g) {
+    const float e = __expf(w[g * 65 + 64] - m);
+    acc = fmaf(e, w[g * 65 + d], acc);
+    sw += e;
+  }
+  out[(long long)b * a.N * a.H * HD + h * HD + d] = opnd_from_float(acc / sw);
+  if (d == 0) lse[((long long)b * a.H + h) * a.N] = m + __logf(sw);
+}
+
+// ================================================================================================ backward
+// shared memory: Q | K | V | dO tiles, a two-atom P / dS buffer, 4 mbarriers, TMEM holder.  TMEM (256 columns): S [0,128) and
+// dP [128,256); dV reuses [0,64), dK [64,128), dQ [128,192) once their previous contents have been consumed.
+constexpr int BWD_SMEM = 6 * ATOM + 64 + 1024;
+
+__global__ void __launch_bounds__(128, 2)
+attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                   const __grid_constant__ CUtensorMap tm_dqkv, const bf16* __restrict__ qkv, const bf16* __restrict__ out,
+                   const bf16* __restrict__ dout, const float* __restrict__ lse, float* __restrict__ cls_ws, TcShape a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sQ = base, sK = base + ATOM, sV = base + 2 * ATOM, sDO = base + 3 * ATOM, sP = base + 4 * ATOM;
+  const uint32_t bar_ld = base + 6 * ATOM, bar_1 = bar_ld + 8, bar_dv = bar_ld + 16, bar_2 = bar_ld + 24, holder = bar_ld + 32;
+  volatile uint32_t* holder_gen = reinterpret_cast<volatile uint32_t*>(gen + 6 * ATOM + 32);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int tok0 = a.mode == 1 ? 1 + g * a.n : 0;
+  const int row0 = b * a.N + tok0;
+  const long long ld = 3LL * a.H * HD, ldo = (long long)a.H * HD;
+
+  if (warp == 0) {
+    tmem_alloc(holder, 256);
+  } else if (warp == 1 && lane == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_dqkv);
+    mbar_init(bar_ld, 1);
+    mbar_init(bar_1, 1);
+    mbar_init(bar_dv, 1);
+    mbar_init(bar_2, 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(bar_ld, 4u * (uint32_t)a.nrow * 128u);
+    tma_load_2d(sQ, &tm_qkv, bar_ld, h * HD, row0);
+    tma_load_2d(sK, &tm_qkv, bar_ld, a.H * HD + h * HD, row0);
+    tma_load_2d(sV, &tm_qkv, bar_ld, 2 * a.H * HD + h * HD, row0);
+    tma_load_2d(sDO, &tm_do, bar_ld, h * HD, row0);
+  } else if (warp == 2) {
+    if (a.mode == 1) {                     // CLS rows of q, k, v, dO -> row n of the four tiles
+      const int m = lane >> 3, c = lane & 7;
+      const bf16* src = m < 3 ? qkv + (long long)b * a.N * ld + (long long)m * a.H * HD + h * HD + c * 8
+                              : dout + (long long)b * a.N * ldo + h * HD + c * 8;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
+      st_shared_v4(base + (uint32_t)m * ATOM + swz(a.n, c), v.x, v.y, v.z, v.w);
+    }
+  } else {
+    // rows [L, LP) of every tile are contraction rows of some MMA (queries for dV / dK, keys for dQ) or feed masked columns: zero them
+    for (int i = lane; i < (a.LP - a.L) * 32; i += 32) {
+      const int m = i / ((a.LP - a.L) * 8), rem = i - m * (a.LP - a.L) * 8;
+      st_shared_v4(base + (uint32_t)m * ATOM + swz(a.L + (rem >> 3), rem & 7), 0u, 0u, 0u, 0u);
+    }
+  }
+  // per-row softmax statistics: lse of the row's FULL key set (the CLS query's covers the whole clip), delta for the CLS query
+  const int r = tid;
+  const bool cls_row = a.mode == 1 && r == a.n;
+  const bool row_ok = r < a.L;
+  float row_lse = 0.f, delta = 0.f;
+  if (row_ok) row_lse = lse[((long long)b * a.H + h) * a.N + (cls_row ? 0 : tok0 + r)];
+  if (cls_row) {                           // delta = dO . O of the CLS row (its keys span every tile, so it cannot come from this tile)
+    const uint4* po = reinterpret_cast<const uint4*>(out + (long long)b * a.N * ldo + h * HD);
+    const uint4* pd = reinterpret_cast<const uint4*>(dout + (long long)b * a.N * ldo + h * HD);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 x = __ldg(po + c), y = __ldg(pd + c);
+      const float2 x0 = unpack_bf16x2(x.x), x1 = unpack_bf16x2(x.y), x2 = unpack_bf16x2(x.z), x3 = unpack_bf16x2(x.w);
+      const float2 y0 = unpack_bf16x2(y.x), y1 = unpack_bf16x2(y.y), y2 = unpack_bf16x2(y.z), y3 = unpack_bf16x2(y.w);
+      delta += x0.x * y0.x + x0.y * y0.y + x1.x * y1.x + x1.y * y1.y + x2.x * y2.x + x2.y * y2.y + x3.x * y3.x + x3.y * y3.y;
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *holder_gen;
+  const int ksteps = a.LP >> 4;
+
+  if (warp == 1 && lane == 0) {
+    mbar_wait(bar_ld, 0);
+    tc_fence_after();
+    const uint32_t idesc = make_idesc(a.LP, false, false);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem, desc_kmajor(sQ, k), desc_kmajor(sK, k), idesc, k > 0 ? 1u : 0u);            // S = Q K^T
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem + 128, desc_kmajor(sDO, k), desc_kmajor(sV, k), idesc, k > 0 ? 1u : 0u);    // dP = dO V^T
+    umma_commit(bar_1);
+  }
+  __syncwarp();
+  mbar_wait(bar_1, 0);
+  tc_fence_after();
+
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  int kend = row_ok ? a.L : 0;
+  if (a.causal) kend = min(kend, r + 1);
+  if (cls_row && g != 0) kend = a.n;
+  const float sl2 = a.scale * LOG2E, lse2 = row_lse * LOG2E;
+  const int nch = (a.LP + 31) >> 5;
+  uint32_t pk[4][16];
+  uint32_t v[32], w[32];
+  // ---- pass A: P = exp(S * scale - lse) -> shared memory (A operand of dV = P^T dO) and registers; delta = sum_j P_ij dP_ij
+  float dsum = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (c < nch) {
+      tmem_ld_row32(trow + c * 32, v);
+      tmem_ld_row32(trow + 128 + c * 32, w);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int col = c * 32 + 2 * j;
+        float p0 = 0.f, p1 = 0.f;
+        if (col < kend) { p0 = exp2f(fmaf(__uint_as_float(v[2 * j]), sl2, -lse2)); dsum = fmaf(p0, __uint_as_float(w[2 * j]), dsum); }
+        if (col + 1 < kend) { p1 = exp2f(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -lse2)); dsum = fmaf(p1, __uint_as_float(w[2 * j + 1]), dsum); }
+        pk[c][j] = pack_bf16x2(p0, p1);
+      }
+      const uint32_t atom = sP + (uint32_t)(c >> 1) * ATOM;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        st_shared_v4(atom + swz(r, (c & 1) * 4 + q), pk[c][4 * q], pk[c][4 * q + 1], pk[c][4 * q + 2], pk[c][4 * q + 3]);
+    }
+  }
+  if (!cls_row) delta = dsum;
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();           // P complete; every thread is done with the S columns (dV overwrites [0,64))
+
+  if (warp == 1 && lane == 0) {
+    tc_fence_after();
+    const uint32_t idesc = make_idesc(HD, true, true);
+    for (int ks = 0; ks < ksteps; ++ks) umma_bf16(tmem, desc_mnmajor(sP, ks), desc_mnmajor(sDO, ks), idesc, ks > 0 ? 1u : 0u);   // dV = P^T dO
+    umma_commit(bar_dv);
+  }
+  __syncwarp();
+  mbar_wait(bar_dv, 0);      // the MMAs have read P: its buffer may now take dS
+  tc_fence_after();
+
+  // ---- pass B: dS = P o (dP - delta) * scale -> the same buffer
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (c < nch) {
+      tmem_ld_row32(trow + 128 + c * 32, w);
+      tmem_ld_wait();
+      uint32_t ds[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int col = c * 32 + 2 * j;
+        const float2 p = unpack_bf16x2(pk[c][j]);
+        const float d0 = col < kend ? p.x * (__uint_as_float(w[2 * j]) - delta) * a.scale : 0.f;
+        const float d1 = col + 1 < kend ? p.y * (__uint_as_float(w[2 * j + 1]) - delta) * a.scale : 0.f;
+        ds[j] = pack_bf16x2(d0, d1);
+      }
+      const uint32_t atom = sP + (uint32_t)(c >> 1) * ATOM;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) st_shared_v4(atom + swz(r, (c & 1) * 4 + q), ds[4 * q], ds[4 * q + 1], ds[4 * q + 2], ds[4 * q + 3]);
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();           // dS complete; every thread is done with the dP columns (dQ overwrites [128,192))
+
+  if (warp == 1 && lane == 0) {
+    tc_fence_after();
+    const uint32_t idesc_k = make_idesc(HD, true, true), idesc_q = make_idesc(HD, false, true);
+    for (int ks = 0; ks < ksteps; ++ks) umma_bf16(tmem + 64, desc_mnmajor(sP, ks), desc_mnmajor(sQ, ks), idesc_k, ks > 0 ? 1u : 0u);   // dK = dS^T Q
+    for (int ks = 0; ks < ksteps; ++ks) umma_bf16(tmem + 128, desc_kmajor(sP, ks), desc_mnmajor(sK, ks), idesc_q, ks > 0 ? 1u : 0u);  // dQ = dS K
+    umma_commit(bar_2);
+  }
+  __syncwarp();
+  mbar_wait(bar_2, 0);
+  tc_fence_after();
+
+  // ---- epilogue: row r of dQ (query r), dK and dV (key r) -> staging tiles (Q, K, V buffers: every MMA has completed) -> TMA stores
+  float* ws = cls_row ? cls_ws + (((long long)b * a.H + h) * a.T + g) * 192 : nullptr;
+#pragma unroll
+  for (int m = 0; m < 3; ++m) {
+    const uint32_t tcol = m == 0 ? 128u : (m == 1 ? 64u : 0u);      // dQ, dK, dV
+    const uint32_t tile = base + (uint32_t)m * ATOM;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      tmem_ld_row32(trow + tcol + c * 32, v);
+      tmem_ld_wait();
+      uint32_t o[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) st_shared_v4(tile + swz(r, c * 4 + q), o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      if (cls_row) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ws[m * 64 + c * 32 + j] = __uint_as_float(v[j]);
+      }
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tma_store_2d(&tm_dqkv, sQ, h * HD, row0);
+    tma_store_2d(&tm_dqkv, sK, a.H * HD + h * HD, row0);
+    tma_store_2d(&tm_dqkv, sV, 2 * a.H * HD + h * HD, row0);
+    bulk_commit();
+    bulk_wait_all();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// sum the T per-frame partials of dq(CLS query), dk / dv(CLS key) -> row 0 of dqkv
+__global__ void __launch_bounds__(192) attn_tc_cls_merge_bwd_kernel(const float* __restrict__ ws, bf16* __restrict__ dqkv, TcShape a) {
+  const int h = blockIdx.x, b = blockIdx.y, i = threadIdx.x;
+  const float* w = ws + (((long long)b * a.H + h) * a.T) * 192;
+  float acc = 0.f;
+  for (int g = 0; g < a.T; ++g) acc += w[g * 192 + i];
+  const int m = i >> 6, d = i & 63;
+  dqkv[(long long)b * a.N * 3 * a.H * HD + (long long)m * a.H * HD + h * HD + d] = opnd_from_float(acc);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+// [rows, cols] 16-bit row-major matrix; box = [64 columns (128 B), box_rows], 128B swizzle
+int make_map(CUtensorMap* m, const void* ptr, long long rows, long long cols, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return tvts_set_error(TVTS_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType t16 = TVTS_OPERAND_IS_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = fn(m, t16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return tvts_set_error(TVTS_ERR_CUDA, "attn_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return TVTS_OK;
+}
+
+bool make_shape(TcShape* s, int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal, float scale) {
+  if (d != HD || B <= 0 || H <= 0) return false;
+  if (mode == 0) {
+    if (N < 1 || N > 128) return false;
+    *s = TcShape{(int)B, (int)N, (int)H, 0, 1, 0, (int)causal, scale, (int)N, (int)N, (int)((N + 15) / 16 * 16)};
+    return true;
+  }
+  if (mode == 1) {
+    if (causal || T < 1 || n < 1 || n > 127 || N != 1 + T * n) return false;
+    *s = TcShape{(int)B, (int)N, (int)H, 1, (int)T, (int)n, 0, scale, (int)n, (int)n + 1, (int)((n + 1 + 15) / 16 * 16)};
+    return true;
+  }
+  return false;
+}
+
+// per-device workspace for the CLS partials (grown on demand; allocation happens outside any stream capture: the first call of a
+// shape runs in the pre-capture warm-up step)
+struct Workspace { float* ptr = nullptr; size_t bytes = 0; };
+float* workspace(size_t bytes) {
+  static Workspace per_dev[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  Workspace& w = per_dev[dev];
+  if (w.bytes < bytes) {
+    // a buffer that is outgrown is NOT freed: CUDA graphs captured earlier keep launching kernels that hold its address
+    w.ptr = nullptr; w.bytes = 0;
+    size_t want = bytes < (32u << 20) ? (32u << 20) : bytes;
+    if (cudaMalloc(&w.ptr, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    w.bytes = want;
+  }
+  return w.ptr;
+}
+
+int g_attn_tc = -1;     // -1: not decided yet (environment TVTS_ATTN_TC=0 switches the tcgen05 path off for the whole process)
+int attn_tc_on() {
+  if (g_attn_tc < 0) {
+    const char* e = getenv("TVTS_ATTN_TC");
+    g_attn_tc = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return g_attn_tc;
+}
+
+}  // namespace
+
+extern "C" int tvts_attn_set_tc(int on) {
+  g_attn_tc = on;
+  return TVTS_OK;
+}
+
+extern "C" int tvts_attn_tc_supported(int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal) {
+  TcShape s;
+  return attn_tc_on() && make_shape(&s, B, N, H, d, mode, T, n, causal, 1.0f) ? 1 : 0;
+}
+
+extern "C" int tvts_attn_tc_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T,
+                                int64_t n, int64_t causal, float scale, void* stream) {
+  TcShape a;
+  TVTS_REQUIRE(make_shape(&a, B, N, H, d, mode, T, n, causal, scale), "attn_tc_fwd: unsupported shape (d=%lld mode=%lld N=%lld n=%lld)",
+               (long long)d, (long long)mode, (long long)N, (long long)n);
+  TVTS_REQUIRE(qkv && out && lse, "attn_tc_fwd: null pointer");
+  TVTS_REQUIRE(B * N < (1ll << 31), "attn_tc_fwd: too many rows");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUtensorMap tq, to;
+  int rc = make_map(&tq, qkv, B * N, 3 * H * HD, a.nrow);
+  if (rc) return rc;
+  rc = make_map(&to, out, B * N, H * HD, a.nrow);
+  if (rc) return rc;
+  float* ws = nullptr;
+  if (a.mode == 1) {
+    ws = workspace((size_t)B * H * T * 192 * sizeof(float));
+    TVTS_REQUIRE(ws != nullptr, "attn_tc_fwd: workspace allocation failed");
+  }
+  static bool attr = false;
+  if (!attr) {
+    TVTS_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    TVTS_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr = true;
+  }
+  dim3 grid((unsigned)(a.mode == 1 ? a.T : 1), (unsigned)H, (unsigned)B);
+  attn_tc_fwd_kernel<<<grid, 128, FWD_SMEM, st>>>(tq, to, reinterpret_cast<const bf16*>(qkv), lse, ws, a);
+  TVTS_LAUNCH_CHECK();
+  if (a.mode == 1) {
+    attn_tc_cls_merge_fwd_kernel<<<dim3((unsigned)H, (unsigned)B), 64, 0, st>>>(ws, reinterpret_cast<bf16*>(out), lse, a);
+    TVTS_LAUNCH_CHECK();
+  }
+  return TVTS_OK;
+}
+
+extern "C" int tvts_attn_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int64_t B, int64_t N,
+                                int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal, float scale, void* stream) {
+  TcShape a;
+  TVTS_REQUIRE(make_shape(&a, B, N, H, d, mode, T, n, causal, scale), "attn_tc_bwd: unsupported shape (d=%lld mode=%lld N=%lld n=%lld)",
+               (long long)d, (long long)mode, (long long)N, (long long)n);
+  TVTS_REQUIRE(qkv && out && dout && lse && dqkv, "attn_tc_bwd: null pointer");
+  TVTS_REQUIRE(B * N < (1ll << 31), "attn_tc_bwd: too many rows");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUtensorMap tq, tdo, tdq;
+  int rc = make_map(&tq, qkv, B * N, 3 * H * HD, a.nrow);
+  if (rc) return rc;
+  rc = make_map(&tdo, dout, B * N, H * HD, a.nrow);
+  if (rc) return rc;
+  rc = make_map(&tdq, dqkv, B * N, 3 * H * HD, a.nrow);
+  if (rc) return rc;
+  float* ws = nullptr;
+  if (a.mode == 1) {
+    ws = workspace((size_t)B * H * T * 192 * sizeof(float));
+    TVTS_REQUIRE(ws != nullptr, "attn_tc_bwd: workspace allocation failed");
+  }
+  static bool attr = false;
+  if (!attr) {
+    TVTS_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    TVTS_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr = true;
+  }
+  dim3 grid((unsigned)(a.mode == 1 ? a.T : 1), (unsigned)H, (unsigned)B);
+  attn_tc_bwd_kernel<<<grid, 128, BWD_SMEM, st>>>(tq, tdo, tdq, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<const bf16*>(out),
+                                                  reinterpret_cast<const bf16*>(dout), lse, ws, a);
+  TVTS_LAUNCH_CHECK();
+  if (a.mode == 1) {
+    attn_tc_cls_merge_bwd_kernel<<<dim3((unsigned)H, (unsigned)B), 192, 0, st>>>(ws, reinterpret_cast<bf16*>(dqkv), a);
+    TVTS_LAUNCH_CHECK();
+  }
+  return TVTS_OK;
+}
