@@ -118,9 +118,11 @@ int tvts_attn_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t N, 
 int tvts_attn_set_side_stream(int on);
 /* tcgen05 path of tvts_attn_fwd / tvts_attn_bwd (csrc/attention_tc.cu) for head dim 64 and groups that fit ONE 128-row UMMA tile:
  * mode 1 (space; n + 1 <= 128 rows per frame group, the CLS query / key folded into every frame tile and merged by a second tiny kernel)
- * and mode 0 with N <= 128 (the 77-token causal CLIP text sequences).  S and O (backward: S, dP, dV, dK, dQ) live in TMEM, Q / K / V / dO
- * tiles arrive by TMA, results leave by TMA stores.  tvts_attn_set_tc(0) routes those shapes back to the mma.sync kernels (A/B
- * comparison in the tests); tvts_attn_tc_supported tells which path tvts_attn_fwd / _bwd take for a shape. */
+ * mode 0 with N <= 128 (the 77-token causal CLIP text sequences), and mode 2 (time: a tile packs floor(127 / T) patch positions x T
+ * frames + CLS, block-diagonal key mask, 4-D TMA boxes over the strided token rows).  S and O (backward: S, dP, dV, dK, dQ) live in TMEM,
+ * Q / K / V / dO tiles arrive by TMA, results leave by TMA stores.  tvts_attn_set_tc(on): bit 0 = modes 0 / 1, bit 1 = mode 2 (default 3;
+ * 0 routes every shape back to the mma.sync kernels -- A/B comparison in the tests; environment TVTS_ATTN_TC=0 / TVTS_ATTN_TC_TIME=0 do
+ * the same per process); tvts_attn_tc_supported tells which path tvts_attn_fwd / _bwd take for a shape. */
 int tvts_attn_set_tc(int on);
 int tvts_attn_tc_supported(int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal);
 int tvts_attn_tc_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n,

@@ -165,7 +165,7 @@ def text_tower(tokens, sd, cfg):
     d = W // h
     n_txt, L = tokens.shape
     x = sd["text_token_embedding.weight"][tokens.to(torch.long)] + sd["text_positional_embedding"]
-    causal = torch.full((L, L), float("-inf"), dtype=x.dtype).triu(1)
+    causal = torch.full((L, L), float("-inf"), dtype=x.dtype, device=x.device).triu(1)
     act = _act(cfg.text_act)
     for i in range(cfg.text_layers):
         p = f"text_model.resblocks.{i}."
@@ -181,7 +181,7 @@ def text_tower(tokens, sd, cfg):
         x = x + linear(act(linear(y, sd[p + "mlp.c_fc.weight"], sd[p + "mlp.c_fc.bias"])),
                        sd[p + "mlp.c_proj.weight"], sd[p + "mlp.c_proj.bias"])
     eot = tokens.to(torch.long).argmax(-1)                               # EOT has the highest id (:107-108)
-    x = x[torch.arange(n_txt), eot]                                      # LN is per-row: gather first
+    x = x[torch.arange(n_txt, device=x.device), eot]                                      # LN is per-row: gather first
     x = layer_norm(x, sd["text_ln_final.weight"], sd["text_ln_final.bias"], cfg.ln_eps)
     return x @ sd["text_projection"]
 
@@ -264,7 +264,7 @@ def step_losses(sd, text, video, keep_ind, labels, cfg, gather=None):
     if gather is not None:
         ve, te = gather(ve), gather(te)
     loss1 = norm_softmax_loss(sim_matrix(ve, te), cfg.temperature)
-    loss2 = sort_ce(pred, labels) if pred is not None else torch.zeros((), dtype=loss1.dtype)
+    loss2 = sort_ce(pred, labels) if pred is not None else torch.zeros((), dtype=loss1.dtype, device=loss1.device)
     return loss1, loss2, (te, ve, pred)
 
 

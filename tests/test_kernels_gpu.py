@@ -133,10 +133,11 @@ ATTN_CASES = [
 
 @pytest.fixture
 def attn_tc(request):
-    """tvts_attn_set_tc: tcgen05 one-tile kernels (csrc/attention_tc.cu; default) or the mma.sync kernels for every shape"""
+    """tvts_attn_set_tc: 3 = tcgen05 one-tile kernels (csrc/attention_tc.cu) for space / short sequences AND time attention (default),
+    1 = tcgen05 for space / short sequences only, 0 = the mma.sync kernels for every shape"""
     L.lib().tvts_attn_set_tc(int(request.param))
     yield request.param
-    L.lib().tvts_attn_set_tc(1)
+    L.lib().tvts_attn_set_tc(3)
 
 
 ATTN_CASES_TC = ATTN_CASES + [
@@ -146,10 +147,14 @@ ATTN_CASES_TC = ATTN_CASES + [
     (2, 2, 0, 0, 0, 17, False),     # a nearly empty tile
     (1, 2, 1, 1, 127, 128, False),  # the largest space group (127 patches + CLS)
     (2, 2, 1, 3, 5, 16, False),     # tiny space groups
+    (1, 2, 2, 8, 23, 185, False),   # time: 2 tiles of 12 positions, the last one ragged (11 positions + 1 zero-filled)
+    (1, 2, 2, 3, 51, 154, False),   # time: 2 tiles of 26 / 25 positions x 3 frames
+    (2, 12, 2, 8, 98, 785, False),  # time at the c3 head count: 7 tiles of 14 positions x 8 frames per (b, h)
+    (1, 2, 2, 1, 30, 31, False),    # time with a single frame (every group = one patch + CLS)
 ]
 
 
-@pytest.mark.parametrize("attn_tc", [1, 0], indirect=True)
+@pytest.mark.parametrize("attn_tc", [3, 1, 0], indirect=True)
 @pytest.mark.parametrize("B,H,mode,T,n,N,causal", ATTN_CASES_TC)
 def test_attention(B, H, mode, T, n, N, causal, attn_tc):
     torch.manual_seed(N + mode)

@@ -27,15 +27,18 @@ constexpr int HD = 64;
 constexpr uint32_t ATOM = 16384;   // one [128 rows x 128 B] 128B-swizzled tile
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr uint32_t kOperandFormat = TVTS_OPERAND_IS_FP16 ? 0u : ((1u << 7) | (1u << 10));
+constexpr int kTcThreads = 256;    // 8 warps: TMEM lane quadrant = warp % 4, column half = warp / 4 (two threads share one row)
 
 struct TcShape {
   int B, N, H;
-  int mode;     // 0: one group per (b, h) = the whole sequence (N <= 128); 1: space groups
+  int mode;     // 0: one tile per (b, h) = the whole sequence (N <= 128); 1: space (tile = frame); 2: time (tile = GP patch positions x T frames)
   int T, n;
   int causal;   // mode 0 only
   float scale;
-  int nrow;     // rows the TMA boxes move per tile (mode 0: N, mode 1: n)
-  int L;        // rows = keys of the tile (mode 0: N, mode 1: n + 1; the last one is the CLS token)
+  int GP;       // mode 2: patch positions per tile (row r of the tile = frame r / GP, position g * GP + r % GP)
+  int chunks;   // tiles per (b, h): 1 | T | ceil(n / GP)
+  int rows;     // rows the TMA box moves per tile: N | n | T * GP
+  int L;        // rows = keys of the tile: `rows` (+ 1 in modes 1 / 2: the CLS token, last)
   int LP;       // L rounded up to a multiple of 16 (UMMA N / K granularity)
 };
 
@@ -50,6 +53,17 @@ __device__ __forceinline__ void tmem_ld_row32(uint32_t taddr, uint32_t* v) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst_smem), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src_smem, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tmap), "r"(src_smem),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 
 // instruction descriptor (kind::f16): D = f32, A/B = the library's 16-bit operand format, majors at bits 15 / 16 (1 = MN-major), N >> 3 at 17,
 // M >> 4 at 24 (same encoding as gemm_tcgen05.cu)
@@ -63,24 +77,74 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int ks) {
 // MN-major operand: tile(s) [k rows x 64 mn] -- 16 k-rows per step = 2048 B; 64-wide MN groups are one atom apart
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int ks) { return umma_smem_desc(tile + (uint32_t)ks * 2048u, ATOM, 1024); }
 
-// ================================================================================================ forward
-// shared memory: Q | K | V tiles (P overlays Q|K once S is complete; the output staging tile overlays P), 3 mbarriers, TMEM holder
-constexpr int FWD_SMEM = 3 * ATOM + 64 + 1024;
+// ---- tile geometry ---------------------------------------------------------------------------------------------------------------
+// token (within the sample) of tile row r < rows, or -1 when the row is padding (mode 2: positions past n in the last tile)
+__device__ __forceinline__ int row_token(const TcShape& a, int g, int r) {
+  if (a.mode == 0) return r;
+  if (a.mode == 1) return 1 + g * a.n + r;
+  const int t = r / a.GP, i = r - t * a.GP, pos = g * a.GP + i;
+  return pos < a.n ? 1 + t * a.n + pos : -1;
+}
+// bit j = key column (col0 + j) is attended by query row r (64 columns: this thread's half of the row)
+__device__ __forceinline__ unsigned long long key_mask(const TcShape& a, int g, int r, int col0) {
+  const bool cls_q = a.mode != 0 && r == a.rows;
+  unsigned long long m = 0ull;
+  if (r >= a.L) return 0ull;
+  if (a.mode != 2) {
+    int kend = a.L;
+    if (a.causal) kend = min(kend, r + 1);
+    if (cls_q && g != 0) kend = a.rows;                   // CLS query: the CLS key (last column) is counted by tile 0 only
+    const int k = min(max(kend - col0, 0), 64);
+    return k == 64 ? ~0ull : ((1ull << k) - 1ull);
+  }
+  const int nvalid = min(a.GP, a.n - g * a.GP);           // positions of this tile that exist
+  if (!cls_q) {
+    const int t = r / a.GP, i = r - t * a.GP;
+    if (i >= nvalid) return 0ull;
+    for (int tt = 0; tt < a.T; ++tt) {                    // the same position in every frame
+      const int j = tt * a.GP + i - col0;
+      if (j >= 0 && j < 64) m |= 1ull << j;
+    }
+    const int jc = a.rows - col0;                         // + the CLS key
+    if (jc >= 0 && jc < 64) m |= 1ull << jc;
+    return m;
+  }
+  for (int tt = 0; tt < a.T; ++tt) {                      // CLS query: every existing patch key of the tile
+    const int lo = max(tt * a.GP - col0, 0), hi = min(tt * a.GP + nvalid - col0, 64);
+    if (hi > lo) m |= (hi - lo == 64 ? ~0ull : ((1ull << (hi - lo)) - 1ull)) << lo;
+  }
+  const int jc = a.rows - col0;
+  if (g == 0 && jc >= 0 && jc < 64) m |= 1ull << jc;
+  return m;
+}
+// TMA coordinates of tile g of sample b (4-D maps: {column, position / row, frame, sample})
+__device__ __forceinline__ void tile_coords(const TcShape& a, int g, int& c1, int& c2) {
+  c1 = a.mode == 2 ? g * a.GP : 0;
+  c2 = a.mode == 1 ? g : 0;
+}
 
-__global__ void __launch_bounds__(128, 4)
+// ================================================================================================ forward
+// shared memory: Q | K | V tiles (P overlays Q|K once S is complete; the output staging tile overlays P), row-statistics exchange
+// between the two column halves, 3 mbarriers, TMEM holder
+constexpr int FWD_XCH = 3 * ATOM;                       // float [2][2][128]
+constexpr int FWD_BAR = FWD_XCH + 2048;
+constexpr int FWD_SMEM = FWD_BAR + 64 + 1024;
+
+__global__ void __launch_bounds__(kTcThreads, 3)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out, const bf16* __restrict__ qkv,
                    float* __restrict__ lse, float* __restrict__ cls_ws, TcShape a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t sQ = base, sK = base + ATOM, sV = base + 2 * ATOM, sP = base;
-  const uint32_t bar_ld = base + 3 * ATOM, bar_s = bar_ld + 8, bar_o = bar_ld + 16, holder = bar_ld + 24;
-  volatile uint32_t* holder_gen = reinterpret_cast<volatile uint32_t*>(gen + 3 * ATOM + 24);
+  float* xch = reinterpret_cast<float*>(gen + FWD_XCH);
+  const uint32_t bar_ld = base + FWD_BAR, bar_s = bar_ld + 8, bar_o = bar_ld + 16, holder = bar_ld + 24;
+  volatile uint32_t* holder_gen = reinterpret_cast<volatile uint32_t*>(gen + FWD_BAR + 24);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int tok0 = a.mode == 1 ? 1 + g * a.n : 0;
-  const int row0 = b * a.N + tok0;
   const long long ld = 3LL * a.H * HD;
+  int c1, c2;
+  tile_coords(a, g, c1, c2);
 
   if (warp == 0) {
     tmem_alloc(holder, 128);
@@ -91,20 +155,24 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     mbar_init(bar_s, 1);
     mbar_init(bar_o, 1);
     mbar_fence_init();
-    mbar_arrive_expect_tx(bar_ld, 3u * (uint32_t)a.nrow * 128u);
-    tma_load_2d(sQ, &tm_qkv, bar_ld, h * HD, row0);
-    tma_load_2d(sK, &tm_qkv, bar_ld, a.H * HD + h * HD, row0);
-    tma_load_2d(sV, &tm_qkv, bar_ld, 2 * a.H * HD + h * HD, row0);
+    mbar_arrive_expect_tx(bar_ld, 3u * (uint32_t)a.rows * 128u);
+    tma_load_4d(sQ, &tm_qkv, bar_ld, h * HD, c1, c2, b);
+    tma_load_4d(sK, &tm_qkv, bar_ld, a.H * HD + h * HD, c1, c2, b);
+    tma_load_4d(sV, &tm_qkv, bar_ld, 2 * a.H * HD + h * HD, c1, c2, b);
   } else if (warp == 2) {
-    if (a.mode == 1 && lane < 24) {      // the CLS token's q / k / v rows -> row n of the three tiles (generic-proxy stores, swizzled by hand)
+    if (a.mode != 0 && lane < 24) {      // the CLS token's q / k / v rows -> row `rows` of the three tiles (generic-proxy stores, swizzled by hand)
       const int m = lane >> 3, c = lane & 7;
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(qkv + (long long)b * a.N * ld + (long long)m * a.H * HD + h * HD + c * 8));
-      st_shared_v4(base + (uint32_t)m * ATOM + swz(a.n, c), v.x, v.y, v.z, v.w);
+      st_shared_v4(base + (uint32_t)m * ATOM + swz(a.rows, c), v.x, v.y, v.z, v.w);
     }
-  } else {
+  } else if (warp == 3) {
     for (int i = lane; i < (a.LP - a.L) * 8; i += 32)      // V rows [L, LP) take part in P V with P = 0: they must be finite
       st_shared_v4(sV + swz(a.L + (i >> 3), i & 7), 0u, 0u, 0u, 0u);
   }
+  const int q4 = warp & 3, half = warp >> 2;
+  const int r = q4 * 32 + lane;                            // query row = TMEM lane
+  const unsigned long long kmask = key_mask(a, g, r, half * 64);
+  const uint32_t km[2] = {(uint32_t)kmask, (uint32_t)(kmask >> 32)};
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -123,43 +191,45 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   mbar_wait(bar_s, 0);
   tc_fence_after();
 
-  // ---- softmax: thread = query row; the row's S values come straight out of TMEM
-  const int r = tid;
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-  int kend = a.L;
-  if (a.causal) kend = min(kend, r + 1);
-  if (a.mode == 1 && r == a.n && g != 0) kend = a.n;     // CLS query: the CLS key (last column) is counted by frame 0's tile only
+  // ---- softmax: two threads per query row (64 key columns each); S comes straight out of TMEM
+  const uint32_t trow = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)half * 64u;
   const float sl2 = a.scale * LOG2E;
-  const int nch = (a.LP + 31) >> 5;
   uint32_t v[32];
   float mx = -INFINITY;
-#pragma unroll 1
-  for (int c = 0; c < nch; ++c) {
-    tmem_ld_row32(trow + c * 32, v);
-    tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (c * 32 + j < kend) mx = fmaxf(mx, __uint_as_float(v[j]));
-  }
-  if (!(fabsf(mx) < INFINITY)) mx = 0.f;                  // padding rows (r >= L) hold whatever the tile's unused rows contained
-  float l = 0.f;
-#pragma unroll 1
-  for (int c = 0; c < nch; ++c) {
-    tmem_ld_row32(trow + c * 32, v);
-    tmem_ld_wait();
-    uint32_t pk[16];
+  for (int c = 0; c < 2; ++c) {
+    if (half * 64 + c * 32 < a.LP) {                       // warp-uniform
+      tmem_ld_row32(trow + c * 32, v);
+      tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int col = c * 32 + 2 * j;
-      const float p0 = col < kend ? exp2f((__uint_as_float(v[2 * j]) - mx) * sl2) : 0.f;
-      const float p1 = col + 1 < kend ? exp2f((__uint_as_float(v[2 * j + 1]) - mx) * sl2) : 0.f;
-      l += p0 + p1;
-      pk[j] = pack_bf16x2(p0, p1);
+      for (int j = 0; j < 32; ++j)
+        if ((km[c] >> j) & 1u) mx = fmaxf(mx, __uint_as_float(v[j]));
     }
-    const uint32_t atom = sP + (uint32_t)(c >> 1) * ATOM;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) st_shared_v4(atom + swz(r, (c & 1) * 4 + q), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
   }
+  xch[half * 128 + r] = mx;
+  __syncthreads();
+  mx = fmaxf(mx, xch[(half ^ 1) * 128 + r]);
+  if (!(fabsf(mx) < INFINITY)) mx = 0.f;                  // rows without any key (padding)
+  float l = 0.f;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    if (half * 64 + c * 32 < a.LP) {
+      tmem_ld_row32(trow + c * 32, v);
+      tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float p0 = ((km[c] >> (2 * j)) & 1u) ? exp2f((__uint_as_float(v[2 * j]) - mx) * sl2) : 0.f;
+        const float p1 = ((km[c] >> (2 * j + 1)) & 1u) ? exp2f((__uint_as_float(v[2 * j + 1]) - mx) * sl2) : 0.f;
+        l += p0 + p1;
+        pk[j] = pack_bf16x2(p0, p1);
+      }
+      const uint32_t atom = sP + (uint32_t)half * ATOM;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) st_shared_v4(atom + swz(r, c * 4 + q), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    }
+  }
+  xch[256 + half * 128 + r] = l;
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();          // every row of P is in shared memory and every thread is done reading S (O overwrites its columns)
@@ -172,37 +242,39 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     umma_commit(bar_o);
   }
   __syncwarp();
+  l += xch[256 + (half ^ 1) * 128 + r];
   mbar_wait(bar_o, 0);
   tc_fence_after();
 
   // ---- epilogue: O / l -> 16-bit rows in the staging tile (overlays P: the P V MMAs have completed) -> one TMA store
   const float inv = 1.0f / l;
-  const bool cls_row = a.mode == 1 && r == a.n;
-  float* ws = cls_row ? cls_ws + (((long long)b * a.H + h) * a.T + g) * 65 : nullptr;
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    tmem_ld_row32(trow + c * 32, v);
+  const bool cls_row = a.mode != 0 && r == a.rows;
+  {
+    tmem_ld_row32(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)half * 32u, v);     // this thread's 32 of the row's 64 output columns
     tmem_ld_wait();
     uint32_t pk[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]) * inv, __uint_as_float(v[2 * j + 1]) * inv);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) st_shared_v4(sP + swz(r, c * 4 + q), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    for (int q = 0; q < 4; ++q) st_shared_v4(sP + swz(r, half * 4 + q), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
     if (cls_row) {
+      float* ws = cls_ws + (((long long)b * a.H + h) * a.chunks + g) * 65;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) ws[c * 32 + j] = __uint_as_float(v[j]) * inv;
+      for (int j = 0; j < 32; ++j) ws[half * 32 + j] = __uint_as_float(v[j]) * inv;
+      if (half == 0) ws[64] = mx * a.scale + __logf(l);
     }
   }
-  const float row_lse = mx * a.scale + __logf(l);
-  if (cls_row) ws[64] = row_lse;
-  if (r < a.nrow) lse[((long long)b * a.H + h) * a.N + tok0 + r] = row_lse;
+  if (half == 0 && r < a.rows) {
+    const int tok = row_token(a, g, r);
+    if (tok >= 0) lse[((long long)b * a.H + h) * a.N + tok] = mx * a.scale + __logf(l);
+  }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   if (tid == 0) {
-    tma_store_2d(&tm_out, sP, h * HD, row0);
+    tma_store_4d(&tm_out, sP, h * HD, c1, c2, b);
     bulk_commit();
-    bulk_wait_all();
+    bulk_wait_read<0>();     // the staging tile has been read out: the CTA may retire while the write drains
   }
   if (warp == 0) {
     __syncwarp();
@@ -211,15 +283,15 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   }
 }
 
-// merge the T per-frame partials of the CLS query: out[b, 0, h, :] and lse[b, h, 0]
+// merge the per-tile partials of the CLS query: out[b, 0, h, :] and lse[b, h, 0]
 __global__ void __launch_bounds__(64) attn_tc_cls_merge_fwd_kernel(const float* __restrict__ ws, bf16* __restrict__ out, float* __restrict__ lse,
                                                                    TcShape a) {
   const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
-  const float* w = ws + (((long long)b * a.H + h) * a.T) * 65;
+  const float* w = ws + (((long long)b * a.H + h) * a.chunks) * 65;
   float m = -INFINITY;
-  for (int g = 0; g < a.T; ++g) m = fmaxf(m, w[g * 65 + 64]);
+  for (int g = 0; g < a.chunks; ++g) m = fmaxf(m, w[g * 65 + 64]);
   float acc = 0.f, sw = 0.f;
-  for (int g = 0; g < a.T; ++g) {
+  for (int g = 0; g < a.chunks; ++g) {
     const float e = __expf(w[g * 65 + 64] - m);
     acc = fmaf(e, w[g * 65 + d], acc);
     sw += e;
@@ -229,11 +301,13 @@ __global__ void __launch_bounds__(64) attn_tc_cls_merge_fwd_kernel(const float* 
 }
 
 // ================================================================================================ backward
-// shared memory: Q | K | V | dO tiles, a two-atom P / dS buffer, 4 mbarriers, TMEM holder.  TMEM (256 columns): S [0,128) and
-// dP [128,256); dV reuses [0,64), dK [64,128), dQ [128,192) once their previous contents have been consumed.
-constexpr int BWD_SMEM = 6 * ATOM + 64 + 1024;
+// shared memory: Q | K | V | dO tiles, a two-atom P / dS buffer, the delta exchange, 4 mbarriers, TMEM holder.  TMEM (256 columns):
+// S [0,128) and dP [128,256); dV reuses [0,64), dK [64,128), dQ [128,192) once their previous contents have been consumed.
+constexpr int BWD_XCH = 6 * ATOM;                        // float [2][128]
+constexpr int BWD_BAR = BWD_XCH + 1024;
+constexpr int BWD_SMEM = BWD_BAR + 64 + 1024;
 
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(kTcThreads, 2)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                    const __grid_constant__ CUtensorMap tm_dqkv, const bf16* __restrict__ qkv, const bf16* __restrict__ out,
                    const bf16* __restrict__ dout, const float* __restrict__ lse, float* __restrict__ cls_ws, TcShape a) {
@@ -241,13 +315,14 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t sQ = base, sK = base + ATOM, sV = base + 2 * ATOM, sDO = base + 3 * ATOM, sP = base + 4 * ATOM;
-  const uint32_t bar_ld = base + 6 * ATOM, bar_1 = bar_ld + 8, bar_dv = bar_ld + 16, bar_2 = bar_ld + 24, holder = bar_ld + 32;
-  volatile uint32_t* holder_gen = reinterpret_cast<volatile uint32_t*>(gen + 6 * ATOM + 32);
+  float* xch = reinterpret_cast<float*>(gen + BWD_XCH);
+  const uint32_t bar_ld = base + BWD_BAR, bar_1 = bar_ld + 8, bar_dv = bar_ld + 16, bar_2 = bar_ld + 24, holder = bar_ld + 32;
+  volatile uint32_t* holder_gen = reinterpret_cast<volatile uint32_t*>(gen + BWD_BAR + 32);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int tok0 = a.mode == 1 ? 1 + g * a.n : 0;
-  const int row0 = b * a.N + tok0;
   const long long ld = 3LL * a.H * HD, ldo = (long long)a.H * HD;
+  int c1, c2;
+  tile_coords(a, g, c1, c2);
 
   if (warp == 0) {
     tmem_alloc(holder, 256);
@@ -260,32 +335,38 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     mbar_init(bar_dv, 1);
     mbar_init(bar_2, 1);
     mbar_fence_init();
-    mbar_arrive_expect_tx(bar_ld, 4u * (uint32_t)a.nrow * 128u);
-    tma_load_2d(sQ, &tm_qkv, bar_ld, h * HD, row0);
-    tma_load_2d(sK, &tm_qkv, bar_ld, a.H * HD + h * HD, row0);
-    tma_load_2d(sV, &tm_qkv, bar_ld, 2 * a.H * HD + h * HD, row0);
-    tma_load_2d(sDO, &tm_do, bar_ld, h * HD, row0);
+    mbar_arrive_expect_tx(bar_ld, 4u * (uint32_t)a.rows * 128u);
+    tma_load_4d(sQ, &tm_qkv, bar_ld, h * HD, c1, c2, b);
+    tma_load_4d(sK, &tm_qkv, bar_ld, a.H * HD + h * HD, c1, c2, b);
+    tma_load_4d(sV, &tm_qkv, bar_ld, 2 * a.H * HD + h * HD, c1, c2, b);
+    tma_load_4d(sDO, &tm_do, bar_ld, h * HD, c1, c2, b);
   } else if (warp == 2) {
-    if (a.mode == 1) {                     // CLS rows of q, k, v, dO -> row n of the four tiles
+    if (a.mode != 0) {                     // CLS rows of q, k, v, dO -> row `rows` of the four tiles
       const int m = lane >> 3, c = lane & 7;
       const bf16* src = m < 3 ? qkv + (long long)b * a.N * ld + (long long)m * a.H * HD + h * HD + c * 8
                               : dout + (long long)b * a.N * ldo + h * HD + c * 8;
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
-      st_shared_v4(base + (uint32_t)m * ATOM + swz(a.n, c), v.x, v.y, v.z, v.w);
+      st_shared_v4(base + (uint32_t)m * ATOM + swz(a.rows, c), v.x, v.y, v.z, v.w);
     }
-  } else {
+  } else if (warp == 3) {
     // rows [L, LP) of every tile are contraction rows of some MMA (queries for dV / dK, keys for dQ) or feed masked columns: zero them
-    for (int i = lane; i < (a.LP - a.L) * 32; i += 32) {
-      const int m = i / ((a.LP - a.L) * 8), rem = i - m * (a.LP - a.L) * 8;
+    const int pad = a.LP - a.L;
+    for (int i = lane; i < pad * 32; i += 32) {
+      const int m = i / (pad * 8), rem = i - m * pad * 8;
       st_shared_v4(base + (uint32_t)m * ATOM + swz(a.L + (rem >> 3), rem & 7), 0u, 0u, 0u, 0u);
     }
   }
   // per-row softmax statistics: lse of the row's FULL key set (the CLS query's covers the whole clip), delta for the CLS query
-  const int r = tid;
-  const bool cls_row = a.mode == 1 && r == a.n;
-  const bool row_ok = r < a.L;
+  const int q4 = warp & 3, half = warp >> 2;
+  const int r = q4 * 32 + lane;
+  const bool cls_row = a.mode != 0 && r == a.rows;
+  const unsigned long long kmask = key_mask(a, g, r, half * 64);
+  const uint32_t km[2] = {(uint32_t)kmask, (uint32_t)(kmask >> 32)};
   float row_lse = 0.f, delta = 0.f;
-  if (row_ok) row_lse = lse[((long long)b * a.H + h) * a.N + (cls_row ? 0 : tok0 + r)];
+  {
+    const int tok = cls_row ? 0 : (r < a.rows ? row_token(a, g, r) : -1);
+    if (tok >= 0) row_lse = lse[((long long)b * a.H + h) * a.N + tok];
+  }
   if (cls_row) {                           // delta = dO . O of the CLS row (its keys span every tile, so it cannot come from this tile)
     const uint4* po = reinterpret_cast<const uint4*>(out + (long long)b * a.N * ldo + h * HD);
     const uint4* pd = reinterpret_cast<const uint4*>(dout + (long long)b * a.N * ldo + h * HD);
@@ -318,37 +399,31 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   mbar_wait(bar_1, 0);
   tc_fence_after();
 
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-  int kend = row_ok ? a.L : 0;
-  if (a.causal) kend = min(kend, r + 1);
-  if (cls_row && g != 0) kend = a.n;
+  const uint32_t trow = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)half * 64u;
   const float sl2 = a.scale * LOG2E, lse2 = row_lse * LOG2E;
-  const int nch = (a.LP + 31) >> 5;
-  uint32_t pk[4][16];
+  uint32_t pk[2][16];
   uint32_t v[32], w[32];
   // ---- pass A: P = exp(S * scale - lse) -> shared memory (A operand of dV = P^T dO) and registers; delta = sum_j P_ij dP_ij
   float dsum = 0.f;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    if (c < nch) {
+  for (int c = 0; c < 2; ++c) {
+    if (half * 64 + c * 32 < a.LP) {       // warp-uniform
       tmem_ld_row32(trow + c * 32, v);
-      tmem_ld_row32(trow + 128 + c * 32, w);
+      tmem_ld_32x32(trow + 128 + c * 32, w);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int col = c * 32 + 2 * j;
         float p0 = 0.f, p1 = 0.f;
-        if (col < kend) { p0 = exp2f(fmaf(__uint_as_float(v[2 * j]), sl2, -lse2)); dsum = fmaf(p0, __uint_as_float(w[2 * j]), dsum); }
-        if (col + 1 < kend) { p1 = exp2f(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -lse2)); dsum = fmaf(p1, __uint_as_float(w[2 * j + 1]), dsum); }
+        if ((km[c] >> (2 * j)) & 1u) { p0 = exp2f(fmaf(__uint_as_float(v[2 * j]), sl2, -lse2)); dsum = fmaf(p0, __uint_as_float(w[2 * j]), dsum); }
+        if ((km[c] >> (2 * j + 1)) & 1u) { p1 = exp2f(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -lse2)); dsum = fmaf(p1, __uint_as_float(w[2 * j + 1]), dsum); }
         pk[c][j] = pack_bf16x2(p0, p1);
       }
-      const uint32_t atom = sP + (uint32_t)(c >> 1) * ATOM;
+      const uint32_t atom = sP + (uint32_t)half * ATOM;
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        st_shared_v4(atom + swz(r, (c & 1) * 4 + q), pk[c][4 * q], pk[c][4 * q + 1], pk[c][4 * q + 2], pk[c][4 * q + 3]);
+      for (int q = 0; q < 4; ++q) st_shared_v4(atom + swz(r, c * 4 + q), pk[c][4 * q], pk[c][4 * q + 1], pk[c][4 * q + 2], pk[c][4 * q + 3]);
     }
   }
-  if (!cls_row) delta = dsum;
+  xch[half * 128 + r] = dsum;
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();           // P complete; every thread is done with the S columns (dV overwrites [0,64))
@@ -360,27 +435,27 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     umma_commit(bar_dv);
   }
   __syncwarp();
+  if (!cls_row) delta = dsum + xch[(half ^ 1) * 128 + r];
   mbar_wait(bar_dv, 0);      // the MMAs have read P: its buffer may now take dS
   tc_fence_after();
 
   // ---- pass B: dS = P o (dP - delta) * scale -> the same buffer
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    if (c < nch) {
+  for (int c = 0; c < 2; ++c) {
+    if (half * 64 + c * 32 < a.LP) {
       tmem_ld_row32(trow + 128 + c * 32, w);
       tmem_ld_wait();
       uint32_t ds[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int col = c * 32 + 2 * j;
         const float2 p = unpack_bf16x2(pk[c][j]);
-        const float d0 = col < kend ? p.x * (__uint_as_float(w[2 * j]) - delta) * a.scale : 0.f;
-        const float d1 = col + 1 < kend ? p.y * (__uint_as_float(w[2 * j + 1]) - delta) * a.scale : 0.f;
+        const float d0 = ((km[c] >> (2 * j)) & 1u) ? p.x * (__uint_as_float(w[2 * j]) - delta) * a.scale : 0.f;
+        const float d1 = ((km[c] >> (2 * j + 1)) & 1u) ? p.y * (__uint_as_float(w[2 * j + 1]) - delta) * a.scale : 0.f;
         ds[j] = pack_bf16x2(d0, d1);
       }
-      const uint32_t atom = sP + (uint32_t)(c >> 1) * ATOM;
+      const uint32_t atom = sP + (uint32_t)half * ATOM;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) st_shared_v4(atom + swz(r, (c & 1) * 4 + q), ds[4 * q], ds[4 * q + 1], ds[4 * q + 2], ds[4 * q + 3]);
+      for (int q = 0; q < 4; ++q) st_shared_v4(atom + swz(r, c * 4 + q), ds[4 * q], ds[4 * q + 1], ds[4 * q + 2], ds[4 * q + 3]);
     }
   }
   fence_proxy_async_smem();
@@ -399,35 +474,33 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   tc_fence_after();
 
   // ---- epilogue: row r of dQ (query r), dK and dV (key r) -> staging tiles (Q, K, V buffers: every MMA has completed) -> TMA stores
-  float* ws = cls_row ? cls_ws + (((long long)b * a.H + h) * a.T + g) * 192 : nullptr;
+  float* ws = cls_row ? cls_ws + (((long long)b * a.H + h) * a.chunks + g) * 192 : nullptr;
+  const uint32_t tq = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)half * 32u;
 #pragma unroll
   for (int m = 0; m < 3; ++m) {
     const uint32_t tcol = m == 0 ? 128u : (m == 1 ? 64u : 0u);      // dQ, dK, dV
     const uint32_t tile = base + (uint32_t)m * ATOM;
+    tmem_ld_row32(tq + tcol, v);
+    tmem_ld_wait();
+    uint32_t o[16];
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      tmem_ld_row32(trow + tcol + c * 32, v);
-      tmem_ld_wait();
-      uint32_t o[16];
+    for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
 #pragma unroll
-      for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+    for (int q = 0; q < 4; ++q) st_shared_v4(tile + swz(r, half * 4 + q), o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    if (cls_row) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) st_shared_v4(tile + swz(r, c * 4 + q), o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-      if (cls_row) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) ws[m * 64 + c * 32 + j] = __uint_as_float(v[j]);
-      }
+      for (int j = 0; j < 32; ++j) ws[m * 64 + half * 32 + j] = __uint_as_float(v[j]);
     }
   }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   if (tid == 0) {
-    tma_store_2d(&tm_dqkv, sQ, h * HD, row0);
-    tma_store_2d(&tm_dqkv, sK, a.H * HD + h * HD, row0);
-    tma_store_2d(&tm_dqkv, sV, 2 * a.H * HD + h * HD, row0);
+    tma_store_4d(&tm_dqkv, sQ, h * HD, c1, c2, b);
+    tma_store_4d(&tm_dqkv, sK, a.H * HD + h * HD, c1, c2, b);
+    tma_store_4d(&tm_dqkv, sV, 2 * a.H * HD + h * HD, c1, c2, b);
     bulk_commit();
-    bulk_wait_all();
+    bulk_wait_read<0>();     // the staging tiles have been read out: the CTA may retire while the writes drain
   }
   if (warp == 0) {
     __syncwarp();
@@ -436,12 +509,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   }
 }
 
-// sum the T per-frame partials of dq(CLS query), dk / dv(CLS key) -> row 0 of dqkv
+// sum the per-tile partials of dq(CLS query), dk / dv(CLS key) -> row 0 of dqkv
 __global__ void __launch_bounds__(192) attn_tc_cls_merge_bwd_kernel(const float* __restrict__ ws, bf16* __restrict__ dqkv, TcShape a) {
   const int h = blockIdx.x, b = blockIdx.y, i = threadIdx.x;
-  const float* w = ws + (((long long)b * a.H + h) * a.T) * 192;
+  const float* w = ws + (((long long)b * a.H + h) * a.chunks) * 192;
   float acc = 0.f;
-  for (int g = 0; g < a.T; ++g) acc += w[g * 192 + i];
+  for (int g = 0; g < a.chunks; ++g) acc += w[g * 192 + i];
   const int m = i >> 6, d = i & 63;
   dqkv[(long long)b * a.N * 3 * a.H * HD + (long long)m * a.H * HD + h * HD + d] = opnd_from_float(acc);
 }
@@ -460,34 +533,57 @@ EncodeTiledFn encode_fn() {
   fn = reinterpret_cast<EncodeTiledFn>(p);
   return fn;
 }
-// [rows, cols] 16-bit row-major matrix; box = [64 columns (128 B), box_rows], 128B swizzle
-int make_map(CUtensorMap* m, const void* ptr, long long rows, long long cols, int box_rows) {
+// 4-D view {column, position, frame, sample} of a [B*N, cols] 16-bit row-major token matrix, 128B swizzle, box = [64 columns, b1, b2, 1]:
+//   mode 0:      {cols, N, 1, B}   -- the whole sequence of a sample
+//   modes 1 / 2: {cols, n, T, B} over the PATCH tokens (base pointer skips the CLS row of sample 0; sample stride N rows)
+int make_map(CUtensorMap* m, const void* ptr, const TcShape& a, long long cols) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return tvts_set_error(TVTS_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
+  const cuuint64_t row = (cuuint64_t)cols * 2;
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4];
+  const char* base = reinterpret_cast<const char*>(ptr);
+  if (a.mode == 0) {
+    dims[0] = (cuuint64_t)cols; dims[1] = (cuuint64_t)a.N; dims[2] = 1; dims[3] = (cuuint64_t)a.B;
+    strides[0] = row; strides[1] = row * a.N; strides[2] = row * a.N;
+    box[0] = 64; box[1] = (cuuint32_t)a.N; box[2] = 1; box[3] = 1;
+  } else {
+    base += row;
+    dims[0] = (cuuint64_t)cols; dims[1] = (cuuint64_t)a.n; dims[2] = (cuuint64_t)a.T; dims[3] = (cuuint64_t)a.B;
+    strides[0] = row; strides[1] = row * a.n; strides[2] = row * a.N;
+    box[0] = 64; box[1] = (cuuint32_t)(a.mode == 1 ? a.n : a.GP); box[2] = (cuuint32_t)(a.mode == 1 ? 1 : a.T); box[3] = 1;
+  }
+  cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUtensorMapDataType t16 = TVTS_OPERAND_IS_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  CUresult r = fn(m, t16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = fn(m, t16, 4, const_cast<char*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return tvts_set_error(TVTS_ERR_CUDA, "attn_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  if (r != CUDA_SUCCESS)
+    return tvts_set_error(TVTS_ERR_CUDA, "attn_tc: cuTensorMapEncodeTiled failed (%d) mode=%d N=%d n=%d T=%d GP=%d", (int)r, a.mode, a.N, a.n, a.T, a.GP);
   return TVTS_OK;
 }
 
 bool make_shape(TcShape* s, int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal, float scale) {
   if (d != HD || B <= 0 || H <= 0) return false;
+  TcShape a{};
+  a.B = (int)B; a.N = (int)N; a.H = (int)H; a.mode = (int)mode; a.T = (int)T; a.n = (int)n; a.causal = (int)causal; a.scale = scale;
   if (mode == 0) {
     if (N < 1 || N > 128) return false;
-    *s = TcShape{(int)B, (int)N, (int)H, 0, 1, 0, (int)causal, scale, (int)N, (int)N, (int)((N + 15) / 16 * 16)};
-    return true;
-  }
-  if (mode == 1) {
+    a.T = 1; a.n = 0; a.GP = 0; a.chunks = 1; a.rows = (int)N; a.L = (int)N;
+  } else if (mode == 1) {
     if (causal || T < 1 || n < 1 || n > 127 || N != 1 + T * n) return false;
-    *s = TcShape{(int)B, (int)N, (int)H, 1, (int)T, (int)n, 0, scale, (int)n, (int)n + 1, (int)((n + 1 + 15) / 16 * 16)};
-    return true;
+    a.GP = 0; a.chunks = (int)T; a.rows = (int)n; a.L = (int)n + 1;
+  } else if (mode == 2) {
+    if (causal || T < 1 || T > 127 || n < 1 || N != 1 + T * n) return false;
+    const int gp_max = 127 / (int)T;                     // T * GP patch rows + the CLS row fit one 128-row tile
+    a.chunks = ((int)n + gp_max - 1) / gp_max;
+    a.GP = ((int)n + a.chunks - 1) / a.chunks;           // balanced tiles (98 positions, T = 8: 7 tiles of 14)
+    a.rows = (int)T * a.GP; a.L = a.rows + 1;
+  } else {
+    return false;
   }
-  return false;
+  a.LP = (a.L + 15) / 16 * 16;
+  *s = a;
+  return true;
 }
 
 // per-device workspace for the CLS partials (grown on demand; allocation happens outside any stream capture: the first call of a
@@ -509,24 +605,31 @@ float* workspace(size_t bytes) {
 }
 
 int g_attn_tc = -1;     // -1: not decided yet (environment TVTS_ATTN_TC=0 switches the tcgen05 path off for the whole process)
-int attn_tc_on() {
+int g_attn_tc_time = -1;   // mode 2 separately (TVTS_ATTN_TC_TIME=0 keeps the warp-per-slot time kernels)
+int attn_tc_on(int mode) {
   if (g_attn_tc < 0) {
     const char* e = getenv("TVTS_ATTN_TC");
     g_attn_tc = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
-  return g_attn_tc;
+  if (g_attn_tc_time < 0) {
+    const char* e = getenv("TVTS_ATTN_TC_TIME");
+    g_attn_tc_time = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return g_attn_tc && (mode != 2 || g_attn_tc_time);
 }
 
 }  // namespace
 
+// on: bit 0 = modes 0 / 1, bit 1 = mode 2 (time); tvts_attn_set_tc(3) = everything (default), 0 = mma.sync kernels everywhere
 extern "C" int tvts_attn_set_tc(int on) {
-  g_attn_tc = on;
+  g_attn_tc = (on & 1) ? 1 : 0;
+  g_attn_tc_time = (on & 2) ? 1 : 0;
   return TVTS_OK;
 }
 
 extern "C" int tvts_attn_tc_supported(int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal) {
   TcShape s;
-  return attn_tc_on() && make_shape(&s, B, N, H, d, mode, T, n, causal, 1.0f) ? 1 : 0;
+  return attn_tc_on((int)mode) && make_shape(&s, B, N, H, d, mode, T, n, causal, 1.0f) ? 1 : 0;
 }
 
 extern "C" int tvts_attn_tc_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T,
@@ -538,13 +641,13 @@ extern "C" int tvts_attn_tc_fwd(const void* qkv, void* out, float* lse, int64_t 
   TVTS_REQUIRE(B * N < (1ll << 31), "attn_tc_fwd: too many rows");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUtensorMap tq, to;
-  int rc = make_map(&tq, qkv, B * N, 3 * H * HD, a.nrow);
+  int rc = make_map(&tq, qkv, a, 3 * H * HD);
   if (rc) return rc;
-  rc = make_map(&to, out, B * N, H * HD, a.nrow);
+  rc = make_map(&to, out, a, H * HD);
   if (rc) return rc;
   float* ws = nullptr;
-  if (a.mode == 1) {
-    ws = workspace((size_t)B * H * T * 192 * sizeof(float));
+  if (a.mode != 0) {
+    ws = workspace((size_t)B * H * a.chunks * 192 * sizeof(float));
     TVTS_REQUIRE(ws != nullptr, "attn_tc_fwd: workspace allocation failed");
   }
   static bool attr = false;
@@ -553,10 +656,10 @@ extern "C" int tvts_attn_tc_fwd(const void* qkv, void* out, float* lse, int64_t 
     TVTS_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr = true;
   }
-  dim3 grid((unsigned)(a.mode == 1 ? a.T : 1), (unsigned)H, (unsigned)B);
-  attn_tc_fwd_kernel<<<grid, 128, FWD_SMEM, st>>>(tq, to, reinterpret_cast<const bf16*>(qkv), lse, ws, a);
+  dim3 grid((unsigned)a.chunks, (unsigned)H, (unsigned)B);
+  attn_tc_fwd_kernel<<<grid, kTcThreads, FWD_SMEM, st>>>(tq, to, reinterpret_cast<const bf16*>(qkv), lse, ws, a);
   TVTS_LAUNCH_CHECK();
-  if (a.mode == 1) {
+  if (a.mode != 0) {
     attn_tc_cls_merge_fwd_kernel<<<dim3((unsigned)H, (unsigned)B), 64, 0, st>>>(ws, reinterpret_cast<bf16*>(out), lse, a);
     TVTS_LAUNCH_CHECK();
   }
@@ -572,15 +675,15 @@ extern "C" int tvts_attn_tc_bwd(const void* qkv, const void* out, const void* do
   TVTS_REQUIRE(B * N < (1ll << 31), "attn_tc_bwd: too many rows");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUtensorMap tq, tdo, tdq;
-  int rc = make_map(&tq, qkv, B * N, 3 * H * HD, a.nrow);
+  int rc = make_map(&tq, qkv, a, 3 * H * HD);
   if (rc) return rc;
-  rc = make_map(&tdo, dout, B * N, H * HD, a.nrow);
+  rc = make_map(&tdo, dout, a, H * HD);
   if (rc) return rc;
-  rc = make_map(&tdq, dqkv, B * N, 3 * H * HD, a.nrow);
+  rc = make_map(&tdq, dqkv, a, 3 * H * HD);
   if (rc) return rc;
   float* ws = nullptr;
-  if (a.mode == 1) {
-    ws = workspace((size_t)B * H * T * 192 * sizeof(float));
+  if (a.mode != 0) {
+    ws = workspace((size_t)B * H * a.chunks * 192 * sizeof(float));
     TVTS_REQUIRE(ws != nullptr, "attn_tc_bwd: workspace allocation failed");
   }
   static bool attr = false;
@@ -589,11 +692,11 @@ extern "C" int tvts_attn_tc_bwd(const void* qkv, const void* out, const void* do
     TVTS_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr = true;
   }
-  dim3 grid((unsigned)(a.mode == 1 ? a.T : 1), (unsigned)H, (unsigned)B);
-  attn_tc_bwd_kernel<<<grid, 128, BWD_SMEM, st>>>(tq, tdo, tdq, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<const bf16*>(out),
-                                                  reinterpret_cast<const bf16*>(dout), lse, ws, a);
+  dim3 grid((unsigned)a.chunks, (unsigned)H, (unsigned)B);
+  attn_tc_bwd_kernel<<<grid, kTcThreads, BWD_SMEM, st>>>(tq, tdo, tdq, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<const bf16*>(out),
+                                                         reinterpret_cast<const bf16*>(dout), lse, ws, a);
   TVTS_LAUNCH_CHECK();
-  if (a.mode == 1) {
+  if (a.mode != 0) {
     attn_tc_cls_merge_bwd_kernel<<<dim3((unsigned)H, (unsigned)B), 192, 0, st>>>(ws, reinterpret_cast<bf16*>(dqkv), a);
     TVTS_LAUNCH_CHECK();
   }
