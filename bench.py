@@ -32,8 +32,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--trim-text", action="store_true",
-                    help="trim the token matrix to the longest caption of the batch (exact for the causal text tower; fewer padded rows)")
+    ap.add_argument("--no-trim-text", dest="trim_text", action="store_false",
+                    help="keep all 77 token columns (default: the token matrix is trimmed to the longest caption of the batch, rounded up to 8 "
+                         "-- what Trainer_TVTSv2 does by default; EXACT for the causal text tower: columns after every sequence's EOT never "
+                         "reach the pooled EOT row, tests/test_h14_v1_staged_gpu.py::test_text_context_trimming_on_the_gpu)")
+    ap.add_argument("--trim-text", dest="trim_text", action="store_true", help=argparse.SUPPRESS)
+    ap.set_defaults(trim_text=True)
     ap.add_argument("--u8-input", action="store_true", help="feed uint8 clips (GPU-side normalisation fused into the patch gather)")
     ap.add_argument("--workload", default="c3", help="c3 = ViT-B/16 T=8 batch 32/GPU (headline); c2 = ViT-B/32 T=8 batch 64; c1 = ViT-B/32 T=2 batch 4; "
                     "c4 = ViT-H/14 T=16 batch 8/GPU; c5 = TVTS v1 (ViT-B/16 tubelets, 16 frames, DistilBERT) batch 24/GPU")
@@ -416,10 +420,17 @@ def run_ours(args):
     roof_mode = "timed region"
     if use_graph:
         step.use_graph = False
+        prev = os.environ.get("TVTS_TEXT_STREAM")
+        os.environ["TVTS_TEXT_STREAM"] = "0"      # one stream: a launch's event pair must bracket that launch alone
         step(resident)
         timed(resident, args.steps, False, True)
+        if prev is None:
+            os.environ.pop("TVTS_TEXT_STREAM")
+        else:
+            os.environ["TVTS_TEXT_STREAM"] = prev
         step.use_graph = True
-        roof_mode = "same steps re-run launch-by-launch (per-launch CUDA events cannot be recorded inside a replayed CUDA graph)"
+        roof_mode = ("same steps re-run launch-by-launch on ONE stream (per-launch CUDA events cannot be recorded inside a replayed CUDA graph; "
+                     "the timed graph overlaps the text tower with the video tower on a second stream)")
 
     import ctypes
     breakdown = None

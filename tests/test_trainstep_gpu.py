@@ -75,11 +75,13 @@ def test_graph_replay_and_eager_steps_match_each_other_and_the_oracle():
     lg, pg, step, _, sk_g = run(cfg, True)
     assert step.launches_per_graph > 100
     assert sk_e == 0 and sk_g == 0                                       # no step was skipped by the dynamic loss scale
+    # measured on the B200 over 6 steps at the reference learning rates: 0 .. 5.8e-5 between the two paths (and the same between two runs of
+    # ONE path: Adam's lr/eps = 100 gain on the 1e-7 atomic-order noise of tiny gradients); bound = 3e-4, a third of the north-star 1e-3
     for (a1, a2), (b1, b2) in zip(le, lg):
-        assert abs(a1 - b1) < 2e-5 and abs(a2 - b2) < 2e-5, (le, lg)
+        assert abs(a1 - b1) < 3e-4 and abs(a2 - b2) < 3e-4, (le, lg)
     for k in pe:
         d = (pe[k] - pg[k]).abs().max().item()
-        assert d < 2e-5 * max(1.0, pe[k].abs().max().item()), (k, d)
+        assert d < 3e-4 * max(1.0, pe[k].abs().max().item()), (k, d)
     lo = oracle_losses(cfg, len(le), groups, frozen)
     for path in (le, lg):
         for (a1, a2), (o1, o2) in zip(path, lo):

@@ -40,6 +40,7 @@ struct TcShape {
   int rows;     // rows the TMA box moves per tile: N | n | T * GP
   int L;        // rows = keys of the tile: `rows` (+ 1 in modes 1 / 2: the CLS token, last)
   int LP;       // L rounded up to a multiple of 16 (UMMA N / K granularity)
+  int ahead;    // L2 prefetch distance in tiles (= CTAs resident on the chip): each CTA requests the tile the SAME slot will run next
 };
 
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4); }
@@ -58,6 +59,10 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const void* tmap,
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst_smem), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const void* tmap, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 __device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src_smem, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tmap), "r"(src_smem),
@@ -159,6 +164,17 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     tma_load_4d(sQ, &tm_qkv, bar_ld, h * HD, c1, c2, b);
     tma_load_4d(sK, &tm_qkv, bar_ld, a.H * HD + h * HD, c1, c2, b);
     tma_load_4d(sV, &tm_qkv, bar_ld, 2 * a.H * HD + h * HD, c1, c2, b);
+    // pull the tile that will run in this slot one wave from now into L2 (CTAs are dispatched in linear block order): its TMA
+    // loads then see L2 latency instead of HBM latency -- the kernel is latency-bound per tile, not bandwidth-bound
+    const long long nl = ((long long)b * a.H + h) * a.chunks + g + a.ahead;
+    if (a.ahead > 0 && nl < (long long)a.B * a.H * a.chunks) {
+      const int g2 = (int)(nl % a.chunks), h2 = (int)((nl / a.chunks) % a.H), b2 = (int)(nl / ((long long)a.chunks * a.H));
+      int d1, d2;
+      tile_coords(a, g2, d1, d2);
+      tma_prefetch_4d(&tm_qkv, h2 * HD, d1, d2, b2);
+      tma_prefetch_4d(&tm_qkv, a.H * HD + h2 * HD, d1, d2, b2);
+      tma_prefetch_4d(&tm_qkv, 2 * a.H * HD + h2 * HD, d1, d2, b2);
+    }
   } else if (warp == 2) {
     if (a.mode != 0 && lane < 24) {      // the CLS token's q / k / v rows -> row `rows` of the three tiles (generic-proxy stores, swizzled by hand)
       const int m = lane >> 3, c = lane & 7;
@@ -340,6 +356,16 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     tma_load_4d(sK, &tm_qkv, bar_ld, a.H * HD + h * HD, c1, c2, b);
     tma_load_4d(sV, &tm_qkv, bar_ld, 2 * a.H * HD + h * HD, c1, c2, b);
     tma_load_4d(sDO, &tm_do, bar_ld, h * HD, c1, c2, b);
+    const long long nl = ((long long)b * a.H + h) * a.chunks + g + a.ahead;     // L2 prefetch of this slot's next tile (see the forward)
+    if (a.ahead > 0 && nl < (long long)a.B * a.H * a.chunks) {
+      const int g2 = (int)(nl % a.chunks), h2 = (int)((nl / a.chunks) % a.H), b2 = (int)(nl / ((long long)a.chunks * a.H));
+      int d1, d2;
+      tile_coords(a, g2, d1, d2);
+      tma_prefetch_4d(&tm_qkv, h2 * HD, d1, d2, b2);
+      tma_prefetch_4d(&tm_qkv, a.H * HD + h2 * HD, d1, d2, b2);
+      tma_prefetch_4d(&tm_qkv, 2 * a.H * HD + h2 * HD, d1, d2, b2);
+      tma_prefetch_4d(&tm_do, h2 * HD, d1, d2, b2);
+    }
   } else if (warp == 2) {
     if (a.mode != 0) {                     // CLS rows of q, k, v, dO -> row `rows` of the four tiles
       const int m = lane >> 3, c = lane & 7;
@@ -604,12 +630,15 @@ float* workspace(size_t bytes) {
   return w.ptr;
 }
 
+int g_attn_tc_prefetch = 1;   // L2 prefetch of the next wave's tiles (tvts_attn_set_tc bit 2 clears it: A/B measurements)
 int g_attn_tc = -1;     // -1: not decided yet (environment TVTS_ATTN_TC=0 switches the tcgen05 path off for the whole process)
 int g_attn_tc_time = -1;   // mode 2 separately (TVTS_ATTN_TC_TIME=0 keeps the warp-per-slot time kernels)
 int attn_tc_on(int mode) {
   if (g_attn_tc < 0) {
     const char* e = getenv("TVTS_ATTN_TC");
     g_attn_tc = (e != nullptr && e[0] == '0') ? 0 : 1;
+    const char* p = getenv("TVTS_ATTN_TC_PREFETCH");
+    if (p != nullptr && p[0] == '0') g_attn_tc_prefetch = 0;
   }
   if (g_attn_tc_time < 0) {
     const char* e = getenv("TVTS_ATTN_TC_TIME");
@@ -620,10 +649,11 @@ int attn_tc_on(int mode) {
 
 }  // namespace
 
-// on: bit 0 = modes 0 / 1, bit 1 = mode 2 (time); tvts_attn_set_tc(3) = everything (default), 0 = mma.sync kernels everywhere
+// on: bit 0 = modes 0 / 1, bit 1 = mode 2 (time), bit 2 = NO L2 prefetch; tvts_attn_set_tc(3) = everything (default), 0 = mma.sync kernels
 extern "C" int tvts_attn_set_tc(int on) {
   g_attn_tc = (on & 1) ? 1 : 0;
   g_attn_tc_time = (on & 2) ? 1 : 0;
+  g_attn_tc_prefetch = (on & 4) ? 0 : 1;
   return TVTS_OK;
 }
 
@@ -656,6 +686,13 @@ extern "C" int tvts_attn_tc_fwd(const void* qkv, void* out, float* lse, int64_t 
     TVTS_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr = true;
   }
+  static int resident = 0;
+  if (resident == 0) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_tc_fwd_kernel, kTcThreads, FWD_SMEM) != cudaSuccess || per_sm < 1) per_sm = 3;
+    resident = per_sm * tvts_num_sms();
+  }
+  a.ahead = g_attn_tc_prefetch ? resident : 0;
   dim3 grid((unsigned)a.chunks, (unsigned)H, (unsigned)B);
   attn_tc_fwd_kernel<<<grid, kTcThreads, FWD_SMEM, st>>>(tq, to, reinterpret_cast<const bf16*>(qkv), lse, ws, a);
   TVTS_LAUNCH_CHECK();
@@ -692,6 +729,13 @@ extern "C" int tvts_attn_tc_bwd(const void* qkv, const void* out, const void* do
     TVTS_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr = true;
   }
+  static int resident = 0;
+  if (resident == 0) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn_tc_bwd_kernel, kTcThreads, BWD_SMEM) != cudaSuccess || per_sm < 1) per_sm = 2;
+    resident = per_sm * tvts_num_sms();
+  }
+  a.ahead = g_attn_tc_prefetch ? resident : 0;
   dim3 grid((unsigned)a.chunks, (unsigned)H, (unsigned)B);
   attn_tc_bwd_kernel<<<grid, kTcThreads, BWD_SMEM, st>>>(tq, tdo, tdq, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<const bf16*>(out),
                                                          reinterpret_cast<const bf16*>(dout), lse, ws, a);

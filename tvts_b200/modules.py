@@ -416,13 +416,37 @@ class TVTSv2Base(BaseModel):
         out = self.video_model(video, keep_ind)
         return out, out[:, 0, :]
 
+    def _tower_stream(self, ref):
+        """The text tower and the video tower are independent until the losses (model_dist_TVTSv2_ViT_B_16.py:61-76), so on a GPU the text
+        tower runs on a second stream: its small GEMMs (M = n_trans x B x ctx rows: one or two tile waves) fill the SMs that the video
+        tower's persistent GEMMs leave idle in their last partial wave, instead of queueing behind them.  Autograd replays each node's
+        backward on the stream its forward used, so the two backward passes overlap in the same way; inside a CUDA-graph capture the
+        fork / join become parallel branches of the graph.  TVTS_TEXT_STREAM=0 keeps everything on one stream."""
+        if not ref.is_cuda or os.environ.get("TVTS_TEXT_STREAM", "1") == "0":
+            return None
+        s = getattr(self, "_side_stream", None)
+        if s is None or s.device != ref.device:
+            s = torch.cuda.Stream(device=ref.device)
+            self._side_stream = s
+        return s
+
     def forward(self, data, return_embeds=True):
         text, video, keep_ind = data["text"], data["video"], data["keep_ind"]
         B = video.shape[0]
-        t, _ = self.compute_text(text)                                # [n_trans*B, E] clip-major
+        side = self._tower_stream(video)
+        if side is None:
+            t, _ = self.compute_text(text)                            # [n_trans*B, E] clip-major
+            video_order_embeddings, video_embeddings = self.compute_video(video, keep_ind)
+        else:
+            cur = torch.cuda.current_stream(video.device)
+            side.wait_stream(cur)                                     # tokens / weights are ready on the caller's stream
+            with torch.cuda.stream(side):
+                t, _ = self.compute_text(text)
+            video_order_embeddings, video_embeddings = self.compute_video(video, keep_ind)
+            cur.wait_stream(side)
+            t.record_stream(cur)                                      # consumed below on the caller's stream
         n_trans = t.shape[0] // B
         text_embeddings = E.group_mean(t, n_trans)                    # :74-76
-        video_order_embeddings, video_embeddings = self.compute_video(video, keep_ind)
         if n_trans != 1:
             predict_order = self.pred_model.forward_clip_major(t, video_order_embeddings)   # :69-70 text is detached
         else:
