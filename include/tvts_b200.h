@@ -129,9 +129,18 @@ int tvts_attn_tc_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t 
                      int64_t causal, float scale, void* stream);
 int tvts_attn_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int64_t B, int64_t N, int64_t H,
                      int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal, float scale, void* stream);
+/* the same, additionally ACCUMULATING the column sums of dqkv over all tokens into dbias[3*H*d] (fp32; = the bias gradient of the qkv
+ * Linear, v2/model/video_encoder_ViT_B_16.py:26,41), taken from the staged 16-bit rows inside the kernel instead of a separate pass */
+int tvts_attn_tc_bwd_bias(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dbias, int64_t B, int64_t N,
+                          int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal, float scale, void* stream);
 int tvts_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv, int64_t B, int64_t N,
                   int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal, float scale, void* stream);
 
+/* tvts_attn_bwd that also ACCUMULATES the qkv Linear's bias gradient, dbias[3*H*d] += column sums of dqkv (fp32): inside the tcgen05
+ * kernels' epilogue where they apply, else tvts_attn_bwd + tvts_colsum_bf16 */
+int tvts_attn_bwd_bias(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv, float* dbias,
+                       int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal, float scale,
+                       void* stream);
 /* The head-dim generic streamed kernels behind tvts_attn_fwd / tvts_attn_bwd for d != 64, callable directly (d = 64 or 80; same
  * arguments and results): with d = 64 they cross-check the generic code against the specialised kernels. */
 /* 1 (default): groups that fit one CTA (space attention of H/14: 77 rows; short full-attention sequences) use the group-resident generic

@@ -122,6 +122,11 @@ def attn_bwd(qkv, out, dout, lse, delta, dqkv, B, N, H, d, mode, T, n, causal, s
     dqkv.view(B, N, 3, H, d).copy_(r.to(BF16))
 
 
+def attn_bwd_bias(qkv, out, dout, lse, delta, dqkv, dbias, B, N, H, d, mode, T, n, causal, scale):
+    attn_bwd(qkv, out, dout, lse, delta, dqkv, B, N, H, d, mode, T, n, causal, scale)
+    dbias.add_(dqkv.view(B * N, 3 * H * d).float().sum(0))
+
+
 def _padded_scores(qkv, klen, B, N, H, d, scale):
     t = qkv.view(B, N, 3, H, d).float()
     q, k, v = (t[:, :, i].transpose(1, 2) for i in range(3))

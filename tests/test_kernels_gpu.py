@@ -179,6 +179,13 @@ def test_attention(B, H, mode, T, n, N, causal, attn_tc):
         grads.append(dqkv)
     assert torch.isfinite(grads[0].float()).all(), "attn_bwd left elements unwritten"
     close(grads[0], grads[1], atol=3e-2, rtol=3e-2, what="attn dqkv")
+    # the variant that also accumulates the qkv bias gradient (column sums of dqkv): same dqkv bit for bit, bias = sums of the stored values
+    dqkv2 = torch.full_like(qkv, float("nan"))
+    dbias = torch.full((3 * H * d,), 0.5, device=DEV)
+    L.call("attn_bwd_bias", qkv, out, dout, lse, torch.empty_like(lse), dqkv2, dbias, B, N, H, d, mode, T, n, int(causal), scale)
+    assert torch.equal(dqkv2, grads[0])
+    want = 0.5 + grads[0].view(B * N, 3 * H * d).float().sum(0)
+    close(dbias, want, atol=2e-3 * max(1.0, want.abs().max().item()), what="attn qkv bias gradient")
 
 
 @pytest.mark.parametrize("B,H,N,q0,qn", [(2, 2, 103, 99, 4), (2, 8, 789, 785, 4), (1, 2, 300, 100, 70)])

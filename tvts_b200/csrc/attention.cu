@@ -1493,6 +1493,19 @@ extern "C" int tvts_attn_bwd(const void* qkv, const void* out, const void* dout,
   return TVTS_OK;
 }
 
+// tvts_attn_bwd + the bias gradient of the qkv Linear (dbias[3*H*d] += column sums of dqkv over all B*N tokens): fused into the tcgen05
+// kernels' epilogue where those run, otherwise the plain backward followed by the column-sum kernel
+extern "C" int tvts_attn_bwd_bias(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv,
+                                  float* dbias, int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n,
+                                  int64_t causal, float scale, void* stream) {
+  TVTS_REQUIRE(dbias != nullptr, "attn_bwd_bias: null dbias");
+  if (d == HD && tvts_attn_tc_supported(B, N, H, d, mode, T, n, causal))
+    return tvts_attn_tc_bwd_bias(qkv, out, dout, lse, dqkv, dbias, B, N, H, d, mode, T, n, causal, scale, stream);
+  int rc = tvts_attn_bwd(qkv, out, dout, lse, delta_ws, dqkv, B, N, H, d, mode, T, n, causal, scale, stream);
+  if (rc) return rc;
+  return tvts_colsum_bf16(dqkv, dbias, B * N, 3 * H * d, 3 * H * d, stream);
+}
+
 // ------------------------------------------------------------------------------------------------ query-window attention
 // Full (non-causal) attention where only rows [q0, q0+qn) of every sample act as QUERIES while all N tokens are keys / values:
 // the last block of the sort head feeds the loss through its n_trans transcript rows only (v2/model/sort_transformer.py:134-142),

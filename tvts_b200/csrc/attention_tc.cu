@@ -326,7 +326,8 @@ constexpr int BWD_SMEM = BWD_BAR + 64 + 1024;
 __global__ void __launch_bounds__(kTcThreads, 2)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                    const __grid_constant__ CUtensorMap tm_dqkv, const bf16* __restrict__ qkv, const bf16* __restrict__ out,
-                   const bf16* __restrict__ dout, const float* __restrict__ lse, float* __restrict__ cls_ws, TcShape a) {
+                   const bf16* __restrict__ dout, const float* __restrict__ lse, float* __restrict__ cls_ws, float* __restrict__ dbias,
+                   TcShape a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -526,8 +527,24 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     tma_store_4d(&tm_dqkv, sK, a.H * HD + h * HD, c1, c2, b);
     tma_store_4d(&tm_dqkv, sV, 2 * a.H * HD + h * HD, c1, c2, b);
     bulk_commit();
-    bulk_wait_read<0>();     // the staging tiles have been read out: the CTA may retire while the writes drain
   }
+  if (dbias != nullptr && tid >= 64) {
+    // bias gradient of the qkv Linear = column sums of dqkv over the tokens: summed here from the staged 16-bit rows (the very values the
+    // stores write), one atomicAdd per (tile, column); the CLS row is added by the merge kernel.  Replaces a separate pass over dqkv.
+    const int i = tid - 64, m = i >> 6, d = i & 63;
+    const uint8_t* tile = gen + (size_t)m * ATOM;
+    float s = 0.f;
+    for (int rr = 0; rr < a.rows; ++rr) {
+      const bf16 x = *reinterpret_cast<const bf16*>(tile + swz(rr, d >> 3) + (d & 7) * 2);
+#ifdef TVTS_OPERAND_FP16
+      s += __half2float(x);
+#else
+      s += __bfloat162float(x);
+#endif
+    }
+    atomicAdd(dbias + (long long)m * a.H * HD + h * HD + d, s);
+  }
+  if (tid == 0) bulk_wait_read<0>();     // the staging tiles have been read out: the CTA may retire while the writes drain
   if (warp == 0) {
     __syncwarp();
     tc_fence_after();
@@ -536,13 +553,22 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 }
 
 // sum the per-tile partials of dq(CLS query), dk / dv(CLS key) -> row 0 of dqkv
-__global__ void __launch_bounds__(192) attn_tc_cls_merge_bwd_kernel(const float* __restrict__ ws, bf16* __restrict__ dqkv, TcShape a) {
+__global__ void __launch_bounds__(192) attn_tc_cls_merge_bwd_kernel(const float* __restrict__ ws, bf16* __restrict__ dqkv,
+                                                                    float* __restrict__ dbias, TcShape a) {
   const int h = blockIdx.x, b = blockIdx.y, i = threadIdx.x;
   const float* w = ws + (((long long)b * a.H + h) * a.chunks) * 192;
   float acc = 0.f;
   for (int g = 0; g < a.chunks; ++g) acc += w[g * 192 + i];
   const int m = i >> 6, d = i & 63;
-  dqkv[(long long)b * a.N * 3 * a.H * HD + (long long)m * a.H * HD + h * HD + d] = opnd_from_float(acc);
+  const bf16 o = opnd_from_float(acc);
+  dqkv[(long long)b * a.N * 3 * a.H * HD + (long long)m * a.H * HD + h * HD + d] = o;
+  if (dbias != nullptr) {
+#ifdef TVTS_OPERAND_FP16
+    atomicAdd(dbias + (long long)m * a.H * HD + h * HD + d, __half2float(o));
+#else
+    atomicAdd(dbias + (long long)m * a.H * HD + h * HD + d, __bfloat162float(o));
+#endif
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -705,6 +731,12 @@ extern "C" int tvts_attn_tc_fwd(const void* qkv, void* out, float* lse, int64_t 
 
 extern "C" int tvts_attn_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int64_t B, int64_t N,
                                 int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal, float scale, void* stream) {
+  return tvts_attn_tc_bwd_bias(qkv, out, dout, lse, dqkv, nullptr, B, N, H, d, mode, T, n, causal, scale, stream);
+}
+
+extern "C" int tvts_attn_tc_bwd_bias(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dbias, int64_t B,
+                                     int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal, float scale,
+                                     void* stream) {
   TcShape a;
   TVTS_REQUIRE(make_shape(&a, B, N, H, d, mode, T, n, causal, scale), "attn_tc_bwd: unsupported shape (d=%lld mode=%lld N=%lld n=%lld)",
                (long long)d, (long long)mode, (long long)N, (long long)n);
@@ -738,10 +770,10 @@ extern "C" int tvts_attn_tc_bwd(const void* qkv, const void* out, const void* do
   a.ahead = g_attn_tc_prefetch ? resident : 0;
   dim3 grid((unsigned)a.chunks, (unsigned)H, (unsigned)B);
   attn_tc_bwd_kernel<<<grid, kTcThreads, BWD_SMEM, st>>>(tq, tdo, tdq, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<const bf16*>(out),
-                                                         reinterpret_cast<const bf16*>(dout), lse, ws, a);
+                                                         reinterpret_cast<const bf16*>(dout), lse, ws, dbias, a);
   TVTS_LAUNCH_CHECK();
   if (a.mode != 0) {
-    attn_tc_cls_merge_bwd_kernel<<<dim3((unsigned)H, (unsigned)B), 192, 0, st>>>(ws, reinterpret_cast<bf16*>(dqkv), a);
+    attn_tc_cls_merge_bwd_kernel<<<dim3((unsigned)H, (unsigned)B), 192, 0, st>>>(ws, reinterpret_cast<bf16*>(dqkv), dbias, a);
     TVTS_LAUNCH_CHECK();
   }
   return TVTS_OK;

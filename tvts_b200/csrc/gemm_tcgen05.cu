@@ -20,6 +20,7 @@
 //           residual add in registers; the warp's [32 rows x 128 B] block goes through a 128B-swizzled shared-memory box to the TMA
 //           engine: cp.async.bulk.tensor store, or cp.reduce.async.bulk .add for split-K / gradient accumulation)
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/tvts_b200.h"
 
@@ -124,6 +125,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder_gen;
+  // Programmatic dependent launch: the launch below carries cudaLaunchAttributeProgrammaticStreamSerialization, so this grid may be
+  // scheduled while the previous kernel of the stream is still draining -- everything above (tensor-map prefetch, barrier init, TMEM
+  // allocation, cluster sync) overlaps that tail; nothing above touches memory the previous kernel writes.  From here on it does.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // ... and let a dependent GEMM grid be scheduled as soon as this grid's CTAs start to retire (persistent grid: every CTA is resident
+  // already, so the dependents only ever take SMs this grid has left; they block at their own griddepcontrol.wait until it completes)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int total_units = s.m_tiles * s.n_tiles * s.splits;
 
@@ -473,6 +481,7 @@ int make_tmap(CUtensorMap* m, const void* ptr, long long d0, long long d1, long 
 int g_dbg_lbo = 0, g_dbg_sbo = 0, g_dbg_kadv = 0, g_dbg_epi = 0;
 int g_pair_mode = -1;   // -1 auto, 0 never use CTA pairs, 1 always when the shape allows
 int g_opnd_prefetch = 1; // TMA prefetch of the residual / aux epilogue operand
+int g_pdl = -1;          // programmatic dependent launch of the GEMM grids (environment TVTS_GEMM_PDL=0 turns it off)
 
 template <int BN, bool A_MN, bool B_MN, int CTAS>
 int launch(const tvts_gemm_args* g, const GemmShape& s, const EpiParams& ep, cudaStream_t stream) {
@@ -512,6 +521,10 @@ int launch(const tvts_gemm_args* g, const GemmShape& s, const EpiParams& ep, cud
     }
   }
   auto kern = gemm_kernel<BN, A_MN, B_MN, CTAS>;
+  if (g_pdl < 0) {
+    const char* e = getenv("TVTS_GEMM_PDL");
+    g_pdl = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     TVTS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -530,11 +543,13 @@ int launch(const tvts_gemm_args* g, const GemmShape& s, const EpiParams& ep, cud
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = L::TOTAL;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_pdl ? 2 : 1;
   cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, tpre, topnd, s, ep2, g_dbg_lbo, g_dbg_sbo, g_dbg_kadv, g_dbg_epi);
   tvts_prof_end(stream, prof_slot);
   tvts_count_launch(1);

@@ -206,7 +206,7 @@ extern "C" int tvts_layernorm_bwd_colsum(const void* dy, int64_t dy_is_bf16, con
   TVTS_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma and dbeta must be given together");
   TVTS_REQUIRE(D % 128 == 0, "layernorm_bwd: D=%lld must be a multiple of 128", (long long)D);
   long long want = (M + kWarps - 1) / kWarps;
-  const long long cap = 4LL * tvts_num_sms();
+  const long long cap = 1LL * tvts_num_sms();      // persistent: the register-resident column accumulators allow one CTA per SM
   const unsigned grid = (unsigned)(want < cap ? want : cap);
 #define LAUNCH(NV_)                                                                                                          \
   if (dy_is_bf16)                                                                                                            \

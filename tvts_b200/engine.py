@@ -189,11 +189,15 @@ def attn_fwd(qkv, B, N, H, mode, T=0, n=0, causal=False):
     return out, lse
 
 
-def attn_bwd(qkv, out, dout, lse, B, N, H, mode, T=0, n=0, causal=False):
+def attn_bwd(qkv, out, dout, lse, B, N, H, mode, T=0, n=0, causal=False, dbias=None):
+    """dbias (optional, ACCUMULATED): the qkv Linear's bias gradient = column sums of dqkv, produced by the attention backward itself."""
     d = qkv.shape[-1] // (3 * H)
     dqkv = torch.empty_like(qkv)
     delta = torch.empty_like(lse)
-    L.call("attn_bwd", qkv, out, dout, lse, delta, dqkv, B, N, H, d, mode, T, n, int(causal), float(d ** -0.5))
+    if dbias is None:
+        L.call("attn_bwd", qkv, out, dout, lse, delta, dqkv, B, N, H, d, mode, T, n, int(causal), float(d ** -0.5))
+    else:
+        L.call("attn_bwd_bias", qkv, out, dout, lse, delta, dqkv, dbias, B, N, H, d, mode, T, n, int(causal), float(d ** -0.5))
     return dqkv
 
 
@@ -325,8 +329,8 @@ def st_block_bwd(P, p, saved, d_out, d_out_bf, B, N, T, n, H, act, prev_cproj_bi
     # space attention
     _linear_bwd(P, p + "attn.proj.weight", None, d_sr_bf, o_s)
     do_s = lin_dgrad(d_sr_bf, P.bf(p + "attn.proj.weight"), BF16)
-    dqkv_s = attn_bwd(qkv_s, o_s, do_s, lse_s, B, N, H, MODE_SPACE, T, n)
-    _linear_bwd(P, p + "attn.qkv.weight", p + "attn.qkv.bias", dqkv_s, a1)
+    dqkv_s = attn_bwd(qkv_s, o_s, do_s, lse_s, B, N, H, MODE_SPACE, T, n, dbias=_bias_buf(P, p + "attn.qkv.bias"))
+    _linear_bwd(P, p + "attn.qkv.weight", None, dqkv_s, a1)
     da1 = lin_dgrad(dqkv_s, P.bf(p + "attn.qkv.weight"), BF16)
     dw, db = _ln_grads(P, p, "ln_1")
     d_tr, d_tr_bf = ln_bwd(da1, tr, mu1, rs1, P[p + "ln_1.weight"], dw=dw, db=db,
@@ -334,8 +338,8 @@ def st_block_bwd(P, p, saved, d_out, d_out_bf, B, N, T, n, H, act, prev_cproj_bi
     # time attention
     _linear_bwd(P, p + "timeattn.proj.weight", None, d_tr_bf, o_t)
     do_t = lin_dgrad(d_tr_bf, P.bf(p + "timeattn.proj.weight"), BF16)
-    dqkv_t = attn_bwd(qkv_t, o_t, do_t, lse_t, B, N, H, MODE_TIME, T, n)
-    _linear_bwd(P, p + "timeattn.qkv.weight", p + "timeattn.qkv.bias", dqkv_t, a3)
+    dqkv_t = attn_bwd(qkv_t, o_t, do_t, lse_t, B, N, H, MODE_TIME, T, n, dbias=_bias_buf(P, p + "timeattn.qkv.bias"))
+    _linear_bwd(P, p + "timeattn.qkv.weight", None, dqkv_t, a3)
     da3 = lin_dgrad(dqkv_t, P.bf(p + "timeattn.qkv.weight"), BF16)
     dw, db = _ln_grads(P, p, "ln_3")
     d_x, d_x_bf = ln_bwd(da3, x, mu3, rs3, P[p + "ln_3.weight"], res1=d_sr, res2=d_tr, dw=dw, db=db, dxsum=_bias_buf(P, prev_cproj_bias))
@@ -385,8 +389,8 @@ def block_bwd(P, nm, saved, d_out, d_out_bf, B, S, H, act, causal):
                            dxsum=_bias_buf(P, nm.out_b))           # out-projection bias gradient = column sums of d_x1
     _linear_bwd(P, nm.out_w, None, d_x1_bf, o)
     do = lin_dgrad(d_x1_bf, P.bf(nm.out_w), BF16)
-    dqkv = attn_bwd(qkv, o, do, lse, B, S, H, MODE_FULL, causal=causal)
-    _linear_bwd(P, nm.qkv_w, nm.qkv_b, dqkv, a1)
+    dqkv = attn_bwd(qkv, o, do, lse, B, S, H, MODE_FULL, causal=causal, dbias=_bias_buf(P, nm.qkv_b))
+    _linear_bwd(P, nm.qkv_w, None, dqkv, a1)
     da1 = lin_dgrad(dqkv, P.bf(nm.qkv_w), BF16)   # LN backward reads its dy as bf16: half the traffic of this stream
     need1 = P.need(nm.ln1 + ".weight") or P.need(nm.ln1 + ".bias")
     d_x, d_x_bf = ln_bwd(da1, x, mu1, rs1, P[nm.ln1 + ".weight"], res1=d_x1,
