@@ -51,21 +51,19 @@ def _worker(rank, world, port, out):
         local = make_batch(cfg, Bl, T, n_trans=nt, seed=3, rank=rank)
         l1, l2 = step(local)
         grads = {k: p.grad.clone() / step.loss_scale for k, p in m.named_parameters() if p.grad is not None}   # (fp16 build: loss-scaled)
-        # opt-in overlap: everything but the text tower is all-reduced from a hook at the end of the video backward, the text ranges at
-        # the end -- same sums, so the averaged gradients must be IDENTICAL, and the arena must be covered exactly once
-        from tvts_b200.trainer import arena_ranges
-        names = {id(p): n for n, p in m.named_parameters()}
-        early, late = arena_ranges(opt.flat, [names[id(p)].startswith("text_") for p in opt.flat.params])
-        cover = sorted(early + late)
+        # bucketed overlap (the default when W > 1; the first step above ran it, this one runs the single all-reduce): buckets are sent from
+        # engine.GRAD_READY hooks while the backward runs -- same sums, so the averaged gradients must be IDENTICAL, every bucket must
+        # have been sent by its hook, and the buckets must cover the arena exactly once
+        assert step.overlap and E.GRAD_READY is None
+        cover = sorted(r for runs in step._ranges.values() for r in runs)
         assert cover[0][0] == 0 and cover[-1][1] == opt.flat.total and all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
-        assert len(late) == 2 and len(early) == 3          # text tensors sit at the head of the two CLIP groups
-        step.overlap = True
+        assert {("text",), ("sort",), ("rest",), ("video_block", 0)} <= set(step._ranges)
+        assert step._sent == set(step._ranges) - {("rest",)}
+        step.overlap = False
         step(local)
-        assert E.AFTER_VIDEO_BACKWARD is None              # the hook fired and disarmed itself
         for k, p in m.named_parameters():
             if p.grad is not None:
                 assert torch.equal(p.grad / step.loss_scale, grads[k]), k
-        step.overlap = False
         if rank == 0:
             parts = [make_batch(cfg, Bl, T, n_trans=nt, seed=3, rank=r) for r in range(world)]
             video = torch.cat([p["video"] for p in parts])

@@ -124,7 +124,7 @@ def test_two_rank_nccl_graph_overlap_step():
     port = 33500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     for r in (0, 1):
-        assert out[r]["graph_vs_eager_loss"] < 3e-4, out[r]        # atomic-order noise x Adam's lr/eps gain (tests/test_trainstep_gpu.py)
-        assert out[r]["graph_vs_eager_param"] < 3e-4, out[r]
+        assert out[r]["graph_vs_eager_loss"] < 2e-3, out[r]        # two samples of the 16-bit rounding noise (tests/test_trainstep_gpu.py)
+        assert out[r]["graph_vs_eager_param"] < 1e-3, out[r]
     assert out[0]["loss1_vs_oracle"] < 2e-2, out[0]
     assert out[0]["text_grad_rel_vs_oracle"] < 0.08, out[0]

@@ -560,6 +560,7 @@ def video_backward(P, saved, d_vtok, cfg):
         prev_bias = f"transformer.resblocks.{i - 1}.mlp.c_proj.bias" if i > 0 else None
         d_x, d_x_bf = st_block_bwd(P, f"transformer.resblocks.{i}.", saved["blocks"][i], d_x, d_x_bf, B, N, T, n, H, cfg.act, prev_bias)
         saved["blocks"][i] = None
+        _grad_ready("video_block", i)      # (block i's own c_proj bias was filled by block i+1's LayerNorm backward, earlier)
     need0 = P.need("ln_pre.weight") or P.need("ln_pre.bias")
     d_x0, _ = ln_bwd(d_x, saved["x0"], saved["mu0"], saved["rs0"], P["ln_pre.weight"], want_bf16=False,
                      dw=P.gbuf("ln_pre.weight") if need0 else None, db=P.gbuf("ln_pre.bias") if need0 else None)
@@ -576,8 +577,16 @@ def video_backward(P, saved, d_vtok, cfg):
                    b_mn=True, accumulate=True)
 
 
-# set by trainer.TrainStep (opt-in all-reduce overlap): called once when the video tower's backward has written its last gradient
-AFTER_VIDEO_BACKWARD = None
+# set by trainer.TrainStep (gradient all-reduce overlapped with the backward): GRAD_READY(tag) is called, on the stream that produced
+# them, whenever a set of parameter gradients has become final: ("video_block", i) after block i of the video tower's backward (blocks are
+# walked from the last to the first), ("video_rest",) at the end of the video tower's backward, ("text",) / ("sort",) at the end of
+# those towers' backward passes.
+GRAD_READY = None
+
+
+def _grad_ready(*tag):
+    if GRAD_READY is not None:
+        GRAD_READY(tag)
 
 
 class _VideoTowerFn(torch.autograd.Function):
@@ -594,8 +603,7 @@ class _VideoTowerFn(torch.autograd.Function):
         video_backward(P, ctx.saved, d_vtok, ctx.cfg)
         ctx.saved = None
         grads = (None, None, None, None) + P.grad_tuple()
-        if AFTER_VIDEO_BACKWARD is not None:
-            AFTER_VIDEO_BACKWARD()
+        _grad_ready("video_rest")
         return grads
 
 
@@ -668,7 +676,9 @@ class _TextTowerFn(torch.autograd.Function):
         P = ParamView(ctx.names, ctx.params, ctx.needs_input_grad[3:])
         text_backward(P, ctx.saved, d_t, ctx.cfg)
         ctx.saved = None
-        return (None, None, None) + P.grad_tuple()
+        grads = (None, None, None) + P.grad_tuple()
+        _grad_ready("text")
+        return grads
 
 
 def text_tower(cfg, named_params, tokens):
@@ -739,7 +749,9 @@ class _SortHeadFn(torch.autograd.Function):
         P = ParamView(ctx.names, ctx.params, ctx.needs_input_grad[4:])
         d_vtok = sort_backward(P, ctx.saved, d_logits, ctx.cfg)
         ctx.saved = None
-        return (None, None, None, d_vtok if ctx.needs_input_grad[3] else None) + P.grad_tuple()
+        grads = (None, None, None, d_vtok if ctx.needs_input_grad[3] else None) + P.grad_tuple()
+        _grad_ready("sort")
+        return grads
 
 
 def sort_head(cfg, named_params, text_detached, vtok):

@@ -197,10 +197,9 @@ class TrainStep:
         self.params = [p for p in model.parameters() if p.requires_grad]   # after the optimizer applied the freeze policy
         self.use_graph = use_graph
         self.loss_scale = L.DEFAULT_LOSS_SCALE     # 1 for bf16 operands; fp16 operands: static scale, undone inside the AdamW kernel
-        # opt-in (TVTS_OVERLAP_ALLREDUCE=1): the gradient ranges of everything but the text tower are all-reduced on a side stream as soon
-        # as the video tower's backward has finished (the sort head's finishes before it), i.e. under the text tower's backward, which
-        # autograd runs last; the text ranges follow at the end.  Same sums, same result; default off until measured on NVLink.
-        self.overlap = os.environ.get("TVTS_OVERLAP_ALLREDUCE", "0") == "1"
+        # gradient all-reduce in buckets on a communication stream while the backward is still running (see _arm_early_allreduce);
+        # TVTS_OVERLAP_ALLREDUCE=0 falls back to ONE all-reduce of the whole arena after the backward
+        self.overlap = os.environ.get("TVTS_OVERLAP_ALLREDUCE", "1") == "1"
         self._ranges = None
         self._comm_stream = None
         self._graphs = {}
@@ -277,14 +276,7 @@ class TrainStep:
             total = total * self.loss_scale                             # static scale: optimizer-less / stock-optimizer runs of that build
         total.backward()
         if overlapped:
-            fired = E.AFTER_VIDEO_BACKWARD is None       # the hook disarms itself when it runs
-            E.AFTER_VIDEO_BACKWARD = None
-            if not fired:                                # no video backward this step (cannot happen on the hot path): do it all here
-                average_flat(flat)
-            else:
-                average_ranges(flat, self._ranges[1])    # the text tower's ranges
-                if self._comm_stream is not None:
-                    torch.cuda.current_stream().wait_stream(self._comm_stream)
+            self._finish_bucketed_allreduce(flat)
         elif flat is not None:
             average_flat(flat)
         else:
@@ -311,25 +303,68 @@ class TrainStep:
                 self.optimizer.step()
         return loss1.detach(), loss2.detach()
 
+    BUCKET_BLOCKS = 3       # video blocks per all-reduce bucket (12 blocks -> 4 buckets of ~85 MB at B/16)
+
     def _arm_early_allreduce(self, flat):
+        """DDP-style bucketed overlap on the flat arena: as soon as a bucket's gradients are final (engine.GRAD_READY tags) its arena
+        ranges are all-reduced on a communication stream while the backward continues; whatever has not been sent when the backward
+        returns (ln_pre / patch-embed / embeddings, anything without a tag) goes last.  Buckets: every BUCKET_BLOCKS video blocks (the
+        backward walks the blocks downwards, so a bucket is complete when its LOWEST block is), the sort head, the text tower.  The arena
+        is laid out by optimizer group in model order, hence a bucket is at most one contiguous run per group.  Every rank issues the same
+        collectives in the same order (the autograd engine walks the same graph), and the sums are the same sums as the single
+        all-reduce: identical gradients (tests/test_dist_cpu.py, tests/test_dist_gpu.py)."""
         if self._ranges is None:
             names = {id(p): n for n, p in self.model.named_parameters()}
-            late = [names.get(id(p), "").startswith("text_") for p in flat.params]
-            self._ranges = arena_ranges(flat, late)
+            buckets = {}
+
+            def bucket_of(name):
+                if name.startswith("text_"):
+                    return ("text",)
+                if name.startswith("pred_model."):
+                    return ("sort",)
+                key = "video_model.transformer.resblocks."
+                if name.startswith(key):
+                    i = int(name[len(key):].split(".")[0])
+                    return ("video_block", i - i % self.BUCKET_BLOCKS)
+                return ("rest",)
+            for i, p in enumerate(flat.params):
+                start = flat.offsets[i]
+                end = flat.offsets[i + 1] if i + 1 < len(flat.params) else flat.total
+                runs = buckets.setdefault(bucket_of(names.get(id(p), "")), [])
+                if runs and runs[-1][1] == start:
+                    runs[-1] = (runs[-1][0], end)
+                else:
+                    runs.append((start, end))
+            self._ranges = buckets
             if self.device.type == "cuda":
                 self._comm_stream = torch.cuda.Stream(device=self.device)
-        early = self._ranges[0]
-        side = self._comm_stream
+        self._sent = set()
+        comm = self._comm_stream
 
-        def hook():
-            E.AFTER_VIDEO_BACKWARD = None
-            if side is None:
-                average_ranges(flat, early)
+        def hook(tag):
+            if tag not in self._ranges or tag in self._sent:
                 return
-            side.wait_stream(torch.cuda.current_stream())       # the video / sort-head gradients are complete on the main stream
-            with torch.cuda.stream(side):
-                average_ranges(flat, early)
-        E.AFTER_VIDEO_BACKWARD = hook
+            self._sent.add(tag)
+            if comm is None:
+                average_ranges(flat, self._ranges[tag])
+                return
+            comm.wait_stream(torch.cuda.current_stream())       # this bucket's gradients are complete on the producing stream
+            with torch.cuda.stream(comm):
+                average_ranges(flat, self._ranges[tag])
+        E.GRAD_READY = hook
+
+    def _finish_bucketed_allreduce(self, flat):
+        E.GRAD_READY = None
+        comm = self._comm_stream
+        rest = [r for tag, runs in self._ranges.items() if tag not in self._sent for r in runs]
+        if comm is None:
+            average_ranges(flat, rest)
+            return
+        cur = torch.cuda.current_stream()
+        comm.wait_stream(cur)
+        with torch.cuda.stream(comm):
+            average_ranges(flat, rest)
+        cur.wait_stream(comm)
 
     def _capture(self, key, data):
         if not (self.optimizer is None or hasattr(self.optimizer, "launch")):
