@@ -49,6 +49,7 @@ def _worker(rank, world, port, out):
         step = TrainStep(m, None, cfg.temperature, torch.device("cpu"))
         step.optimizer = types.SimpleNamespace(flat=opt.flat, zero_grad=opt.zero_grad, step=lambda *a: None, launch=lambda *a: None)   # keep the weights fixed
         local = make_batch(cfg, Bl, T, n_trans=nt, seed=3, rank=rank)
+        step.overlap = True                                # the opt-in bucketed all-reduce first, then the single all-reduce
         l1, l2 = step(local)
         grads = {k: p.grad.clone() / step.loss_scale for k, p in m.named_parameters() if p.grad is not None}   # (fp16 build: loss-scaled)
         # bucketed overlap (the default when W > 1; the first step above ran it, this one runs the single all-reduce): buckets are sent from

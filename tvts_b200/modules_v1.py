@@ -195,6 +195,10 @@ def load_distilbert(name):
         import transformers
         hf = transformers.AutoModel.from_pretrained(name, local_files_only=True)
         shell.load_state_dict({k: v for k, v in hf.state_dict().items() if k in dict(shell.named_parameters())}, strict=True)
+        p_drop = max(float(getattr(hf.config, "dropout", 0.0)), float(getattr(hf.config, "attention_dropout", 0.0)))
+        if p_drop > 0.0:         # the reference trains with text_model.train(): HF dropout is active there, and is NOT modelled here
+            warnings.warn(f"'{name}' is configured with dropout {p_drop:g}; the tvts_b200 DistilBERT kernels run without dropout "
+                          "(v1 pre-training here lacks that regulariser; parity with the reference is shown at p = 0)")
     except Exception as e:   # noqa: BLE001 -- missing cache / package: keep the random init
         warnings.warn(f"'{name}' weights not available locally ({type(e).__name__}): DistilBERT text encoder random-initialised")
     return shell

@@ -197,9 +197,11 @@ class TrainStep:
         self.params = [p for p in model.parameters() if p.requires_grad]   # after the optimizer applied the freeze policy
         self.use_graph = use_graph
         self.loss_scale = L.DEFAULT_LOSS_SCALE     # 1 for bf16 operands; fp16 operands: static scale, undone inside the AdamW kernel
-        # gradient all-reduce in buckets on a communication stream while the backward is still running (see _arm_early_allreduce);
-        # TVTS_OVERLAP_ALLREDUCE=0 falls back to ONE all-reduce of the whole arena after the backward
-        self.overlap = os.environ.get("TVTS_OVERLAP_ALLREDUCE", "1") == "1"
+        # TVTS_OVERLAP_ALLREDUCE=1: gradient all-reduce in buckets on a communication stream while the backward is still running (see
+        # _arm_early_allreduce).  Default OFF = ONE all-reduce of the whole arena after the backward: measured on 8 B200s (round 2,
+        # profiles/r2_scaling.md) the bucketed variant is not faster (32.77 vs 32.60 ms / step) -- the backward is a chain of persistent
+        # GEMM grids that own every SM's registers and shared memory, so the NCCL kernels cannot co-reside and only move the wait around.
+        self.overlap = os.environ.get("TVTS_OVERLAP_ALLREDUCE", "0") == "1"
         self._ranges = None
         self._comm_stream = None
         self._graphs = {}
