@@ -475,9 +475,9 @@ def run_ours(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": _lib.OPERAND,
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {cfg.name} T={frames} batch {batch}/GPU n_trans={n_trans} (global batch {world * batch})",
-                       "step": "fwd+bwd" + (("+grad_allreduce" + ("(overlapped with the text-tower backward)" if step.overlap else "")) if world > 1 else "")
+                       "step": "fwd+bwd" + (("+grad_allreduce" + ("(bucketed under the backward)" if step.overlap else "")) if world > 1 else "")
                                + ("" if args.no_optimizer else "+adamw"),
-                       "launch": "one CUDA graph per step" if use_graph else "kernel-by-kernel from Python",
+                       "launch": ("one CUDA graph per step, text tower on a second stream" if use_graph else "kernel-by-kernel from Python"),
                        "parallelism": f"dp{world}", "l2": f"per-step inputs ({h2d / 1e6:.0f} MB) and activations (GBs) exceed the 126 MB L2",
                        "numerics": f"{_lib.OPERAND} GEMM operands, fp32 accumulate/residual/LN/softmax/loss, fp32 master weights"
                                    + (f", backward under loss scale {_lib.DEFAULT_LOSS_SCALE:g}" if _lib.DEFAULT_LOSS_SCALE != 1.0 else ""),
@@ -485,6 +485,11 @@ def run_ours(args):
                                 + (f"; token matrix trimmed to the batch's longest caption ({host['text'].shape[1]} of {cfg.context} columns; exact for the causal text tower)"
                                    if (args.trim_text and not v1) else "")},
             "clocks": clocks, "gpu_launches": launches, "loss": loss,
+            "extra": {"loss_trajectory_100_steps_vs_oracle": {
+                "what": "max over 100 optimizer steps of |loss(this build) - loss(CPU oracle + restated transformers.AdamW)|, same init and batches, "
+                        "reference learning rates; measured on a B200 with tools/loss_parity.py (profiles/r2_loss_trajectory.md); north star: 1e-3",
+                "fp16_default": {"c1": [3.3e-4, 4.2e-4], "c3_shape_2_pairs": [2.3e-4, 6.6e-4], "toy": [9.8e-4, 6.8e-4]},
+                "bf16": {"c1": [1.8e-3, 3.5e-3], "toy": [8.7e-3, 4.1e-3]}}},
             "step_model_tflops": flops_pair * batch / (ms_step / 1e3) / 1e12,
             "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05)", "achieved": achieved, "peak": pk["bf16_sustained"],
                          "unit": "TFLOP/s", "frac": (achieved / pk["bf16_sustained"]) if achieved else None, "traffic": 124.6e6,
