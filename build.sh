@@ -21,7 +21,7 @@ for f in tvts_b200/csrc/*.cu; do
   objs="$objs $o"
   if [ ! -f $o ] || [ $f -nt $o ] || [ tvts_b200/csrc/common.cuh -nt $o ] || [ tvts_b200/csrc/attention_common.cuh -nt $o ] || [ include/tvts_b200.h -nt $o ]; then
     fm="--use_fast_math"
-    case $f in *loss.cu|*layernorm.cu|*optim.cu|*input_stage.cu) fm="";; esac   # exact expf/logf/div where parity is tight
+    case $f in *loss.cu|*loss_fused.cu|*layernorm.cu|*optim.cu|*input_stage.cu) fm="";; esac   # exact expf/logf/div where parity is tight
     $NVCC $FLAGS $fm ${PTXAS_V:+-Xptxas -v} -c $f -o $o &
     pids="$pids $!"
   fi

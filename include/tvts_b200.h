@@ -267,6 +267,15 @@ int tvts_nsl_bwd(const float* S, const float* lse_r, const float* lse_c, const f
                  void* stream);
 int tvts_sort_ce(const float* logits, const int64_t* labels, const float* gout, float* loss, float* dlogits, int64_t R, int64_t C,
                  float weight, void* stream);
+/* All of the above in ONE launch (csrc/loss_fused.cu; a cluster of up to 8 CTAs, S and dloss/dS in distributed shared memory): from the
+ * GATHERED embeddings video_all / text_all [Bg, E] (Bg <= 256, E <= 1024: tvts_contrastive_sortce_fused_supported) to loss1 =
+ * NormSoftmaxLoss(sim_matrix(video_all, text_all) / temperature), its gradient w.r.t. rows [row0, row0 + nloc) of both embeddings
+ * (d_video, d_text [nloc, E]: AllGather_multi's local-slice backward, v2/trainer/trainer.py:53-57), and -- when logits != NULL -- loss2 =
+ * ce_weight * mean CE(logits [R, C], labels) with dlogits.  Gradients are for unit upstream gradients. */
+int tvts_contrastive_sortce_fused_supported(int64_t Bg, int64_t E);
+int tvts_contrastive_sortce_fused(const float* video_all, const float* text_all, int64_t Bg, int64_t E, int64_t row0, int64_t nloc,
+                                  float temperature, float eps, const float* logits, const int64_t* labels, int64_t R, int64_t C,
+                                  float ce_weight, float* loss1, float* loss2, float* d_video, float* d_text, float* dlogits, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Optimizer: transformers==4.10.2 AdamW (v2/train_dist_TVTSv2_ViT_B_16.py:119-125) over one flat arena, single launch.

@@ -425,6 +425,26 @@ def sort_ce(logits, labels, gout, loss, dlogits, R, C, weight):
         dlogits.view(R, C).copy_((torch.exp(x - l[:, None]) - oh) * g)
 
 
+def contrastive_sortce_fused(video_all, text_all, Bg, E, row0, nloc, temperature, eps, logits, labels, R, C, weight, loss1, loss2, dv, dt, dx):
+    a = video_all.detach().clone().float().requires_grad_(True)
+    b = text_all.detach().clone().float().requires_grad_(True)
+    an = a / a.norm(dim=1, keepdim=True).clamp_min(eps)
+    bn = b / b.norm(dim=1, keepdim=True).clamp_min(eps)
+    z = an @ bn.t() / temperature
+    l1 = -torch.diagonal(torch.log_softmax(z, 1)).mean() - torch.diagonal(torch.log_softmax(z.t(), 1)).mean()
+    l1.backward()
+    loss1.copy_(l1.detach())
+    dv.copy_(a.grad[row0:row0 + nloc])
+    dt.copy_(b.grad[row0:row0 + nloc])
+    if logits is not None:
+        x = logits.detach().clone().float().requires_grad_(True)
+        l2 = weight * torch.nn.functional.cross_entropy(x.view(R, C), labels.view(R).long())
+        l2.backward()
+        loss2.copy_(l2.detach())
+        if dx is not None:
+            dx.copy_(x.grad)
+
+
 def adamw_flat(p, g, m, v, pb, chunk_tensor, table, n_chunks, chunk, b1, b2, eps, gscale):
     t = table[chunk_tensor.long()]                                   # [n_chunks, 4]
     step = t[:, 0:1]; lrwd = t[:, 1:2]; act = t[:, 2:3] != 0

@@ -323,3 +323,54 @@ def test_losses(Bg, E):
     r2.backward()
     assert abs(l2.item() - r2.item()) < 1e-5 * max(1.0, r2.item())
     close(x.grad, x2.grad, atol=1e-6)
+
+
+@pytest.mark.parametrize("Bg,E,row0,nloc,with_ce", [(8, 128, 0, 8, True), (256, 512, 96, 32, True), (37, 512, 5, 9, True), (32, 512, 0, 32, True),
+                                                      (64, 1024, 32, 32, False), (256, 512, 0, 256, True), (16, 128, 8, 8, True)])
+def test_fused_contrastive_sortce(Bg, E, row0, nloc, with_ce):
+    """csrc/loss_fused.cu (ONE launch, cluster of up to 8 CTAs) against the torch restatement of sim_matrix + NormSoftmaxLoss + 2 * CE:
+    losses and the gradient of the LOCAL rows of both gathered embeddings; sort labels are exact integers."""
+    torch.manual_seed(Bg + E)
+    v = rnd(Bg, E)
+    t = rnd(Bg, E) + 0.5 * v
+    v[Bg // 2] *= 1e-12                          # a row below the eps clamp of sim_matrix
+    R, C = 4 * nloc, 4
+    x = rnd(R, C) if with_ce else None
+    y = torch.arange(4, device=DEV).repeat(nloc) if with_ce else None
+    outs = []
+    for fn in (L.call, lambda nme, *a: emu.OPS[nme](*a)):
+        loss1, loss2 = torch.full((), float("nan"), device=DEV), torch.full((), float("nan"), device=DEV)
+        dv, dt = torch.full((nloc, E), float("nan"), device=DEV), torch.full((nloc, E), float("nan"), device=DEV)
+        dx = torch.full((R, C), float("nan"), device=DEV) if with_ce else None
+        fn("contrastive_sortce_fused", v, t, Bg, E, row0, nloc, 0.05, 1e-8, x, y, R if with_ce else 0, C if with_ce else 0, 2.0,
+           loss1, loss2 if with_ce else None, dv, dt, dx)
+        outs.append((loss1, loss2, dv, dt, dx))
+    a, b = outs
+    assert abs(a[0].item() - b[0].item()) < 1e-4 * max(1.0, abs(b[0].item())), (a[0].item(), b[0].item())
+    close(a[2], b[2], atol=1e-5 + 1e-3 * b[2].abs().max().item(), what="d video (local rows)")
+    close(a[3], b[3], atol=1e-5 + 1e-3 * b[3].abs().max().item(), what="d text (local rows)")
+    if with_ce:
+        assert abs(a[1].item() - b[1].item()) < 1e-5 * max(1.0, b[1].item())
+        close(a[4], b[4], atol=1e-6, what="d logits")
+
+
+def test_fused_losses_autograd_matches_the_separate_kernels():
+    """engine.fused_losses (what TrainStep uses) against engine.sim_matrix + norm_softmax_loss + sort_ce: same losses, same gradients."""
+    from tvts_b200 import engine as Eng
+    from tvts_b200.trainer import gather_for_fused_loss
+    torch.manual_seed(3)
+    B, E, nt = 6, 128, 4
+    v0, t0, p0 = rnd(B, E), rnd(B, E), rnd(B, nt, nt)
+    y = torch.arange(nt, device=DEV).repeat(B, 1)
+    res = []
+    for fused in (True, False):
+        v, t, p = (z.clone().requires_grad_(True) for z in (v0, t0, p0))
+        if fused:
+            l1, l2 = Eng.fused_losses(v, t, p, y, 0.05, gather_for_fused_loss)
+        else:
+            l1, l2 = Eng.norm_softmax_loss(Eng.sim_matrix(v, t), 0.05), Eng.sort_ce(p, y, 2.0)
+        ((l1 + l2) * 8.0).backward()
+        res.append((l1.item(), l2.item(), v.grad, t.grad, p.grad))
+    assert abs(res[0][0] - res[1][0]) < 1e-5 and abs(res[0][1] - res[1][1]) < 1e-5
+    for i in (2, 3, 4):
+        close(res[0][i], res[1][i], atol=1e-6 + 1e-4 * res[1][i].abs().max().item(), what=f"grad {i}")

@@ -877,3 +877,50 @@ class _SortCEFn(torch.autograd.Function):
 
 def sort_ce(pred, labels, weight=2.0):
     return _SortCEFn.apply(pred, labels, weight)
+
+
+class _FusedLossesFn(torch.autograd.Function):
+    """Everything between the towers and their backward passes as ONE kernel launch (csrc/loss_fused.cu): the embedding all-gather
+    (one NCCL collective, AllGather_multi semantics: v2/trainer/trainer.py:41-57), sim_matrix + NormSoftmaxLoss on the gathered
+    embeddings with the gradient of the LOCAL rows, and 2 * CE of the sort logits.  Returns (loss1, loss2)."""
+
+    @staticmethod
+    def forward(ctx, video, text, pred, labels, temperature, eps, weight, gather):
+        video, text = video.contiguous().float(), text.contiguous().float()
+        B, E_ = video.shape
+        video_all, text_all, row0 = gather(video, text)
+        Bg = video_all.shape[0]
+        loss1 = _empty((), F32, video)
+        loss2 = torch.zeros((), dtype=F32, device=video.device)
+        dv, dt = torch.empty_like(video), torch.empty_like(text)
+        if pred is not None:
+            C = pred.shape[-1]
+            x = pred.reshape(-1, C).contiguous().float()
+            y = labels.reshape(-1).to(device=x.device, dtype=torch.int64).contiguous()
+            dx = torch.empty_like(x)
+            L.call("contrastive_sortce_fused", video_all, text_all, Bg, E_, row0, B, float(temperature), float(eps), x, y, x.shape[0], C,
+                   float(weight), loss1, loss2, dv, dt, dx)
+            ctx.pred_shape = pred.shape
+        else:
+            dx = None
+            L.call("contrastive_sortce_fused", video_all, text_all, Bg, E_, row0, B, float(temperature), float(eps), None, None, 0, 0,
+                   float(weight), loss1, None, dv, dt, None)
+            ctx.pred_shape = None
+        ctx.saved = (dv, dt, dx)
+        ctx.mark_non_differentiable(loss2) if pred is None else None
+        return loss1, loss2
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        dv, dt, dx = ctx.saved
+        ctx.saved = None
+        dpred = (dx * g2).view(ctx.pred_shape) if dx is not None else None
+        return dv * g1, dt * g1, dpred, None, None, None, None, None
+
+
+def fused_losses_supported(Bg, E_):
+    return bool(L.lib().tvts_contrastive_sortce_fused_supported(int(Bg), int(E_)))
+
+
+def fused_losses(video, text, pred, labels, temperature, gather, eps=1e-8, weight=2.0):
+    return _FusedLossesFn.apply(video, text, pred, labels, temperature, eps, weight, gather)

@@ -81,6 +81,19 @@ def gather_embeddings(video_embeds, text_embeds):
     return _GatherPair.apply(video_embeds, text_embeds)
 
 
+def gather_for_fused_loss(video, text):
+    """(video_all, text_all, first local row) for engine.fused_losses: the same single collective as _GatherPair, no autograd (the fused
+    kernel returns the gradient of the local rows itself, which is what AllGather_multi.backward keeps)."""
+    W, r = _world(), _rank()
+    if W == 1:
+        return video, text, 0
+    B, Edim = video.shape
+    local = torch.cat([video, text], 1).contiguous()
+    out = torch.empty((W * B, 2 * Edim), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local)
+    return out[:, :Edim].contiguous(), out[:, Edim:].contiguous(), r * B
+
+
 def average_flat(fs):
     """Gradient averaging over the flat arena: one NCCL all-reduce (AVG), no flatten / unflatten copies."""
     if _world() == 1:
@@ -196,6 +209,7 @@ class TrainStep:
         self.device = device if device is not None else next(model.parameters()).device
         self.params = [p for p in model.parameters() if p.requires_grad]   # after the optimizer applied the freeze policy
         self.use_graph = use_graph
+        self.fused_loss = os.environ.get("TVTS_FUSED_LOSS", "1") != "0"      # the single-launch loss kernel (Bg <= 256, E <= 1024)
         self.loss_scale = L.DEFAULT_LOSS_SCALE     # 1 for bf16 operands; fp16 operands: static scale, undone inside the AdamW kernel
         # TVTS_OVERLAP_ALLREDUCE=1: gradient all-reduce in buckets on a communication stream while the backward is still running (see
         # _arm_early_allreduce).  Default OFF = ONE all-reduce of the whole arena after the backward: measured on 8 B200s (round 2,
@@ -262,15 +276,22 @@ class TrainStep:
         if overlapped:
             self._arm_early_allreduce(flat)
         text_embeds, video_embeds, pred_order = self.model(data)
-        video_all, text_all = gather_embeddings(video_embeds, text_embeds)
-        output = M.sim_matrix(video_all, text_all)                      # rows videos, cols texts (trainer.py:484)
-        loss1 = self.loss(output)
-        if pred_order is not None:
-            loss2 = E.sort_ce(pred_order, data["label"], 2.0)           # trainer.py:487-492
-            total = loss1 + loss2
+        Bg = video_embeds.shape[0] * _world()
+        if self.fused_loss and video_embeds.is_cuda and E.fused_losses_supported(Bg, video_embeds.shape[1]):
+            # one launch: all-gather (NCCL) -> sim_matrix + NormSoftmaxLoss + local-slice gradient + 2 * sort CE (csrc/loss_fused.cu)
+            loss1, loss2 = E.fused_losses(video_embeds, text_embeds, pred_order, data.get("label"), self.loss.temperature,
+                                          gather_for_fused_loss)
+            total = loss1 + loss2 if pred_order is not None else loss1
         else:
-            loss2 = torch.zeros((), device=loss1.device)
-            total = loss1
+            video_all, text_all = gather_embeddings(video_embeds, text_embeds)
+            output = M.sim_matrix(video_all, text_all)                  # rows videos, cols texts (trainer.py:484)
+            loss1 = self.loss(output)
+            if pred_order is not None:
+                loss2 = E.sort_ce(pred_order, data["label"], 2.0)       # trainer.py:487-492
+                total = loss1 + loss2
+            else:
+                loss2 = torch.zeros((), device=loss1.device)
+                total = loss1
         dynamic = getattr(self.optimizer, "dynamic_scale", False)
         if dynamic:
             total = total * self.optimizer.scale_tensor                 # device-resident dynamic loss scale (IEEE-half operand build)
