@@ -354,8 +354,12 @@ class TVTSv2Base(BaseModel):
         from .clip_compat import load as clip_load
         # an explicit `arch=` (tests, bench: synthetic weights) or a checkpoint that overwrites every weight anyway may run without the
         # released CLIP file; the plain reference-style construction raises like clip.load does (v2/CLIP/clip/clip.py:120-127)
+        # (the reference's ConfigParser.initialize fills every constructor parameter whose NAME is a top-level config key -- `arch` is
+        # one: it would hand the {"type", "args"} dict of the config file over here; anything that is not an ArchConfig is ignored)
+        if not isinstance(arch, C.ArchConfig):
+            arch = None
         allow_missing = arch is not None or load_checkpoint not in ["", None] or os.environ.get("TVTS_ALLOW_RANDOM_CLIP") == "1"
-        arch = arch or (C.TVTSV2_B_16 if self.PATCH == 16 else C.TVTSV2_B_32)
+        arch = arch or self._default_arch()
         self.arch = arch
         clip_model, clip_visual_sd = clip_load(self.CLIP_FILE, arch, open_clip=self.OPEN_CLIP, allow_missing=allow_missing)
         self.text_model = clip_model.transformer
@@ -382,6 +386,9 @@ class TVTSv2Base(BaseModel):
             self.load_state_dict(state_dict_data_parallel_fix(state_dict, self.state_dict()), strict=True)
             print("loading checkpoint from {}".format(load_checkpoint))
         self._text_named = None
+
+    def _default_arch(self):
+        return C.TVTSV2_B_16 if self.PATCH == 16 else C.TVTSV2_B_32
 
     def _build_video_model(self, arch):
         return VisionTransformer(input_resolution=arch.resolution, patch_size=arch.patch, width=arch.width, layers=arch.layers,
@@ -474,8 +481,11 @@ class TVTSv2_H_14(TVTSv2Base):
     PATCH, MASK_RATIO, CLIP_FILE = 14, 0.7, "OpenCLIP/models/open_clip_pytorch_model.bin"
     OPEN_CLIP = True
 
+    def _default_arch(self):
+        return C.TVTSV2_H_14
+
     def __init__(self, args, load_checkpoint=None, arch=None):
-        super().__init__(args, load_checkpoint, arch=arch or C.TVTSV2_H_14)
+        super().__init__(args, load_checkpoint, arch=arch)
         ctx = self.arch.context
         self.text_attn_mask = torch.full((ctx, ctx), float("-inf")).triu_(1)     # OpenCLIP build_attention_mask; plain attribute (:36)
 
@@ -499,9 +509,11 @@ class TVTSv2Downstream(TVTSv2Base):
     SORT_HEAD = False
     MEAN_OVER_CLIPS = True        # False in the *_mc variants (model_TVTSv2_ViT_B_16_mc.py:64: the mean over n_trans is commented out)
 
+    def _default_arch(self):
+        return {16: C.TVTSV2_B_16, 32: C.TVTSV2_B_32, 14: C.TVTSV2_H_14}[self.PATCH].small(mask_ratio=0.0)
+
     def __init__(self, load_checkpoint=None, arch=None):
-        base = arch or {16: C.TVTSV2_B_16, 32: C.TVTSV2_B_32, 14: C.TVTSV2_H_14}[self.PATCH]
-        super().__init__(None, load_checkpoint, arch=base.small(mask_ratio=0.0))
+        super().__init__(None, load_checkpoint, arch=arch.small(mask_ratio=0.0) if isinstance(arch, C.ArchConfig) else None)
 
     def _checkpoint_location(self):
         return None               # downstream/model_TVTSv2_ViT_B_16.py:42 torch.load(load_checkpoint)
