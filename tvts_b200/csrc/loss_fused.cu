@@ -21,6 +21,7 @@ namespace {
 constexpr int kThreads = 512;
 constexpr int kMaxBg = 256;
 constexpr int EC = 32;   // embedding columns per staged chunk
+constexpr int GT = 8;    // local rows whose gradient is produced per pass of phase 4
 
 struct FusedArgs {
   const float* a;      // video_all [Bg, E]  (rows of S)
@@ -53,9 +54,10 @@ __global__ void __launch_bounds__(kThreads, 1) contrastive_sortce_fused_kernel(F
   float* cols = colm + Bg;                  // [Bg] column sum of exp(x - colm) over MY rows
   float* lsec = cols + Bg;                  // [Bg]
   float* lser = lsec + Bg;                  // [rp]
-  float* coef = lser + rp;                  // [Bg]
-  float* red = coef + Bg;                   // [32]  (16 warp partials; slot 16 = this CTA's share of loss1)
-  float* As = red + 32;                     // [EC][rp + 1]
+  float* coef = lser + rp;                  // [GT][Bg]
+  float* red = coef + GT * Bg;              // [32]  (16 warp partials; slot 16 = this CTA's share of loss1)
+  float* red2 = red + 32;                   // [16][GT]
+  float* As = red2 + (kThreads / 32) * GT;  // [EC][rp + 1]
   float* Bs = As + EC * (rp + 1);           // [EC][Bg + 1]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r_lo = cta * rp, nrows = max(0, min(rp, Bg - r_lo));
@@ -167,46 +169,76 @@ __global__ void __launch_bounds__(kThreads, 1) contrastive_sortce_fused_kernel(F
     *p.loss1 = l;
   }
 
-  // ---- phase 4: gradients of the LOCAL rows.  Local index t -> global index g = row0 + t, handled by CTA t % C.
+  // ---- phase 4: gradients of the LOCAL rows.  Local index t -> global index g = row0 + t, handled by CTA t % C, GT of them per pass
   //   side 0 (a / video): coefficients G[g, :] live in the CTA that owns row g;  d an_g = sum_k G[g,k] bn_k
   //   side 1 (b / text):  coefficients G[:, g] are spread over all CTAs;        d bn_g = sum_k G[k,g] an_k
+  // (every row of the other side is read ONCE per pass for all GT local rows; one block reduction per pass for the GT dot products)
   for (int side = 0; side < 2; ++side) {
     const float* self = side == 0 ? p.a : p.b;
     const float* other = side == 0 ? p.b : p.a;
     const float* inv_self = side == 0 ? inva : invb;
     const float* inv_other = side == 0 ? invb : inva;
     float* out = side == 0 ? p.da : p.db;
-    for (int t = cta; t < p.nloc; t += C) {
-      const int g = p.row0 + t;
+    const int mine = p.nloc > cta ? (p.nloc - cta + C - 1) / C : 0;       // local indices cta, cta + C, ...
+    for (int m0 = 0; m0 < mine; m0 += GT) {
+      const int ng = min(GT, mine - m0);
       __syncthreads();
-      for (int k = tid; k < Bg; k += kThreads) {
+      for (int i = tid; i < ng * Bg; i += kThreads) {
+        const int q = i / Bg, k = i - q * Bg;
+        const int g = p.row0 + cta + (m0 + q) * C;
         float c;
         if (side == 0) c = cluster.map_shared_rank(Srow, g / rp)[(g % rp) * Bg + k];
         else c = cluster.map_shared_rank(Srow, k / rp)[(k % rp) * Bg + g];
-        coef[k] = c * fabsf(inv_other[k]);                       // folds the other side's normalisation in
+        coef[q * Bg + k] = c * fabsf(inv_other[k]);              // folds the other side's normalisation in
       }
       __syncthreads();
-      const float is = inv_self[g];
-      const bool clamped = is < 0.f;
-      float dn[2] = {0.f, 0.f};
-      float dotp = 0.f;
+      float dn[2][GT];
+      float dotp[GT];
+#pragma unroll
+      for (int q = 0; q < GT; ++q) { dn[0][q] = dn[1][q] = 0.f; dotp[q] = 0.f; }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int e = tid + c * kThreads;
         if (e < E) {
-          float acc1 = 0.f;
-          for (int k = 0; k < Bg; ++k) acc1 = fmaf(coef[k], other[(long long)k * E + e], acc1);
-          dn[c] = acc1;
-          dotp += acc1 * self[(long long)g * E + e] * fabsf(is);
+          for (int k = 0; k < Bg; ++k) {
+            const float x = other[(long long)k * E + e];
+#pragma unroll
+            for (int q = 0; q < GT; ++q) dn[c][q] = fmaf(coef[q * Bg + k], x, dn[c][q]);
+          }
+#pragma unroll
+          for (int q = 0; q < GT; ++q)
+            if (q < ng) {
+              const int g = p.row0 + cta + (m0 + q) * C;
+              dotp[q] += dn[c][q] * self[(long long)g * E + e] * fabsf(inv_self[g]);
+            }
         }
       }
-      const float tot = block_sum(dotp, red);
+      // block reduction of the GT dot products: warp sums -> red2[warp][q] -> every thread adds the 16 partials it needs
+#pragma unroll
+      for (int q = 0; q < GT; ++q) dotp[q] = warp_sum(dotp[q]);
+      __syncthreads();
+      if (lane == 0)
+#pragma unroll
+        for (int q = 0; q < GT; ++q) red2[warp * GT + q] = dotp[q];
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < GT; ++q) {
+        float t2 = 0.f;
+        for (int w = 0; w < kThreads / 32; ++w) t2 += red2[w * GT + q];
+        dotp[q] = t2;
+      }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int e = tid + c * kThreads;
         if (e < E) {
-          const float sn = self[(long long)g * E + e] * fabsf(is);
-          out[(long long)t * E + e] = clamped ? dn[c] * fabsf(is) : (dn[c] - sn * tot) * fabsf(is);
+#pragma unroll
+          for (int q = 0; q < GT; ++q)
+            if (q < ng) {
+              const int t = cta + (m0 + q) * C, g = p.row0 + t;
+              const float is = inv_self[g];
+              const float sn = self[(long long)g * E + e] * fabsf(is);
+              out[(long long)t * E + e] = is < 0.f ? dn[c][q] * fabsf(is) : (dn[c][q] - sn * dotp[q]) * fabsf(is);
+            }
         }
       }
     }
@@ -236,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, 1) contrastive_sortce_fused_kernel(F
 }
 
 size_t fused_smem_bytes(int Bg, int rp) {
-  return sizeof(float) * ((size_t)rp * Bg + 6 * (size_t)Bg + rp + 32 + (size_t)EC * (rp + 1) + (size_t)EC * (Bg + 1));
+  return sizeof(float) * ((size_t)rp * Bg + (5 + GT) * (size_t)Bg + rp + 32 + (kThreads / 32) * GT + (size_t)EC * (rp + 1) + (size_t)EC * (Bg + 1));
 }
 
 }  // namespace
@@ -252,7 +284,7 @@ extern "C" int tvts_contrastive_sortce_fused(const float* video_all, const float
   TVTS_REQUIRE(video_all && text_all && loss1 && d_video && d_text && temperature > 0.f, "contrastive_sortce_fused: bad arguments");
   TVTS_REQUIRE(row0 >= 0 && nloc >= 0 && row0 + nloc <= Bg, "contrastive_sortce_fused: local row range out of bounds");
   TVTS_REQUIRE(logits == nullptr || (labels && loss2 && R > 0 && C > 0), "contrastive_sortce_fused: sort-CE arguments");
-  int csize = Bg >= 64 ? 8 : (Bg >= 16 ? 4 : 1);
+  int csize = Bg >= 32 ? 8 : (Bg >= 16 ? 4 : 1);
   const int rp = (int)((Bg + csize - 1) / csize);
   TVTS_REQUIRE(rp <= 32, "contrastive_sortce_fused: rows per CTA");
   FusedArgs p{video_all, text_all, (int)Bg, (int)E, (int)row0, (int)nloc, rp, 1.0f / temperature, eps,
