@@ -13,9 +13,9 @@
 //
 // CLS token (space mode).  The CLS QUERY attends to every token of the clip and the CLS KEY is seen by every query.  It rides along as
 // row / column n of every frame tile: the tile computes the CLS query's softmax over ITS keys (the CLS key itself is counted by frame
-// 0 only) and writes a normalised partial (o, lse) to a small workspace; a tiny second kernel merges the T partials
-// (log-sum-exp combine).  The backward does the same with partial dq(CLS query), dk / dv(CLS key) sums.  This replaces the separate
-// latency-bound attn_cls_* launches (and their side stream) of the mma.sync path.
+// 0 only) and writes a normalised partial (o, lse) to a small workspace; the LAST tile of a (batch, head) to finish (an atomic ticket
+// per (b, h)) merges the partials (log-sum-exp combine).  The backward does the same with partial dq(CLS query), dk / dv(CLS key) sums.
+// This replaces the separate latency-bound attn_cls_* launches (and their side stream) of the mma.sync path; there is no second launch.
 #include <cuda.h>
 #include <stdlib.h>
 #include "common.cuh"
@@ -137,7 +137,8 @@ constexpr int FWD_SMEM = FWD_BAR + 64 + 1024;
 
 __global__ void __launch_bounds__(kTcThreads, 3)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out, const bf16* __restrict__ qkv,
-                   float* __restrict__ lse, float* __restrict__ cls_ws, TcShape a) {
+                   bf16* __restrict__ out, float* __restrict__ lse, float* __restrict__ cls_ws, int* __restrict__ tickets, TcShape a) {
+  __shared__ int s_last;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -278,6 +279,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 #pragma unroll
       for (int j = 0; j < 32; ++j) ws[half * 32 + j] = __uint_as_float(v[j]) * inv;
       if (half == 0) ws[64] = mx * a.scale + __logf(l);
+      __threadfence();          // the partial must be visible to whichever CTA of this (b, h) finishes last
     }
   }
   if (half == 0 && r < a.rows) {
@@ -290,30 +292,36 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   if (tid == 0) {
     tma_store_4d(&tm_out, sP, h * HD, c1, c2, b);
     bulk_commit();
-    bulk_wait_read<0>();     // the staging tile has been read out: the CTA may retire while the write drains
   }
+  if (a.mode != 0) {
+    // CLS query: the LAST tile of this (b, h) to get here merges the per-tile partials (log-sum-exp combine) -> out[b, 0, h, :], lse[b, h, 0]
+    if (tid == 0) {
+      const int t = atomicAdd(tickets + b * a.H + h, 1);
+      s_last = t == a.chunks - 1;
+      if (s_last) tickets[b * a.H + h] = 0;        // ready for the next launch (stream-ordered)
+    }
+    __syncthreads();
+    if (s_last && tid < 64) {
+      __threadfence();
+      const volatile float* w = cls_ws + (((long long)b * a.H + h) * a.chunks) * 65;
+      float m = -INFINITY;
+      for (int gg = 0; gg < a.chunks; ++gg) m = fmaxf(m, w[gg * 65 + 64]);
+      float acc = 0.f, sw = 0.f;
+      for (int gg = 0; gg < a.chunks; ++gg) {
+        const float e = __expf(w[gg * 65 + 64] - m);
+        acc = fmaf(e, w[gg * 65 + tid], acc);
+        sw += e;
+      }
+      out[(long long)b * a.N * a.H * HD + h * HD + tid] = opnd_from_float(acc / sw);
+      if (tid == 0) lse[((long long)b * a.H + h) * a.N] = m + __logf(sw);
+    }
+  }
+  if (tid == 0) bulk_wait_read<0>();     // the staging tile has been read out: the CTA may retire while the write drains
   if (warp == 0) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem, 128);
   }
-}
-
-// merge the per-tile partials of the CLS query: out[b, 0, h, :] and lse[b, h, 0]
-__global__ void __launch_bounds__(64) attn_tc_cls_merge_fwd_kernel(const float* __restrict__ ws, bf16* __restrict__ out, float* __restrict__ lse,
-                                                                   TcShape a) {
-  const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
-  const float* w = ws + (((long long)b * a.H + h) * a.chunks) * 65;
-  float m = -INFINITY;
-  for (int g = 0; g < a.chunks; ++g) m = fmaxf(m, w[g * 65 + 64]);
-  float acc = 0.f, sw = 0.f;
-  for (int g = 0; g < a.chunks; ++g) {
-    const float e = __expf(w[g * 65 + 64] - m);
-    acc = fmaf(e, w[g * 65 + d], acc);
-    sw += e;
-  }
-  out[(long long)b * a.N * a.H * HD + h * HD + d] = opnd_from_float(acc / sw);
-  if (d == 0) lse[((long long)b * a.H + h) * a.N] = m + __logf(sw);
 }
 
 // ================================================================================================ backward
@@ -327,7 +335,8 @@ __global__ void __launch_bounds__(kTcThreads, 2)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                    const __grid_constant__ CUtensorMap tm_dqkv, const bf16* __restrict__ qkv, const bf16* __restrict__ out,
                    const bf16* __restrict__ dout, const float* __restrict__ lse, float* __restrict__ cls_ws, float* __restrict__ dbias,
-                   TcShape a) {
+                   bf16* __restrict__ dqkv, int* __restrict__ tickets, TcShape a) {
+  __shared__ int s_last;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -517,6 +526,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     if (cls_row) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) ws[m * 64 + half * 32 + j] = __uint_as_float(v[j]);
+      if (m == 2) __threadfence();      // partials visible to the CTA of this (b, h) that finishes last
     }
   }
   fence_proxy_async_smem();
@@ -530,7 +540,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   }
   if (dbias != nullptr && tid >= 64) {
     // bias gradient of the qkv Linear = column sums of dqkv over the tokens: summed here from the staged 16-bit rows (the very values the
-    // stores write), one atomicAdd per (tile, column); the CLS row is added by the merge kernel.  Replaces a separate pass over dqkv.
+    // stores write), one atomicAdd per (tile, column); the CLS row is added by the tile that merges it.  Replaces a separate pass over dqkv.
     const int i = tid - 64, m = i >> 6, d = i & 63;
     const uint8_t* tile = gen + (size_t)m * ATOM;
     float s = 0.f;
@@ -544,30 +554,36 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     }
     atomicAdd(dbias + (long long)m * a.H * HD + h * HD + d, s);
   }
+  if (a.mode != 0) {
+    // CLS token: the LAST tile of this (b, h) sums the per-tile partials of dq(CLS query), dk / dv(CLS key) -> row 0 of dqkv (+ bias gradient)
+    if (tid == 0) {
+      const int t = atomicAdd(tickets + b * a.H + h, 1);
+      s_last = t == a.chunks - 1;
+      if (s_last) tickets[b * a.H + h] = 0;
+    }
+    __syncthreads();
+    if (s_last && tid < 192) {
+      __threadfence();
+      const volatile float* w = cls_ws + (((long long)b * a.H + h) * a.chunks) * 192;
+      float acc = 0.f;
+      for (int gg = 0; gg < a.chunks; ++gg) acc += w[gg * 192 + tid];
+      const int m = tid >> 6, d = tid & 63;
+      const bf16 o = opnd_from_float(acc);
+      dqkv[(long long)b * a.N * 3 * a.H * HD + (long long)m * a.H * HD + h * HD + d] = o;
+      if (dbias != nullptr) {
+#ifdef TVTS_OPERAND_FP16
+        atomicAdd(dbias + (long long)m * a.H * HD + h * HD + d, __half2float(o));
+#else
+        atomicAdd(dbias + (long long)m * a.H * HD + h * HD + d, __bfloat162float(o));
+#endif
+      }
+    }
+  }
   if (tid == 0) bulk_wait_read<0>();     // the staging tiles have been read out: the CTA may retire while the writes drain
   if (warp == 0) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem, 256);
-  }
-}
-
-// sum the per-tile partials of dq(CLS query), dk / dv(CLS key) -> row 0 of dqkv
-__global__ void __launch_bounds__(192) attn_tc_cls_merge_bwd_kernel(const float* __restrict__ ws, bf16* __restrict__ dqkv,
-                                                                    float* __restrict__ dbias, TcShape a) {
-  const int h = blockIdx.x, b = blockIdx.y, i = threadIdx.x;
-  const float* w = ws + (((long long)b * a.H + h) * a.chunks) * 192;
-  float acc = 0.f;
-  for (int g = 0; g < a.chunks; ++g) acc += w[g * 192 + i];
-  const int m = i >> 6, d = i & 63;
-  const bf16 o = opnd_from_float(acc);
-  dqkv[(long long)b * a.N * 3 * a.H * HD + (long long)m * a.H * HD + h * HD + d] = o;
-  if (dbias != nullptr) {
-#ifdef TVTS_OPERAND_FP16
-    atomicAdd(dbias + (long long)m * a.H * HD + h * HD + d, __half2float(o));
-#else
-    atomicAdd(dbias + (long long)m * a.H * HD + h * HD + d, __bfloat162float(o));
-#endif
   }
 }
 
@@ -638,10 +654,12 @@ bool make_shape(TcShape* s, int64_t B, int64_t N, int64_t H, int64_t d, int64_t 
   return true;
 }
 
-// per-device workspace for the CLS partials (grown on demand; allocation happens outside any stream capture: the first call of a
-// shape runs in the pre-capture warm-up step)
+// per-device workspace: [64 KB of int tickets, one per (b, h), zero between launches] [CLS partials] (grown on demand; allocation happens
+// outside any stream capture: the first call of a shape runs in the pre-capture warm-up step)
+constexpr size_t kTicketBytes = 64 * 1024;
 struct Workspace { float* ptr = nullptr; size_t bytes = 0; };
 float* workspace(size_t bytes) {
+  bytes += kTicketBytes;
   static Workspace per_dev[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
@@ -651,6 +669,7 @@ float* workspace(size_t bytes) {
     w.ptr = nullptr; w.bytes = 0;
     size_t want = bytes < (32u << 20) ? (32u << 20) : bytes;
     if (cudaMalloc(&w.ptr, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaMemset(w.ptr, 0, kTicketBytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     w.bytes = want;
   }
   return w.ptr;
@@ -694,7 +713,7 @@ extern "C" int tvts_attn_tc_fwd(const void* qkv, void* out, float* lse, int64_t 
   TVTS_REQUIRE(make_shape(&a, B, N, H, d, mode, T, n, causal, scale), "attn_tc_fwd: unsupported shape (d=%lld mode=%lld N=%lld n=%lld)",
                (long long)d, (long long)mode, (long long)N, (long long)n);
   TVTS_REQUIRE(qkv && out && lse, "attn_tc_fwd: null pointer");
-  TVTS_REQUIRE(B * N < (1ll << 31), "attn_tc_fwd: too many rows");
+  TVTS_REQUIRE(B * N < (1ll << 31) && B * H <= (int64_t)(kTicketBytes / sizeof(int)), "attn_tc_fwd: too many rows / (b, h) pairs");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUtensorMap tq, to;
   int rc = make_map(&tq, qkv, a, 3 * H * HD);
@@ -720,12 +739,9 @@ extern "C" int tvts_attn_tc_fwd(const void* qkv, void* out, float* lse, int64_t 
   }
   a.ahead = g_attn_tc_prefetch ? resident : 0;
   dim3 grid((unsigned)a.chunks, (unsigned)H, (unsigned)B);
-  attn_tc_fwd_kernel<<<grid, kTcThreads, FWD_SMEM, st>>>(tq, to, reinterpret_cast<const bf16*>(qkv), lse, ws, a);
+  attn_tc_fwd_kernel<<<grid, kTcThreads, FWD_SMEM, st>>>(tq, to, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), lse,
+                                                         ws ? ws + kTicketBytes / sizeof(float) : nullptr, reinterpret_cast<int*>(ws), a);
   TVTS_LAUNCH_CHECK();
-  if (a.mode != 0) {
-    attn_tc_cls_merge_fwd_kernel<<<dim3((unsigned)H, (unsigned)B), 64, 0, st>>>(ws, reinterpret_cast<bf16*>(out), lse, a);
-    TVTS_LAUNCH_CHECK();
-  }
   return TVTS_OK;
 }
 
@@ -741,7 +757,7 @@ extern "C" int tvts_attn_tc_bwd_bias(const void* qkv, const void* out, const voi
   TVTS_REQUIRE(make_shape(&a, B, N, H, d, mode, T, n, causal, scale), "attn_tc_bwd: unsupported shape (d=%lld mode=%lld N=%lld n=%lld)",
                (long long)d, (long long)mode, (long long)N, (long long)n);
   TVTS_REQUIRE(qkv && out && dout && lse && dqkv, "attn_tc_bwd: null pointer");
-  TVTS_REQUIRE(B * N < (1ll << 31), "attn_tc_bwd: too many rows");
+  TVTS_REQUIRE(B * N < (1ll << 31) && B * H <= (int64_t)(kTicketBytes / sizeof(int)), "attn_tc_bwd: too many rows / (b, h) pairs");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUtensorMap tq, tdo, tdq;
   int rc = make_map(&tq, qkv, a, 3 * H * HD);
@@ -770,11 +786,9 @@ extern "C" int tvts_attn_tc_bwd_bias(const void* qkv, const void* out, const voi
   a.ahead = g_attn_tc_prefetch ? resident : 0;
   dim3 grid((unsigned)a.chunks, (unsigned)H, (unsigned)B);
   attn_tc_bwd_kernel<<<grid, kTcThreads, BWD_SMEM, st>>>(tq, tdo, tdq, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<const bf16*>(out),
-                                                         reinterpret_cast<const bf16*>(dout), lse, ws, dbias, a);
+                                                         reinterpret_cast<const bf16*>(dout), lse,
+                                                         ws ? ws + kTicketBytes / sizeof(float) : nullptr, dbias, reinterpret_cast<bf16*>(dqkv),
+                                                         reinterpret_cast<int*>(ws), a);
   TVTS_LAUNCH_CHECK();
-  if (a.mode != 0) {
-    attn_tc_cls_merge_bwd_kernel<<<dim3((unsigned)H, (unsigned)B), 192, 0, st>>>(ws, reinterpret_cast<bf16*>(dqkv), dbias, a);
-    TVTS_LAUNCH_CHECK();
-  }
   return TVTS_OK;
 }

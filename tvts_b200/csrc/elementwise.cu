@@ -524,8 +524,8 @@ extern "C" int tvts_small_linear_bwd(const float* dy, const float* x, const floa
                                      int64_t K, int64_t O, void* stream) {
   TVTS_REQUIRE(dy && x && w && dx && dw, "small_linear_bwd: bad arguments");
   if (R == 0) return TVTS_OK;
-  // gridDim.y must be 1 for dx (each (r,k) written once); rows are few on this path (B * n_trans)
-  dim3 grid((unsigned)((K + 255) / 256), 1);
+  // rows are strided over gridDim.y: every (r, k) of dx is written by exactly one block, dw / db partials meet in atomics
+  dim3 grid((unsigned)((K + 255) / 256), (unsigned)(R < 32 ? R : 32));
   small_linear_bwd_kernel<<<grid, 256, 0, ST(stream)>>>(dy, x, w, dx, dw, db, R, (int)K, (int)O);
   TVTS_LAUNCH_CHECK();
   return TVTS_OK;
