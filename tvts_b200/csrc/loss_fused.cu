@@ -200,7 +200,8 @@ __global__ void __launch_bounds__(kThreads, 1) contrastive_sortce_fused_kernel(F
       for (int c = 0; c < 2; ++c) {
         const int e = tid + c * kThreads;
         if (e < E) {
-          for (int k = 0; k < Bg; ++k) {
+#pragma unroll 8
+          for (int k = 0; k < Bg; ++k) {                       // 8 independent row loads in flight (rows come out of L2)
             const float x = other[(long long)k * E + e];
 #pragma unroll
             for (int q = 0; q < GT; ++q) dn[c][q] = fmaf(coef[q * Bg + k], x, dn[c][q]);
