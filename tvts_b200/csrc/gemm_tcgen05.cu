@@ -315,6 +315,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * COLS_PER_WARP;
+      int pend_col = -1;
 #pragma unroll 1
       for (int c0 = 0; c0 < COLS_PER_WARP; c0 += CH) {
         const int col0 = col_base + c0;
@@ -324,8 +325,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           buf_o = ring + (nuse & 1u) * 4096u;            // the operand box of this chunk; the result overwrites it
           mbar_wait(opnd_bar(ew, nuse & 1u), (nuse >> 1) & 1u);
           ++nuse;
-        } else if (has_pre) { box_acquire(true); buf_p = ring; buf_o = ring + 4096u; }
-        else { box_acquire(false); buf_o = ring + (nstore & 1u) * 4096u; ++nstore; }
+        } else if (has_pre) { buf_p = ring; buf_o = ring + 4096u; }
+        else { buf_o = ring + (nstore & 1u) * 4096u; ++nstore; }
+        // the ring box(es) of this chunk are acquired (= their previous TMA store has been read out) only right before the first write
+        // below, i.e. AFTER the chunk's first TMEM load and bias add: with two outputs per chunk (c_fc: pre-activation + activation)
+        // both boxes are still being read out when the chunk starts, and that wait used to be fully exposed
+        bool acquired = tile_opnd;
 #pragma unroll 1
         for (int sub = 0; sub < CH; sub += 32) {   // 32 accumulator columns per pass
           const int cs = col0 + sub;
@@ -374,6 +379,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
             }
           }
+          if (!acquired) { box_acquire(has_pre); acquired = true; }      // warp-uniform
+          if (pend_col >= 0) {                                           // warp-uniform: the operand box two chunks ahead (see below)
+            if (lane == 0) { bulk_wait_read<0>(); opnd_request(pend_col, row0); }
+            ++nload;
+            pend_col = -1;
+          }
           if (has_pre) {                               // bf16 copy of the pre-activation
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
@@ -415,10 +426,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           // request the operand box two chunks ahead: it reuses THIS chunk's box once the store just issued has been read out
           const int cn = c0 + 2 * CH;
           const bool more = cn < COLS_PER_WARP && col_base + cn < s.N;     // warp-uniform
-          if (more) {
-            if (lane == 0) { bulk_wait_read<0>(); opnd_request(col_base + cn, row0); }   // chunk c0's box has been read out
-            ++nload;
-          }
+          if (more) pend_col = col_base + cn;      // issued from the NEXT chunk, after its TMEM load: by then this store has been read out
         }
       }
       tc_fence_before();
