@@ -120,3 +120,23 @@ def test_v1_drop_in_paths_resolve():
             "assert a.TVTS and a.sim_matrix and v.VisionTransformer and s.SortTransformer and l.NormSoftmaxLoss and t.AllGather_multi")
     env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "tvts_b200", "dropin_v1") + os.pathsep + ROOT)
     subprocess.run([sys.executable, "-c", code], check=True, env=env, cwd="/tmp")
+
+
+def test_v1_epoch_length_is_the_longest_loader(emu_backend):
+    """v1/trainer/trainer.py:50-54: `len_epoch = max(len(x) for x in data_loader)` (v2 takes the YT loader instead): the longest loader
+    drives an epoch, the others are cycled (round-1 ADVICE)."""
+    from tvts_b200.trainer import Trainer_TVTS
+    E.WEIGHTS.clear()
+    g, dims, cfg, names, sd, data = v1_fixture.load()
+    m = build(dims)
+    m.load_state_dict(sd, strict=True)
+    opt = optim.AdamW([p for p in m.parameters() if p.requires_grad], lr=1e-3, weight_decay=0.0)
+    batch = dict(video=data["video"], keep_ind=data["keep_ind"], label=data["label"], text=data["text"])
+    try:
+        tr = Trainer_TVTS(types.SimpleNamespace(rank=0, local_rank=0, world_size=1, schedule=[]), m, M.NormSoftmaxLoss(0.05), [], opt,
+                          {"trainer": {"epochs": 1}}, [Loader([batch]), Loader([batch, batch, batch])], use_graph=False)
+        assert tr.len_epoch == 3
+        hist = tr.train()
+        assert max(opt.sync_steps()) == 6            # 3 iterations x 2 loaders, the short loader cycled
+    finally:
+        opt.flat.release()
