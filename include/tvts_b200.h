@@ -122,7 +122,9 @@ int tvts_attn_set_side_stream(int on);
  * frames + CLS, block-diagonal key mask, 4-D TMA boxes over the strided token rows).  S and O (backward: S, dP, dV, dK, dQ) live in TMEM,
  * Q / K / V / dO tiles arrive by TMA, results leave by TMA stores.  tvts_attn_set_tc(on): bit 0 = modes 0 / 1, bit 1 = mode 2 (default 3;
  * 0 routes every shape back to the mma.sync kernels -- A/B comparison in the tests; environment TVTS_ATTN_TC=0 / TVTS_ATTN_TC_TIME=0 do
- * the same per process); tvts_attn_tc_supported tells which path tvts_attn_fwd / _bwd take for a shape. */
+ * the same per process); tvts_attn_tc_supported tells which path tvts_attn_fwd / _bwd take for a shape.
+ * Modes 1 / 2 keep the CLS partials and the per-(b, h) merge tickets in ONE per-device workspace (allocated on first use, outside any
+ * stream capture): such calls on one device must be ordered with respect to each other (one stream, or explicit dependencies). */
 int tvts_attn_set_tc(int on);
 int tvts_attn_tc_supported(int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal);
 int tvts_attn_tc_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n,

@@ -489,6 +489,7 @@ int make_tmap(CUtensorMap* m, const void* ptr, long long d0, long long d1, long 
 int g_dbg_lbo = 0, g_dbg_sbo = 0, g_dbg_kadv = 0, g_dbg_epi = 0;
 int g_pair_mode = -1;   // -1 auto, 0 never use CTA pairs, 1 always when the shape allows
 int g_opnd_prefetch = 1; // TMA prefetch of the residual / aux epilogue operand
+int g_solo_penalty = -1; // see tvts_gemm: solo-vs-pair tile choice against wave quantisation (-1: read the environment)
 int g_pdl = -1;          // programmatic dependent launch of the GEMM grids (environment TVTS_GEMM_PDL=0 turns it off)
 
 template <int BN, bool A_MN, bool B_MN, int CTAS>
@@ -637,8 +638,23 @@ extern "C" int tvts_gemm(const tvts_gemm_args* g, void* stream_) {
 
   const bool small_n = g->N <= 128;
   const int BN = small_n ? 128 : 256;
-  // CTA pairs (256 x 256 tiles) when there are enough rows to fill the machine with them
+  // CTA pairs (256 x 256 tiles) when there are enough rows to fill the machine with them ...
   bool pair = !small_n && g->M > 128;
+  // ... unless wave quantisation eats their advantage: M = 25120 rows are 98.1 pair tiles, so an N = 768 problem is 297 tiles on 74
+  // pair workers = 5 waves where 4.01 would do, while 128-row tiles (591 on 148 workers) fill 4 waves exactly.  A solo tile costs a CTA
+  // about as long as its half of a pair tile (same MMAs per SM; ~7 % slower mainloop: each CTA stages the whole B tile), so compare
+  // waves_pair against waves_solo * penalty (environment TVTS_GEMM_SOLO_PENALTY, per cent; 0 = never choose solo tiles this way).
+  if (pair && !g->accumulate && g_solo_penalty != 0) {
+    if (g_solo_penalty < 0) {
+      const char* e = getenv("TVTS_GEMM_SOLO_PENALTY");
+      g_solo_penalty = e ? atoi(e) : 107;
+    }
+    const long long nt = (g->N + BN - 1) / BN;
+    const long long tiles_pair = ((g->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * nt, tiles_solo = ((g->M + BLOCK_M - 1) / BLOCK_M) * nt;
+    const long long w_pair = tvts_num_sms() / 2, w_solo = tvts_num_sms();
+    const long long waves_pair = (tiles_pair + w_pair - 1) / w_pair, waves_solo = (tiles_solo + w_solo - 1) / w_solo;
+    if (g_solo_penalty > 0 && waves_solo * g_solo_penalty < waves_pair * 100) pair = false;
+  }
   if (g_pair_mode == 0) pair = false;
   if (g_pair_mode == 1) pair = !small_n;
   const int tile_m = pair ? 2 * BLOCK_M : BLOCK_M;
