@@ -644,10 +644,12 @@ extern "C" int tvts_gemm(const tvts_gemm_args* g, void* stream_) {
   // pair workers = 5 waves where 4.01 would do, while 128-row tiles (591 on 148 workers) fill 4 waves exactly.  A solo tile costs a CTA
   // about as long as its half of a pair tile (same MMAs per SM; ~7 % slower mainloop: each CTA stages the whole B tile), so compare
   // waves_pair against waves_solo * penalty (environment TVTS_GEMM_SOLO_PENALTY, per cent; 0 = never choose solo tiles this way).
+  // OFF by default: measured on the c3 step (round 2, profiles/r2/call12_*) it speeds the N = 768 GEMMs up by 4-14 % (GEMM time 21.95 ->
+  // 21.78 ms) but not the step (31.7 -> 31.9 ms): the step runs at the board's power cap, and the SM clock drops by what was gained.
   if (pair && !g->accumulate && g_solo_penalty != 0) {
     if (g_solo_penalty < 0) {
       const char* e = getenv("TVTS_GEMM_SOLO_PENALTY");
-      g_solo_penalty = e ? atoi(e) : 107;
+      g_solo_penalty = e ? atoi(e) : 0;
     }
     const long long nt = (g->N + BN - 1) / BN;
     const long long tiles_pair = ((g->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * nt, tiles_solo = ((g->M + BLOCK_M - 1) / BLOCK_M) * nt;
