@@ -21,6 +21,8 @@ if OPERAND not in ("bf16", "fp16"):
 OPERAND_DTYPE = torch.float16 if OPERAND == "fp16" else torch.bfloat16
 DEFAULT_LOSS_SCALE = float(os.environ.get("TVTS_LOSS_SCALE", "1024" if OPERAND == "fp16" else "1"))
 LIB_PATH = os.path.join(_HERE, "lib", "libtvts_b200_fp16.so" if OPERAND == "fp16" else "libtvts_b200.so")
+if os.environ.get("TVTS_LIB_PATH"):       # A/B measurements against an earlier build of the same library on the same box
+    LIB_PATH = os.path.abspath(os.environ["TVTS_LIB_PATH"])
 
 _lib = None
 

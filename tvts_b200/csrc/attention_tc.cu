@@ -27,7 +27,26 @@ constexpr int HD = 64;
 constexpr uint32_t ATOM = 16384;   // one [128 rows x 128 B] 128B-swizzled tile
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr uint32_t kOperandFormat = TVTS_OPERAND_IS_FP16 ? 0u : ((1u << 7) | (1u << 10));
+constexpr size_t kTicketBytes = 8u << 20;      // per-device ticket area of the CLS merge: 192 int tickets per (b, h)
 constexpr int kTcThreads = 256;    // 8 warps: TMEM lane quadrant = warp % 4, column half = warp / 4 (two threads share one row)
+
+// -DTVTS_ATTN_PROF (measurement builds only, tools/attn_phase_prof.py): thread 0 of every CTA stamps clock64 at the phase boundaries
+#ifdef TVTS_ATTN_PROF
+constexpr int kProfStamps = 12, kProfTiles = 8192;
+__device__ long long g_prof[kProfTiles][kProfStamps + 1];
+#define PROF_STAMP(i)                                                                                   \
+  do {                                                                                                  \
+    if (threadIdx.x == 0) {                                                                             \
+      const long long lin_ = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x; \
+      if (lin_ < kProfTiles) {                                                                          \
+        g_prof[lin_][i] = clock64();                                                                    \
+        if ((i) == 0) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); g_prof[lin_][kProfStamps] = sm_; } \
+      }                                                                                                 \
+    }                                                                                                   \
+  } while (0)
+#else
+#define PROF_STAMP(i) do {} while (0)
+#endif
 
 struct TcShape {
   int B, N, H;
@@ -82,6 +101,14 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int ks) {
 // MN-major operand: tile(s) [k rows x 64 mn] -- 16 k-rows per step = 2048 B; 64-wide MN groups are one atom apart
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int ks) { return umma_smem_desc(tile + (uint32_t)ks * 2048u, ATOM, 1024); }
 
+// L2 prefetch of plain global memory (the per-row statistics and the CLS rows the NEXT tile of this SM slot will read with ld.global)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// lanes [lane0, lane0 + nl) of a warp touch every 128-byte line of [p, p + bytes)
+__device__ __forceinline__ void prefetch_l2_range(const void* p, int bytes, int idx, int nl) {
+  const uintptr_t lo = reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)127, hi = reinterpret_cast<uintptr_t>(p) + (uintptr_t)bytes;
+  for (uintptr_t x = lo + (uintptr_t)idx * 128u; x < hi; x += (uintptr_t)nl * 128u) prefetch_l2(reinterpret_cast<const void*>(x));
+}
+
 // ---- tile geometry ---------------------------------------------------------------------------------------------------------------
 // token (within the sample) of tile row r < rows, or -1 when the row is padding (mode 2: positions past n in the last tile)
 __device__ __forceinline__ int row_token(const TcShape& a, int g, int r) {
@@ -128,6 +155,16 @@ __device__ __forceinline__ void tile_coords(const TcShape& a, int g, int& c1, in
   c2 = a.mode == 1 ? g : 0;
 }
 
+// the tile the same SM slot runs one wave from now (CTAs are dispatched in linear block order, `ahead` = CTAs resident on the chip)
+__device__ __forceinline__ bool next_tile(const TcShape& a, int b, int h, int g, int& b2, int& h2, int& g2) {
+  const long long nl = ((long long)b * a.H + h) * a.chunks + g + a.ahead;
+  if (a.ahead <= 0 || nl >= (long long)a.B * a.H * a.chunks) return false;
+  g2 = (int)(nl % a.chunks);
+  h2 = (int)((nl / a.chunks) % a.H);
+  b2 = (int)(nl / ((long long)a.chunks * a.H));
+  return true;
+}
+
 // ================================================================================================ forward
 // shared memory: Q | K | V tiles (P overlays Q|K once S is complete; the output staging tile overlays P), row-statistics exchange
 // between the two column halves, 3 mbarriers, TMEM holder
@@ -138,7 +175,7 @@ constexpr int FWD_SMEM = FWD_BAR + 64 + 1024;
 __global__ void __launch_bounds__(kTcThreads, 3)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out, const bf16* __restrict__ qkv,
                    bf16* __restrict__ out, float* __restrict__ lse, float* __restrict__ cls_ws, int* __restrict__ tickets, TcShape a) {
-  __shared__ int s_last;
+  __shared__ float s_cls[65];     // the CLS query's normalised partial output of this tile (64 columns) and its log-sum-exp
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -147,6 +184,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const uint32_t bar_ld = base + FWD_BAR, bar_s = bar_ld + 8, bar_o = bar_ld + 16, holder = bar_ld + 24;
   volatile uint32_t* holder_gen = reinterpret_cast<volatile uint32_t*>(gen + FWD_BAR + 24);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  PROF_STAMP(0);
   const int g = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const long long ld = 3LL * a.H * HD;
   int c1, c2;
@@ -154,27 +192,32 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 
   if (warp == 0) {
     tmem_alloc(holder, 128);
-  } else if (warp == 1 && lane == 0) {
-    tma_prefetch_desc(&tm_qkv);
-    tma_prefetch_desc(&tm_out);
-    mbar_init(bar_ld, 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_o, 1);
-    mbar_fence_init();
-    mbar_arrive_expect_tx(bar_ld, 3u * (uint32_t)a.rows * 128u);
-    tma_load_4d(sQ, &tm_qkv, bar_ld, h * HD, c1, c2, b);
-    tma_load_4d(sK, &tm_qkv, bar_ld, a.H * HD + h * HD, c1, c2, b);
-    tma_load_4d(sV, &tm_qkv, bar_ld, 2 * a.H * HD + h * HD, c1, c2, b);
+  } else if (warp == 1) {
     // pull the tile that will run in this slot one wave from now into L2 (CTAs are dispatched in linear block order): its TMA
-    // loads then see L2 latency instead of HBM latency -- the kernel is latency-bound per tile, not bandwidth-bound
-    const long long nl = ((long long)b * a.H + h) * a.chunks + g + a.ahead;
-    if (a.ahead > 0 && nl < (long long)a.B * a.H * a.chunks) {
-      const int g2 = (int)(nl % a.chunks), h2 = (int)((nl / a.chunks) % a.H), b2 = (int)(nl / ((long long)a.chunks * a.H));
-      int d1, d2;
-      tile_coords(a, g2, d1, d2);
-      tma_prefetch_4d(&tm_qkv, h2 * HD, d1, d2, b2);
-      tma_prefetch_4d(&tm_qkv, a.H * HD + h2 * HD, d1, d2, b2);
-      tma_prefetch_4d(&tm_qkv, 2 * a.H * HD + h2 * HD, d1, d2, b2);
+    // loads -- and the plain loads of its CLS rows -- then see L2 latency instead of HBM latency: the kernel is latency-bound per
+    // tile, not bandwidth-bound
+    int b2 = 0, h2 = 0, g2 = 0;
+    const bool nxt = next_tile(a, b, h, g, b2, h2, g2);
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_qkv);
+      tma_prefetch_desc(&tm_out);
+      mbar_init(bar_ld, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_o, 1);
+      mbar_fence_init();
+      mbar_arrive_expect_tx(bar_ld, 3u * (uint32_t)a.rows * 128u);
+      tma_load_4d(sQ, &tm_qkv, bar_ld, h * HD, c1, c2, b);
+      tma_load_4d(sK, &tm_qkv, bar_ld, a.H * HD + h * HD, c1, c2, b);
+      tma_load_4d(sV, &tm_qkv, bar_ld, 2 * a.H * HD + h * HD, c1, c2, b);
+      if (nxt) {
+        int d1, d2;
+        tile_coords(a, g2, d1, d2);
+        tma_prefetch_4d(&tm_qkv, h2 * HD, d1, d2, b2);
+        tma_prefetch_4d(&tm_qkv, a.H * HD + h2 * HD, d1, d2, b2);
+        tma_prefetch_4d(&tm_qkv, 2 * a.H * HD + h2 * HD, d1, d2, b2);
+      }
+    } else if (nxt && a.mode != 0 && lane <= 3) {      // the CLS token's q / k / v rows of that tile's sample (one 128-byte line each)
+      prefetch_l2(qkv + (long long)b2 * a.N * ld + (long long)(lane - 1) * a.H * HD + h2 * HD);
     }
   } else if (warp == 2) {
     if (a.mode != 0 && lane < 24) {      // the CLS token's q / k / v rows -> row `rows` of the three tiles (generic-proxy stores, swizzled by hand)
@@ -195,6 +238,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *holder_gen;
+  PROF_STAMP(7);
 
   if (warp == 1 && lane == 0) {
     mbar_wait(bar_ld, 0);
@@ -206,6 +250,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   }
   __syncwarp();
   mbar_wait(bar_s, 0);
+  PROF_STAMP(1);
   tc_fence_after();
 
   // ---- softmax: two threads per query row (64 key columns each); S comes straight out of TMEM
@@ -250,6 +295,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();          // every row of P is in shared memory and every thread is done reading S (O overwrites its columns)
+  PROF_STAMP(2);
 
   if (warp == 1 && lane == 0) {
     tc_fence_after();
@@ -261,6 +307,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   __syncwarp();
   l += xch[256 + (half ^ 1) * 128 + r];
   mbar_wait(bar_o, 0);
+  PROF_STAMP(3);
   tc_fence_after();
 
   // ---- epilogue: O / l -> 16-bit rows in the staging tile (overlays P: the P V MMAs have completed) -> one TMA store
@@ -274,12 +321,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]) * inv, __uint_as_float(v[2 * j + 1]) * inv);
 #pragma unroll
     for (int q = 0; q < 4; ++q) st_shared_v4(sP + swz(r, half * 4 + q), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-    if (cls_row) {
-      float* ws = cls_ws + (((long long)b * a.H + h) * a.chunks + g) * 65;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) ws[half * 32 + j] = __uint_as_float(v[j]) * inv;
-      if (half == 0) ws[64] = mx * a.scale + __logf(l);
-      __threadfence();          // the partial must be visible to whichever CTA of this (b, h) finishes last
+    if (cls_row) {              // handed to 64 threads through shared memory: a single thread writing (and fencing) 65 words to global
+#pragma unroll                  // memory used to hold the whole CTA at the barrier below
+      for (int j = 0; j < 32; ++j) s_cls[half * 32 + j] = __uint_as_float(v[j]) * inv;
+      if (half == 0) s_cls[64] = mx * a.scale + __logf(l);
     }
   }
   if (half == 0 && r < a.rows) {
@@ -289,34 +334,39 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  PROF_STAMP(4);
   if (tid == 0) {
     tma_store_4d(&tm_out, sP, h * HD, c1, c2, b);
     bulk_commit();
   }
-  if (a.mode != 0) {
-    // CLS query: the LAST tile of this (b, h) to get here merges the per-tile partials (log-sum-exp combine) -> out[b, 0, h, :], lse[b, h, 0]
-    if (tid == 0) {
-      const int t = atomicAdd(tickets + b * a.H + h, 1);
-      s_last = t == a.chunks - 1;
-      if (s_last) tickets[b * a.H + h] = 0;        // ready for the next launch (stream-ordered)
-    }
-    __syncthreads();
-    if (s_last && tid < 64) {
+  if (a.mode != 0 && tid < 64) {
+    // CLS query: thread j publishes column j of this tile's partial (o_j, lse) and takes a ticket of column j; the thread that draws the
+    // LAST ticket of its column (any tile of this (b, h)) merges the column's partials (log-sum-exp combine, fixed order) ->
+    // out[b, 0, h, j], lse[b, h, 0].  Per-column tickets: no CTA-wide barrier waits for an atomic's round trip.
+    const long long bh = (long long)b * a.H + h;
+    float2* ws2 = reinterpret_cast<float2*>(cls_ws) + bh * a.chunks * 64;
+    ws2[g * 64 + tid] = make_float2(s_cls[tid], s_cls[64]);
+    __threadfence();                               // the partial is visible before the ticket is
+    int* tk = tickets + bh * 64 + tid;
+    if (atomicAdd(tk, 1) == a.chunks - 1) {
+      *tk = 0;                                     // ready for the next launch (stream-ordered)
       __threadfence();
-      const volatile float* w = cls_ws + (((long long)b * a.H + h) * a.chunks) * 65;
+      const volatile float* w = reinterpret_cast<const volatile float*>(ws2);
       float m = -INFINITY;
-      for (int gg = 0; gg < a.chunks; ++gg) m = fmaxf(m, w[gg * 65 + 64]);
+      for (int gg = 0; gg < a.chunks; ++gg) m = fmaxf(m, w[(gg * 64 + tid) * 2 + 1]);
       float acc = 0.f, sw = 0.f;
       for (int gg = 0; gg < a.chunks; ++gg) {
-        const float e = __expf(w[gg * 65 + 64] - m);
-        acc = fmaf(e, w[gg * 65 + tid], acc);
+        const float e = __expf(w[(gg * 64 + tid) * 2 + 1] - m);
+        acc = fmaf(e, w[(gg * 64 + tid) * 2], acc);
         sw += e;
       }
       out[(long long)b * a.N * a.H * HD + h * HD + tid] = opnd_from_float(acc / sw);
-      if (tid == 0) lse[((long long)b * a.H + h) * a.N] = m + __logf(sw);
+      if (tid == 0) lse[bh * a.N] = m + __logf(sw);
     }
   }
+  PROF_STAMP(5);
   if (tid == 0) bulk_wait_read<0>();     // the staging tile has been read out: the CTA may retire while the write drains
+  PROF_STAMP(6);
   if (warp == 0) {
     __syncwarp();
     tc_fence_after();
@@ -336,7 +386,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                    const __grid_constant__ CUtensorMap tm_dqkv, const bf16* __restrict__ qkv, const bf16* __restrict__ out,
                    const bf16* __restrict__ dout, const float* __restrict__ lse, float* __restrict__ cls_ws, float* __restrict__ dbias,
                    bf16* __restrict__ dqkv, int* __restrict__ tickets, TcShape a) {
-  __shared__ int s_last;
+  __shared__ float s_cls[192];    // this tile's partial dq (CLS query), dk, dv (CLS key), fp32
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -345,6 +395,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const uint32_t bar_ld = base + BWD_BAR, bar_1 = bar_ld + 8, bar_dv = bar_ld + 16, bar_2 = bar_ld + 24, holder = bar_ld + 32;
   volatile uint32_t* holder_gen = reinterpret_cast<volatile uint32_t*>(gen + BWD_BAR + 32);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  PROF_STAMP(0);
   const int g = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const long long ld = 3LL * a.H * HD, ldo = (long long)a.H * HD;
   int c1, c2;
@@ -352,29 +403,46 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 
   if (warp == 0) {
     tmem_alloc(holder, 256);
-  } else if (warp == 1 && lane == 0) {
-    tma_prefetch_desc(&tm_qkv);
-    tma_prefetch_desc(&tm_do);
-    tma_prefetch_desc(&tm_dqkv);
-    mbar_init(bar_ld, 1);
-    mbar_init(bar_1, 1);
-    mbar_init(bar_dv, 1);
-    mbar_init(bar_2, 1);
-    mbar_fence_init();
-    mbar_arrive_expect_tx(bar_ld, 4u * (uint32_t)a.rows * 128u);
-    tma_load_4d(sQ, &tm_qkv, bar_ld, h * HD, c1, c2, b);
-    tma_load_4d(sK, &tm_qkv, bar_ld, a.H * HD + h * HD, c1, c2, b);
-    tma_load_4d(sV, &tm_qkv, bar_ld, 2 * a.H * HD + h * HD, c1, c2, b);
-    tma_load_4d(sDO, &tm_do, bar_ld, h * HD, c1, c2, b);
-    const long long nl = ((long long)b * a.H + h) * a.chunks + g + a.ahead;     // L2 prefetch of this slot's next tile (see the forward)
-    if (a.ahead > 0 && nl < (long long)a.B * a.H * a.chunks) {
-      const int g2 = (int)(nl % a.chunks), h2 = (int)((nl / a.chunks) % a.H), b2 = (int)(nl / ((long long)a.chunks * a.H));
-      int d1, d2;
-      tile_coords(a, g2, d1, d2);
-      tma_prefetch_4d(&tm_qkv, h2 * HD, d1, d2, b2);
-      tma_prefetch_4d(&tm_qkv, a.H * HD + h2 * HD, d1, d2, b2);
-      tma_prefetch_4d(&tm_qkv, 2 * a.H * HD + h2 * HD, d1, d2, b2);
-      tma_prefetch_4d(&tm_do, h2 * HD, d1, d2, b2);
+  } else if (warp == 1) {
+    int b2 = 0, h2 = 0, g2 = 0;
+    const bool nxt = next_tile(a, b, h, g, b2, h2, g2);     // L2 prefetch of this slot's next tile (see the forward)
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_qkv);
+      tma_prefetch_desc(&tm_do);
+      tma_prefetch_desc(&tm_dqkv);
+      mbar_init(bar_ld, 1);
+      mbar_init(bar_1, 1);
+      mbar_init(bar_dv, 1);
+      mbar_init(bar_2, 1);
+      mbar_fence_init();
+      mbar_arrive_expect_tx(bar_ld, 4u * (uint32_t)a.rows * 128u);
+      tma_load_4d(sQ, &tm_qkv, bar_ld, h * HD, c1, c2, b);
+      tma_load_4d(sK, &tm_qkv, bar_ld, a.H * HD + h * HD, c1, c2, b);
+      tma_load_4d(sV, &tm_qkv, bar_ld, 2 * a.H * HD + h * HD, c1, c2, b);
+      tma_load_4d(sDO, &tm_do, bar_ld, h * HD, c1, c2, b);
+      if (nxt) {
+        int d1, d2;
+        tile_coords(a, g2, d1, d2);
+        tma_prefetch_4d(&tm_qkv, h2 * HD, d1, d2, b2);
+        tma_prefetch_4d(&tm_qkv, a.H * HD + h2 * HD, d1, d2, b2);
+        tma_prefetch_4d(&tm_qkv, 2 * a.H * HD + h2 * HD, d1, d2, b2);
+        tma_prefetch_4d(&tm_do, h2 * HD, d1, d2, b2);
+      }
+    } else if (nxt) {
+      // ... and of what that tile reads with plain loads: the rows' log-sum-exp, and the CLS token's q / k / v / dO / O rows
+      const float* l2 = lse + ((long long)b2 * a.H + h2) * a.N;
+      if (a.mode != 0) {
+        if (lane <= 3) prefetch_l2(qkv + (long long)b2 * a.N * ld + (long long)(lane - 1) * a.H * HD + h2 * HD);
+        else if (lane == 4) prefetch_l2(dout + (long long)b2 * a.N * ldo + h2 * HD);
+        else if (lane == 5) prefetch_l2(out + (long long)b2 * a.N * ldo + h2 * HD);
+        else if (lane == 6) prefetch_l2(l2);
+      }
+      if (lane >= 8) {
+        if (a.mode == 0) prefetch_l2_range(l2, a.N * 4, lane - 8, 24);
+        else if (a.mode == 1) prefetch_l2_range(l2 + 1 + g2 * a.n, a.n * 4, lane - 8, 24);
+        else
+          for (int t = lane - 8; t < a.T; t += 24) prefetch_l2_range(l2 + 1 + t * a.n + g2 * a.GP, a.GP * 4, 0, 1);
+      }
     }
   } else if (warp == 2) {
     if (a.mode != 0) {                     // CLS rows of q, k, v, dO -> row `rows` of the four tiles
@@ -417,6 +485,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  PROF_STAMP(1);
   tc_fence_after();
   const uint32_t tmem = *holder_gen;
   const int ksteps = a.LP >> 4;
@@ -433,6 +502,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   }
   __syncwarp();
   mbar_wait(bar_1, 0);
+  PROF_STAMP(2);
   tc_fence_after();
 
   const uint32_t trow = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)half * 64u;
@@ -463,6 +533,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();           // P complete; every thread is done with the S columns (dV overwrites [0,64))
+  PROF_STAMP(3);
 
   if (warp == 1 && lane == 0) {
     tc_fence_after();
@@ -473,6 +544,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   __syncwarp();
   if (!cls_row) delta = dsum + xch[(half ^ 1) * 128 + r];
   mbar_wait(bar_dv, 0);      // the MMAs have read P: its buffer may now take dS
+  PROF_STAMP(4);
   tc_fence_after();
 
   // ---- pass B: dS = P o (dP - delta) * scale -> the same buffer
@@ -497,6 +569,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();           // dS complete; every thread is done with the dP columns (dQ overwrites [128,192))
+  PROF_STAMP(5);
 
   if (warp == 1 && lane == 0) {
     tc_fence_after();
@@ -506,15 +579,20 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     umma_commit(bar_2);
   }
   __syncwarp();
-  mbar_wait(bar_2, 0);
-  tc_fence_after();
 
-  // ---- epilogue: row r of dQ (query r), dK and dV (key r) -> staging tiles (Q, K, V buffers: every MMA has completed) -> TMA stores
-  float* ws = cls_row ? cls_ws + (((long long)b * a.H + h) * a.chunks + g) * 192 : nullptr;
+  // ---- epilogue: row r of dQ (query r), dK and dV (key r) -> staging tiles (the Q, K, V buffers) -> TMA stores.  dV first, WHILE the
+  // dK / dQ MMAs run: its accumulator has been complete since bar_dv and the V tile was last read by the dP MMAs (bar_1).
   const uint32_t tq = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)half * 32u;
 #pragma unroll
-  for (int m = 0; m < 3; ++m) {
-    const uint32_t tcol = m == 0 ? 128u : (m == 1 ? 64u : 0u);      // dQ, dK, dV
+  for (int mi = 0; mi < 3; ++mi) {
+    const int m = mi == 0 ? 2 : mi - 1;                              // dV, dQ, dK
+    if (mi == 1) {
+      PROF_STAMP(6);
+      mbar_wait(bar_2, 0);                                           // every MMA has completed: the Q and K buffers are free
+      PROF_STAMP(7);
+      tc_fence_after();
+    }
+    const uint32_t tcol = m == 0 ? 128u : (m == 1 ? 64u : 0u);
     const uint32_t tile = base + (uint32_t)m * ATOM;
     tmem_ld_row32(tq + tcol, v);
     tmem_ld_wait();
@@ -523,48 +601,63 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
 #pragma unroll
     for (int q = 0; q < 4; ++q) st_shared_v4(tile + swz(r, half * 4 + q), o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-    if (cls_row) {
+    if (cls_row) {              // CLS partials (fp32): handed to 192 threads through shared memory (see the forward)
 #pragma unroll
-      for (int j = 0; j < 32; ++j) ws[m * 64 + half * 32 + j] = __uint_as_float(v[j]);
-      if (m == 2) __threadfence();      // partials visible to the CTA of this (b, h) that finishes last
+      for (int j = 0; j < 32; ++j) s_cls[m * 64 + half * 32 + j] = __uint_as_float(v[j]);
     }
   }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  PROF_STAMP(8);
   if (tid == 0) {
     tma_store_4d(&tm_dqkv, sQ, h * HD, c1, c2, b);
     tma_store_4d(&tm_dqkv, sK, a.H * HD + h * HD, c1, c2, b);
     tma_store_4d(&tm_dqkv, sV, 2 * a.H * HD + h * HD, c1, c2, b);
     bulk_commit();
   }
+  // CLS token: thread j < 192 publishes element j of this tile's partial dq (CLS query) / dk / dv (CLS key) now, and takes a ticket of
+  // element j after the bias sums below (by then the store has long landed: the fence in front of the ticket is cheap)
+  const long long bh = (long long)b * a.H + h;
+  const bool cls_pub = a.mode != 0 && tid < 192;
+  if (cls_pub) cls_ws[(bh * a.chunks + g) * 192 + tid] = s_cls[tid];
   if (dbias != nullptr && tid >= 64) {
     // bias gradient of the qkv Linear = column sums of dqkv over the tokens: summed here from the staged 16-bit rows (the very values the
-    // stores write), one atomicAdd per (tile, column); the CLS row is added by the tile that merges it.  Replaces a separate pass over dqkv.
-    const int i = tid - 64, m = i >> 6, d = i & 63;
+    // stores write), one atomicAdd per (tile, column); the CLS row is added by the thread that merges it.  Replaces a separate pass over
+    // dqkv.  Two warps per staged tile: a lane owns one 16-byte chunk (8 columns) of every 8th row, then the eight row groups are
+    // combined by a transposing butterfly that leaves lane (chunk, rg) with the sum of column 8 * chunk + rg.
+    const int i = tid - 64, m = i >> 6, c = (i & 63) >> 3, rg = i & 7;
     const uint8_t* tile = gen + (size_t)m * ATOM;
-    float s = 0.f;
-    for (int rr = 0; rr < a.rows; ++rr) {
-      const bf16 x = *reinterpret_cast<const bf16*>(tile + swz(rr, d >> 3) + (d & 7) * 2);
-#ifdef TVTS_OPERAND_FP16
-      s += __half2float(x);
-#else
-      s += __bfloat162float(x);
-#endif
+    float s8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int rr = rg; rr < a.rows; rr += 8) {
+      const uint4 x = *reinterpret_cast<const uint4*>(tile + swz(rr, c));
+      const float2 x0 = unpack_bf16x2(x.x), x1 = unpack_bf16x2(x.y), x2 = unpack_bf16x2(x.z), x3 = unpack_bf16x2(x.w);
+      s8[0] += x0.x; s8[1] += x0.y; s8[2] += x1.x; s8[3] += x1.y; s8[4] += x2.x; s8[5] += x2.y; s8[6] += x3.x; s8[7] += x3.y;
     }
-    atomicAdd(dbias + (long long)m * a.H * HD + h * HD + d, s);
+    float s4[4], s2[2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float mine = (rg & 4) ? s8[4 + k] : s8[k], other = (rg & 4) ? s8[k] : s8[4 + k];
+      s4[k] = mine + __shfl_xor_sync(0xffffffffu, other, 4);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float mine = (rg & 2) ? s4[2 + k] : s4[k], other = (rg & 2) ? s4[k] : s4[2 + k];
+      s2[k] = mine + __shfl_xor_sync(0xffffffffu, other, 2);
+    }
+    const float mine = (rg & 1) ? s2[1] : s2[0], other = (rg & 1) ? s2[0] : s2[1];
+    const float sum = mine + __shfl_xor_sync(0xffffffffu, other, 1);
+    atomicAdd(dbias + (long long)m * a.H * HD + h * HD + c * 8 + rg, sum);
   }
-  if (a.mode != 0) {
-    // CLS token: the LAST tile of this (b, h) sums the per-tile partials of dq(CLS query), dk / dv(CLS key) -> row 0 of dqkv (+ bias gradient)
-    if (tid == 0) {
-      const int t = atomicAdd(tickets + b * a.H + h, 1);
-      s_last = t == a.chunks - 1;
-      if (s_last) tickets[b * a.H + h] = 0;
-    }
-    __syncthreads();
-    if (s_last && tid < 192) {
+  if (cls_pub) {
+    // the thread that draws the LAST ticket of element j (any tile of this (b, h)) sums the partials in tile order -> row 0 of dqkv
+    // (+ its bias gradient).  Per-element tickets: no CTA-wide barrier waits for an atomic's round trip.
+    __threadfence();
+    int* tk = tickets + bh * 192 + tid;
+    if (atomicAdd(tk, 1) == a.chunks - 1) {
+      *tk = 0;                                     // ready for the next launch (stream-ordered)
       __threadfence();
-      const volatile float* w = cls_ws + (((long long)b * a.H + h) * a.chunks) * 192;
+      const volatile float* w = cls_ws + bh * a.chunks * 192;
       float acc = 0.f;
       for (int gg = 0; gg < a.chunks; ++gg) acc += w[gg * 192 + tid];
       const int m = tid >> 6, d = tid & 63;
@@ -579,7 +672,9 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       }
     }
   }
+  PROF_STAMP(9);
   if (tid == 0) bulk_wait_read<0>();     // the staging tiles have been read out: the CTA may retire while the writes drain
+  PROF_STAMP(10);
   if (warp == 0) {
     __syncwarp();
     tc_fence_after();
@@ -631,7 +726,7 @@ int make_map(CUtensorMap* m, const void* ptr, const TcShape& a, long long cols) 
 }
 
 bool make_shape(TcShape* s, int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal, float scale) {
-  if (d != HD || B <= 0 || H <= 0) return false;
+  if (d != HD || B <= 0 || H <= 0 || B * H * 192 > (int64_t)(kTicketBytes / sizeof(int))) return false;
   TcShape a{};
   a.B = (int)B; a.N = (int)N; a.H = (int)H; a.mode = (int)mode; a.T = (int)T; a.n = (int)n; a.causal = (int)causal; a.scale = scale;
   if (mode == 0) {
@@ -654,9 +749,8 @@ bool make_shape(TcShape* s, int64_t B, int64_t N, int64_t H, int64_t d, int64_t 
   return true;
 }
 
-// per-device workspace: [64 KB of int tickets, one per (b, h), zero between launches] [CLS partials] (grown on demand; allocation happens
+// per-device workspace: [8 MB of int tickets, 64 (forward) / 192 (backward) per (b, h), zero between launches] [CLS partials] (grown on demand; allocation happens
 // outside any stream capture: the first call of a shape runs in the pre-capture warm-up step)
-constexpr size_t kTicketBytes = 64 * 1024;
 struct Workspace { float* ptr = nullptr; size_t bytes = 0; };
 float* workspace(size_t bytes) {
   bytes += kTicketBytes;
@@ -702,6 +796,13 @@ extern "C" int tvts_attn_set_tc(int on) {
   return TVTS_OK;
 }
 
+#ifdef TVTS_ATTN_PROF
+// copies the stamps of the last launch: dst = long long [8192][13] (12 stamps + the SM id)
+extern "C" int tvts_attn_tc_prof_read(void* dst) {
+  return cudaMemcpyFromSymbol(dst, g_prof, sizeof(g_prof)) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 extern "C" int tvts_attn_tc_supported(int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal) {
   TcShape s;
   return attn_tc_on((int)mode) && make_shape(&s, B, N, H, d, mode, T, n, causal, 1.0f) ? 1 : 0;
@@ -713,7 +814,7 @@ extern "C" int tvts_attn_tc_fwd(const void* qkv, void* out, float* lse, int64_t 
   TVTS_REQUIRE(make_shape(&a, B, N, H, d, mode, T, n, causal, scale), "attn_tc_fwd: unsupported shape (d=%lld mode=%lld N=%lld n=%lld)",
                (long long)d, (long long)mode, (long long)N, (long long)n);
   TVTS_REQUIRE(qkv && out && lse, "attn_tc_fwd: null pointer");
-  TVTS_REQUIRE(B * N < (1ll << 31) && B * H <= (int64_t)(kTicketBytes / sizeof(int)), "attn_tc_fwd: too many rows / (b, h) pairs");
+  TVTS_REQUIRE(B * N < (1ll << 31) && B * H * 192 <= (int64_t)(kTicketBytes / sizeof(int)), "attn_tc_fwd: too many rows / (b, h) pairs");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUtensorMap tq, to;
   int rc = make_map(&tq, qkv, a, 3 * H * HD);
@@ -757,7 +858,7 @@ extern "C" int tvts_attn_tc_bwd_bias(const void* qkv, const void* out, const voi
   TVTS_REQUIRE(make_shape(&a, B, N, H, d, mode, T, n, causal, scale), "attn_tc_bwd: unsupported shape (d=%lld mode=%lld N=%lld n=%lld)",
                (long long)d, (long long)mode, (long long)N, (long long)n);
   TVTS_REQUIRE(qkv && out && dout && lse && dqkv, "attn_tc_bwd: null pointer");
-  TVTS_REQUIRE(B * N < (1ll << 31) && B * H <= (int64_t)(kTicketBytes / sizeof(int)), "attn_tc_bwd: too many rows / (b, h) pairs");
+  TVTS_REQUIRE(B * N < (1ll << 31) && B * H * 192 <= (int64_t)(kTicketBytes / sizeof(int)), "attn_tc_bwd: too many rows / (b, h) pairs");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUtensorMap tq, tdo, tdq;
   int rc = make_map(&tq, qkv, a, 3 * H * HD);
