@@ -32,42 +32,28 @@ def stamps():
 
 
 def report(name, st, ntiles, labels):
-    st = st[:ntiles]
-    t = st[:, :len(labels) + 1].astype(np.float64)
-    print(f"== {name}: {ntiles} tiles; mean cycles per phase (thread 0)")
+    t = st[:ntiles, :len(labels) + 1].astype(np.float64)
+    print(f"== {name}: {ntiles} tiles; mean cycles per phase of the persistent tile loop (thread 0)")
     for i, lab in enumerate(labels):
         dphase = t[:, i + 1] - t[:, i]
-        print(f"  {lab:38s} {dphase.mean():8.0f}  (p10 {np.percentile(dphase, 10):6.0f}  p90 {np.percentile(dphase, 90):6.0f})")
+        print(f"  {lab:52s} {dphase.mean():8.0f}  (p10 {np.percentile(dphase, 10):6.0f}  p90 {np.percentile(dphase, 90):6.0f})")
     life = t[:, len(labels)] - t[:, 0]
-    print(f"  {'CTA lifetime':38s} {life.mean():8.0f}")
-    # gaps between consecutive CTAs on one SM: sort by start per SM; with R resident CTAs per SM the k-th start follows the (k-R)-th end
-    sm = st[:, 12]
-    gaps = []
-    for s_ in np.unique(sm):
-        idx = np.where(sm == s_)[0]
-        starts = np.sort(t[idx, 0])
-        ends = np.sort(t[idx, len(labels)])
-        R = int((starts < ends[0]).sum())
-        for k in range(R, len(starts)):
-            gaps.append(starts[k] - ends[k - R])
-    if gaps:
-        print(f"  gap end(CTA k-R) -> start(CTA k), same SM    {np.mean(gaps):8.0f}  (p10 {np.percentile(gaps, 10):6.0f}  p90 {np.percentile(gaps, 90):6.0f}); resident per SM ~{R}")
-    tiles_per_sm = ntiles / len(np.unique(sm))
-    span = max(t[:, len(labels)].max() - t[:, 0].min(), 1)
-    print(f"  tiles per SM {tiles_per_sm:.1f}")
+    print(f"  {'one loop iteration':52s} {life.mean():8.0f}")
+    sm = st[:ntiles, 12]
+    print(f"  tiles per SM {ntiles / len(np.unique(sm)):.1f}")
 
 
 for _ in range(3):
     L.call("attn_fwd", qkv, out, lse, B, N, H, d, mode, T, n, 0, scale)
 chunks = T if mode == 1 else 7
 st = stamps()
-lab_f = ["setup (alloc, barriers, CLS rows) + sync", "TMA load + S MMA (bar_s)", "softmax -> P, sync", "PV MMA (bar_o)", "epilogue staging, sync",
-         "store issue + CLS publish/merge", "bulk_wait_read"]
-stf = st[:, [0, 7, 1, 2, 3, 4, 5, 6, 8, 9, 10, 11, 12]]
-report(f"forward mode {mode}", stf, B * H * chunks, lab_f)
+lab_f = ["wait TMA boxes + S MMA (bar_s)", "softmax -> P, sync", "P V MMA (bar_o; previous tile's CLS ticket drawn)", "epilogue staging, sync",
+         "store issue, CLS publish, next tile's setup, (merge)", "store read-out wait + loop-end sync"]
+report(f"forward mode {mode}", st, B * H * chunks, lab_f)
 for _ in range(3):
     L.call("attn_bwd_bias", qkv, out, dout, lse, torch.empty_like(lse), dqkv, dbias, B, N, H, d, mode, T, n, 0, scale)
 st = stamps()
-lab_b = ["setup (alloc, CLS rows, lse, delta) + sync", "TMA load + S, dP MMAs (bar_1)", "pass A (P, delta), sync", "dV MMA (bar_dv)", "pass B (dS), sync",
-         "dV epilogue (under dK, dQ MMAs)", "wait dK, dQ MMAs (bar_2)", "dQ, dK epilogue, sync", "store issue, bias sums, CLS publish", "bulk_wait_read"]
+lab_b = ["wait TMA boxes + S, dP MMAs (bar_1)", "pass A (P, delta), sync", "dV MMA (bar_dv; previous tile's CLS ticket drawn)", "pass B (dS), sync",
+         "dV epilogue (under the dK, dQ MMAs)", "wait dK, dQ MMAs (bar_2)", "dQ, dK epilogue, sync",
+         "stores, CLS publish, next tile's setup, bias sums, (merge)", "store read-out wait + loop-end sync"]
 report(f"backward mode {mode}", st, B * H * chunks, lab_b)
