@@ -138,8 +138,11 @@ int tvts_attn_tc_bwd_bias(const void* qkv, const void* out, const void* dout, co
 int tvts_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv, int64_t B, int64_t N,
                   int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal, float scale, void* stream);
 
-/* tvts_attn_bwd that also ACCUMULATES the qkv Linear's bias gradient, dbias[3*H*d] += column sums of dqkv (fp32): inside the tcgen05
- * kernels' epilogue where they apply, else tvts_attn_bwd + tvts_colsum_bf16 */
+/* tvts_attn_bwd that also ACCUMULATES the qkv Linear's bias gradient, dbias[3*H*d] += column sums of dqkv over the tokens (fp32).  The
+ * tcgen05 kernels produce it inside the backward, in exact-arithmetic form: q third = column sums of dQ (from the fp32 accumulators);
+ * v third = column sums of dO (every softmax row sums to 1, so sum_j dV[j,:] = sum_i dO[i,:]); k third = 0 (a constant added to every key
+ * shifts all scores of a query alike: its gradient vanishes identically, what a column sum of the stored dK only approximates by its
+ * rounding noise).  Elsewhere: tvts_attn_bwd + tvts_colsum_bf16 (column sums of the stored 16-bit dqkv). */
 int tvts_attn_bwd_bias(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv, float* dbias,
                        int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal, float scale,
                        void* stream);

@@ -1,4 +1,4 @@
-"""Phase timing of the tcgen05 attention kernels (measurement tool; needs a library built with -DTVTS_ATTN_PROF, see the build line in
+"""Phase timing of the persistent tcgen05 attention BACKWARD kernel (measurement tool; needs a library built with -DTVTS_ATTN_PROF, see the build line in
 tools/r2_call15.sh):  TVTS_LIB_PATH=build_ab/prof_fp16.so python tools/attn_phase_prof.py [mode]
 Thread 0 of every CTA stamps clock64 at the phase boundaries; this prints the mean cycles per phase over the tiles of one launch at the
 c3 shape (B=32, H=12, T=8, n=98) and the gap between consecutive CTAs of one SM slot."""
@@ -41,19 +41,25 @@ def report(name, st, ntiles, labels):
     print(f"  {'one loop iteration':52s} {life.mean():8.0f}")
     sm = st[:ntiles, 12]
     print(f"  tiles per SM {ntiles / len(np.unique(sm)):.1f}")
+    ns0, ns1, cta = st[:ntiles, 10], st[:ntiles, 9], st[:ntiles, 11]
+    print(f"  kernel span by globaltimer: {(ns1.max() - ns0.min()) / 1e3:.1f} us; first tile start spread {(ns0[:int(cta.max()) + 1].max() - ns0.min()) / 1e3:.1f} us")
+    per = {}
+    for c_, a_, b_, cyc in zip(cta, ns0, ns1, life):
+        e = per.setdefault(int(c_), [a_, b_, 0, 0.0])
+        e[0] = min(e[0], a_); e[1] = max(e[1], b_); e[2] += 1; e[3] += cyc
+    busy = np.array([(v[1] - v[0]) / 1e3 for v in per.values()])
+    ntile = np.array([v[2] for v in per.values()])
+    cyc = np.array([v[3] for v in per.values()])
+    print(f"  per CTA: tiles {ntile.min()}..{ntile.max()}, first-start-to-last-end {busy.mean():.1f} us (min {busy.min():.1f} max {busy.max():.1f}), "
+          f"loop cycles {cyc.mean():.0f} (min {cyc.min():.0f} max {cyc.max():.0f}) -> implied clock {cyc.mean() / busy.mean() / 1e3:.2f} GHz")
 
 
-for _ in range(3):
-    L.call("attn_fwd", qkv, out, lse, B, N, H, d, mode, T, n, 0, scale)
+L.call("attn_fwd", qkv, out, lse, B, N, H, d, mode, T, n, 0, scale)      # produces out / lse for the backward (the forward kernel carries no stamps)
 chunks = T if mode == 1 else 7
-st = stamps()
-lab_f = ["wait TMA boxes + S MMA (bar_s)", "softmax -> P, sync", "P V MMA (bar_o; previous tile's CLS ticket drawn)", "epilogue staging, sync",
-         "store issue, CLS publish, next tile's setup, (merge)", "store read-out wait + loop-end sync"]
-report(f"forward mode {mode}", st, B * H * chunks, lab_f)
 for _ in range(3):
     L.call("attn_bwd_bias", qkv, out, dout, lse, torch.empty_like(lse), dqkv, dbias, B, N, H, d, mode, T, n, 0, scale)
 st = stamps()
-lab_b = ["wait TMA boxes + S, dP MMAs (bar_1)", "pass A (P, delta), sync", "dV MMA (bar_dv; previous tile's CLS ticket drawn)", "pass B (dS), sync",
-         "dV epilogue (under the dK, dQ MMAs)", "wait dK, dQ MMAs (bar_2)", "dQ, dK epilogue, sync",
-         "stores, CLS publish, next tile's setup, bias sums, (merge)", "store read-out wait + loop-end sync"]
+lab_b = ["wait TMA boxes + S, dP MMAs (bar_1; previous CLS partial published)", "pass A (P, delta), sync", "dV MMA (bar_dv; CLS ticket drawn)",
+         "pass B (dS), sync", "dV epilogue + bias (under the dK, dQ MMAs)", "wait dK, dQ MMAs (bar_2)", "dQ, dK epilogue + bias",
+         "next tile's setup, (merge), loop-end sync"]
 report(f"backward mode {mode}", st, B * H * chunks, lab_b)
