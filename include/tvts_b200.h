@@ -78,6 +78,10 @@ int tvts_gemm_debug_set(int lbo_bytes, int sbo_bytes, int k_advance_bytes);
 int tvts_gemm_set_pair_mode(int mode);
 /* 1 (default): the residual / aux epilogue operand is prefetched by TMA into the store ring; 0: read straight from global memory */
 int tvts_gemm_set_operand_prefetch(int on);
+/* 0 (default): results leave through 128B-swizzled shared-memory boxes and TMA stores; 1: results that are STORED (not accumulated:
+ * accumulate = 1 always uses cp.reduce.async.bulk .add) leave straight from registers with 32-byte stores (measured neutral on the
+ * hot path; environment TVTS_GEMM_EPI_DIRECT=1 selects it for a whole process) */
+int tvts_gemm_set_epilogue_direct(int on);
 /* debug: co-resident clusters of the pair kernel for a given cluster size (cudaOccupancyMaxActiveClusters) */
 int tvts_gemm_debug_max_clusters(int cluster_size);
 /* debug knob: 0 normal epilogue, 1 no global stores, 2 direct row-per-thread bf16 stores, 3 skip epilogue (timing experiments) */

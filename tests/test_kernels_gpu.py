@@ -42,8 +42,23 @@ GEMM_CASES = [
 ]
 
 
+GEMM_CASES += [
+    (2000, 3072, 768, 0, 0, "bias_act_pre", True),     # the c_fc shape class: two outputs, several tiles per worker
+    (2000, 3072, 768, 0, 1, "dact", True),             # the c_proj dgrad shape class: act' operand prefetched through the ring
+]
+
+
+@pytest.fixture
+def epi_direct(request):
+    """tvts_gemm_set_epilogue_direct: 0 = shared-memory boxes + TMA stores (default), 1 = results stored straight from registers"""
+    L.lib().tvts_gemm_set_epilogue_direct(int(request.param))
+    yield request.param
+    L.lib().tvts_gemm_set_epilogue_direct(0)
+
+
+@pytest.mark.parametrize("epi_direct", [0, 1], indirect=True)
 @pytest.mark.parametrize("M,N,K,a_mn,b_mn,mode,out_bf16", GEMM_CASES)
-def test_gemm(M, N, K, a_mn, b_mn, mode, out_bf16):
+def test_gemm(M, N, K, a_mn, b_mn, mode, out_bf16, epi_direct):
     torch.manual_seed(M + N + K)
     if mode == "empty":
         with pytest.raises(RuntimeError):
@@ -78,6 +93,27 @@ def test_gemm(M, N, K, a_mn, b_mn, mode, out_bf16):
     close(out, ref, atol=(1e-2 if out_bf16 else 2e-5) * max(scale, 1.0), what="gemm out")
     if "out_pre" in kw:
         close(kw["out_pre"], kw_ref["out_pre"], atol=1e-2 * max(scale, 1.0), what="gemm out_pre")
+
+
+@pytest.mark.parametrize("N,ldo,out_bf16,res", [(72, 96, True, False), (88, 96, True, False), (44, 48, False, True), (36, 64, False, False),
+                                                (200, 208, True, False)])
+@pytest.mark.parametrize("epi_direct", [1, 0], indirect=True)
+def test_gemm_direct_epilogue_edges(N, ldo, out_bf16, res, epi_direct):
+    """Register-store epilogue (and, for comparison, the TMA-store one) at the right edge of the matrix: the last 32-column pass holds 8 / 24 valid bf16 or 12 / 4 valid fp32 columns
+    (16-byte and 32-byte pieces), rows are ldo apart; nothing outside [M, N] may be written."""
+    torch.manual_seed(N)
+    M, K = 300, 128
+    A, B = rnd(M, K, scale=0.5).to(BF16), rnd(N, K, scale=0.5).to(BF16)
+    kw = dict(bias=rnd(N))
+    if res:
+        kw.update(residual=rnd(M, N), act="quick_gelu")
+    out = torch.full((M + 3, ldo), 7.0, device=DEV, dtype=BF16 if out_bf16 else F32)
+    ref = out.clone()
+    emu.gemm(A, B, ref, M=M, N=N, K=K, lda=K, ldb=K, ldo=ldo, **kw)
+    L.gemm(A, B, out, M=M, N=N, K=K, lda=K, ldb=K, ldo=ldo, **kw)
+    torch.cuda.synchronize()
+    close(out[:M, :N], ref[:M, :N], atol=(1e-2 if out_bf16 else 2e-5) * max(ref[:M, :N].float().abs().max().item(), 1.0), what="gemm out")
+    assert torch.equal(out[:M, N:], ref[:M, N:]) and torch.equal(out[M:], ref[M:]), "written outside the matrix"
 
 
 # ------------------------------------------------------------------------------------------------ LayerNorm

@@ -63,8 +63,29 @@ struct EpiParams {
   int dact;        // multiply by act'(aux) (dgrad through an activation)
   int accumulate;  // 0 store, 1 red.add into fp32 out (split-K / grad accumulation)
   int opnd_mode;   // 0: residual / aux read straight from global memory; 1: residual, 2: aux prefetched by TMA into the store ring
+  int direct;      // 1: outputs leave straight from registers (32-byte stores per thread), no shared-memory box / TMA store (see the epilogue)
   float alpha;
 };
+
+// 32 bytes (8 registers) to global memory in one instruction (STG.256, sm_100+); the address must be 32-byte aligned
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t* w) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]),
+               "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+__device__ __forceinline__ void st_global_v4(void* p, const uint32_t* w) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+}
+// this thread's `nwords` 32-bit words (a multiple of 8) of one output row, of which the first `valid` (a multiple of 4) lie inside the matrix
+__device__ __forceinline__ void store_row_words(void* p, const uint32_t* w, int nwords, int valid) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (8 * j < nwords) {
+      if (valid >= 8 * j + 8) st_global_v8(reinterpret_cast<uint32_t*>(p) + 8 * j, w + 8 * j);
+      else if (valid >= 8 * j + 4) st_global_v4(reinterpret_cast<uint32_t*>(p) + 8 * j, w + 8 * j);
+    }
+  }
+}
 
 struct GemmShape {
   int M, N, K;
@@ -265,6 +286,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
     };
     const bool has_pre = ep.out_pre != nullptr;
+    // Direct mode (opt-in, tvts_gemm_set_epilogue_direct): the results leave straight from registers -- every thread owns one output row,
+    // 32 consecutive columns per pass = 64 (bf16) or 128 (fp32) contiguous bytes, written with 32-byte stores (whole sectors).  No
+    // shared-memory box, no proxy fence, no TMA store whose read-out gates the reuse of a two-box ring; the epilogue operand (residual /
+    // act' input) is still prefetched by TMA into the ring, whose boxes are then free again as soon as they are read.  Built to test
+    // whether the store path bounds the K = 768 problems (qkv, c_fc with two outputs, proj + residual): it does not (see g_epi_direct).
+    const bool direct = ep.direct != 0;
     // Epilogue operand (the fp32 residual, or the bf16 pre-activation whose act' multiplies a dgrad) is PREFETCHED by TMA into
     // the very ring box the result will be stored from ([32 rows x 128 B] = 32 fp32 / 64 bf16 columns, same shape as the output
     // box): the first two boxes of a tile are requested before the accumulator is even ready, the following ones as soon as the
@@ -320,17 +347,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       for (int c0 = 0; c0 < COLS_PER_WARP; c0 += CH) {
         const int col0 = col_base + c0;
         if (col0 >= s.N || dbg_epi == 3) break;  // warp-uniform
-        uint32_t buf_o, buf_p = 0;
+        uint32_t buf_o = ring, buf_p = 0;
         if (tile_opnd) {
-          buf_o = ring + (nuse & 1u) * 4096u;            // the operand box of this chunk; the result overwrites it
+          buf_o = ring + (nuse & 1u) * 4096u;            // the operand box of this chunk; the result overwrites it (TMA-store mode)
           mbar_wait(opnd_bar(ew, nuse & 1u), (nuse >> 1) & 1u);
           ++nuse;
-        } else if (has_pre) { buf_p = ring; buf_o = ring + 4096u; }
+        } else if (direct) { }                           // no output box
+        else if (has_pre) { buf_p = ring; buf_o = ring + 4096u; }
         else { buf_o = ring + (nstore & 1u) * 4096u; ++nstore; }
         // the ring box(es) of this chunk are acquired (= their previous TMA store has been read out) only right before the first write
         // below, i.e. AFTER the chunk's first TMEM load and bias add: with two outputs per chunk (c_fc: pre-activation + activation)
         // both boxes are still being read out when the chunk starts, and that wait used to be fully exposed
-        bool acquired = tile_opnd;
+        bool acquired = tile_opnd || direct;
 #pragma unroll 1
         for (int sub = 0; sub < CH; sub += 32) {   // 32 accumulator columns per pass
           const int cs = col0 + sub;
@@ -388,7 +416,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if (has_pre) {                               // bf16 copy of the pre-activation
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-            box_write(buf_p, sub >> 3, v, 4);
+            if (!direct) box_write(buf_p, sub >> 3, v, 4);
+            else if (row_ok) store_row_words(reinterpret_cast<bf16*>(ep.out_pre) + grow * ep.ldo + cs, v, 16, min(s.N - cs, 32) >> 1);
           }
           if (ep.act != TVTS_ACT_NONE) {
 #pragma unroll
@@ -411,22 +440,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if (out_bf16) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-            box_write(buf_o, sub >> 3, v, 4);          // 32 bf16 columns = 64 bytes = 4 chunks
+            if (!direct) box_write(buf_o, sub >> 3, v, 4);          // 32 bf16 columns = 64 bytes = 4 chunks
+            else if (row_ok) store_row_words(reinterpret_cast<bf16*>(ep.out) + grow * ep.ldo + cs, v, 16, min(s.N - cs, 32) >> 1);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(f[j]);
-            box_write(buf_o, 0, v, 8);                 // 32 fp32 columns = the whole 128-byte row
+            if (!direct) box_write(buf_o, 0, v, 8);                 // 32 fp32 columns = the whole 128-byte row
+            else if (row_ok) store_row_words(reinterpret_cast<float*>(ep.out) + grow * ep.ldo + cs, v, 32, min(s.N - cs, 32));
           }
         }
-        if (dbg_epi != 1) {
+        if (dbg_epi != 1 && !direct) {
           if (has_pre) box_issue(&tmap_pre, buf_p, col0, row0, false);
           box_issue(&tmap_out, buf_o, col0, row0, ep.accumulate != 0);
         }
         if (tile_opnd) {
-          // request the operand box two chunks ahead: it reuses THIS chunk's box once the store just issued has been read out
+          // request the operand box two chunks ahead: it reuses THIS chunk's box ...
           const int cn = c0 + 2 * CH;
           const bool more = cn < COLS_PER_WARP && col_base + cn < s.N;     // warp-uniform
-          if (more) pend_col = col_base + cn;      // issued from the NEXT chunk, after its TMEM load: by then this store has been read out
+          if (more) {
+            if (direct) {          // ... right away: every lane has read its row of the box into registers, nothing else touches it
+              __syncwarp();
+              if (lane == 0) opnd_request(col_base + cn, row0);
+              ++nload;
+            } else {
+              pend_col = col_base + cn;      // ... from the NEXT chunk, after its TMEM load: by then the store just issued has been read out
+            }
+          }
         }
       }
       tc_fence_before();
@@ -490,6 +529,9 @@ int g_dbg_lbo = 0, g_dbg_sbo = 0, g_dbg_kadv = 0, g_dbg_epi = 0;
 int g_pair_mode = -1;   // -1 auto, 0 never use CTA pairs, 1 always when the shape allows
 int g_opnd_prefetch = 1; // TMA prefetch of the residual / aux epilogue operand
 int g_solo_penalty = -1; // see tvts_gemm: solo-vs-pair tile choice against wave quantisation (-1: read the environment)
+int g_epi_direct = -1;   // outputs stored straight from registers instead of through TMA-store boxes (environment TVTS_GEMM_EPI_DIRECT=1: on).
+                         // OFF by default: measured neutral on the c3 step (round 2, profiles/r2/call24_*: GEMM time 22.15 vs 22.15 ms, c_fc with
+                         // two outputs +3.5 %, proj + fp32 residual -4.6 %): those epilogues are bound by the bytes they move, not by the store path
 int g_pdl = -1;          // programmatic dependent launch of the GEMM grids (environment TVTS_GEMM_PDL=0 turns it off)
 
 template <int BN, bool A_MN, bool B_MN, int CTAS>
@@ -529,6 +571,14 @@ int launch(const tvts_gemm_args* g, const GemmShape& s, const EpiParams& ep, cud
       ep2.opnd_mode = 2;
     }
   }
+  ep2.direct = 0;
+  if (g_epi_direct < 0) {
+    const char* e = getenv("TVTS_GEMM_EPI_DIRECT");
+    g_epi_direct = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  if (g_epi_direct && !g->accumulate && (uintptr_t)g->out % 32 == 0 && (g->ldo * oes) % 32 == 0 &&
+      (!g->out_pre || (uintptr_t)g->out_pre % 32 == 0))
+    ep2.direct = 1;
   auto kern = gemm_kernel<BN, A_MN, B_MN, CTAS>;
   if (g_pdl < 0) {
     const char* e = getenv("TVTS_GEMM_PDL");
@@ -590,6 +640,10 @@ extern "C" int tvts_gemm_debug_max_clusters(int cluster_size) {
 }
 extern "C" int tvts_gemm_set_pair_mode(int mode) {
   g_pair_mode = mode;
+  return TVTS_OK;
+}
+extern "C" int tvts_gemm_set_epilogue_direct(int on) {
+  g_epi_direct = on ? 1 : 0;
   return TVTS_OK;
 }
 extern "C" int tvts_gemm_set_operand_prefetch(int on) {
