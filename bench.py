@@ -476,7 +476,8 @@ def run_ours(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": _lib.OPERAND,
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {cfg.name} T={frames} batch {batch}/GPU n_trans={n_trans} (global batch {world * batch})",
-                       "step": "fwd+bwd" + (("+grad_allreduce" + ("(bucketed under the backward)" if step.overlap else "")) if world > 1 else "")
+                       "step": "fwd+bwd" + (("+grad_allreduce" + ("(bucketed under the backward)" if step.overlap else "")
+                                                        + ("(4 buckets, AdamW of bucket i under the all-reduce of bucket i+1)" if getattr(step, "pipelined", False) and not step.overlap else "")) if world > 1 else "")
                                + ("" if args.no_optimizer else "+adamw"),
                        "launch": ("one CUDA graph per step, text tower on a second stream" if use_graph else "kernel-by-kernel from Python"),
                        "parallelism": f"dp{world}", "l2": f"per-step inputs ({h2d / 1e6:.0f} MB) and activations (GBs) exceed the 126 MB L2",

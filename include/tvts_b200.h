@@ -304,6 +304,20 @@ int tvts_adamw_flat_dyn(float* p, const float* g, float* m, float* v, void* p_bf
                         int32_t* steps, float* state, int64_t n_tensors, int64_t n_chunks, int64_t chunk_elems, float beta1, float beta2,
                         float eps, float growth_interval, float max_scale, void* stream);
 
+/* The three phases of tvts_adamw_flat_dyn as separate launches, for a data-parallel step that updates the arena bucket by bucket while
+ * the NEXT bucket's gradient all-reduce is still on the wire (trainer.TrainStep, TVTS_PIPELINED_ADAMW):
+ *   _check  : finite check over g[0, n_elems) -> state[2] (run on the LOCAL gradients before the all-reduce; the flag is then
+ *             MAX-reduced across the ranks -- a sum of finite fp32 gradients stays finite short of 3.4e38);
+ *   _apply  : the update of chunks [0, n_chunks) of the arenas passed in (pass pointers offset to the bucket's first chunk; no-op
+ *             when state[2] is set);
+ *   _finish : the scale policy + the per-tensor step counters (once per step, after every bucket). */
+int tvts_adamw_dyn_check(const float* g, int64_t n_elems, float* state, void* stream);
+int tvts_adamw_dyn_apply(float* p, const float* g, float* m, float* v, void* p_bf16, const int32_t* chunk_tensor, const float* table,
+                         const int32_t* steps, const float* state, int64_t n_chunks, int64_t chunk_elems, float beta1, float beta2, float eps,
+                         void* stream);
+int tvts_adamw_dyn_finish(int32_t* steps, const float* table, float* state, int64_t n_tensors, float growth_interval, float max_scale,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

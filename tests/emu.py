@@ -480,6 +480,37 @@ def adamw_flat_dyn(p, g, m, v, pb, chunk_tensor, table, steps, state, n_tensors,
     state[2] = 0
 
 
+def adamw_dyn_check(g, n_elems, state):
+    if not bool(torch.isfinite(g.view(-1)[:n_elems]).all()):
+        state[2] = 1.0
+
+
+def adamw_dyn_apply(p, g, m, v, pb, chunk_tensor, table, steps, state, n_chunks, chunk, b1, b2, eps):
+    if float(state[2]) != 0.0:
+        return
+    t = (steps.float() + 1.0)
+    tab = table.clone()
+    corr = torch.sqrt(1.0 - torch.pow(torch.tensor(b2), t)) / (1.0 - torch.pow(torch.tensor(b1), t))
+    tab[:, 0] = torch.where(table[:, 3] != 0, table[:, 0] * corr, table[:, 0])
+    n = n_chunks * chunk
+    adamw_flat(p.view(-1)[:n], g.view(-1)[:n], m.view(-1)[:n], v.view(-1)[:n], None if pb is None else pb.view(-1)[:n], chunk_tensor[:n_chunks], tab,
+               n_chunks, chunk, b1, b2, eps, 1.0 / float(state[0]))
+
+
+def adamw_dyn_finish(steps, table, state, n_tensors, growth_interval, max_scale):
+    if float(state[2]) == 0.0:
+        steps += (table[:, 2] != 0).to(steps.dtype)
+        state[1] += 1
+        if float(state[1]) >= growth_interval:
+            state[0] = min(float(state[0]) * 2.0, max_scale)
+            state[1] = 0
+    else:
+        state[0] = max(float(state[0]) * 0.5, 1.0)
+        state[1] = 0
+        state[3] += 1
+    state[2] = 0
+
+
 OPS = {k: v for k, v in list(globals().items()) if callable(v) and not k.startswith("_") and k not in ("install", "uninstall", "gemm")}
 
 _saved = {}

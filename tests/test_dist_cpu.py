@@ -159,3 +159,76 @@ def test_two_rank_v1_step_matches_single_process_oracle():
     a, b = out["loss1"]
     assert abs(a - b) < 5e-2, (a, b)
     assert out["worst_text_grad_rel"] < 0.08, out["worst_text_grad_rel"]
+
+
+def _worker_pipelined(rank, world, port, out):
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import emu
+        from tvts_b200 import config as C
+        from tvts_b200 import engine as E
+        from tvts_b200 import modules as M
+        from tvts_b200 import optim
+        from tvts_b200.synthetic import make_batch, make_state_dict
+        from tvts_b200.trainer import TrainStep
+        emu.install()
+        torch.set_num_threads(2)
+        cfg = C.TINY_B
+        sd = make_state_dict(cfg, seed=1234)
+        batches = [make_batch(cfg, 2, 2, n_trans=4, seed=10 + i, rank=rank) for i in range(3)]
+        results = []
+        for pipelined in (False, True):
+            m = M.TVTSv2Base(types.SimpleNamespace(local_rank=0, rank=rank), arch=cfg)
+            m.load_state_dict(sd, strict=True)
+            opt = optim.build_reference_optimizer(m)
+            for g in opt.param_groups:
+                g["lr"] = g["lr"] * 100.0                   # make three steps move the weights visibly
+            E.WEIGHTS.clear()
+            step = TrainStep(m, opt, cfg.temperature, torch.device("cpu"))
+            step.pipelined = pipelined
+            step.PIPELINE_BUCKETS = 3
+            losses = [tuple(x.item() for x in step(b)) for b in batches]
+            results.append((losses, {k: v.detach().clone() for k, v in m.state_dict().items()}, opt.sync_steps()[:], float(opt.scale_state[0])))
+            if pipelined and opt.dynamic_scale:
+                # a non-finite LOCAL gradient on one rank only: the flag travels, BOTH ranks skip the step and halve the scale
+                w0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+                s0 = float(opt.scale_state[0])
+                orig = opt.launch_check
+
+                def poisoned():
+                    if rank == 1:
+                        opt.flat.g[5] = float("inf")
+                    orig()
+                opt.launch_check = poisoned
+                step(batches[0])
+                opt.launch_check = orig
+                assert all(torch.equal(v, w0[k]) for k, v in m.state_dict().items()), "a rank updated its weights in a step the other rank skipped"
+                assert float(opt.scale_state[0]) == s0 * 0.5 and opt.skipped_steps == 1
+                out[f"skip{rank}"] = True
+            opt.flat.release()
+        (l_a, w_a, st_a, sc_a), (l_b, w_b, st_b, sc_b) = results
+        assert l_a == l_b, (l_a, l_b)
+        assert st_a == st_b and sc_a == sc_b
+        for k in w_a:
+            assert torch.equal(w_a[k], w_b[k]), k
+        out[f"ok{rank}"] = True
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_pipelined_allreduce_adamw_matches_single_allreduce():
+    """TVTS_PIPELINED_ADAMW: bucketed all-reduce with the AdamW update of bucket i under the all-reduce of bucket i + 1 -- identical
+    losses, weights, step counters and loss scale to one all-reduce followed by one AdamW launch, over three steps on 2 ranks; and a
+    non-finite gradient on ONE rank makes BOTH ranks skip the step (dynamic loss scale: the finite flag is MAX-reduced)."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29500 + ((os.getpid() + 977) % 2000)
+    mp.spawn(_worker_pipelined, args=(2, port, out), nprocs=2, join=True)
+    assert out.get("ok0") and out.get("ok1"), dict(out)
+

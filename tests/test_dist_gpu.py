@@ -57,13 +57,14 @@ def _worker(rank, world, port, out):
             b["text"] = trim_text_context(_clamp_captions(b["text"], ll[rank], eot))
             yield b
 
-    def run(use_graph, overlap):
+    def run(use_graph, overlap, pipelined=False):
         m = M.TVTSv2Base(types.SimpleNamespace(local_rank=rank, rank=rank), arch=cfg)
         m.load_state_dict(make_state_dict(cfg, seed=1234), strict=True)
         m = m.to(dev)
         opt = optim.build_reference_optimizer(m)
         step = TrainStep(m, opt, cfg.temperature, dev, use_graph=use_graph)
         step.overlap = overlap
+        step.pipelined = pipelined
         losses, keys = [], set()
         g0 = None
         try:
@@ -86,6 +87,10 @@ def _worker(rank, world, port, out):
     worst_l = max(max(abs(a[0] - b[0]), abs(a[1] - b[1])) for a, b in zip(le, lg))
     worst_p = max((pe[k] - pg[k]).abs().max().item() / max(1.0, pe[k].abs().max().item()) for k in pe)
     res = {"graph_vs_eager_loss": worst_l, "graph_vs_eager_param": worst_p, "losses": le}
+    # pipelined all-reduce + AdamW (bucket i updated while bucket i + 1 is on the wire; finite flag MAX-reduced), captured in the graph
+    lp, pp, _, _, _ = run(True, False, pipelined=True)
+    res["pipelined_vs_eager_loss"] = max(max(abs(a[0] - b[0]), abs(a[1] - b[1])) for a, b in zip(le, lp))
+    res["pipelined_vs_eager_param"] = max((pe[k] - pp[k]).abs().max().item() / max(1.0, pe[k].abs().max().item()) for k in pe)
     if rank == 0:
         # oracle on the concatenated global batch of step 0 (clip-major text rows over the GLOBAL batch; contexts padded back to a common width)
         parts = []
@@ -126,5 +131,7 @@ def test_two_rank_nccl_graph_overlap_step():
     for r in (0, 1):
         assert out[r]["graph_vs_eager_loss"] < 2e-3, out[r]        # two samples of the 16-bit rounding noise (tests/test_trainstep_gpu.py)
         assert out[r]["graph_vs_eager_param"] < 1e-3, out[r]
+        assert out[r]["pipelined_vs_eager_loss"] < 2e-3, out[r]
+        assert out[r]["pipelined_vs_eager_param"] < 1e-3, out[r]
     assert out[0]["loss1_vs_oracle"] < 2e-2, out[0]
     assert out[0]["text_grad_rel_vs_oracle"] < 0.08, out[0]

@@ -131,6 +131,44 @@ __global__ void scale_update_kernel(float* __restrict__ state, int32_t* __restri
 
 }  // namespace
 
+extern "C" int tvts_adamw_dyn_check(const float* g, int64_t n_elems, float* state, void* stream) {
+  if (n_elems == 0) return TVTS_OK;
+  TVTS_REQUIRE(g && state, "adamw_dyn_check: null pointer");
+  TVTS_REQUIRE(n_elems > 0 && n_elems % 4 == 0 && (uintptr_t)g % 16 == 0, "adamw_dyn_check: n_elems=%lld must be a multiple of 4, g 16-byte aligned",
+               (long long)n_elems);
+  const long long n4 = n_elems / 4;
+  const int blocks = (int)((n4 + 255) / 256 < (long long)tvts_num_sms() * 8 ? (n4 + 255) / 256 : (long long)tvts_num_sms() * 8);
+  grad_check_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(g), n4, state);
+  TVTS_LAUNCH_CHECK();
+  return TVTS_OK;
+}
+
+extern "C" int tvts_adamw_dyn_apply(float* p, const float* g, float* m, float* v, void* p_bf16, const int32_t* chunk_tensor, const float* table,
+                                    const int32_t* steps, const float* state, int64_t n_chunks, int64_t chunk_elems, float beta1, float beta2,
+                                    float eps, void* stream) {
+  if (n_chunks == 0) return TVTS_OK;
+  TVTS_REQUIRE(p && g && m && v && chunk_tensor && table && steps && state, "adamw_dyn_apply: null pointer");
+  TVTS_REQUIRE(chunk_elems > 0 && chunk_elems % 4 == 0, "adamw_dyn_apply: chunk_elems=%lld must be a positive multiple of 4", (long long)chunk_elems);
+  TVTS_REQUIRE(n_chunks > 0 && n_chunks < (1ll << 31), "adamw_dyn_apply: bad sizes");
+  TVTS_REQUIRE(((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)table) % 16 == 0 && (uintptr_t)p_bf16 % 8 == 0,
+               "adamw_dyn_apply: arena pointers must be 16-byte aligned");
+  adamw_flat_dyn_kernel<<<(unsigned)n_chunks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      p, g, m, v, reinterpret_cast<bf16*>(p_bf16), chunk_tensor, reinterpret_cast<const float4*>(table), steps, state, (int)chunk_elems, beta1,
+      beta2, eps);
+  TVTS_LAUNCH_CHECK();
+  return TVTS_OK;
+}
+
+extern "C" int tvts_adamw_dyn_finish(int32_t* steps, const float* table, float* state, int64_t n_tensors, float growth_interval,
+                                     float max_scale, void* stream) {
+  TVTS_REQUIRE(steps && table && state, "adamw_dyn_finish: null pointer");
+  TVTS_REQUIRE(n_tensors > 0 && n_tensors < (1ll << 31) && (uintptr_t)table % 16 == 0, "adamw_dyn_finish: bad sizes");
+  scale_update_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(state, steps, reinterpret_cast<const float4*>(table), (int)n_tensors,
+                                                                           growth_interval, max_scale);
+  TVTS_LAUNCH_CHECK();
+  return TVTS_OK;
+}
+
 extern "C" int tvts_adamw_flat_dyn(float* p, const float* g, float* m, float* v, void* p_bf16, const int32_t* chunk_tensor, const float* table,
                                    int32_t* steps, float* state, int64_t n_tensors, int64_t n_chunks, int64_t chunk_elems, float beta1,
                                    float beta2, float eps, float growth_interval, float max_scale, void* stream) {
@@ -138,20 +176,11 @@ extern "C" int tvts_adamw_flat_dyn(float* p, const float* g, float* m, float* v,
   TVTS_REQUIRE(p && g && m && v && chunk_tensor && table && steps && state, "adamw_flat_dyn: null pointer");
   TVTS_REQUIRE(chunk_elems > 0 && chunk_elems % 4 == 0, "adamw_flat_dyn: chunk_elems=%lld must be a positive multiple of 4", (long long)chunk_elems);
   TVTS_REQUIRE(n_chunks < (1ll << 31) && n_tensors > 0 && n_tensors < (1ll << 31), "adamw_flat_dyn: bad sizes");
-  TVTS_REQUIRE(((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)table) % 16 == 0 && (uintptr_t)p_bf16 % 8 == 0,
-               "adamw_flat_dyn: arena pointers must be 16-byte aligned");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const long long n4 = n_chunks * chunk_elems / 4;
-  const int blocks = (int)((n4 + 255) / 256 < (long long)tvts_num_sms() * 8 ? (n4 + 255) / 256 : (long long)tvts_num_sms() * 8);
-  grad_check_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(g), n4, state);
-  TVTS_LAUNCH_CHECK();
-  adamw_flat_dyn_kernel<<<(unsigned)n_chunks, 256, 0, st>>>(p, g, m, v, reinterpret_cast<bf16*>(p_bf16), chunk_tensor,
-                                                            reinterpret_cast<const float4*>(table), steps, state, (int)chunk_elems, beta1,
-                                                            beta2, eps);
-  TVTS_LAUNCH_CHECK();
-  scale_update_kernel<<<1, 256, 0, st>>>(state, steps, reinterpret_cast<const float4*>(table), (int)n_tensors, growth_interval, max_scale);
-  TVTS_LAUNCH_CHECK();
-  return TVTS_OK;
+  int rc = tvts_adamw_dyn_check(g, n_chunks * chunk_elems, state, stream);
+  if (rc) return rc;
+  rc = tvts_adamw_dyn_apply(p, g, m, v, p_bf16, chunk_tensor, table, steps, state, n_chunks, chunk_elems, beta1, beta2, eps, stream);
+  if (rc) return rc;
+  return tvts_adamw_dyn_finish(steps, table, state, n_tensors, growth_interval, max_scale, stream);
 }
 
 extern "C" int tvts_adamw_flat(float* p, const float* g, float* m, float* v, void* p_bf16, const int32_t* chunk_tensor, const float* table,

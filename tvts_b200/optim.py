@@ -293,6 +293,39 @@ class AdamW:
             if p.grad is not None:
                 fs.synced[i] = p._version      # the kernel refreshed the bf16 copy of every active tensor
 
+    # ---- launch() in phases: the data-parallel step updates the arena bucket by bucket while the next bucket's gradient all-reduce is
+    # still on the wire (trainer.TrainStep, pipelined AdamW).  launch_check() -> [share scale_state[2] across ranks] -> launch_range() per
+    # bucket of whole chunks -> launch_finish(); together they are exactly launch().
+    def launch_check(self):
+        """dynamic scale only: finite check over the (LOCAL) gradient arena -> scale_state[2]"""
+        fs = self.flat
+        if self.dynamic_scale:
+            L.call("adamw_dyn_check", fs.g, fs.n_chunks * fs.chunk, self.scale_state)
+
+    def launch_range(self, c0, c1, grad_scale=1.0):
+        """the update of chunks [c0, c1) of the arena"""
+        fs = self.flat
+        if c1 <= c0:
+            return
+        b1, b2 = self.param_groups[0]["betas"]
+        a, b = c0 * fs.chunk, c1 * fs.chunk
+        ct = self.chunk_tensor_arg()[c0:c1]
+        if self.dynamic_scale:
+            L.call("adamw_dyn_apply", fs.p[a:b], fs.g[a:b], fs.m[a:b], fs.v[a:b], fs.bf[a:b], ct, self.table, self.steps_dev, self.scale_state,
+                   c1 - c0, fs.chunk, float(b1), float(b2), float(self.param_groups[0]["eps"]))
+        else:
+            L.call("adamw_flat", fs.p[a:b], fs.g[a:b], fs.m[a:b], fs.v[a:b], fs.bf[a:b], ct, self.table, c1 - c0, fs.chunk, float(b1),
+                   float(b2), float(self.param_groups[0]["eps"]), float(grad_scale))
+
+    def launch_finish(self):
+        fs = self.flat
+        if self.dynamic_scale:
+            L.call("adamw_dyn_finish", self.steps_dev, self.table, self.scale_state, len(fs.params), float(self.GROWTH_INTERVAL),
+                   float(self.MAX_SCALE))
+        for i, p in enumerate(fs.params):
+            if p.grad is not None:
+                fs.synced[i] = p._version      # the kernels refreshed the bf16 copy of every active tensor
+
     def step(self, grad_scale=1.0):
         self.prepare()
         self.launch(grad_scale)

@@ -216,6 +216,11 @@ class TrainStep:
         # profiles/r2_scaling.md) the bucketed variant is not faster (32.77 vs 32.60 ms / step) -- the backward is a chain of persistent
         # GEMM grids that own every SM's registers and shared memory, so the NCCL kernels cannot co-reside and only move the wait around.
         self.overlap = os.environ.get("TVTS_OVERLAP_ALLREDUCE", "0") == "1"
+        # TVTS_PIPELINED_ADAMW=1 (world > 1): all-reduce in buckets, AdamW on bucket i while bucket i + 1 is on the wire
+        # (_pipelined_allreduce_adamw).  Default OFF: identical weights (tests/test_dist_cpu.py, tests/test_dist_gpu.py) but measured not
+        # faster on B200s (round 2, profiles/r2/call28_*, call29_*): 31.7 vs 31.4 ms at 2 GPUs, 33.26 vs 33.12 ms at 8 -- the AdamW pass and
+        # the NCCL kernels both live on HBM bandwidth, and five small collectives replace one.
+        self.pipelined = os.environ.get("TVTS_PIPELINED_ADAMW", "0") == "1"
         self._ranges = None
         self._comm_stream = None
         self._graphs = {}
@@ -298,6 +303,10 @@ class TrainStep:
         elif self.loss_scale != 1.0:
             total = total * self.loss_scale                             # static scale: optimizer-less / stock-optimizer runs of that build
         total.backward()
+        if (self.pipelined and not overlapped and flat is not None and _world() > 1 and hasattr(self.optimizer, "launch_range")
+                and not skip_optimizer and (dynamic or hasattr(self.optimizer, "launch"))):
+            self._pipelined_allreduce_adamw(flat, dynamic, optimizer_launch_only)
+            return loss1.detach(), loss2.detach()
         if overlapped:
             self._finish_bucketed_allreduce(flat)
         elif flat is not None:
@@ -325,6 +334,52 @@ class TrainStep:
             else:
                 self.optimizer.step()
         return loss1.detach(), loss2.detach()
+
+    PIPELINE_BUCKETS = 4    # gradient all-reduce / AdamW pipeline depth (see _pipelined_allreduce_adamw)
+
+    def _pipelined_allreduce_adamw(self, flat, dynamic, launch_only):
+        """world > 1: the gradient arena is all-reduced in PIPELINE_BUCKETS contiguous buckets of whole chunks on a communication stream,
+        and the fused AdamW updates bucket i on the compute stream while bucket i + 1 is still on the wire -- the optimizer pass (HBM-bound,
+        0.7 ms at B/16) hides under the all-reduce (NVLink-bound) instead of following it.  Same sums, same update: identical weights to
+        average_flat() + optimizer.launch() (tests/test_dist_cpu.py, tests/test_dist_gpu.py).
+        Dynamic loss scale (IEEE-half build): the whole-step skip decision has to exist before the first bucket is updated, so the finite
+        check runs on the LOCAL gradients right after the backward and its flag is MAX-reduced across the ranks (4 bytes) -- a rank with a
+        non-finite gradient makes every rank skip; what this cannot see, a sum of finite fp32 gradients overflowing 3.4e38, does not occur
+        under a loss scale <= 2^24."""
+        opt = self.optimizer
+        if not launch_only:
+            opt.prepare()
+        scale = 1.0 if dynamic else 1.0 / self.loss_scale
+        if dynamic:
+            opt.launch_check()
+            flag = opt.scale_state[2:3]
+            if dist.get_backend() == "nccl" or flat.device.type == "cpu":
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        nb = max(1, min(self.PIPELINE_BUCKETS, flat.n_chunks))
+        cuts = [flat.n_chunks * i // nb for i in range(nb + 1)]
+        comm = None
+        if flat.device.type == "cuda":
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream(device=self.device)
+            comm = self._comm_stream
+        if comm is None:
+            for c0, c1 in zip(cuts[:-1], cuts[1:]):
+                _average_tensor(flat.g[c0 * flat.chunk: c1 * flat.chunk])
+                opt.launch_range(c0, c1, scale)
+        else:
+            cur = torch.cuda.current_stream()
+            comm.wait_stream(cur)                   # the backward (and the finite flag) are complete on the compute stream
+            done = []
+            with torch.cuda.stream(comm):
+                for c0, c1 in zip(cuts[:-1], cuts[1:]):
+                    _average_tensor(flat.g[c0 * flat.chunk: c1 * flat.chunk])
+                    ev = torch.cuda.Event()
+                    ev.record(comm)
+                    done.append(ev)
+            for ev, c0, c1 in zip(done, cuts[:-1], cuts[1:]):
+                cur.wait_event(ev)
+                opt.launch_range(c0, c1, scale)
+        opt.launch_finish()
 
     BUCKET_BLOCKS = 3       # video blocks per all-reduce bucket (12 blocks -> 4 buckets of ~85 MB at B/16)
 
