@@ -494,8 +494,8 @@ def run_ours(args):
                 "bf16": {"c1": [1.8e-3, 3.5e-3], "toy": [8.7e-3, 4.1e-3]}}},
             "step_model_tflops": flops_pair * batch / (ms_step / 1e3) / 1e12,
             "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05)", "achieved": achieved, "peak": pk["bf16_sustained"],
-                         "unit": "TFLOP/s", "frac": (achieved / pk["bf16_sustained"]) if achieved else None, "traffic": 171.2e6,
-                         "traffic_note": "mean dram__bytes_read+write per launch (bytes) over the 8 GEMM launches of the round-2 ncu --set full capture profiles/r2/gemm.ncu-summary.md (forward qkv / proj / c_fc / c_proj of two c3 video blocks, GPU call 8, the GEMM kernel as shipped); at or below the algorithmic operand+output bytes of those launches (116-347 MB): no re-read amplification",
+                         "unit": "TFLOP/s", "frac": (achieved / pk["bf16_sustained"]) if achieved else None, "traffic": 171.3e6,
+                         "traffic_note": "mean dram__bytes_read+write per launch (bytes) over the 8 GEMM launches of the round-2 ncu --set full capture profiles/r2/call30_gemm.ncu-summary.md (forward qkv / proj / c_fc / c_proj of two c3 video blocks, GPU call 30 = the last call of round 2, the GEMM kernel as shipped; call 8's capture of the earlier kernel gave 171.2 MB); at or below the algorithmic operand+output bytes of those launches (116-347 MB): no re-read amplification",
                          "launches": int(n_gemm), "gemm_ms_per_step": t_ms.value / args.steps,
                          "gemm_share_of_step": (t_ms.value / args.steps) / ms_step, "measured_in": roof_mode, "peak_source": pk["source"] + " (sustained figure: kernel timed inside a long step)"},
         }
