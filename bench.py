@@ -513,6 +513,8 @@ def run_ours(args):
             line["eager_gpu_baseline"] = eager
         print(json.dumps(line), flush=True)
     step.close()            # destroy the captured graphs (they hold the step's NCCL kernels) BEFORE the process group goes away
+    from tvts_b200.trainer import shutdown_native_comm
+    shutdown_native_comm()  # (TVTS_COMM=native only)
     if world > 1:
         sys.stdout.flush()
         sys.stderr.flush()

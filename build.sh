@@ -27,5 +27,5 @@ for f in tvts_b200/csrc/*.cu; do
   fi
 done
 for p in $pids; do wait $p; done
-$NVCC -shared -o $LIB $objs -Xcompiler -fPIC
+$NVCC -shared -o $LIB $objs -Xcompiler -fPIC -ldl
 echo "built $LIB"

@@ -318,6 +318,25 @@ int tvts_adamw_dyn_apply(float* p, const float* g, float* m, float* v, void* p_b
 int tvts_adamw_dyn_finish(int32_t* steps, const float* table, float* state, int64_t n_tensors, float growth_interval, float max_scale,
                           void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * The two exchange steps of the data-parallel path over NCCL (one process per GPU, one communicator per process):
+ *   tvts_comm_allgather : every rank's `bytes_per_rank` bytes, concatenated in rank order -- the [B_local, 2E] embeddings of
+ *                         AllGather_multi.forward (v2/trainer/trainer.py:41-57, :481-482)
+ *   tvts_comm_allreduce : in-place sum (average != 0: mean) of n floats -- DistributedDataParallel's gradient averaging
+ *                         (v2/base/base_trainer.py:23-25) on the flat gradient arena
+ * Rank 0 creates the 128-byte id with tvts_comm_unique_id and hands it to the other ranks by any side channel (a TCP store, a file);
+ * tvts_comm_init is collective and binds the communicator to the caller's current CUDA device.  Collectives are enqueued on `stream`
+ * (capturable in a CUDA graph); nothing synchronises.  NCCL is resolved at run time (the libnccl.so.2 the process has loaded, else the
+ * system one).  The host side uses these when TVTS_COMM=native; by default the same two collectives are torch.distributed calls.
+ */
+#define TVTS_COMM_ID_BYTES 128
+typedef struct tvts_comm tvts_comm;
+int tvts_comm_unique_id(void* id_out);
+int tvts_comm_init(tvts_comm** comm, const void* id_bytes, int64_t rank, int64_t world);
+int tvts_comm_allgather(tvts_comm* comm, const void* send, void* recv, int64_t bytes_per_rank, void* stream);
+int tvts_comm_allreduce(tvts_comm* comm, float* buf, int64_t n, int64_t average, void* stream);
+int tvts_comm_destroy(tvts_comm* comm);
+
 #ifdef __cplusplus
 }
 #endif

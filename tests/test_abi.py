@@ -65,6 +65,13 @@ def test_entry_points_validate_arguments_before_touching_the_device():
     # optimizer: null arena
     rc = lib.tvts_adamw_flat(None, None, None, None, None, None, None, i64(4), i64(4096), f32(0.9), f32(0.999), f32(1e-6), f32(1.0), None)
     assert rc < 0 and "adamw_flat" in _err(lib)
+    # communicator entry points: argument errors are reported, not crashed on; destroying nothing is fine (no NCCL call is made here)
+    h = ctypes.c_void_p()
+    assert lib.tvts_comm_init(ctypes.byref(h), None, i64(0), i64(2)) < 0 and "comm_init" in _err(lib)
+    assert lib.tvts_comm_init(ctypes.byref(h), p, i64(3), i64(2)) < 0 and "rank 3 of 2" in _err(lib)
+    assert lib.tvts_comm_allreduce(None, None, i64(4), i64(1), None) < 0 and "comm_allreduce" in _err(lib)
+    assert lib.tvts_comm_allgather(None, p, p, i64(4), None) < 0 and "comm_allgather" in _err(lib)
+    assert lib.tvts_comm_destroy(None) == 0
     # empty problems are no-ops, not errors
     assert lib.tvts_attn_fwd(p, p, p, i64(0), i64(16), i64(2), i64(64), i64(0), i64(0), i64(0), i64(0), f32(0.1), None) == 0
     assert lib.tvts_layernorm_fwd(p, p, p, p, i64(1), p, p, i64(0), i64(128), f32(1e-5), None) == 0

@@ -87,6 +87,28 @@ def _worker(rank, world, port, out):
     worst_l = max(max(abs(a[0] - b[0]), abs(a[1] - b[1])) for a, b in zip(le, lg))
     worst_p = max((pe[k] - pg[k]).abs().max().item() / max(1.0, pe[k].abs().max().item()) for k in pe)
     res = {"graph_vs_eager_loss": worst_l, "graph_vs_eager_param": worst_p, "losses": le}
+    # the same eager steps with the two collectives going through the C ABI's own NCCL communicator (tvts_comm_*, TVTS_COMM=native)
+    from tvts_b200 import trainer as TR
+    os.environ["TVTS_COMM"] = "native"
+    try:
+        ln, pn, _, _, _ = run(False, False)
+        nc = TR.native_comm(dev)
+        assert nc is not None and nc.world == world
+        x = torch.full((4,), float(rank + 1), device=dev)
+        nc.all_reduce_avg(x)
+        gathered = torch.empty(world * 3, device=dev)
+        nc.all_gather(gathered, torch.full((3,), float(rank), device=dev))
+        torch.cuda.synchronize()
+        assert torch.allclose(x, torch.full_like(x, (world + 1) / 2.0))
+        assert torch.equal(gathered, torch.arange(world, device=dev, dtype=torch.float32).repeat_interleave(3))
+        lng, png, _, _, _ = run(True, False)            # ... and captured in the step graph
+    finally:
+        TR.shutdown_native_comm()
+        os.environ["TVTS_COMM"] = "torch"
+    res["native_vs_eager_loss"] = max(max(abs(a[0] - b[0]), abs(a[1] - b[1])) for a, b in zip(le, ln))
+    res["native_vs_eager_param"] = max((pe[k] - pn[k]).abs().max().item() / max(1.0, pe[k].abs().max().item()) for k in pe)
+    res["native_graph_vs_eager_loss"] = max(max(abs(a[0] - b[0]), abs(a[1] - b[1])) for a, b in zip(le, lng))
+    res["native_graph_vs_eager_param"] = max((pe[k] - png[k]).abs().max().item() / max(1.0, pe[k].abs().max().item()) for k in pe)
     # pipelined all-reduce + AdamW (bucket i updated while bucket i + 1 is on the wire; finite flag MAX-reduced), captured in the graph
     lp, pp, _, _, _ = run(True, False, pipelined=True)
     res["pipelined_vs_eager_loss"] = max(max(abs(a[0] - b[0]), abs(a[1] - b[1])) for a, b in zip(le, lp))
@@ -131,6 +153,8 @@ def test_two_rank_nccl_graph_overlap_step():
     for r in (0, 1):
         assert out[r]["graph_vs_eager_loss"] < 2e-3, out[r]        # two samples of the 16-bit rounding noise (tests/test_trainstep_gpu.py)
         assert out[r]["graph_vs_eager_param"] < 1e-3, out[r]
+        assert out[r]["native_vs_eager_loss"] < 2e-3 and out[r]["native_graph_vs_eager_loss"] < 2e-3, out[r]
+        assert out[r]["native_vs_eager_param"] < 1e-3 and out[r]["native_graph_vs_eager_param"] < 1e-3, out[r]
         assert out[r]["pipelined_vs_eager_loss"] < 2e-3, out[r]
         assert out[r]["pipelined_vs_eager_param"] < 1e-3, out[r]
     assert out[0]["loss1_vs_oracle"] < 2e-2, out[0]

@@ -34,6 +34,81 @@ def _rank():
     return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
 
 
+class NativeComm:
+    """The two collectives of the step through the C ABI's own NCCL communicator (include/tvts_b200.h: tvts_comm_*) instead of
+    torch.distributed -- selected with TVTS_COMM=native.  torch.distributed is still what brings the ranks together: it carries the
+    128-byte NCCL id from rank 0 to the others (the side channel tvts_comm_init asks for).  One instance per process."""
+
+    def __init__(self, device):
+        import ctypes
+        self._ct = ctypes
+        lib = L.lib()
+        rank, world = dist.get_rank(), dist.get_world_size()
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (ctypes.c_ubyte * 128)()
+            L.check(lib.tvts_comm_unique_id(buf), "comm_unique_id")
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        box = [ident.tolist()]
+        dist.broadcast_object_list(box, src=0)
+        buf = (ctypes.c_ubyte * 128)(*box[0])
+        self.handle = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            L.check(lib.tvts_comm_init(ctypes.byref(self.handle), buf, ctypes.c_int64(rank), ctypes.c_int64(world)), "comm_init")
+        self.rank, self.world, self.device = rank, world, device
+
+    def _stream(self):
+        return self._ct.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def all_gather(self, out, local):
+        ct = self._ct
+        L.check(L.lib().tvts_comm_allgather(self.handle, ct.c_void_p(local.data_ptr()), ct.c_void_p(out.data_ptr()),
+                                            ct.c_int64(local.numel() * local.element_size()), self._stream()), "comm_allgather")
+
+    def all_reduce_avg(self, t):
+        ct = self._ct
+        assert t.dtype == torch.float32 and t.is_contiguous()
+        L.check(L.lib().tvts_comm_allreduce(self.handle, ct.c_void_p(t.data_ptr()), ct.c_int64(t.numel()), ct.c_int64(1), self._stream()),
+                "comm_allreduce")
+
+    def destroy(self):
+        if self.handle:
+            torch.cuda.synchronize(self.device)
+            L.check(L.lib().tvts_comm_destroy(self.handle), "comm_destroy")
+            self.handle = None
+
+
+_NATIVE = None
+
+
+def native_comm(device=None):
+    """The process's NativeComm when TVTS_COMM=native, more than one rank and a CUDA device; else None (torch.distributed collectives)."""
+    global _NATIVE
+    if os.environ.get("TVTS_COMM", "torch") != "native" or _world() == 1:
+        return None
+    if _NATIVE is None:
+        if device is None or torch.device(device).type != "cuda":
+            return None
+        _NATIVE = NativeComm(torch.device(device))
+    return _NATIVE
+
+
+def shutdown_native_comm():
+    """Destroy the native communicator (after every CUDA graph that holds its kernels is gone, before the process group goes away)."""
+    global _NATIVE
+    if _NATIVE is not None:
+        _NATIVE.destroy()
+        _NATIVE = None
+
+
+def _all_gather(out, local):
+    nc = native_comm(local.device)
+    if nc is not None:
+        nc.all_gather(out, local)
+    else:
+        dist.all_gather_into_tensor(out, local)
+
+
 class AllGather_multi(torch.autograd.Function):
     """apply(tensor, n_gpu, args) -> rank-ordered concatenation; backward = this rank's slice of grad_output.
     (`args.rank` is the GLOBAL rank, v2/trainer/trainer.py:53-57.)"""
@@ -48,7 +123,7 @@ class AllGather_multi(torch.autograd.Function):
             ctx.rank = 0
             return tensor.clone()
         out = torch.empty((W * tensor.shape[0],) + tuple(tensor.shape[1:]), dtype=tensor.dtype, device=tensor.device)
-        dist.all_gather_into_tensor(out, tensor)
+        _all_gather(out, tensor)
         return out
 
     @staticmethod
@@ -68,7 +143,7 @@ class _GatherPair(torch.autograd.Function):
             return video.clone(), text.clone()
         local = torch.cat([video, text], 1).contiguous()
         out = torch.empty((W * B, 2 * Edim), dtype=local.dtype, device=local.device)
-        dist.all_gather_into_tensor(out, local)
+        _all_gather(out, local)
         return out[:, :Edim].contiguous(), out[:, Edim:].contiguous()
 
     @staticmethod
@@ -90,7 +165,7 @@ def gather_for_fused_loss(video, text):
     B, Edim = video.shape
     local = torch.cat([video, text], 1).contiguous()
     out = torch.empty((W * B, 2 * Edim), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, local)
+    _all_gather(out, local)
     return out[:, :Edim].contiguous(), out[:, Edim:].contiguous(), r * B
 
 
@@ -98,7 +173,10 @@ def average_flat(fs):
     """Gradient averaging over the flat arena: one NCCL all-reduce (AVG), no flatten / unflatten copies."""
     if _world() == 1:
         return 0
-    if dist.get_backend() == "nccl":
+    nc = native_comm(fs.g.device)
+    if nc is not None:
+        nc.all_reduce_avg(fs.g)
+    elif dist.get_backend() == "nccl":
         dist.all_reduce(fs.g, op=dist.ReduceOp.AVG)
     else:                                   # gloo (CPU tests) has no AVG
         dist.all_reduce(fs.g, op=dist.ReduceOp.SUM)
@@ -107,7 +185,10 @@ def average_flat(fs):
 
 
 def _average_tensor(t):
-    if dist.get_backend() == "nccl":
+    nc = native_comm(t.device)
+    if nc is not None:
+        nc.all_reduce_avg(t)
+    elif dist.get_backend() == "nccl":
         dist.all_reduce(t, op=dist.ReduceOp.AVG)
     else:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -238,7 +319,8 @@ class TrainStep:
         flat = getattr(self.optimizer, "flat", None)
         t = torch.zeros(8, dtype=torch.float32, device=self.device)
         out = torch.empty(8 * _world(), dtype=torch.float32, device=self.device)
-        dist.all_gather_into_tensor(out, t)
+        native_comm(self.device)               # TVTS_COMM=native: the C ABI's communicator is created here, collectively
+        _all_gather(out, t)
         if flat is not None:
             average_flat(flat)                 # gradients are zeroed at the start of every step: averaging them here is harmless
         else:
