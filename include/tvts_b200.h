@@ -121,22 +121,25 @@ int tvts_attn_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t N, 
  * with events (graph-capture safe); 0: everything on `stream` */
 int tvts_attn_set_side_stream(int on);
 /* tcgen05 path of tvts_attn_fwd / tvts_attn_bwd (csrc/attention_tc.cu) for head dim 64 and groups that fit ONE 128-row UMMA tile:
- * mode 1 (space; n + 1 <= 128 rows per frame group, the CLS query / key folded into every frame tile and merged by a second tiny kernel)
+ * mode 1 (space; n + 1 <= 128 rows per frame group, the CLS query / key folded into every frame tile and merged inside the kernel)
  * mode 0 with N <= 128 (the 77-token causal CLIP text sequences), and mode 2 (time: a tile packs floor(127 / T) patch positions x T
  * frames + CLS, block-diagonal key mask, 4-D TMA boxes over the strided token rows).  S and O (backward: S, dP, dV, dK, dQ) live in TMEM,
- * Q / K / V / dO tiles arrive by TMA, results leave by TMA stores.  tvts_attn_set_tc(on): bit 0 = modes 0 / 1, bit 1 = mode 2 (default 3;
+ * Q / K / V / dO tiles arrive by TMA; the forward's result leaves by a TMA store, the backward (a persistent kernel that draws its tiles
+ * from a dynamic scheduler) stores dq / dk / dv straight from registers.  tvts_attn_set_tc(on): bit 0 = modes 0 / 1, bit 1 = mode 2 (default 3;
  * 0 routes every shape back to the mma.sync kernels -- A/B comparison in the tests; environment TVTS_ATTN_TC=0 / TVTS_ATTN_TC_TIME=0 do
  * the same per process); tvts_attn_tc_supported tells which path tvts_attn_fwd / _bwd take for a shape.
- * Modes 1 / 2 keep the CLS partials and the per-(b, h) merge tickets in ONE per-device workspace (allocated on first use, outside any
- * stream capture): such calls on one device must be ordered with respect to each other (one stream, or explicit dependencies). */
+ * The CLS partials, the per-column merge tickets (modes 1 / 2) and the backward's tile-scheduler state live in ONE per-device workspace
+ * (allocated on first use, outside any stream capture).  Calls of the same KIND on one device -- forward or backward, mode 0 or modes
+ * 1 / 2 -- must therefore be ordered with respect to each other (one stream, or explicit dependencies); different kinds may overlap
+ * (the text tower's mode-0 calls run on a second stream next to the video tower's mode-1 / 2 calls). */
 int tvts_attn_set_tc(int on);
 int tvts_attn_tc_supported(int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal);
 int tvts_attn_tc_fwd(const void* qkv, void* out, float* lse, int64_t B, int64_t N, int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n,
                      int64_t causal, float scale, void* stream);
 int tvts_attn_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int64_t B, int64_t N, int64_t H,
                      int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal, float scale, void* stream);
-/* the same, additionally ACCUMULATING the column sums of dqkv over all tokens into dbias[3*H*d] (fp32; = the bias gradient of the qkv
- * Linear, v2/model/video_encoder_ViT_B_16.py:26,41), taken from the staged 16-bit rows inside the kernel instead of a separate pass */
+/* the same, additionally ACCUMULATING the bias gradient of the qkv Linear (v2/model/video_encoder_ViT_B_16.py:26,41) into dbias[3*H*d]
+ * (fp32) inside the kernel instead of a separate pass over dqkv -- in exact-arithmetic form, see tvts_attn_bwd_bias */
 int tvts_attn_tc_bwd_bias(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dbias, int64_t B, int64_t N,
                           int64_t H, int64_t d, int64_t mode, int64_t T, int64_t n, int64_t causal, float scale, void* stream);
 int tvts_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv, int64_t B, int64_t N,
